@@ -1,0 +1,121 @@
+/*
+ * nldpc.h — C ABI of libnldpc_b200.so: B200 (sm_100a) neural belief-propagation LDPC decode.
+ *
+ * This is the drop-in boundary for ONE hot path of ShapeLayer/neural-ldpc-decoder-torch: the
+ * iteration loops of
+ *     NeuralLDPCDecoder.forward         src/neural_ldpc_decoder/NeuralLDPCDecoder.py:44-100
+ *     BoostedNeuralLDPCDecoder.forward  src/boosted_neural_ldpc_decoder/BoostedNeuralLDPCDecoder.py:260-538
+ * and their backward (autograd of the above + LDPCDecoderLoss.py:73-108).  The reference has no
+ * FFI of its own (pure PyTorch); these entry points are what a ctypes / torch.library binding on
+ * the reference side binds.  Plain pointers and sizes only, no torch types.
+ *
+ * Conventions
+ *   - All `*_dev` pointers are device pointers on the graph's device; `*_host` are host pointers.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All device entry
+ *     points are asynchronous on that stream and never synchronise.
+ *   - Return value: 0 on success; >0 = cudaError_t; <0 = NLDPC_E_*.  nldpc_last_error() returns a
+ *     thread-local human readable message for the last failure on the calling thread.
+ *   - Edge index e is the reference's ROW-MAJOR edge index (check row outer, variable column inner,
+ *     ConnectingMatrix.py:78-85): the layout of weights_var[t] / biases_var[t] / weight_CN_t.
+ *   - xa is [B][N][Z] fp32 (channel LLR, LLR>0 <=> bit 1 as in the reference), outputs are
+ *     [.., B][N*Z] fp32 with bit index j*Z+z.  Packed hard decisions: bit q of codeword b is
+ *     bit (q%8) of byte hard[b*ceil(N*Z/8) + q/8], value (out < 0) — the reference predicate of
+ *     Functions.evaluate_ber_fer (Functions.py:90).
+ */
+#ifndef NLDPC_H_
+#define NLDPC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NLDPC_ABI_VERSION 1
+
+/* error codes (negative); positive return values are cudaError_t */
+#define NLDPC_OK 0
+#define NLDPC_E_INVALID (-1)     /* bad argument (null pointer, non-positive size, bad enum) */
+#define NLDPC_E_UNSUPPORTED (-2) /* graph too large for the on-chip design (see nldpc_graph_create) */
+#define NLDPC_E_NOMEM (-3)
+#define NLDPC_E_NODEVICE (-4)    /* no CUDA device / not an sm_100 device */
+
+typedef struct nldpc_graph nldpc_graph_t; /* opaque: per-device Tanner-graph tables */
+
+/* output selection for the per-iteration soft outputs / hard decisions */
+#define NLDPC_OUT_NONE 0
+#define NLDPC_OUT_ALL 1  /* every iteration: soft [T][B][N*Z], hard [T][B][ceil(N*Z/8)] */
+#define NLDPC_OUT_LAST 2 /* last iteration only: soft [B][N*Z], hard [B][ceil(N*Z/8)] */
+
+/* decoder arithmetic of the Boosted decoder (struct/DecoderType.py) */
+#define NLDPC_DEC_SP 0
+#define NLDPC_DEC_MS 1
+#define NLDPC_DEC_QMS 2
+
+const char *nldpc_last_error(void);
+int nldpc_abi_version(void);
+
+/* Replaces ConnectingMatrix.__init__/_init_conn_matrix + ConnectingMatrixTorch.__init__
+ * (neural ConnectingMatrix.py:4-140, ConnectingMatrixTorch.py:7-46; boosted :5-163 / :7-54):
+ * builds the edge/shift tables for `basegraph` ([M][N] row-major int32, -1 = no edge, entry used
+ * modulo Z) on CUDA device `device` instead of dense 0/1 matrices.
+ * NLDPC_E_UNSUPPORTED if one codeword's state ((N + #edges in columns of degree>=2) * Z floats)
+ * does not fit the 227 KB of shared memory, or a node degree exceeds 32. */
+int nldpc_graph_create(const int32_t *basegraph, int M, int N, int Z, int device, nldpc_graph_t **out);
+void nldpc_graph_destroy(nldpc_graph_t *g);
+/* info[0..7] = {M, N, Z, E, stored_slots, codewords_per_cta, threads_per_cta, specialised(0/1)} */
+int nldpc_graph_info(const nldpc_graph_t *g, int32_t info[8]);
+
+/* Replaces the loop of NeuralLDPCDecoder.forward (NeuralLDPCDecoder.py:54-98) for B codewords and
+ * T iterations: VN update (:56-58), circulant gather (:59-63), min-sum CN with the reference's
+ * zero/10000 masking and sign rule (:66-80), scatter (:82-86), learned |m|*w+b, ReLU, sign (:89-91)
+ * and the marginal (:94-98) in ONE kernel; messages never leave shared memory.
+ *   w_dev, b_dev : [T][E] fp32 (weights_var / biases_var stacked)
+ *   soft_dev     : per soft_mode (may be NULL with NLDPC_OUT_NONE)
+ *   hard_dev     : per hard_mode (may be NULL with NLDPC_OUT_NONE), packed (out<0) bits
+ * Results are bit-identical to the reference's CPU fp32 results (same operations, same order). */
+int nldpc_neural_forward(const nldpc_graph_t *g, const float *xa_dev, const float *w_dev, const float *b_dev,
+                         int B, int T, int soft_mode, float *soft_dev, int hard_mode, uint8_t *hard_dev,
+                         void *stream);
+
+/* Host-buffer convenience used for end-to-end timing and by non-torch callers: copies xa from host
+ * memory (pinned or pageable) in chunks, decodes, copies the selected results back; H2D / kernel / D2H
+ * of consecutive chunks overlap on internal streams.  Synchronous: returns when the host buffers are
+ * filled.  Shapes as in nldpc_neural_forward with host pointers (w_host/b_host are [T][E]). */
+int nldpc_neural_decode_host(const nldpc_graph_t *g, const float *xa_host, const float *w_host, const float *b_host,
+                             int B, int T, int soft_mode, float *soft_host, int hard_mode, uint8_t *hard_host);
+
+/* Backward of nldpc_neural_forward w.r.t. w and b (closed form of autograd through
+ * NeuralLDPCDecoder.py:54-98): recomputes the forward per codeword tile
+ * keeping the c2v history on chip, then walks the iterations backwards.
+ *   gout_dev : [T][B][N*Z] upstream gradients dL/dout_t (zeros where an iteration is unused)
+ *   gw_dev, gb_dev : [T][E] fp32, OVERWRITTEN with the batch-summed gradients. */
+int nldpc_neural_backward(const nldpc_graph_t *g, const float *xa_dev, const float *w_dev, const float *b_dev,
+                          const float *gout_dev, int B, int T, float *gw_dev, float *gb_dev, void *stream);
+
+/* Configuration of the Boosted decoder loop body, sharing types already folded by the caller into
+ * per-iteration rows (NULL = "no weight of that kind"):
+ *   vn_w  [T][N]  multiplies the (compounding) channel input per column  (:325-334, sharing 2/3)
+ *   cn_w  [T][E]  check-node weight per edge                               (:431-503, sharing 1-4)
+ *   ucn_w [T][E]  weight used instead of cn_w on unsatisfied checks        (:436-488, ucn == cn type) */
+typedef struct nldpc_boosted_cfg {
+    int32_t decoder_type; /* NLDPC_DEC_* */
+    int32_t qbit;         /* decoder_qms_qbit: 6, 5, -5, 4, 3; anything else = no quantisation (:187-214) */
+    float llr_lo, llr_hi; /* allowed_llr_range (default -20, 20) */
+    int32_t compute_ucn;  /* UCN sharing > 0: evaluate the unsatisfied-check indicator (:339-374) */
+    int32_t reserved;
+} nldpc_boosted_cfg_t;
+
+/* Replaces the loop of BoostedNeuralLDPCDecoder.forward (:320-531) for iterations 0..T-1 from a
+ * zero message state (the target_iter=None / range(T) call of train/…py:278 and the validation loop).
+ *   llr_last_dev : optional [B][Z][E] fp32, receives self.llr[T] (c2v of the last iteration). */
+int nldpc_boosted_forward(const nldpc_graph_t *g, const nldpc_boosted_cfg_t *cfg, const float *xa_dev,
+                          const float *vn_w_dev, const float *cn_w_dev, const float *ucn_w_dev,
+                          int B, int T, int soft_mode, float *soft_dev, int hard_mode, uint8_t *hard_dev,
+                          float *llr_last_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NLDPC_H_ */

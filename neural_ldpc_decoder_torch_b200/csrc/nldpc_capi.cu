@@ -1,0 +1,301 @@
+// nldpc_capi.cu — extern "C" entry points of libnldpc_b200.so (see include/nldpc.h).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/nldpc.h"
+#include "nldpc_common.cuh"
+#include "nldpc_spec.cuh"
+
+using namespace nldpc;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                    \
+    do {                                                                                                  \
+        cudaError_t _e = (expr);                                                                          \
+        if (_e != cudaSuccess) {                                                                          \
+            cudaGetLastError();                                                                           \
+            return fail((int)_e, std::string(#expr) + ": " + cudaGetErrorString(_e));                     \
+        }                                                                                                 \
+    } while (0)
+
+struct nldpc_graph {
+    int device = 0;
+    int M = 0, N = 0, Z = 0, E = 0, S = 0;
+    GraphDev dev{};
+    int *tables = nullptr;       // one device allocation holding every int table
+    int cw_per_cta = 0, threads = 0, use_tma = 0;
+    size_t smem_bytes = 0;
+    int sm_count = 0;
+    int spec_id = -1;            // index into the specialised-kernel registry, -1 = generic only
+    std::vector<int32_t> bg;     // host copy
+    // host-API staging
+    cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t events[3] = {nullptr, nullptr, nullptr};
+};
+
+extern "C" const char *nldpc_last_error(void) { return g_err.c_str(); }
+extern "C" int nldpc_abi_version(void) { return NLDPC_ABI_VERSION; }
+
+extern "C" int nldpc_graph_create(const int32_t *basegraph, int M, int N, int Z, int device, nldpc_graph_t **out) {
+    if (!basegraph || !out || M <= 0 || N <= 0 || Z <= 0) return fail(NLDPC_E_INVALID, "nldpc_graph_create: bad argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return fail(NLDPC_E_NODEVICE, "nldpc_graph_create: no such CUDA device");
+    }
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(NLDPC_E_NODEVICE, "nldpc_graph_create: device is not sm_100 (this library is built for sm_100a only)");
+    CUDA_TRY(cudaSetDevice(device));
+
+    // ---- host tables (row-major edges; column lists in ascending check row) ----
+    std::vector<int> erow, ecol, eshift, row_ptr(M + 1, 0);
+    for (int i = 0; i < M; i++) {
+        row_ptr[i] = (int)erow.size();
+        for (int j = 0; j < N; j++) {
+            const int v = basegraph[(size_t)i * N + j];
+            if (v == -1) continue;
+            if (v < -1) return fail(NLDPC_E_INVALID, "nldpc_graph_create: basegraph entries must be >= -1");
+            erow.push_back(i); ecol.push_back(j); eshift.push_back(v % Z);
+        }
+    }
+    const int E = (int)erow.size();
+    row_ptr[M] = E;
+    if (E == 0) return fail(NLDPC_E_INVALID, "nldpc_graph_create: graph has no edges");
+    std::vector<int> col_deg(N, 0);
+    for (int e = 0; e < E; e++) col_deg[ecol[e]]++;
+    for (int i = 0; i < M; i++)
+        if (row_ptr[i + 1] - row_ptr[i] > kMaxDeg) return fail(NLDPC_E_UNSUPPORTED, "nldpc_graph_create: check degree > 32");
+    for (int j = 0; j < N; j++)
+        if (col_deg[j] > kMaxDeg) return fail(NLDPC_E_UNSUPPORTED, "nldpc_graph_create: variable degree > 32");
+    // stored slots: edges of variable blocks with degree >= 2, numbered column-major (block by block)
+    std::vector<int> slot(E, -1), vcol_j, vcol_ptr(1, 0), vcol_row;
+    int S = 0;
+    for (int j = 0; j < N; j++) {
+        if (col_deg[j] < 2) continue;
+        vcol_j.push_back(j);
+        for (int e = 0; e < E; e++)
+            if (ecol[e] == j) { slot[e] = S++; vcol_row.push_back(N + slot[e]); }
+        vcol_ptr.push_back((int)vcol_row.size());
+    }
+    std::vector<int> e_row(E), e_col1(E);
+    for (int e = 0; e < E; e++) {
+        e_row[e] = slot[e] >= 0 ? N + slot[e] : ecol[e];
+        e_col1[e] = slot[e] >= 0 ? -1 : ecol[e];
+    }
+    // slab stride == Z (mod 32): thread (cw, z) then maps to bank (cw*Z + z + const) mod 32 -> conflict-free
+    int stride = (N + S) * Z;
+    while ((stride & 31) != (Z & 31)) stride++;
+    const int NZ = N * Z;
+    const int use_tma = ((NZ % 4) == 0) && ((stride % 4) == 0);
+    const int hwords = (NZ + 31) / 32;
+    // per-CTA budget: aim for 2 CTAs / SM
+    const size_t per_cw = (size_t)stride * 4 + (size_t)hwords * 4;
+    if (Z > 256 || per_cw + 64 > (size_t)kSmemBudget)
+        return fail(NLDPC_E_UNSUPPORTED, "nldpc_graph_create: one codeword's message state does not fit in 227 KB of shared memory");
+    const size_t half_budget = (size_t)(kSmemBudget - 2048) / 2;
+    int cw = (int)std::min<size_t>((half_budget - 64) / per_cw, (size_t)(256 / Z));
+    if (cw < 1) cw = (int)std::min<size_t>(((size_t)kSmemBudget - 64) / per_cw, (size_t)(256 / Z));
+    if (cw < 1) cw = 1;
+    const int threads = ((cw * Z + 31) / 32) * 32;
+
+    nldpc_graph *g = new (std::nothrow) nldpc_graph();
+    if (!g) return fail(NLDPC_E_NOMEM, "nldpc_graph_create: out of host memory");
+    g->device = device; g->M = M; g->N = N; g->Z = Z; g->E = E; g->S = S;
+    g->bg.assign(basegraph, basegraph + (size_t)M * N);
+    g->cw_per_cta = cw; g->threads = threads; g->use_tma = use_tma;
+    g->smem_bytes = (size_t)cw * stride * 4 + (((size_t)cw * hwords + 1) & ~(size_t)1) * 4 + 16;
+    g->sm_count = prop.multiProcessorCount;
+
+    std::vector<int> all;
+    auto push = [&](const std::vector<int> &v) { size_t o = all.size(); all.insert(all.end(), v.begin(), v.end()); return o; };
+    const size_t o_vj = push(vcol_j), o_vp = push(vcol_ptr), o_vr = push(vcol_row), o_rp = push(row_ptr), o_er = push(e_row),
+                 o_es = push(eshift), o_c1 = push(e_col1);
+    cudaError_t ce = cudaMalloc(&g->tables, all.size() * sizeof(int));
+    if (ce == cudaSuccess) ce = cudaMemcpy(g->tables, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) {
+        cudaGetLastError();
+        if (g->tables) cudaFree(g->tables);
+        delete g;
+        return fail((int)ce, std::string("nldpc_graph_create: table upload failed: ") + cudaGetErrorString(ce));
+    }
+    GraphDev &d = g->dev;
+    d.M = M; d.N = N; d.Z = Z; d.E = E; d.S = S; d.n_vcols = (int)vcol_j.size(); d.slab_stride = stride;
+    d.vcol_j = g->tables + o_vj; d.vcol_ptr = g->tables + o_vp; d.vcol_row = g->tables + o_vr;
+    d.row_ptr = g->tables + o_rp; d.e_row = g->tables + o_er; d.e_shift = g->tables + o_es; d.e_col1 = g->tables + o_c1;
+
+    ce = (cudaError_t)generic_prepare(g->smem_bytes);
+    if (ce != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(g->tables);
+        delete g;
+        return fail((int)ce, std::string("nldpc_graph_create: cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
+    }
+    g->spec_id = spec_find(g->bg.data(), M, N, Z);
+    if (g->spec_id >= 0) {
+        int rc = spec_prepare(g->spec_id);
+        if (rc != 0) { cudaFree(g->tables); delete g; return fail(rc, "nldpc_graph_create: specialised kernel setup failed"); }
+    }
+    *out = g;
+    return NLDPC_OK;
+}
+
+extern "C" void nldpc_graph_destroy(nldpc_graph_t *g) {
+    if (!g) return;
+    cudaSetDevice(g->device);
+    for (int i = 0; i < 3; i++) {
+        if (g->streams[i]) cudaStreamDestroy(g->streams[i]);
+        if (g->events[i]) cudaEventDestroy(g->events[i]);
+    }
+    if (g->tables) cudaFree(g->tables);
+    delete g;
+}
+
+extern "C" int nldpc_graph_info(const nldpc_graph_t *g, int32_t info[8]) {
+    if (!g || !info) return fail(NLDPC_E_INVALID, "nldpc_graph_info: null argument");
+    info[0] = g->M; info[1] = g->N; info[2] = g->Z; info[3] = g->E; info[4] = g->S;
+    info[5] = g->spec_id >= 0 ? spec_cw_per_cta(g->spec_id) : g->cw_per_cta;
+    info[6] = g->spec_id >= 0 ? spec_threads(g->spec_id) : g->threads;
+    info[7] = g->spec_id >= 0 ? 1 : 0;
+    return NLDPC_OK;
+}
+
+static int check_modes(int soft_mode, const void *soft, int hard_mode, const void *hard) {
+    if (soft_mode < 0 || soft_mode > 2 || hard_mode < 0 || hard_mode > 2) return fail(NLDPC_E_INVALID, "bad output mode");
+    if ((soft_mode != 0 && !soft) || (hard_mode != 0 && !hard)) return fail(NLDPC_E_INVALID, "output pointer is NULL for a requested output");
+    return 0;
+}
+
+// NLDPC_FORCE_GENERIC=1 routes the built-in graphs through the table-driven kernel too (tests compare both).
+static bool force_generic() {
+    const char *e = getenv("NLDPC_FORCE_GENERIC");
+    return e && e[0] == '1';
+}
+
+extern "C" int nldpc_neural_forward(const nldpc_graph_t *g, const float *xa_dev, const float *w_dev, const float *b_dev,
+                                    int B, int T, int soft_mode, float *soft_dev, int hard_mode, uint8_t *hard_dev,
+                                    void *stream) {
+    if (!g || !xa_dev || !w_dev || !b_dev || B < 0 || T <= 0) return fail(NLDPC_E_INVALID, "nldpc_neural_forward: bad argument");
+    if (int rc = check_modes(soft_mode, soft_dev, hard_mode, hard_dev)) return rc;
+    if (B == 0) return NLDPC_OK;
+    CUDA_TRY(cudaSetDevice(g->device));
+    DecodeArgs a{};
+    a.xa = xa_dev; a.w = w_dev; a.b = b_dev; a.B = B; a.T = T;
+    a.soft_mode = soft_mode; a.soft = soft_dev; a.hard_mode = hard_mode; a.hard = hard_dev;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (g->spec_id >= 0 && !force_generic()) {
+        int rc = spec_launch_neural(g->spec_id, a, g->sm_count, st);
+        if (rc > 0) return fail(rc, std::string("nldpc_neural_forward (specialised): ") + cudaGetErrorString((cudaError_t)rc));
+        if (rc == 0) return NLDPC_OK;
+        // rc < 0: configuration not covered by the specialised kernel -> generic
+    }
+    const int n_tiles = (B + g->cw_per_cta - 1) / g->cw_per_cta;
+    const int ctas_per_sm = std::max(1, (int)((size_t)kSmemBudget / (g->smem_bytes + 1024)));
+    const int grid = std::min(n_tiles, g->sm_count * ctas_per_sm);
+    CUDA_TRY((cudaError_t)generic_launch_neural(g->dev, a, g->cw_per_cta, g->threads, g->smem_bytes, g->use_tma, grid, st));
+    return NLDPC_OK;
+}
+
+// ---- host-buffer API: chunked, H2D / decode / D2H of consecutive chunks overlap on 3 streams ----
+static int ensure_streams(nldpc_graph *g) {
+    for (int i = 0; i < 3; i++) {
+        if (!g->streams[i]) CUDA_TRY(cudaStreamCreateWithFlags(&g->streams[i], cudaStreamNonBlocking));
+        if (!g->events[i]) CUDA_TRY(cudaEventCreateWithFlags(&g->events[i], cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+extern "C" int nldpc_neural_decode_host(const nldpc_graph_t *gc, const float *xa_host, const float *w_host, const float *b_host,
+                                        int B, int T, int soft_mode, float *soft_host, int hard_mode, uint8_t *hard_host) {
+    nldpc_graph *g = const_cast<nldpc_graph *>(gc);
+    if (!g || !xa_host || !w_host || !b_host || B < 0 || T <= 0) return fail(NLDPC_E_INVALID, "nldpc_neural_decode_host: bad argument");
+    if (int rc = check_modes(soft_mode, soft_host, hard_mode, hard_host)) return rc;
+    if (B == 0) return NLDPC_OK;
+    CUDA_TRY(cudaSetDevice(g->device));
+    if (int rc = ensure_streams(g)) return rc;
+    const size_t NZ = (size_t)g->N * g->Z, nb = (NZ + 7) / 8, E = (size_t)g->E;
+    // chunking: enough codewords to fill the GPU a few times, small enough to overlap copies
+    const int chunk = std::min(B, 16384);
+    const int nchunk = (B + chunk - 1) / chunk;
+    const size_t soft_per_cw = soft_mode == NLDPC_OUT_ALL ? (size_t)T * NZ : (soft_mode == NLDPC_OUT_LAST ? NZ : 0);
+    const size_t hard_per_cw = hard_mode == NLDPC_OUT_ALL ? (size_t)T * nb : (hard_mode == NLDPC_OUT_LAST ? nb : 0);
+    const int nbuf = std::min(nchunk, 3);
+    float *d_w = nullptr, *d_b = nullptr;
+    float *d_xa[3] = {nullptr, nullptr, nullptr}, *d_soft[3] = {nullptr, nullptr, nullptr};
+    uint8_t *d_hard[3] = {nullptr, nullptr, nullptr};
+    int rc = 0;
+    auto cleanup = [&]() {
+        cudaFree(d_w); cudaFree(d_b);
+        for (int i = 0; i < 3; i++) { cudaFree(d_xa[i]); cudaFree(d_soft[i]); cudaFree(d_hard[i]); }
+    };
+#define HTRY(expr)                                                                                 \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            cudaGetLastError(); cudaDeviceSynchronize(); cleanup();                                \
+            return fail((int)_e, std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+        }                                                                                          \
+    } while (0)
+    HTRY(cudaMalloc(&d_w, (size_t)T * E * 4));
+    HTRY(cudaMalloc(&d_b, (size_t)T * E * 4));
+    for (int i = 0; i < nbuf; i++) {
+        HTRY(cudaMalloc(&d_xa[i], (size_t)chunk * NZ * 4));
+        if (soft_per_cw) HTRY(cudaMalloc(&d_soft[i], (size_t)chunk * soft_per_cw * 4));
+        if (hard_per_cw) HTRY(cudaMalloc(&d_hard[i], (size_t)chunk * hard_per_cw));
+    }
+    HTRY(cudaMemcpyAsync(d_w, w_host, (size_t)T * E * 4, cudaMemcpyHostToDevice, g->streams[0]));
+    HTRY(cudaMemcpyAsync(d_b, b_host, (size_t)T * E * 4, cudaMemcpyHostToDevice, g->streams[0]));
+    HTRY(cudaEventRecord(g->events[0], g->streams[0]));
+    for (int i = 1; i < nbuf; i++) HTRY(cudaStreamWaitEvent(g->streams[i], g->events[0], 0));
+    for (int c = 0; c < nchunk; c++) {
+        const int s = c % nbuf;
+        cudaStream_t st = g->streams[s];
+        const int b0 = c * chunk, nbw = std::min(chunk, B - b0);
+        HTRY(cudaMemcpyAsync(d_xa[s], xa_host + (size_t)b0 * NZ, (size_t)nbw * NZ * 4, cudaMemcpyHostToDevice, st));
+        rc = nldpc_neural_forward(g, d_xa[s], d_w, d_b, nbw, T, soft_mode, d_soft[s], hard_mode, d_hard[s], st);
+        if (rc) { cudaDeviceSynchronize(); cleanup(); return rc; }
+        // the chunk's device layout is [T][nbw][..]; the host layout is [T][B][..]
+        if (soft_mode == NLDPC_OUT_ALL) {
+            HTRY(cudaMemcpy2DAsync(soft_host + (size_t)b0 * NZ, (size_t)B * NZ * 4, d_soft[s], (size_t)nbw * NZ * 4,
+                                   (size_t)nbw * NZ * 4, T, cudaMemcpyDeviceToHost, st));
+        } else if (soft_mode == NLDPC_OUT_LAST) {
+            HTRY(cudaMemcpyAsync(soft_host + (size_t)b0 * NZ, d_soft[s], (size_t)nbw * NZ * 4, cudaMemcpyDeviceToHost, st));
+        }
+        if (hard_mode == NLDPC_OUT_ALL) {
+            HTRY(cudaMemcpy2DAsync(hard_host + (size_t)b0 * nb, (size_t)B * nb, d_hard[s], (size_t)nbw * nb, (size_t)nbw * nb, T,
+                                   cudaMemcpyDeviceToHost, st));
+        } else if (hard_mode == NLDPC_OUT_LAST) {
+            HTRY(cudaMemcpyAsync(hard_host + (size_t)b0 * nb, d_hard[s], (size_t)nbw * nb, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    for (int i = 0; i < nbuf; i++) HTRY(cudaStreamSynchronize(g->streams[i]));
+    cleanup();
+#undef HTRY
+    return NLDPC_OK;
+}
+
+extern "C" int nldpc_neural_backward(const nldpc_graph_t *g, const float *xa_dev, const float *w_dev, const float *b_dev,
+                                     const float *gout_dev, int B, int T, float *gw_dev, float *gb_dev, void *stream) {
+    (void)g; (void)xa_dev; (void)w_dev; (void)b_dev; (void)gout_dev; (void)B; (void)T; (void)gw_dev; (void)gb_dev; (void)stream;
+    return fail(NLDPC_E_UNSUPPORTED, "nldpc_neural_backward: not implemented yet");
+}
+
+extern "C" int nldpc_boosted_forward(const nldpc_graph_t *g, const nldpc_boosted_cfg_t *cfg, const float *xa_dev,
+                                     const float *vn_w_dev, const float *cn_w_dev, const float *ucn_w_dev, int B, int T,
+                                     int soft_mode, float *soft_dev, int hard_mode, uint8_t *hard_dev, float *llr_last_dev,
+                                     void *stream) {
+    (void)g; (void)cfg; (void)xa_dev; (void)vn_w_dev; (void)cn_w_dev; (void)ucn_w_dev; (void)B; (void)T; (void)soft_mode;
+    (void)soft_dev; (void)hard_mode; (void)hard_dev; (void)llr_last_dev; (void)stream;
+    return fail(NLDPC_E_UNSUPPORTED, "nldpc_boosted_forward: not implemented yet");
+}

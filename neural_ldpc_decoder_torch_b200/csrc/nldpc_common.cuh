@@ -1,0 +1,97 @@
+// nldpc_common.cuh — shared device helpers (mbarrier / 1-D bulk TMA / exact fp32 primitives) and the
+// device-side Tanner graph descriptor.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nldpc {
+
+constexpr int kMaxDeg = 32;        // max check / variable degree supported by the generic kernel
+constexpr int kSmemBudget = 227 * 1024;
+
+// Device tables of one lifted Tanner graph (all int32 arrays live in one device allocation).
+// Shared-memory state of ONE codeword ("slab"): rows of Z floats,
+//   rows [0, N)        channel LLR of variable block j          (xa[b][j][:])
+//   rows [N, N+S)      messages of the S edges whose variable block has degree >= 2 ("stored" edges);
+//                      in place: c2v after the CN phase, v2c after the VN phase.
+// Edges of degree-1 variable blocks need no storage: their v2c is the channel LLR and their c2v only
+// feeds that block's own marginal, which the CN phase writes directly.
+struct GraphDev {
+    int M, N, Z, E, S;
+    int n_vcols;           // number of variable blocks with degree >= 2
+    int slab_stride;       // floats between consecutive codeword slabs (== Z mod 32 -> conflict-free lanes)
+    const int *vcol_j;     // [n_vcols]   variable block index
+    const int *vcol_ptr;   // [n_vcols+1] offsets into vcol_row
+    const int *vcol_row;   // slab row (N + slot) of each edge of the block, ascending check row
+    const int *row_ptr;    // [M+1] row-major edge ranges per check
+    const int *e_row;      // [E] slab row read by the CN phase: N+slot (stored) or j (degree-1 block)
+    const int *e_shift;    // [E] circulant shift (mod Z)
+    const int *e_col1;     // [E] variable block j if it has degree 1, else -1
+};
+
+struct DecodeArgs {
+    const float *xa;   // [B][N][Z]
+    const float *w;    // Neural: weights_var [T][E];  Boosted: cn_w [T][E] or nullptr
+    const float *b;    // Neural: biases_var  [T][E];  Boosted: ucn_w [T][E] or nullptr
+    const float *vn_w; // Boosted: [T][N] or nullptr
+    int B, T;
+    int soft_mode; float *soft;
+    int hard_mode; uint8_t *hard;
+    float *llr_last;   // Boosted: [B][Z][E] or nullptr
+    // boosted config
+    int decoder_type, qbit, compute_ucn;
+    float llr_lo, llr_hi;
+};
+
+// host-side launch helpers of the table-driven kernel (nldpc_generic.cu)
+int generic_prepare(size_t smem_bytes);
+int generic_launch_neural(const GraphDev &g, const DecodeArgs &a, int cw_per_cta, int threads, size_t smem_bytes, int use_tma,
+                          int grid, cudaStream_t st);
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier + 1-D bulk TMA (cp.async.bulk) ------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// global -> shared, `bytes` multiple of 16, both addresses 16-byte aligned; completes on `bar` (complete_tx).
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global bulk store (bytes multiple of 16, 16-byte aligned), tracked by the bulk async-group.
+__device__ __forceinline__ void tma_store_1d(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// ---- exact fp32 primitives: one IEEE rounding each, never contracted into FMA -----------------------------
+__device__ __forceinline__ float addf(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float mulf(float a, float b) { return __fmul_rn(a, b); }
+
+__device__ __forceinline__ void st_global_stream(float *p, float v) { __stcs(p, v); }
+
+}  // namespace nldpc

@@ -1,0 +1,13 @@
+// nldpc_spec.cuh — registry of the specialised (fully unrolled, graph-as-immediates) kernels.
+#pragma once
+#include "nldpc_common.cuh"
+
+namespace nldpc {
+// returns the registry index of a kernel specialised for exactly this base graph and lifting size, or -1
+int spec_find(const int32_t *bg, int M, int N, int Z);
+int spec_prepare(int id);                 // one-time cudaFuncSetAttribute; 0 or cudaError_t
+int spec_cw_per_cta(int id);
+int spec_threads(int id);
+// 0 = launched, >0 = cudaError_t, <0 = configuration not covered (caller falls back to the generic kernel)
+int spec_launch_neural(int id, const DecodeArgs &a, int sm_count, cudaStream_t st);
+}  // namespace nldpc

@@ -1,0 +1,69 @@
+"""ConnectingMatrixTorch — same constructor/attributes as the reference
+(/root/reference/src/neural_ldpc_decoder/ConnectingMatrixTorch.py:6-46).  The torch copies of the dense
+matrices are lazy (checkpoint compatibility only); the hot path uses `graph_id(device)` — a handle to the
+edge/shift tables that live on the GPU (nldpc_graph_create)."""
+import numpy as np
+import torch
+
+from .ConnectingMatrix import ConnectingMatrix
+
+_DENSE_DTYPE = {
+    "W_odd2even": "dtype_w_odd2even", "W_skipconn2even": "dtype_w_skipconn2even", "W_even2odd": "dtype_w_even2odd",
+    "W_output": "dtype_w_output", "lifting_matrix_1": "dtype_lifting_matrix", "lifting_matrix_2": "dtype_lifting_matrix",
+}
+
+
+class ConnectingMatrixTorch:
+    _DENSE_DTYPE = _DENSE_DTYPE
+
+    def __init__(
+            self,
+            connecting_matrix: ConnectingMatrix,
+            device: torch.device = torch.device('cpu'),
+            dtype_w_odd2even: torch.dtype = torch.float32,
+            dtype_w_skipconn2even: torch.dtype = torch.float32,
+            dtype_w_even2odd: torch.dtype = torch.float32,
+            dtype_w_output: torch.dtype = torch.float32,
+            dtype_lifting_matrix: torch.dtype = torch.float32,
+    ):
+        self.device = torch.device(device)
+        self._cm = connecting_matrix
+        self.graph = connecting_matrix.graph
+        self.N = connecting_matrix.N
+        self.M = connecting_matrix.M
+        self.Z = connecting_matrix.Z
+        self.basegraph = connecting_matrix.basegraph.copy()
+        self.sum_edge_c = connecting_matrix.sum_edge_c.copy()
+        self.sum_edge_v = connecting_matrix.sum_edge_v.copy()
+        self.sum_edge = connecting_matrix.sum_edge.copy()
+        self.dtype_w_odd2even = dtype_w_odd2even
+        self.dtype_w_skipconn2even = dtype_w_skipconn2even
+        self.dtype_w_even2odd = dtype_w_even2odd
+        self.dtype_w_output = dtype_w_output
+        self.dtype_lifting_matrix = dtype_lifting_matrix
+        self.neurons_per_even_layer = np.copy(self.sum_edge)
+        self.neurons_per_odd_layer = np.copy(self.sum_edge)
+        self._dense_t = {}
+
+    def __getattr__(self, name):
+        table = type(self)._DENSE_DTYPE
+        if name in table:
+            d = self.__dict__.setdefault("_dense_t", {})
+            if name not in d:
+                d[name] = torch.tensor(getattr(self._cm, name), dtype=getattr(self, table[name]), device=self.device)
+            return d[name]
+        raise AttributeError(name)
+
+    def dense(self, name, device=None):
+        """Dense matrix `name` as a tensor on `device` (default: this object's device), not cached."""
+        t = torch.as_tensor(getattr(self._cm, name))
+        return t.to(device=device if device is not None else self.device, dtype=getattr(self, type(self)._DENSE_DTYPE[name]))
+
+    def graph_id(self, device):
+        """Handle of the device-resident Tanner tables for CUDA device `device` (created on first use)."""
+        from .. import _lib
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise _lib.NldpcError(f"the B200 decode path needs a CUDA device, got {device}")
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        return _lib.graph_id_for(self.basegraph, self.Z, idx)

@@ -1,0 +1,113 @@
+"""NeuralLDPCDecoder — drop-in for /root/reference/src/neural_ldpc_decoder/NeuralLDPCDecoder.py:6-100.
+
+Same constructor, attributes, parameter names (`weights_var.{t}`, `biases_var.{t}`, row-major edge order,
+init 0.5 / 0), forward signature and return value (list of T tensors [B, N*Z], differentiable w.r.t. the
+parameters).  The T-iteration loop (:54-98) is ONE sm_100a kernel behind `torch.ops.nldpc.neural_forward`.
+
+`state_dict()` carries the reference's dense buffers (`W_odd2even`, …, `Lift_Matrix2`) so checkpoints
+interchange with the reference (CheckPointUtil.load is strict, CheckPointUtil.py:154); they are synthesised
+on demand and never occupy GPU memory.
+"""
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from .ConnectingMatrixTorch import ConnectingMatrixTorch
+from .. import ops  # noqa: F401  (registers torch.ops.nldpc.*)
+
+_BUFFERS = (("W_odd2even", "W_odd2even"), ("W_skipconn2even", "W_skipconn2even"), ("W_even2odd", "W_even2odd"),
+            ("W_output", "W_output"), ("Lift_Matrix1", "lifting_matrix_1"), ("Lift_Matrix2", "lifting_matrix_2"))
+
+
+class NeuralLDPCDecoder(nn.Module):
+    def __init__(
+            self,
+            iter_node_counts,
+            batch_size,
+            connecting_matrix: ConnectingMatrixTorch,
+    ):
+        super(NeuralLDPCDecoder, self).__init__()
+        self.iter_node_counts = iter_node_counts
+        self.batch_size = batch_size      # stored, unused in forward (reference :45 uses xa.shape[0])
+
+        self.conn_mat = connecting_matrix
+
+        self.N = self.conn_mat.N
+        self.M = self.conn_mat.M
+        self.Z = self.conn_mat.Z
+        self.sum_edge = self.conn_mat.sum_edge
+        self.neurons_per_odd_layer = self.conn_mat.neurons_per_odd_layer
+        self.neurons_per_even_layer = self.conn_mat.neurons_per_even_layer
+
+        self.weights_var = nn.ParameterList([
+            nn.Parameter(0.5 * torch.ones(int(self.conn_mat.sum_edge), dtype=torch.float32))
+            for _ in range(iter_node_counts)
+        ])
+        self.biases_var = nn.ParameterList([
+            nn.Parameter(torch.zeros(int(self.conn_mat.sum_edge), dtype=torch.float32))
+            for _ in range(iter_node_counts)
+        ])
+        self._register_state_dict_hook(_add_dense_buffers)
+        self._register_load_state_dict_pre_hook(_drop_dense_buffers)
+
+    # dense buffers of the reference (:27-32) as read-only attributes, for code that inspects them
+    def __getattr__(self, name):
+        for key, attr in _BUFFERS:
+            if name == key:
+                return self.conn_mat.dense(attr, device=self._param_device())
+        return super().__getattr__(name)
+
+    def _param_device(self):
+        return self.weights_var[0].device if len(self.weights_var) else torch.device("cpu")
+
+    def _stacked(self):
+        return torch.stack(list(self.weights_var)), torch.stack(list(self.biases_var))
+
+    def forward(self, xa):
+        """xa [B, N, Z] float32 on a CUDA device -> list of T tensors [B, N*Z] (iteration outputs, :94-98)."""
+        w, b = self._stacked()
+        gid = self.conn_mat.graph_id(xa.device)
+        if w.device != xa.device:
+            w, b = w.to(xa.device), b.to(xa.device)
+        out = torch.ops.nldpc.neural_forward(xa, w, b, gid)
+        return list(out.unbind(0))
+
+    @torch.no_grad()
+    def decode_hard(self, xa, all_iters=False):
+        """Throughput mode: packed hard decisions `(out < 0)` (Functions.py:90 predicate), uint8
+        [B, ceil(N*Z/8)] of the last iteration (or [T, B, ...]); soft outputs are never written to HBM."""
+        w, b = self._stacked()
+        gid = self.conn_mat.graph_id(xa.device)
+        return torch.ops.nldpc.neural_hard(xa, w.to(xa.device), b.to(xa.device), gid, all_iters)
+
+    @torch.no_grad()
+    def decode_host(self, xa_cpu, device=None, soft=False, hard=True):
+        """End-to-end host API: CPU float32 tensor in, CPU results out (chunked H2D / decode / D2H overlap)."""
+        from .. import _lib
+        device = torch.device(device if device is not None else "cuda")
+        gid = self.conn_mat.graph_id(device)
+        w, b = self._stacked()
+        return ops.neural_decode_host(gid, xa_cpu.contiguous(), w.detach().cpu().contiguous(), b.detach().cpu().contiguous(),
+                                      _lib.NLDPC_OUT_ALL if soft else _lib.NLDPC_OUT_NONE,
+                                      _lib.NLDPC_OUT_LAST if hard else _lib.NLDPC_OUT_NONE)
+
+
+def _add_dense_buffers(module, state_dict, prefix, local_metadata):
+    """state_dict hook: emit the reference's buffer keys, in the reference's order (buffers first)."""
+    dev = module._param_device()
+    items = list(state_dict.items())
+    own = [(k, v) for k, v in items if k.startswith(prefix)]
+    for k, _ in own:
+        del state_dict[k]
+    for key, attr in _BUFFERS:
+        state_dict[prefix + key] = module.conn_mat.dense(attr, device=dev)
+    for k, v in own:
+        state_dict[k] = v
+    return state_dict
+
+
+def _drop_dense_buffers(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+    """load_state_dict pre-hook: the dense structure matrices are derived from the base graph; accept and drop them."""
+    for key, _ in _BUFFERS:
+        state_dict.pop(prefix + key, None)

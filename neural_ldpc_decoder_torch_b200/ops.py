@@ -1,0 +1,142 @@
+"""torch.library custom ops over the C ABI (include/nldpc.h).  PyTorch is plumbing only: it owns the
+device memory and the current stream; the arithmetic is in libnldpc_b200.so (hand-written sm_100a CUDA).
+
+  nldpc::neural_forward(xa, w, b, graph_id) -> out [T, B, N*Z]       NeuralLDPCDecoder.py:54-98
+  nldpc::neural_hard(xa, w, b, graph_id, all_iters) -> packed uint8  + Functions.py:90 predicate
+  nldpc::neural_backward(xa, w, b, gout, graph_id) -> (gw, gb)       autograd of the above
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_vp = ctypes.c_void_p
+
+
+def _ptr(t):
+    return _vp(t.data_ptr()) if t is not None else _vp(0)
+
+
+def _stream(t):
+    return _vp(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _check_cuda_f32(name, t):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise _lib.NldpcError(f"{name} is on {t.device}: the B200 decode path has no CPU fallback — move it to a CUDA device")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32 (got {t.dtype})")
+
+
+def _prep(xa, w, b, graph_id):
+    g = _lib.graph_by_id(graph_id)
+    for n, t in (("xa", xa), ("w", w), ("b", b)):
+        _check_cuda_f32(n, t)
+    if xa.dim() != 3 or xa.shape[1] != g.N or xa.shape[2] != g.Z:
+        raise ValueError(f"xa must be [B, {g.N}, {g.Z}], got {tuple(xa.shape)}")
+    if w.dim() != 2 or w.shape[1] != g.E or b.shape != w.shape:
+        raise ValueError(f"w and b must be [T, {g.E}]")
+    if xa.device.index != g.device_index:
+        raise ValueError("graph handle and tensors live on different devices")
+    return g, xa.contiguous(), w.contiguous(), b.contiguous()
+
+
+@torch.library.custom_op("nldpc::neural_forward", mutates_args=())
+def neural_forward(xa: torch.Tensor, w: torch.Tensor, b: torch.Tensor, graph_id: int) -> torch.Tensor:
+    g, xa, w, b = _prep(xa, w, b, graph_id)
+    B, T = xa.shape[0], w.shape[0]
+    out = torch.empty((T, B, g.NZ), dtype=torch.float32, device=xa.device)
+    with torch.cuda.device(xa.device):
+        rc = _lib.lib().nldpc_neural_forward(g.ptr, _ptr(xa), _ptr(w), _ptr(b), B, T, _lib.NLDPC_OUT_ALL, _ptr(out),
+                                             _lib.NLDPC_OUT_NONE, _vp(0), _stream(xa))
+    _lib.check(rc, "nldpc_neural_forward")
+    return out
+
+
+@neural_forward.register_fake
+def _(xa, w, b, graph_id):
+    g = _lib.graph_by_id(graph_id)
+    return xa.new_empty((w.shape[0], xa.shape[0], g.NZ))
+
+
+@torch.library.custom_op("nldpc::neural_hard", mutates_args=())
+def neural_hard(xa: torch.Tensor, w: torch.Tensor, b: torch.Tensor, graph_id: int, all_iters: bool) -> torch.Tensor:
+    """Packed hard decisions (out < 0), uint8 [B, ceil(N*Z/8)] (last iteration) or [T, B, ...] (all_iters)."""
+    g, xa, w, b = _prep(xa, w, b, graph_id)
+    B, T = xa.shape[0], w.shape[0]
+    shape = (T, B, g.hard_bytes) if all_iters else (B, g.hard_bytes)
+    hard = torch.empty(shape, dtype=torch.uint8, device=xa.device)
+    with torch.cuda.device(xa.device):
+        rc = _lib.lib().nldpc_neural_forward(g.ptr, _ptr(xa), _ptr(w), _ptr(b), B, T, _lib.NLDPC_OUT_NONE, _vp(0),
+                                             _lib.NLDPC_OUT_ALL if all_iters else _lib.NLDPC_OUT_LAST, _ptr(hard), _stream(xa))
+    _lib.check(rc, "nldpc_neural_forward")
+    return hard
+
+
+@neural_hard.register_fake
+def _(xa, w, b, graph_id, all_iters):
+    g = _lib.graph_by_id(graph_id)
+    shape = (w.shape[0], xa.shape[0], g.hard_bytes) if all_iters else (xa.shape[0], g.hard_bytes)
+    return xa.new_empty(shape, dtype=torch.uint8)
+
+
+@torch.library.custom_op("nldpc::neural_backward", mutates_args=())
+def neural_backward(xa: torch.Tensor, w: torch.Tensor, b: torch.Tensor, gout: torch.Tensor,
+                    graph_id: int) -> tuple[torch.Tensor, torch.Tensor]:
+    g, xa, w, b = _prep(xa, w, b, graph_id)
+    _check_cuda_f32("gout", gout)
+    B, T = xa.shape[0], w.shape[0]
+    if tuple(gout.shape) != (T, B, g.NZ):
+        raise ValueError("gout must be [T, B, N*Z]")
+    gout = gout.contiguous()
+    gw = torch.empty_like(w)
+    gb = torch.empty_like(b)
+    with torch.cuda.device(xa.device):
+        rc = _lib.lib().nldpc_neural_backward(g.ptr, _ptr(xa), _ptr(w), _ptr(b), _ptr(gout), B, T, _ptr(gw), _ptr(gb),
+                                              _stream(xa))
+    _lib.check(rc, "nldpc_neural_backward")
+    return gw, gb
+
+
+@neural_backward.register_fake
+def _(xa, w, b, gout, graph_id):
+    return torch.empty_like(w), torch.empty_like(b)
+
+
+def _neural_setup_ctx(ctx, inputs, output):
+    xa, w, b, graph_id = inputs
+    ctx.save_for_backward(xa, w, b)
+    ctx.graph_id = graph_id
+
+
+def _neural_bwd(ctx, gout):
+    xa, w, b = ctx.saved_tensors
+    gw, gb = torch.ops.nldpc.neural_backward(xa, w, b, gout.contiguous(), ctx.graph_id)
+    return None, gw, gb, None
+
+
+neural_forward.register_autograd(_neural_bwd, setup_context=_neural_setup_ctx)
+
+
+def neural_decode_host(graph_id, xa_host, w_host, b_host, soft_mode=_lib.NLDPC_OUT_NONE, hard_mode=_lib.NLDPC_OUT_LAST):
+    """End-to-end host-buffer decode (nldpc_neural_decode_host): CPU tensors in, CPU tensors out; the
+    H2D copy, the kernel and the D2H copy of consecutive chunks overlap inside the library."""
+    g = _lib.graph_by_id(graph_id)
+    for n, t in (("xa", xa_host), ("w", w_host), ("b", b_host)):
+        if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError(f"{n} must be a contiguous float32 CPU tensor")
+    B, T = xa_host.shape[0], w_host.shape[0]
+    soft = hard = None
+    if soft_mode != _lib.NLDPC_OUT_NONE:
+        soft = torch.empty((T, B, g.NZ) if soft_mode == _lib.NLDPC_OUT_ALL else (B, g.NZ), dtype=torch.float32,
+                           pin_memory=True)
+    if hard_mode != _lib.NLDPC_OUT_NONE:
+        hard = torch.empty((T, B, g.hard_bytes) if hard_mode == _lib.NLDPC_OUT_ALL else (B, g.hard_bytes),
+                           dtype=torch.uint8, pin_memory=True)
+    rc = _lib.lib().nldpc_neural_decode_host(g.ptr, _ptr(xa_host), _ptr(w_host), _ptr(b_host), B, T, soft_mode, _ptr(soft),
+                                             hard_mode, _ptr(hard))
+    _lib.check(rc, "nldpc_neural_decode_host")
+    return soft, hard
