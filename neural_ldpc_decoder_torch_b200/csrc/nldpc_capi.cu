@@ -41,6 +41,11 @@ struct nldpc_graph {
     // host-API staging
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t events[3] = {nullptr, nullptr, nullptr};
+    // grow-only device workspace of the host-buffer API (per stream: xa chunk, soft chunk, hard chunk; + weights)
+    void *ws[3][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    size_t ws_bytes[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    void *ws_wb = nullptr;
+    size_t ws_wb_bytes = 0;
 };
 
 extern "C" const char *nldpc_last_error(void) { return g_err.c_str(); }
@@ -158,6 +163,10 @@ extern "C" void nldpc_graph_destroy(nldpc_graph_t *g) {
         if (g->streams[i]) cudaStreamDestroy(g->streams[i]);
         if (g->events[i]) cudaEventDestroy(g->events[i]);
     }
+    for (int i = 0; i < 3; i++)
+        for (int k = 0; k < 3; k++)
+            if (g->ws[i][k]) cudaFree(g->ws[i][k]);
+    if (g->ws_wb) cudaFree(g->ws_wb);
     if (g->tables) cudaFree(g->tables);
     delete g;
 }
@@ -186,9 +195,10 @@ static bool force_generic() {
 extern "C" int nldpc_neural_forward(const nldpc_graph_t *g, const float *xa_dev, const float *w_dev, const float *b_dev,
                                     int B, int T, int soft_mode, float *soft_dev, int hard_mode, uint8_t *hard_dev,
                                     void *stream) {
-    if (!g || !xa_dev || !w_dev || !b_dev || B < 0 || T <= 0) return fail(NLDPC_E_INVALID, "nldpc_neural_forward: bad argument");
+    if (!g || B < 0 || T <= 0) return fail(NLDPC_E_INVALID, "nldpc_neural_forward: bad argument");
+    if (B == 0) return NLDPC_OK;   // empty batch: nothing to do (pointers may be NULL)
+    if (!xa_dev || !w_dev || !b_dev) return fail(NLDPC_E_INVALID, "nldpc_neural_forward: NULL input pointer");
     if (int rc = check_modes(soft_mode, soft_dev, hard_mode, hard_dev)) return rc;
-    if (B == 0) return NLDPC_OK;
     CUDA_TRY(cudaSetDevice(g->device));
     DecodeArgs a{};
     a.xa = xa_dev; a.w = w_dev; a.b = b_dev; a.B = B; a.T = T;
@@ -216,44 +226,46 @@ static int ensure_streams(nldpc_graph *g) {
     return 0;
 }
 
+static int ws_reserve(void **p, size_t *have, size_t need) {
+    if (need <= *have) return 0;
+    if (*p) { CUDA_TRY(cudaFree(*p)); *p = nullptr; *have = 0; }
+    CUDA_TRY(cudaMalloc(p, need));
+    *have = need;
+    return 0;
+}
+
 extern "C" int nldpc_neural_decode_host(const nldpc_graph_t *gc, const float *xa_host, const float *w_host, const float *b_host,
                                         int B, int T, int soft_mode, float *soft_host, int hard_mode, uint8_t *hard_host) {
     nldpc_graph *g = const_cast<nldpc_graph *>(gc);
-    if (!g || !xa_host || !w_host || !b_host || B < 0 || T <= 0) return fail(NLDPC_E_INVALID, "nldpc_neural_decode_host: bad argument");
-    if (int rc = check_modes(soft_mode, soft_host, hard_mode, hard_host)) return rc;
+    if (!g || B < 0 || T <= 0) return fail(NLDPC_E_INVALID, "nldpc_neural_decode_host: bad argument");
     if (B == 0) return NLDPC_OK;
+    if (!xa_host || !w_host || !b_host) return fail(NLDPC_E_INVALID, "nldpc_neural_decode_host: NULL input pointer");
+    if (int rc = check_modes(soft_mode, soft_host, hard_mode, hard_host)) return rc;
     CUDA_TRY(cudaSetDevice(g->device));
     if (int rc = ensure_streams(g)) return rc;
     const size_t NZ = (size_t)g->N * g->Z, nb = (NZ + 7) / 8, E = (size_t)g->E;
-    // chunking: enough codewords to fill the GPU a few times, small enough to overlap copies
-    const int chunk = std::min(B, 16384);
+    // chunks: big enough to fill the GPU (>= 2 waves of resident codewords), small enough that the H2D copy of
+    // chunk k+1, the decode of chunk k and the D2H copy of chunk k-1 overlap on three streams
+    const int chunk = std::min(B, 8192);
     const int nchunk = (B + chunk - 1) / chunk;
     const size_t soft_per_cw = soft_mode == NLDPC_OUT_ALL ? (size_t)T * NZ : (soft_mode == NLDPC_OUT_LAST ? NZ : 0);
     const size_t hard_per_cw = hard_mode == NLDPC_OUT_ALL ? (size_t)T * nb : (hard_mode == NLDPC_OUT_LAST ? nb : 0);
     const int nbuf = std::min(nchunk, 3);
-    float *d_w = nullptr, *d_b = nullptr;
-    float *d_xa[3] = {nullptr, nullptr, nullptr}, *d_soft[3] = {nullptr, nullptr, nullptr};
-    uint8_t *d_hard[3] = {nullptr, nullptr, nullptr};
-    int rc = 0;
-    auto cleanup = [&]() {
-        cudaFree(d_w); cudaFree(d_b);
-        for (int i = 0; i < 3; i++) { cudaFree(d_xa[i]); cudaFree(d_soft[i]); cudaFree(d_hard[i]); }
-    };
+    if (int rc = ws_reserve(&g->ws_wb, &g->ws_wb_bytes, 2 * (size_t)T * E * 4)) return rc;
+    for (int i = 0; i < nbuf; i++) {
+        if (int rc = ws_reserve(&g->ws[i][0], &g->ws_bytes[i][0], (size_t)chunk * NZ * 4)) return rc;
+        if (soft_per_cw) if (int rc = ws_reserve(&g->ws[i][1], &g->ws_bytes[i][1], (size_t)chunk * soft_per_cw * 4)) return rc;
+        if (hard_per_cw) if (int rc = ws_reserve(&g->ws[i][2], &g->ws_bytes[i][2], (size_t)chunk * hard_per_cw)) return rc;
+    }
+    float *d_w = (float *)g->ws_wb, *d_b = d_w + (size_t)T * E;
 #define HTRY(expr)                                                                                 \
     do {                                                                                           \
         cudaError_t _e = (expr);                                                                   \
         if (_e != cudaSuccess) {                                                                   \
-            cudaGetLastError(); cudaDeviceSynchronize(); cleanup();                                \
+            cudaGetLastError(); cudaDeviceSynchronize();                                           \
             return fail((int)_e, std::string(#expr) + ": " + cudaGetErrorString(_e));              \
         }                                                                                          \
     } while (0)
-    HTRY(cudaMalloc(&d_w, (size_t)T * E * 4));
-    HTRY(cudaMalloc(&d_b, (size_t)T * E * 4));
-    for (int i = 0; i < nbuf; i++) {
-        HTRY(cudaMalloc(&d_xa[i], (size_t)chunk * NZ * 4));
-        if (soft_per_cw) HTRY(cudaMalloc(&d_soft[i], (size_t)chunk * soft_per_cw * 4));
-        if (hard_per_cw) HTRY(cudaMalloc(&d_hard[i], (size_t)chunk * hard_per_cw));
-    }
     HTRY(cudaMemcpyAsync(d_w, w_host, (size_t)T * E * 4, cudaMemcpyHostToDevice, g->streams[0]));
     HTRY(cudaMemcpyAsync(d_b, b_host, (size_t)T * E * 4, cudaMemcpyHostToDevice, g->streams[0]));
     HTRY(cudaEventRecord(g->events[0], g->streams[0]));
@@ -261,26 +273,27 @@ extern "C" int nldpc_neural_decode_host(const nldpc_graph_t *gc, const float *xa
     for (int c = 0; c < nchunk; c++) {
         const int s = c % nbuf;
         cudaStream_t st = g->streams[s];
+        float *d_xa = (float *)g->ws[s][0], *d_soft = (float *)g->ws[s][1];
+        uint8_t *d_hard = (uint8_t *)g->ws[s][2];
         const int b0 = c * chunk, nbw = std::min(chunk, B - b0);
-        HTRY(cudaMemcpyAsync(d_xa[s], xa_host + (size_t)b0 * NZ, (size_t)nbw * NZ * 4, cudaMemcpyHostToDevice, st));
-        rc = nldpc_neural_forward(g, d_xa[s], d_w, d_b, nbw, T, soft_mode, d_soft[s], hard_mode, d_hard[s], st);
-        if (rc) { cudaDeviceSynchronize(); cleanup(); return rc; }
+        HTRY(cudaMemcpyAsync(d_xa, xa_host + (size_t)b0 * NZ, (size_t)nbw * NZ * 4, cudaMemcpyHostToDevice, st));
+        int rc = nldpc_neural_forward(g, d_xa, d_w, d_b, nbw, T, soft_mode, d_soft, hard_mode, d_hard, st);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
         // the chunk's device layout is [T][nbw][..]; the host layout is [T][B][..]
         if (soft_mode == NLDPC_OUT_ALL) {
-            HTRY(cudaMemcpy2DAsync(soft_host + (size_t)b0 * NZ, (size_t)B * NZ * 4, d_soft[s], (size_t)nbw * NZ * 4,
+            HTRY(cudaMemcpy2DAsync(soft_host + (size_t)b0 * NZ, (size_t)B * NZ * 4, d_soft, (size_t)nbw * NZ * 4,
                                    (size_t)nbw * NZ * 4, T, cudaMemcpyDeviceToHost, st));
         } else if (soft_mode == NLDPC_OUT_LAST) {
-            HTRY(cudaMemcpyAsync(soft_host + (size_t)b0 * NZ, d_soft[s], (size_t)nbw * NZ * 4, cudaMemcpyDeviceToHost, st));
+            HTRY(cudaMemcpyAsync(soft_host + (size_t)b0 * NZ, d_soft, (size_t)nbw * NZ * 4, cudaMemcpyDeviceToHost, st));
         }
         if (hard_mode == NLDPC_OUT_ALL) {
-            HTRY(cudaMemcpy2DAsync(hard_host + (size_t)b0 * nb, (size_t)B * nb, d_hard[s], (size_t)nbw * nb, (size_t)nbw * nb, T,
+            HTRY(cudaMemcpy2DAsync(hard_host + (size_t)b0 * nb, (size_t)B * nb, d_hard, (size_t)nbw * nb, (size_t)nbw * nb, T,
                                    cudaMemcpyDeviceToHost, st));
         } else if (hard_mode == NLDPC_OUT_LAST) {
-            HTRY(cudaMemcpyAsync(hard_host + (size_t)b0 * nb, d_hard[s], (size_t)nbw * nb, cudaMemcpyDeviceToHost, st));
+            HTRY(cudaMemcpyAsync(hard_host + (size_t)b0 * nb, d_hard, (size_t)nbw * nb, cudaMemcpyDeviceToHost, st));
         }
     }
     for (int i = 0; i < nbuf; i++) HTRY(cudaStreamSynchronize(g->streams[i]));
-    cleanup();
 #undef HTRY
     return NLDPC_OK;
 }

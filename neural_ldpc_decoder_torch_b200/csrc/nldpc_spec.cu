@@ -1,9 +1,75 @@
-// nldpc_spec.cu — specialised kernels (placeholder registry until the generated kernels land).
+// nldpc_spec.cu — registry + instantiation of the specialised kernels for the built-in codes
+// (5G NR BG2 set 0 at Z=16, 802.16e N=576 R=3/4 at Z=24).
 #include "nldpc_spec.cuh"
+
+#include <algorithm>
+
+#include "generated/nldpc_graph_bg2z16.cuh"
+#include "generated/nldpc_graph_wimaxz24.cuh"
+
 namespace nldpc {
-int spec_find(const int32_t *, int, int, int) { return -1; }
-int spec_prepare(int) { return 0; }
-int spec_cw_per_cta(int) { return 0; }
-int spec_threads(int) { return 0; }
-int spec_launch_neural(int, const DecodeArgs &, int, cudaStream_t) { return -1; }
+
+namespace {
+
+template <class G>
+bool graph_matches(const int32_t *bg, int M, int N, int Z) {
+    if (M != G::M || N != G::N || Z != G::Z) return false;
+    const int32_t *ref = G::basegraph();
+    for (int i = 0; i < M * N; i++) {
+        const bool a = bg[i] == -1, b = ref[i] == -1;
+        if (a != b) return false;
+        if (!a && (bg[i] % Z) != (ref[i] % Z)) return false;
+    }
+    return true;
+}
+
+template <class G>
+int prepare() {
+    cudaError_t e = cudaFuncSetAttribute(nldpc_spec_neural_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)SpecCfg<G>::kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(nldpc_spec_neural_kernel<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)SpecCfg<G>::kSmemBytes);
+    return (int)e;
+}
+
+template <class G>
+int launch_neural(const DecodeArgs &a, int sm_count, cudaStream_t st) {
+    using Cfg = SpecCfg<G>;
+    const int n_units = (a.B + Cfg::Shape::kCw - 1) / Cfg::Shape::kCw;
+    const int ctas = (n_units + Cfg::kGroups - 1) / Cfg::kGroups;
+    const int grid = std::min(ctas, sm_count * 2);
+    const bool every = a.soft_mode == 1 || a.hard_mode == 1;
+    if (every) nldpc_spec_neural_kernel<G, true><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(a);
+    else nldpc_spec_neural_kernel<G, false><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+int spec_find(const int32_t *bg, int M, int N, int Z) {
+    if (graph_matches<gen::Bg2Z16>(bg, M, N, Z)) return 0;
+    if (graph_matches<gen::WimaxZ24>(bg, M, N, Z)) return 1;
+    return -1;
+}
+
+int spec_prepare(int id) {
+    switch (id) {
+        case 0: return prepare<gen::Bg2Z16>();
+        case 1: return prepare<gen::WimaxZ24>();
+        default: return -1;
+    }
+}
+
+int spec_cw_per_cta(int id) { return id == 0 ? SpecCfg<gen::Bg2Z16>::kCwPerCta : (id == 1 ? SpecCfg<gen::WimaxZ24>::kCwPerCta : 0); }
+int spec_threads(int id) { return id == 0 ? SpecCfg<gen::Bg2Z16>::kThreads : (id == 1 ? SpecCfg<gen::WimaxZ24>::kThreads : 0); }
+
+int spec_launch_neural(int id, const DecodeArgs &a, int sm_count, cudaStream_t st) {
+    switch (id) {
+        case 0: return launch_neural<gen::Bg2Z16>(a, sm_count, st);
+        case 1: return launch_neural<gen::WimaxZ24>(a, sm_count, st);
+        default: return -1;
+    }
+}
+
 }  // namespace nldpc

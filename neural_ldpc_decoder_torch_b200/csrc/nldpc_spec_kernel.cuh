@@ -1,0 +1,371 @@
+// nldpc_spec_kernel.cuh — hand-written templates that turn a generated compile-time graph program
+// (csrc/generated/nldpc_graph_*.cuh) into a fully unrolled decode kernel for sm_100a.
+//
+// Execution model ("codeword group"): Z lanes per codeword, one thread per (codeword, lane).  A group is
+// lcm(Z,32) consecutive threads: 1 warp = 2 codewords for Z=16, 3 warps = 4 codewords for Z=24.  Groups are
+// fully independent: each owns its codewords' shared-memory slabs, its own mbarrier (bulk-TMA loads of the
+// channel LLRs) and synchronises only inside the group (__syncwarp / a named barrier) between the VN and CN
+// phases.  A group loops over its share of the batch (persistent); there is no CTA-wide barrier in steady
+// state, so warps drift apart and FMA-heavy VN phases overlap ALU/LSU-heavy CN phases of other warps.
+//
+// Per codeword slab (floats): rows [0,N) channel LLR, rows [N,N+S) messages of edges whose variable block
+// has degree >= 2 (in place: c2v after CN, v2c after VN).  The slab stride is == Z (mod 32), so lane
+// (cw, z) sits in bank (cw*Z + z + const) mod 32: conflict-free for the un-rotated VN accesses and, because
+// the circulant rotation permutes lanes inside a codeword's own Z-block, for the rotated CN accesses too
+// when Z divides 32.
+//
+// Exactness contract: see nldpc_generic.cu / oracle/nldpc_oracle.c.
+#pragma once
+#include "nldpc_common.cuh"
+
+namespace nldpc {
+
+// one edge of a check row: slab row accessed by the CN phase, circulant shift, row-major edge index
+// (index into the weight vectors), and the variable block when it has degree 1 (message not stored).
+template <int ROW, int SHIFT, int EIDX, int COL1>
+struct Ed {
+    static constexpr int row = ROW, shift = SHIFT, e = EIDX, col1 = COL1;
+};
+
+template <int Z>
+struct GroupShape {
+    static constexpr int kLanes = (Z == 16 || Z == 32) ? 32 : (Z == 24 ? 96 : 0);
+    static constexpr int kCw = kLanes / Z;      // codewords per group
+    static constexpr int kWarps = kLanes / 32;
+    static_assert(kLanes != 0, "specialised kernels exist for Z in {16, 24, 32}");
+};
+
+template <int kLanes>
+__device__ __forceinline__ void group_sync(int group_in_cta) {
+    if constexpr (kLanes == 32) {
+        __syncwarp();
+    } else {
+        asm volatile("bar.sync %0, %1;" ::"r"(group_in_cta + 1), "n"(kLanes) : "memory");
+    }
+}
+
+// -----------------------------------------------------------------------------------------------------------
+// Per-thread state of the Neural decode (NeuralLDPCDecoder.py:44-100).
+template <class G>
+struct NeuralLane {
+    static constexpr int Z = G::Z, N = G::N, NZ = G::N * G::Z;
+    float *lane;             // &slab[z]               un-rotated accesses (VN phase)
+    float *rot[Z];           // &slab[(z + s) mod Z]   rotated accesses   (CN phase), indexed by the immediate shift
+    const float *wt, *bt;    // weights_var[t], biases_var[t]
+    float *soft;             // &soft_t[b][0] of the iteration being emitted, or nullptr (also when b >= B)
+    uint8_t *hb;             // this codeword's hard-decision staging bytes in shared memory (N*Z/8), or nullptr
+    int z;
+    bool valid;
+
+    // ---- emission of one marginal value -------------------------------------------------------------------
+    // un-rotated: this lane holds bit (J, z)
+    template <int J>
+    __device__ __forceinline__ void emit(float v) {
+        if (soft) st_global_stream(soft + J * Z + z, v);
+        if (hb) {
+            if constexpr (Z == 16 || Z == 32) {
+                const unsigned bal = __ballot_sync(0xffffffffu, v < 0.0f);
+                if constexpr (Z == 16) {
+                    if (z == 0) reinterpret_cast<uint16_t *>(hb)[J] = (uint16_t)((threadIdx.x & 16) ? (bal >> 16) : (bal & 0xffffu));
+                } else {
+                    if (z == 0) reinterpret_cast<uint32_t *>(hb)[J] = bal;
+                }
+            } else {
+                if (v < 0.0f) atomicOr(reinterpret_cast<unsigned *>(hb) + ((J * Z + z) >> 5), 1u << ((J * Z + z) & 31));
+            }
+        }
+    }
+    // rotated by SHIFT: this lane (check lane h = z) holds bit (J, (h + SHIFT) mod Z)
+    // (J and SHIFT are compile-time constants after unrolling/inlining)
+    __device__ __forceinline__ void emit_rot(const int J, const int SHIFT, float v) {
+        const int zz = (int)(rot[SHIFT] - (lane - z));      // (z + SHIFT) mod Z
+        if (soft) st_global_stream(soft + J * Z + zz, v);
+        if (hb) {
+            if constexpr (Z == 16 || Z == 32) {
+                const unsigned bal = __ballot_sync(0xffffffffu, v < 0.0f);
+                if constexpr (Z == 16) {
+                    unsigned w = (threadIdx.x & 16) ? (bal >> 16) : (bal & 0xffffu);
+                    w = ((w << SHIFT) | (w >> (16 - SHIFT))) & 0xffffu;      // bit h -> bit (h + SHIFT) mod 16
+                    if (z == 0) reinterpret_cast<uint16_t *>(hb)[J] = (uint16_t)w;
+                } else {
+                    if (z == 0) reinterpret_cast<uint32_t *>(hb)[J] = __funnelshift_l(bal, bal, SHIFT);
+                }
+            } else {
+                if (v < 0.0f) atomicOr(reinterpret_cast<unsigned *>(hb) + ((J * Z + zz) >> 5), 1u << ((J * Z + zz) & 31));
+            }
+        }
+    }
+};
+
+// ---- VN phase functors (one `col<J, R...>()` call per variable block of degree >= 2) --------------------------
+// iteration 0: all c2v are zero -> v2c = xa + 0  (:49, :56-58)
+template <class G>
+struct VnFirst {
+    NeuralLane<G> &c;
+    template <int J, int... R>
+    __device__ __forceinline__ void col() {
+        const float v = addf(c.lane[J * G::Z], 0.0f);
+        ((c.lane[R * G::Z] = v), ...);
+    }
+};
+
+// iterations >= 1: v2c[k] = x + (((0 + c[0]) + c[1]) + ... skipping k); kEmit: marginal of the previous iteration
+template <class G, bool kEmit>
+struct VnStep {
+    NeuralLane<G> &c;
+    template <int J, int... R>
+    __device__ __forceinline__ void col() {
+        constexpr int D = sizeof...(R);
+        constexpr int rows[D] = {R...};
+        float m[D], s[D];
+#pragma unroll
+        for (int k = 0; k < D; k++) m[k] = c.lane[rows[k] * G::Z];
+        const float x = c.lane[J * G::Z];
+        float p = 0.0f;
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            s[k] = p;
+            p = addf(p, m[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+#pragma unroll
+            for (int q = k + 1; q < D; q++) s[k] = addf(s[k], m[q]);
+        }
+#pragma unroll
+        for (int k = 0; k < D; k++) c.lane[rows[k] * G::Z] = addf(x, s[k]);
+        if constexpr (kEmit) c.template emit<J>(addf(x, p));       // out = xa + llr @ W_output (:94-96)
+    }
+};
+
+// marginal only (after the last CN phase)
+template <class G>
+struct Marginal {
+    NeuralLane<G> &c;
+    template <int J, int... R>
+    __device__ __forceinline__ void col() {
+        float p = 0.0f;
+        ((p = addf(p, c.lane[R * G::Z])), ...);
+        c.template emit<J>(addf(c.lane[J * G::Z], p));
+    }
+};
+
+// ---- CN phase functor (one `chk<Ed...>()` call per check row), NeuralLDPCDecoder.py:59-91 ---------------------
+// kEmit: also produce the marginals of degree-1 variable blocks (their c2v is needed for nothing else).
+template <class G, bool kEmit>
+struct CnNeural {
+    NeuralLane<G> &c;
+    template <class... Es>
+    __device__ __forceinline__ void chk() {
+        constexpr int D = sizeof...(Es);
+        constexpr int rows[D] = {Es::row...};
+        constexpr int shf[D] = {Es::shift...};
+        constexpr int eix[D] = {Es::e...};
+        constexpr int col1[D] = {Es::col1...};
+        float u[D], raw[D];
+        unsigned x = (D & 1) ? 0x80000000u : 0u;
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            raw[k] = c.rot[shf[k]][rows[k] * G::Z];                      // gather u[h] = v2c[(h+s) mod Z] (:59-63)
+            u[k] = (raw[k] == 0.0f) ? -10000.0f : raw[k];                // exact zero: magnitude 10000, "not positive" (:74, :78)
+            x ^= __float_as_uint(u[k]);
+        }
+        // min over the other edges, capped at 10000 (:74-75): pairwise prefix/suffix minima with 3-input FMNMX
+        constexpr int H = (D + 1) / 2;
+        float se[H + 1];
+        se[H] = 10000.0f;
+#pragma unroll
+        for (int q = H - 1; q >= 0; q--) {
+            if (2 * q + 1 < D) se[q] = fminf(fminf(fabsf(u[2 * q]), fabsf(u[2 * q + 1])), se[q + 1]);
+            else se[q] = fminf(fabsf(u[2 * q]), se[q + 1]);
+        }
+        float pe = 10000.0f;
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            const int q = k >> 1;
+            float mag;
+            if ((k & 1) == 0) {
+                if (k + 1 < D) mag = fminf(fminf(pe, fabsf(u[k + 1])), se[q + 1]);
+                else mag = fminf(pe, se[q + 1]);
+            } else {
+                mag = fminf(fminf(pe, fabsf(u[k - 1])), se[q + 1]);
+                pe = fminf(fminf(pe, fabsf(u[k - 1])), fabsf(u[k]));
+            }
+            if (col1[k] >= 0 && !kEmit) continue;                        // unstored edge, marginal not wanted now
+            // |o| * w + b, ReLU, sign: negative iff the number of positive OTHER inputs is even (:77-80, :89-91)
+            float m = addf(mulf(mag, __ldg(c.wt + eix[k])), __ldg(c.bt + eix[k]));
+            m = fmaxf(m, 0.0f);
+            const unsigned sb = (x ^ __float_as_uint(u[k])) & 0x80000000u;
+            const float c2v = __uint_as_float(__float_as_uint(m) | sb);
+            if (col1[k] < 0) {
+                c.rot[shf[k]][rows[k] * G::Z] = c2v;                     // scatter back (:82-86), in place
+            } else {
+                // degree-1 block col1: out = xa + (0 + c2v) at lane (h + s) mod Z (:94-98)
+                if constexpr (kEmit) c.emit_rot(col1[k], shf[k], addf(raw[k], addf(0.0f, c2v)));
+            }
+        }
+    }
+};
+
+// -----------------------------------------------------------------------------------------------------------
+template <class G>
+struct SpecCfg {
+    using Shape = GroupShape<G::Z>;
+    static constexpr int kHardBytes = (G::N * G::Z + 7) / 8;
+    static constexpr int kHardStride = (kHardBytes + 15) & ~15;           // per-codeword staging, 16 B multiple
+    static constexpr int kPerCw = G::kSlab * 4 + kHardStride;            // shared bytes per codeword
+    // groups per CTA so that two CTAs fit one SM (227 KB), threads <= 384
+    static constexpr int kBudget = (kSmemBudget - 2 * 1024) / 2 - 256;
+    static constexpr int kGroupsRaw = kBudget / (kPerCw * Shape::kCw);
+    static constexpr int kGroups = kGroupsRaw < 1 ? 1 : (kGroupsRaw * Shape::kLanes > 384 ? 384 / Shape::kLanes : kGroupsRaw);
+    static constexpr int kThreads = kGroups * Shape::kLanes;
+    static constexpr int kCwPerCta = kGroups * Shape::kCw;
+    static constexpr size_t kSmemBytes = (size_t)kCwPerCta * kPerCw + (size_t)kGroups * 8 + 16;
+};
+
+// kEvery: outputs are produced after every iteration (drop-in list mode / per-iteration hard decisions);
+// otherwise only after the last one (throughput mode) and the loop body carries no output code at all.
+template <class G, bool kEvery>
+__global__ void __launch_bounds__(SpecCfg<G>::kThreads, 2) nldpc_spec_neural_kernel(const DecodeArgs a) {
+    using Cfg = SpecCfg<G>;
+    using Shape = typename Cfg::Shape;
+    constexpr int Z = G::Z, NZ = G::N * G::Z;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *slabs = reinterpret_cast<float *>(smem_raw);
+    uint8_t *hstage = smem_raw + (size_t)Cfg::kCwPerCta * G::kSlab * 4;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(hstage + (size_t)Cfg::kCwPerCta * Cfg::kHardStride);
+
+    const int grp = threadIdx.x / Shape::kLanes;            // group within the CTA
+    const int gl = threadIdx.x - grp * Shape::kLanes;       // lane within the group
+    const int cwl = gl / Z;                                 // codeword within the group
+    const int z = gl - cwl * Z;
+    const int cw_in_cta = grp * Shape::kCw + cwl;
+    float *slab = slabs + (size_t)cw_in_cta * G::kSlab;
+    uint64_t *bar = bars + grp;
+
+    if (gl == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    group_sync<Shape::kLanes>(grp);
+
+    NeuralLane<G> c;
+    c.lane = slab + z;
+    c.z = z;
+#pragma unroll
+    for (int s = 0; s < Z; s++) c.rot[s] = slab + ((z + s) % Z);
+    uint8_t *hb_mine = hstage + (size_t)cw_in_cta * Cfg::kHardStride;
+
+    const int n_units = (a.B + Shape::kCw - 1) / Shape::kCw;
+    const int unit_stride = gridDim.x * Cfg::kGroups;
+    uint32_t phase = 0;
+    const bool soft_all = a.soft_mode == 1, hard_all = a.hard_mode == 1;
+    const bool soft_any = a.soft_mode != 0, hard_any = a.hard_mode != 0;
+
+    for (int unit = blockIdx.x * Cfg::kGroups + grp; unit < n_units; unit += unit_stride) {
+        const int b0 = unit * Shape::kCw;
+        const int b = b0 + cwl;
+        c.valid = b < a.B;
+        // ---- bulk-TMA the group's channel LLRs (one 1-D copy per codeword) ----
+        if (gl == 0) {
+            const int ncw = min(Shape::kCw, a.B - b0);
+            fence_proxy_async();
+            mbar_arrive_expect_tx(bar, (uint32_t)(ncw * NZ * sizeof(float)));
+            for (int q = 0; q < ncw; q++)
+                tma_load_1d(slabs + (size_t)(grp * Shape::kCw + q) * G::kSlab, a.xa + (size_t)(b0 + q) * NZ,
+                            (uint32_t)(NZ * sizeof(float)), bar);
+        }
+        if constexpr (Z != 16 && Z != 32) {   // atomicOr staging must start from zero
+            if (hard_any) for (int q = z; q < Cfg::kHardStride / 4; q += Z) reinterpret_cast<unsigned *>(hb_mine)[q] = 0u;
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+
+        float *soft_cw = (soft_any && c.valid) ? a.soft + (size_t)b * NZ : nullptr;     // + t*B*NZ in ALL mode
+        const size_t soft_iter = (size_t)a.B * NZ;
+        uint8_t *hb_cw = hard_any ? hb_mine : nullptr;
+        auto flush_hard = [&](int t_out) {
+            // group-cooperative copy of the staged packed decisions to global memory (16 B per lane-step)
+            group_sync<Shape::kLanes>(grp);
+            uint8_t *dst = a.hard + ((hard_all ? (size_t)t_out * a.B : 0) + b0) * Cfg::kHardBytes;
+            const int ncw = min(Shape::kCw, a.B - b0);
+            const uint8_t *src = hstage + (size_t)(grp * Shape::kCw) * Cfg::kHardStride;
+            if constexpr (Cfg::kHardBytes % 4 == 0) {
+                constexpr int W = Cfg::kHardBytes / 4;
+                for (int i = gl; i < ncw * W; i += Shape::kLanes) {
+                    const int q = i / W, r = i - q * W;
+                    reinterpret_cast<uint32_t *>(dst + (size_t)q * Cfg::kHardBytes)[r] =
+                        reinterpret_cast<const uint32_t *>(src + (size_t)q * Cfg::kHardStride)[r];
+                }
+            } else {
+                for (int i = gl; i < ncw * Cfg::kHardBytes; i += Shape::kLanes) {
+                    const int q = i / Cfg::kHardBytes, r = i - q * Cfg::kHardBytes;
+                    dst[(size_t)q * Cfg::kHardBytes + r] = src[(size_t)q * Cfg::kHardStride + r];
+                }
+            }
+            if constexpr (Z != 16 && Z != 32) {
+                group_sync<Shape::kLanes>(grp);
+                for (int q = z; q < Cfg::kHardStride / 4; q += Z) reinterpret_cast<unsigned *>(hb_mine)[q] = 0u;
+            }
+            group_sync<Shape::kLanes>(grp);
+        };
+
+        if constexpr (kEvery) {
+            for (int t = 0; t < a.T; t++) {
+                c.wt = a.w + (size_t)t * G::E;
+                c.bt = a.b + (size_t)t * G::E;
+                if (t == 0) {
+                    VnFirst<G> f{c};
+                    G::vcols(f);
+                } else {
+                    c.soft = (soft_all && soft_cw) ? soft_cw + (size_t)(t - 1) * soft_iter : nullptr;
+                    c.hb = hard_all ? hb_cw : nullptr;
+                    VnStep<G, true> f{c};
+                    G::vcols(f);
+                    if (hard_all) flush_hard(t - 1);
+                }
+                group_sync<Shape::kLanes>(grp);
+                const bool last = t == a.T - 1;
+                c.soft = (soft_cw && (soft_all || last)) ? soft_cw + (soft_all ? (size_t)t * soft_iter : 0) : nullptr;
+                c.hb = (hard_all || last) ? hb_cw : nullptr;
+                CnNeural<G, true> f{c};
+                G::checks(f);
+                group_sync<Shape::kLanes>(grp);
+            }
+        } else {
+            for (int t = 0; t < a.T; t++) {
+                c.wt = a.w + (size_t)t * G::E;
+                c.bt = a.b + (size_t)t * G::E;
+                if (t == 0) {
+                    VnFirst<G> f{c};
+                    G::vcols(f);
+                } else {
+                    VnStep<G, false> f{c};
+                    G::vcols(f);
+                }
+                group_sync<Shape::kLanes>(grp);
+                if (t < a.T - 1) {
+                    CnNeural<G, false> f{c};
+                    G::checks(f);
+                } else {
+                    c.soft = soft_cw;
+                    c.hb = hb_cw;
+                    CnNeural<G, true> f{c};
+                    G::checks(f);
+                }
+                group_sync<Shape::kLanes>(grp);
+            }
+        }
+        // marginal of the last iteration for the blocks of degree >= 2
+        {
+            c.soft = soft_cw ? soft_cw + (soft_all ? (size_t)(a.T - 1) * soft_iter : 0) : nullptr;
+            c.hb = hb_cw;
+            Marginal<G> f{c};
+            G::vcols(f);
+            if (hard_any) flush_hard(a.T - 1);
+        }
+        group_sync<Shape::kLanes>(grp);   // all lanes done with the slabs before the next TMA overwrites them
+    }
+}
+
+}  // namespace nldpc

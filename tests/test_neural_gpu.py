@@ -149,19 +149,21 @@ def test_full_size_properties_bg2_65536(graphs):
     sigma = 1.2559
     xa = (2.0 * (sigma * torch.randn((B, 52, 16), generator=g, device="cuda") - 1.0) / sigma ** 2).float()
     m = make_model(bg, Z, T, B)
-    outs = m(xa)
+    with torch.no_grad():
+        outs = m(xa)
     hard = m.decode_hard(xa)
     # (1) packed decisions == predicate on the soft output, everywhere
-    bits = (outs[-1] < 0).cpu().numpy()
+    bits = (outs[-1] < 0).detach().cpu().numpy()
     assert np.array_equal(hard.cpu().numpy(), np.packbits(bits, axis=1, bitorder="little"))
     # (2) permutation equivariance over the batch: decoding a shuffled batch gives the shuffled result
     perm = torch.randperm(B, device="cuda", generator=g)
-    outs_p = m(xa[perm])
+    with torch.no_grad():
+        outs_p = m(xa[perm])
     assert torch.equal(outs_p[-1], outs[-1][perm])
     # (3) oracle on a strided subset of codewords (every 128th), all iterations
     idx = np.arange(0, B, 128)
     ref = oracle.neural_forward(bg, Z, xa[idx].cpu().numpy(), np.full((T, E), 0.5, np.float32), np.zeros((T, E), np.float32))
-    got = np.stack([o[idx].cpu().numpy() for o in outs])
+    got = np.stack([o[idx].detach().cpu().numpy() for o in outs])
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
     # (4) decoding works: at 2 dB almost every codeword converges to the all-zero word (bit 0 <-> LLR < 0)
     frame_ok = bits.all(axis=1).mean()
