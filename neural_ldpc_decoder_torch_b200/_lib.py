@@ -9,7 +9,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnldpc_b200.so")
+LIB_PATH = os.environ.get("NLDPC_LIB_PATH") or os.path.join(_HERE, "libnldpc_b200.so")   # env override: kernel experiments only
 
 NLDPC_OUT_NONE, NLDPC_OUT_ALL, NLDPC_OUT_LAST = 0, 1, 2
 NLDPC_DEC_SP, NLDPC_DEC_MS, NLDPC_DEC_QMS = 0, 1, 2

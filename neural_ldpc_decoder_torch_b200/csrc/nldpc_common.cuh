@@ -38,6 +38,7 @@ struct DecodeArgs {
     int soft_mode; float *soft;
     int hard_mode; uint8_t *hard;
     float *llr_last;   // Boosted: [B][Z][E] or nullptr
+    int wb_off;        // specialised kernels: offset (float2 units) of this launch's weights in the constant arena, -1 = use w/b pointers
     // boosted config
     int decoder_type, qbit, compute_ucn;
     float llr_lo, llr_hi;

@@ -20,6 +20,16 @@
 
 namespace nldpc {
 
+// Learned weights live in constant memory for the duration of a launch: {w, b} pairs [T][E], read through the
+// uniform datapath (LDCU) so they cost no LSU bandwidth.  The arena is a ring shared by in-flight launches
+// (see ConstArena in nldpc_spec.cu); launches whose weights do not fit use the LDG variant (kConstW = false).
+constexpr int kConstFloat2 = 7680;                 // 60 KB of the 64 KB constant bank
+__constant__ float2 c_wb[kConstFloat2];   // this header is included by exactly one translation unit (nldpc_spec.cu)
+
+#ifndef NLDPC_CTA_LOCKSTEP
+#define NLDPC_CTA_LOCKSTEP 0   // 1: CTA-wide barrier between phases (warps share the instruction stream)
+#endif
+
 // one edge of a check row: slab row accessed by the CN phase, circulant shift, row-major edge index
 // (index into the weight vectors), and the variable block when it has degree 1 (message not stored).
 template <int ROW, int SHIFT, int EIDX, int COL1>
@@ -51,7 +61,8 @@ struct NeuralLane {
     static constexpr int Z = G::Z, N = G::N, NZ = G::N * G::Z;
     float *lane;             // &slab[z]               un-rotated accesses (VN phase)
     float *rot[Z];           // &slab[(z + s) mod Z]   rotated accesses   (CN phase), indexed by the immediate shift
-    const float *wt, *bt;    // weights_var[t], biases_var[t]
+    const float *wt, *bt;    // weights_var[t], biases_var[t]          (kConstW == false)
+    int wb_base;             // offset of {w,b}[t][0] in the constant arena (kConstW == true)
     float *soft;             // &soft_t[b][0] of the iteration being emitted, or nullptr (also when b >= B)
     uint8_t *hb;             // this codeword's hard-decision staging bytes in shared memory (N*Z/8), or nullptr
     int z;
@@ -152,7 +163,7 @@ struct Marginal {
 
 // ---- CN phase functor (one `chk<Ed...>()` call per check row), NeuralLDPCDecoder.py:59-91 ---------------------
 // kEmit: also produce the marginals of degree-1 variable blocks (their c2v is needed for nothing else).
-template <class G, bool kEmit>
+template <class G, bool kEmit, bool kConstW>
 struct CnNeural {
     NeuralLane<G> &c;
     template <class... Es>
@@ -193,7 +204,14 @@ struct CnNeural {
             }
             if (col1[k] >= 0 && !kEmit) continue;                        // unstored edge, marginal not wanted now
             // |o| * w + b, ReLU, sign: negative iff the number of positive OTHER inputs is even (:77-80, :89-91)
-            float m = addf(mulf(mag, __ldg(c.wt + eix[k])), __ldg(c.bt + eix[k]));
+            float wk, bk;
+            if constexpr (kConstW) {
+                const float2 wb = c_wb[c.wb_base + eix[k]];
+                wk = wb.x; bk = wb.y;
+            } else {
+                wk = __ldg(c.wt + eix[k]); bk = __ldg(c.bt + eix[k]);
+            }
+            float m = addf(mulf(mag, wk), bk);
             m = fmaxf(m, 0.0f);
             const unsigned sb = (x ^ __float_as_uint(u[k])) & 0x80000000u;
             const float c2v = __uint_as_float(__float_as_uint(m) | sb);
@@ -225,7 +243,7 @@ struct SpecCfg {
 
 // kEvery: outputs are produced after every iteration (drop-in list mode / per-iteration hard decisions);
 // otherwise only after the last one (throughput mode) and the loop body carries no output code at all.
-template <class G, bool kEvery>
+template <class G, bool kEvery, bool kConstW>
 __global__ void __launch_bounds__(SpecCfg<G>::kThreads, 2) nldpc_spec_neural_kernel(const DecodeArgs a) {
     using Cfg = SpecCfg<G>;
     using Shape = typename Cfg::Shape;
@@ -262,13 +280,20 @@ __global__ void __launch_bounds__(SpecCfg<G>::kThreads, 2) nldpc_spec_neural_ker
     const bool soft_all = a.soft_mode == 1, hard_all = a.hard_mode == 1;
     const bool soft_any = a.soft_mode != 0, hard_any = a.hard_mode != 0;
 
-    for (int unit = blockIdx.x * Cfg::kGroups + grp; unit < n_units; unit += unit_stride) {
+    // phase barrier: group-local by default; CTA-wide in lockstep mode (all warps then stream the same code)
+    auto phase_sync = [&]() {
+        if constexpr (NLDPC_CTA_LOCKSTEP) __syncthreads();
+        else group_sync<Shape::kLanes>(grp);
+    };
+    for (int unit0 = blockIdx.x * Cfg::kGroups; unit0 < n_units; unit0 += unit_stride) {
+        const int unit = unit0 + grp;
+        if (!NLDPC_CTA_LOCKSTEP && unit >= n_units) break;
         const int b0 = unit * Shape::kCw;
         const int b = b0 + cwl;
         c.valid = b < a.B;
+        const int ncw = max(0, min(Shape::kCw, a.B - b0));
         // ---- bulk-TMA the group's channel LLRs (one 1-D copy per codeword) ----
-        if (gl == 0) {
-            const int ncw = min(Shape::kCw, a.B - b0);
+        if (gl == 0 && ncw > 0) {
             fence_proxy_async();
             mbar_arrive_expect_tx(bar, (uint32_t)(ncw * NZ * sizeof(float)));
             for (int q = 0; q < ncw; q++)
@@ -278,8 +303,10 @@ __global__ void __launch_bounds__(SpecCfg<G>::kThreads, 2) nldpc_spec_neural_ker
         if constexpr (Z != 16 && Z != 32) {   // atomicOr staging must start from zero
             if (hard_any) for (int q = z; q < Cfg::kHardStride / 4; q += Z) reinterpret_cast<unsigned *>(hb_mine)[q] = 0u;
         }
-        mbar_wait(bar, phase);
-        phase ^= 1;
+        if (ncw > 0) {
+            mbar_wait(bar, phase);
+            phase ^= 1;
+        }
 
         float *soft_cw = (soft_any && c.valid) ? a.soft + (size_t)b * NZ : nullptr;     // + t*B*NZ in ALL mode
         const size_t soft_iter = (size_t)a.B * NZ;
@@ -288,7 +315,6 @@ __global__ void __launch_bounds__(SpecCfg<G>::kThreads, 2) nldpc_spec_neural_ker
             // group-cooperative copy of the staged packed decisions to global memory (16 B per lane-step)
             group_sync<Shape::kLanes>(grp);
             uint8_t *dst = a.hard + ((hard_all ? (size_t)t_out * a.B : 0) + b0) * Cfg::kHardBytes;
-            const int ncw = min(Shape::kCw, a.B - b0);
             const uint8_t *src = hstage + (size_t)(grp * Shape::kCw) * Cfg::kHardStride;
             if constexpr (Cfg::kHardBytes % 4 == 0) {
                 constexpr int W = Cfg::kHardBytes / 4;
@@ -314,6 +340,7 @@ __global__ void __launch_bounds__(SpecCfg<G>::kThreads, 2) nldpc_spec_neural_ker
             for (int t = 0; t < a.T; t++) {
                 c.wt = a.w + (size_t)t * G::E;
                 c.bt = a.b + (size_t)t * G::E;
+                c.wb_base = a.wb_off + t * G::E;
                 if (t == 0) {
                     VnFirst<G> f{c};
                     G::vcols(f);
@@ -324,18 +351,19 @@ __global__ void __launch_bounds__(SpecCfg<G>::kThreads, 2) nldpc_spec_neural_ker
                     G::vcols(f);
                     if (hard_all) flush_hard(t - 1);
                 }
-                group_sync<Shape::kLanes>(grp);
+                phase_sync();
                 const bool last = t == a.T - 1;
                 c.soft = (soft_cw && (soft_all || last)) ? soft_cw + (soft_all ? (size_t)t * soft_iter : 0) : nullptr;
                 c.hb = (hard_all || last) ? hb_cw : nullptr;
-                CnNeural<G, true> f{c};
+                CnNeural<G, true, kConstW> f{c};
                 G::checks(f);
-                group_sync<Shape::kLanes>(grp);
+                phase_sync();
             }
         } else {
             for (int t = 0; t < a.T; t++) {
                 c.wt = a.w + (size_t)t * G::E;
                 c.bt = a.b + (size_t)t * G::E;
+                c.wb_base = a.wb_off + t * G::E;
                 if (t == 0) {
                     VnFirst<G> f{c};
                     G::vcols(f);
@@ -343,17 +371,17 @@ __global__ void __launch_bounds__(SpecCfg<G>::kThreads, 2) nldpc_spec_neural_ker
                     VnStep<G, false> f{c};
                     G::vcols(f);
                 }
-                group_sync<Shape::kLanes>(grp);
+                phase_sync();
                 if (t < a.T - 1) {
-                    CnNeural<G, false> f{c};
+                    CnNeural<G, false, kConstW> f{c};
                     G::checks(f);
                 } else {
                     c.soft = soft_cw;
                     c.hb = hb_cw;
-                    CnNeural<G, true> f{c};
+                    CnNeural<G, true, kConstW> f{c};
                     G::checks(f);
                 }
-                group_sync<Shape::kLanes>(grp);
+                phase_sync();
             }
         }
         // marginal of the last iteration for the blocks of degree >= 2

@@ -165,9 +165,11 @@ def test_full_size_properties_bg2_65536(graphs):
     ref = oracle.neural_forward(bg, Z, xa[idx].cpu().numpy(), np.full((T, E), 0.5, np.float32), np.zeros((T, E), np.float32))
     got = np.stack([o[idx].detach().cpu().numpy() for o in outs])
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
-    # (4) decoding works: at 2 dB almost every codeword converges to the all-zero word (bit 0 <-> LLR < 0)
-    frame_ok = bits.all(axis=1).mean()
-    assert frame_ok > 0.5
+    # (4) decoding works: at 2 dB the decisions converge to the all-zero word (bit 0 <-> LLR < 0); the reference
+    #     itself reaches 6652/6656 correct bits on its 8-codeword fixture
+    assert bits.mean() > 0.995, bits.mean()
+    first = (outs[0] < 0).float().mean().item()
+    assert bits.mean() > first, (first, bits.mean())
 
 
 def test_cpu_tensor_fails_loudly(graphs):
