@@ -37,6 +37,27 @@ struct Ed {
     static constexpr int row = ROW, shift = SHIFT, e = EIDX, col1 = COL1;
 };
 
+// ---- packed helpers ----------------------------------------------------------------------------------------------
+// f2 = two fp32 values {low word, high word} in one 64-bit register pair; add2 is PTX add.rn.f32x2 (SASS FADD2):
+// two individually rounded IEEE additions in one issue slot.  It is used to advance TWO adjacent chains of the
+// exact-order VN sums of the same codeword at once.
+// NOTE: there is deliberately no packed multiply: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into ONE FFMA2
+// (single rounding) even with explicit .rn and -fmad=false, which would break the bit-exactness of |o|*w + b.
+using f2 = unsigned long long;
+__device__ __forceinline__ f2 pack2(float a, float b) { return (f2)__float_as_uint(a) | ((f2)__float_as_uint(b) << 32); }
+__device__ __forceinline__ float lo(f2 v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float hi(f2 v) { return __uint_as_float((unsigned)(v >> 32)); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+    f2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));   // one FMNMX3
+    return d;
+}
+
 template <int Z>
 struct GroupShape {
     static constexpr int kLanes = (Z == 16 || Z == 32) ? 32 : (Z == 24 ? 96 : 0);
@@ -67,6 +88,7 @@ struct NeuralLane {
     uint8_t *hb;             // this codeword's hard-decision staging bytes in shared memory (N*Z/8), or nullptr
     int z;
     bool valid;
+    float zmin;              // min |v2c| written by this lane in the current VN phase (0 => the zero-safe CN phase is needed)
 
     // ---- emission of one marginal value -------------------------------------------------------------------
     // un-rotated: this lane holds bit (J, z)
@@ -116,6 +138,7 @@ struct VnFirst {
     template <int J, int... R>
     __device__ __forceinline__ void col() {
         const float v = addf(c.lane[J * G::Z], 0.0f);
+        c.zmin = fminf(c.zmin, fabsf(v));
         ((c.lane[R * G::Z] = v), ...);
     }
 };
@@ -128,23 +151,33 @@ struct VnStep {
     __device__ __forceinline__ void col() {
         constexpr int D = sizeof...(R);
         constexpr int rows[D] = {R...};
-        float m[D], s[D];
+        float m[D], pre[D];
 #pragma unroll
         for (int k = 0; k < D; k++) m[k] = c.lane[rows[k] * G::Z];
         const float x = c.lane[J * G::Z];
-        float p = 0.0f;
+        float p = 0.0f;                       // running prefix ((0 + m0) + m1) + ...
 #pragma unroll
         for (int k = 0; k < D; k++) {
-            s[k] = p;
+            pre[k] = p;
             p = addf(p, m[k]);
         }
+        // chains k and k+1 advance together on the packed pipe: chain k is pre[k] + m[k+1] + m[k+2] + ...,
+        // chain k+1 is pre[k+1] + m[k+2] + ...; from m[k+2] on both add the same operand (FADD2, broadcast).
 #pragma unroll
-        for (int k = 0; k < D; k++) {
+        for (int k = 0; k + 1 < D; k += 2) {
+            f2 s = pack2(addf(pre[k], m[k + 1]), pre[k + 1]);
 #pragma unroll
-            for (int q = k + 1; q < D; q++) s[k] = addf(s[k], m[q]);
+            for (int q = k + 2; q < D; q++) s = add2(s, pack2(m[q], m[q]));
+            s = add2(pack2(x, x), s);
+            c.zmin = fmin3(c.zmin, fabsf(lo(s)), fabsf(hi(s)));
+            c.lane[rows[k] * G::Z] = lo(s);
+            c.lane[rows[k + 1] * G::Z] = hi(s);
         }
-#pragma unroll
-        for (int k = 0; k < D; k++) c.lane[rows[k] * G::Z] = addf(x, s[k]);
+        if constexpr (D & 1) {
+            const float v = addf(x, pre[D - 1]);
+            c.zmin = fminf(c.zmin, fabsf(v));
+            c.lane[rows[D - 1] * G::Z] = v;
+        }
         if constexpr (kEmit) c.template emit<J>(addf(x, p));       // out = xa + llr @ W_output (:94-96)
     }
 };
@@ -161,69 +194,105 @@ struct Marginal {
     }
 };
 
-// ---- CN phase functor (one `chk<Ed...>()` call per check row), NeuralLDPCDecoder.py:59-91 ---------------------
+// ---- CN phase (one `chk<Ed...>()` call per check row), NeuralLDPCDecoder.py:59-91 -----------------------------
 // kEmit: also produce the marginals of degree-1 variable blocks (their c2v is needed for nothing else).
-template <class G, bool kEmit, bool kConstW>
+// kZeroSafe = false is the fast path: it assumes that no CN input of this warp is exactly 0.  The VN phase tracks
+// min |v2c| (half an instruction per edge) and the channel LLRs are screened once per codeword; when a zero is seen
+// the warp runs the out-of-line kZeroSafe = true phase, which applies the reference's "exact zero -> magnitude 10000,
+// not positive" rule (:74, :78) at two extra instructions per edge.  Exact-zero v2c only occur for punctured /
+// quantised channel values, so the hot loop does not pay for them, and the whole CN phase stays one basic block.
+template <class G, bool kEmit, bool kConstW, bool kZeroSafe, class... Es>
+__device__ __forceinline__ void cn_check_core(NeuralLane<G> &c) {
+    constexpr int D = sizeof...(Es);
+    constexpr int rows[D] = {Es::row...};
+    constexpr int shf[D] = {Es::shift...};
+    constexpr int eix[D] = {Es::e...};
+    constexpr int col1[D] = {Es::col1...};
+    float u[D], raw[D];
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        raw[k] = c.rot[shf[k]][rows[k] * G::Z];                          // gather u[h] = v2c[(h+s) mod Z] (:59-63)
+        u[k] = (kZeroSafe && raw[k] == 0.0f) ? -10000.0f : raw[k];
+    }
+    // min over the other edges, capped at 10000 (:74-75): pairwise prefix/suffix minima with 3-input FMNMX
+    constexpr int H = (D + 1) / 2;
+    float se[H + 1];
+    se[H] = 10000.0f;
+#pragma unroll
+    for (int q = H - 1; q >= 0; q--) {
+        if (2 * q + 1 < D) se[q] = fmin3(fabsf(u[2 * q]), fabsf(u[2 * q + 1]), se[q + 1]);
+        else se[q] = fminf(fabsf(u[2 * q]), se[q + 1]);
+    }
+    unsigned x = (D & 1) ? 0x80000000u : 0u;
+#pragma unroll
+    for (int k = 0; k < D; k++) x ^= __float_as_uint(u[k]);
+    float pe = 10000.0f;
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        const int q = k >> 1;
+        float mag;
+        if ((k & 1) == 0) {
+            if (k + 1 < D) mag = fmin3(pe, fabsf(u[k + 1]), se[q + 1]);
+            else mag = fminf(pe, se[q + 1]);
+        } else {
+            mag = fmin3(pe, fabsf(u[k - 1]), se[q + 1]);
+            pe = fmin3(pe, fabsf(u[k - 1]), fabsf(u[k]));
+        }
+        if (col1[k] >= 0 && !kEmit) continue;                            // unstored edge, marginal not wanted now
+        // |o| * w + b, ReLU, sign: negative iff the number of positive OTHER inputs is even (:77-80, :89-91)
+        float wk, bk;
+        if constexpr (kConstW) {
+            const float2 wb = c_wb[c.wb_base + eix[k]];
+            wk = wb.x; bk = wb.y;
+        } else {
+            wk = __ldg(c.wt + eix[k]); bk = __ldg(c.bt + eix[k]);
+        }
+        float m = addf(mulf(mag, wk), bk);
+        m = fmaxf(m, 0.0f);
+        const unsigned sb = (x ^ __float_as_uint(u[k])) & 0x80000000u;
+        const float c2v = __uint_as_float(__float_as_uint(m) | sb);
+        if (col1[k] < 0) {
+            c.rot[shf[k]][rows[k] * G::Z] = c2v;                         // scatter back (:82-86), in place
+        } else {
+            // degree-1 block col1: out = xa + (0 + c2v) at lane (h + s) mod Z (:94-98)
+            if constexpr (kEmit) c.emit_rot(col1[k], shf[k], addf(raw[k], addf(0.0f, c2v)));
+        }
+    }
+}
+
+template <class G, bool kEmit, bool kConstW, bool kZeroSafe>
 struct CnNeural {
     NeuralLane<G> &c;
     template <class... Es>
     __device__ __forceinline__ void chk() {
-        constexpr int D = sizeof...(Es);
-        constexpr int rows[D] = {Es::row...};
-        constexpr int shf[D] = {Es::shift...};
-        constexpr int eix[D] = {Es::e...};
-        constexpr int col1[D] = {Es::col1...};
-        float u[D], raw[D];
-        unsigned x = (D & 1) ? 0x80000000u : 0u;
-#pragma unroll
-        for (int k = 0; k < D; k++) {
-            raw[k] = c.rot[shf[k]][rows[k] * G::Z];                      // gather u[h] = v2c[(h+s) mod Z] (:59-63)
-            u[k] = (raw[k] == 0.0f) ? -10000.0f : raw[k];                // exact zero: magnitude 10000, "not positive" (:74, :78)
-            x ^= __float_as_uint(u[k]);
-        }
-        // min over the other edges, capped at 10000 (:74-75): pairwise prefix/suffix minima with 3-input FMNMX
-        constexpr int H = (D + 1) / 2;
-        float se[H + 1];
-        se[H] = 10000.0f;
-#pragma unroll
-        for (int q = H - 1; q >= 0; q--) {
-            if (2 * q + 1 < D) se[q] = fminf(fminf(fabsf(u[2 * q]), fabsf(u[2 * q + 1])), se[q + 1]);
-            else se[q] = fminf(fabsf(u[2 * q]), se[q + 1]);
-        }
-        float pe = 10000.0f;
-#pragma unroll
-        for (int k = 0; k < D; k++) {
-            const int q = k >> 1;
-            float mag;
-            if ((k & 1) == 0) {
-                if (k + 1 < D) mag = fminf(fminf(pe, fabsf(u[k + 1])), se[q + 1]);
-                else mag = fminf(pe, se[q + 1]);
-            } else {
-                mag = fminf(fminf(pe, fabsf(u[k - 1])), se[q + 1]);
-                pe = fminf(fminf(pe, fabsf(u[k - 1])), fabsf(u[k]));
-            }
-            if (col1[k] >= 0 && !kEmit) continue;                        // unstored edge, marginal not wanted now
-            // |o| * w + b, ReLU, sign: negative iff the number of positive OTHER inputs is even (:77-80, :89-91)
-            float wk, bk;
-            if constexpr (kConstW) {
-                const float2 wb = c_wb[c.wb_base + eix[k]];
-                wk = wb.x; bk = wb.y;
-            } else {
-                wk = __ldg(c.wt + eix[k]); bk = __ldg(c.bt + eix[k]);
-            }
-            float m = addf(mulf(mag, wk), bk);
-            m = fmaxf(m, 0.0f);
-            const unsigned sb = (x ^ __float_as_uint(u[k])) & 0x80000000u;
-            const float c2v = __uint_as_float(__float_as_uint(m) | sb);
-            if (col1[k] < 0) {
-                c.rot[shf[k]][rows[k] * G::Z] = c2v;                     // scatter back (:82-86), in place
-            } else {
-                // degree-1 block col1: out = xa + (0 + c2v) at lane (h + s) mod Z (:94-98)
-                if constexpr (kEmit) c.emit_rot(col1[k], shf[k], addf(raw[k], addf(0.0f, c2v)));
-            }
-        }
+        cn_check_core<G, kEmit, kConstW, kZeroSafe, Es...>(c);
     }
 };
+
+// out-of-line zero-safe CN phase; takes the lane state by value (a pointer to it would force it into local memory)
+template <class G, bool kEmit, bool kConstW>
+__device__ __noinline__ void cn_phase_zero_safe(float *lane, int z, const float *wt, const float *bt, int wb_base, float *soft,
+                                                uint8_t *hb) {
+    NeuralLane<G> c;
+    c.lane = lane; c.z = z; c.wt = wt; c.bt = bt; c.wb_base = wb_base; c.soft = soft; c.hb = hb; c.valid = true; c.zmin = 1.0f;
+#pragma unroll
+    for (int s = 0; s < G::Z; s++) c.rot[s] = (lane - z) + ((z + s) % G::Z);
+    CnNeural<G, kEmit, kConstW, true> f{c};
+    G::checks(f);
+}
+
+// CN phase dispatch: warp-uniform choice between the inlined fast phase and the out-of-line zero-safe phase
+template <class G, bool kEmit, bool kConstW>
+__device__ __forceinline__ void cn_phase(NeuralLane<G> &c, bool xa_zero) {
+    const bool need_safe = __any_sync(0xffffffffu, xa_zero || c.zmin == 0.0f);
+    c.zmin = 10000.0f;
+    if (need_safe) {
+        cn_phase_zero_safe<G, kEmit, kConstW>(c.lane, c.z, c.wt, c.bt, c.wb_base, c.soft, c.hb);
+    } else {
+        CnNeural<G, kEmit, kConstW, false> f{c};
+        G::checks(f);
+    }
+}
 
 // -----------------------------------------------------------------------------------------------------------
 template <class G>
@@ -308,6 +377,14 @@ __global__ void __launch_bounds__(SpecCfg<G>::kThreads, 2) nldpc_spec_neural_ker
             phase ^= 1;
         }
 
+        // screen the channel LLRs of this lane for exact zeros once (degree-1 blocks feed the CN phase directly)
+        bool xa_zero = false;
+        {
+            float zm = 1.0f;
+            for (int j = 0; j < G::N; j++) zm = fminf(zm, fabsf(c.lane[j * Z]));
+            xa_zero = (zm == 0.0f);
+        }
+        c.zmin = 10000.0f;
         float *soft_cw = (soft_any && c.valid) ? a.soft + (size_t)b * NZ : nullptr;     // + t*B*NZ in ALL mode
         const size_t soft_iter = (size_t)a.B * NZ;
         uint8_t *hb_cw = hard_any ? hb_mine : nullptr;
@@ -355,8 +432,7 @@ __global__ void __launch_bounds__(SpecCfg<G>::kThreads, 2) nldpc_spec_neural_ker
                 const bool last = t == a.T - 1;
                 c.soft = (soft_cw && (soft_all || last)) ? soft_cw + (soft_all ? (size_t)t * soft_iter : 0) : nullptr;
                 c.hb = (hard_all || last) ? hb_cw : nullptr;
-                CnNeural<G, true, kConstW> f{c};
-                G::checks(f);
+                cn_phase<G, true, kConstW>(c, xa_zero);
                 phase_sync();
             }
         } else {
@@ -373,13 +449,11 @@ __global__ void __launch_bounds__(SpecCfg<G>::kThreads, 2) nldpc_spec_neural_ker
                 }
                 phase_sync();
                 if (t < a.T - 1) {
-                    CnNeural<G, false, kConstW> f{c};
-                    G::checks(f);
+                    cn_phase<G, false, kConstW>(c, xa_zero);
                 } else {
                     c.soft = soft_cw;
                     c.hb = hb_cw;
-                    CnNeural<G, true, kConstW> f{c};
-                    G::checks(f);
+                    cn_phase<G, true, kConstW>(c, xa_zero);
                 }
                 phase_sync();
             }
