@@ -104,12 +104,20 @@ typedef struct nldpc_boosted_cfg {
     int32_t qbit;         /* decoder_qms_qbit: 6, 5, -5, 4, 3; anything else = no quantisation (:187-214) */
     float llr_lo, llr_hi; /* allowed_llr_range (default -20, 20) */
     int32_t compute_ucn;  /* UCN sharing > 0: evaluate the unsatisfied-check indicator (:339-374) */
-    int32_t reserved;
+    int32_t ucn_mix;      /* UCN type == CN type in {1,2,3}: W = unsatisfied ? ucn_w : cn_w (:436-488) */
+    /* Optional state for runs that do not start from the zero state (the module is stateful: self.llr / self.outputs,
+     * :94-101; partial target_iter runs read what earlier calls left).  NULL = default. */
+    const float *llr_init_dev; /* [B][Z][E] c2v entering the first executed iteration (self.llr[t0]); NULL = zeros */
+    const float *xin_init_dev; /* [B][N][Z] compounding channel input entering the first iteration; NULL = xa */
+    float *xin_out_dev;        /* [B][N][Z] receives it after the last executed iteration; NULL = not wanted */
+    const float *app_init_dev; /* [B][N*Z] previous output used by the UCN indicator of the first executed iteration;
+                                  NULL = use the channel input (the curr_iter == 0 rule, :340-341) */
 } nldpc_boosted_cfg_t;
 
 /* Replaces the loop of BoostedNeuralLDPCDecoder.forward (:320-531) for iterations 0..T-1 from a
- * zero message state (the target_iter=None / range(T) call of train/…py:278 and the validation loop).
- *   llr_last_dev : optional [B][Z][E] fp32, receives self.llr[T] (c2v of the last iteration). */
+ * zero message state (the target_iter=None / range(T) call of train/…py:278 and the validation loop), or for T consecutive
+ * iterations from the state given in cfg.  vn_w/cn_w/ucn_w rows are indexed by EXECUTED iteration (0..T-1).
+ *   llr_last_dev : optional [B][Z][E] fp32, receives self.llr[t_last + 1] (c2v of the last executed iteration). */
 int nldpc_boosted_forward(const nldpc_graph_t *g, const nldpc_boosted_cfg_t *cfg, const float *xa_dev,
                           const float *vn_w_dev, const float *cn_w_dev, const float *ucn_w_dev,
                           int B, int T, int soft_mode, float *soft_dev, int hard_mode, uint8_t *hard_dev,

@@ -24,7 +24,9 @@ class NldpcError(RuntimeError):
 
 class BoostedCfg(ctypes.Structure):
     _fields_ = [("decoder_type", ctypes.c_int32), ("qbit", ctypes.c_int32), ("llr_lo", ctypes.c_float),
-                ("llr_hi", ctypes.c_float), ("compute_ucn", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("llr_hi", ctypes.c_float), ("compute_ucn", ctypes.c_int32), ("ucn_mix", ctypes.c_int32),
+                ("llr_init", ctypes.c_void_p), ("xin_init", ctypes.c_void_p), ("xin_out", ctypes.c_void_p),
+                ("app_init", ctypes.c_void_p)]
 
 
 def build(verbose=False):

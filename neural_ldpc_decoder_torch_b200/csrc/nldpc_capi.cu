@@ -126,7 +126,7 @@ extern "C" int nldpc_graph_create(const int32_t *basegraph, int M, int N, int Z,
     std::vector<int> all;
     auto push = [&](const std::vector<int> &v) { size_t o = all.size(); all.insert(all.end(), v.begin(), v.end()); return o; };
     const size_t o_vj = push(vcol_j), o_vp = push(vcol_ptr), o_vr = push(vcol_row), o_rp = push(row_ptr), o_er = push(e_row),
-                 o_es = push(eshift), o_c1 = push(e_col1);
+                 o_es = push(eshift), o_c1 = push(e_col1), o_cj = push(ecol);
     cudaError_t ce = cudaMalloc(&g->tables, all.size() * sizeof(int));
     if (ce == cudaSuccess) ce = cudaMemcpy(g->tables, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice);
     if (ce != cudaSuccess) {
@@ -138,9 +138,10 @@ extern "C" int nldpc_graph_create(const int32_t *basegraph, int M, int N, int Z,
     GraphDev &d = g->dev;
     d.M = M; d.N = N; d.Z = Z; d.E = E; d.S = S; d.n_vcols = (int)vcol_j.size(); d.slab_stride = stride;
     d.vcol_j = g->tables + o_vj; d.vcol_ptr = g->tables + o_vp; d.vcol_row = g->tables + o_vr;
-    d.row_ptr = g->tables + o_rp; d.e_row = g->tables + o_er; d.e_shift = g->tables + o_es; d.e_col1 = g->tables + o_c1;
+    d.row_ptr = g->tables + o_rp; d.e_row = g->tables + o_er; d.e_shift = g->tables + o_es; d.e_col1 = g->tables + o_c1; d.e_colj = g->tables + o_cj;
 
     ce = (cudaError_t)generic_prepare(g->smem_bytes);
+    if (ce == cudaSuccess) ce = (cudaError_t)generic_boosted_prepare();
     if (ce != cudaSuccess) {
         cudaGetLastError();
         cudaFree(g->tables);
@@ -308,7 +309,25 @@ extern "C" int nldpc_boosted_forward(const nldpc_graph_t *g, const nldpc_boosted
                                      const float *vn_w_dev, const float *cn_w_dev, const float *ucn_w_dev, int B, int T,
                                      int soft_mode, float *soft_dev, int hard_mode, uint8_t *hard_dev, float *llr_last_dev,
                                      void *stream) {
-    (void)g; (void)cfg; (void)xa_dev; (void)vn_w_dev; (void)cn_w_dev; (void)ucn_w_dev; (void)B; (void)T; (void)soft_mode;
-    (void)soft_dev; (void)hard_mode; (void)hard_dev; (void)llr_last_dev; (void)stream;
-    return fail(NLDPC_E_UNSUPPORTED, "nldpc_boosted_forward: not implemented yet");
+    if (!g || !cfg || B < 0 || T <= 0) return fail(NLDPC_E_INVALID, "nldpc_boosted_forward: bad argument");
+    if (B == 0) return NLDPC_OK;
+    if (!xa_dev) return fail(NLDPC_E_INVALID, "nldpc_boosted_forward: NULL input pointer");
+    if (cfg->decoder_type < 0 || cfg->decoder_type > 2) return fail(NLDPC_E_INVALID, "nldpc_boosted_forward: bad decoder_type");
+    if (!(cfg->llr_lo <= cfg->llr_hi)) return fail(NLDPC_E_INVALID, "nldpc_boosted_forward: bad llr range");
+    if (cfg->ucn_mix && (!cn_w_dev || !ucn_w_dev || !cfg->compute_ucn))
+        return fail(NLDPC_E_INVALID, "nldpc_boosted_forward: ucn_mix needs cn_w, ucn_w and compute_ucn");
+    if (int rc = check_modes(soft_mode, soft_dev, hard_mode, hard_dev)) return rc;
+    CUDA_TRY(cudaSetDevice(g->device));
+    DecodeArgs a{};
+    a.xa = xa_dev; a.w = cn_w_dev; a.b = ucn_w_dev; a.vn_w = vn_w_dev; a.B = B; a.T = T;
+    a.soft_mode = soft_mode; a.soft = soft_dev; a.hard_mode = hard_mode; a.hard = hard_dev; a.llr_last = llr_last_dev;
+    a.wb_off = -1;
+    a.decoder_type = cfg->decoder_type; a.qbit = cfg->qbit; a.compute_ucn = cfg->compute_ucn; a.ucn_mix = cfg->ucn_mix;
+    a.llr_lo = cfg->llr_lo; a.llr_hi = cfg->llr_hi;
+    a.llr_init = cfg->llr_init_dev; a.xin_init = cfg->xin_init_dev; a.xin_out = cfg->xin_out_dev; a.app_init = cfg->app_init_dev;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rc = generic_launch_boosted(g->dev, a, g->sm_count, st);
+    if (rc == -2) return fail(NLDPC_E_UNSUPPORTED, "nldpc_boosted_forward: one codeword's boosted state does not fit in shared memory");
+    if (rc != 0) return fail(rc, std::string("nldpc_boosted_forward: ") + cudaGetErrorString((cudaError_t)rc));
+    return NLDPC_OK;
 }

@@ -27,6 +27,7 @@ struct GraphDev {
     const int *e_row;      // [E] slab row read by the CN phase: N+slot (stored) or j (degree-1 block)
     const int *e_shift;    // [E] circulant shift (mod Z)
     const int *e_col1;     // [E] variable block j if it has degree 1, else -1
+    const int *e_colj;     // [E] variable block j of the edge
 };
 
 struct DecodeArgs {
@@ -40,14 +41,21 @@ struct DecodeArgs {
     float *llr_last;   // Boosted: [B][Z][E] or nullptr
     int wb_off;        // specialised kernels: offset (float2 units) of this launch's weights in the constant arena, -1 = use w/b pointers
     // boosted config
-    int decoder_type, qbit, compute_ucn;
+    int decoder_type, qbit, compute_ucn, ucn_mix;
     float llr_lo, llr_hi;
+    // boosted state for runs that do not start from a zero state (nullptr = default)
+    const float *llr_init;   // [B][Z][E] c2v entering the first executed iteration
+    const float *xin_init;   // [B][N][Z] compounding channel input entering the first executed iteration
+    float *xin_out;          // [B][N][Z] receives it after the last one
+    const float *app_init;   // [B][N*Z] previous output for the UCN indicator of the first executed iteration
 };
 
 // host-side launch helpers of the table-driven kernel (nldpc_generic.cu)
 int generic_prepare(size_t smem_bytes);
 int generic_launch_neural(const GraphDev &g, const DecodeArgs &a, int cw_per_cta, int threads, size_t smem_bytes, int use_tma,
                           int grid, cudaStream_t st);
+int generic_boosted_prepare();
+int generic_launch_boosted(const GraphDev &g, const DecodeArgs &a, int sm_count, cudaStream_t st);   // -2: does not fit
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

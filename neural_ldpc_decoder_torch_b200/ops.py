@@ -140,3 +140,66 @@ def neural_decode_host(graph_id, xa_host, w_host, b_host, soft_mode=_lib.NLDPC_O
                                              hard_mode, _ptr(hard))
     _lib.check(rc, "nldpc_neural_decode_host")
     return soft, hard
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Boosted decoder (BoostedNeuralLDPCDecoder.py:320-531)
+from typing import Optional  # noqa: E402
+
+
+def _opt_f32(name, t, shape, device):
+    if t is None:
+        return None
+    _check_cuda_f32(name, t)
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+    if t.device != device:
+        raise ValueError(f"{name} is on {t.device}, expected {device}")
+    return t.contiguous()
+
+
+@torch.library.custom_op("nldpc::boosted_forward", mutates_args=())
+def boosted_forward(xa: torch.Tensor, vn_w: Optional[torch.Tensor], cn_w: Optional[torch.Tensor], ucn_w: Optional[torch.Tensor],
+                    graph_id: int, T: int, decoder_type: int, qbit: int, llr_lo: float, llr_hi: float, compute_ucn: bool,
+                    ucn_mix: bool, llr_init: Optional[torch.Tensor], xin_init: Optional[torch.Tensor],
+                    app_init: Optional[torch.Tensor], want_llr: bool,
+                    want_xin: bool) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """T consecutive iterations of the Boosted loop body.  Returns (soft [T,B,N*Z], llr_last [B,Z,E] | empty,
+    xin_out [B,N,Z] | empty).  Weight rows are indexed by executed iteration."""
+    g = _lib.graph_by_id(graph_id)
+    _check_cuda_f32("xa", xa)
+    if xa.dim() != 3 or xa.shape[1] != g.N or xa.shape[2] != g.Z:
+        raise ValueError(f"xa must be [B, {g.N}, {g.Z}], got {tuple(xa.shape)}")
+    if xa.device.index != g.device_index:
+        raise ValueError("graph handle and tensors live on different devices")
+    B, dev = xa.shape[0], xa.device
+    xa = xa.contiguous()
+    vn_w = _opt_f32("vn_w", vn_w, (T, g.N), dev)
+    cn_w = _opt_f32("cn_w", cn_w, (T, g.E), dev)
+    ucn_w = _opt_f32("ucn_w", ucn_w, (T, g.E), dev)
+    llr_init = _opt_f32("llr_init", llr_init, (B, g.Z, g.E), dev)
+    xin_init = _opt_f32("xin_init", xin_init, (B, g.N, g.Z), dev)
+    app_init = _opt_f32("app_init", app_init, (B, g.NZ), dev)
+    soft = torch.empty((T, B, g.NZ), dtype=torch.float32, device=dev)
+    llr_last = torch.empty((B, g.Z, g.E) if want_llr else (0,), dtype=torch.float32, device=dev)
+    xin_out = torch.empty((B, g.N, g.Z) if want_xin else (0,), dtype=torch.float32, device=dev)
+    cfg = _lib.BoostedCfg(decoder_type, qbit, llr_lo, llr_hi, int(compute_ucn), int(ucn_mix),
+                          llr_init.data_ptr() if llr_init is not None else None,
+                          xin_init.data_ptr() if xin_init is not None else None,
+                          xin_out.data_ptr() if want_xin else None,
+                          app_init.data_ptr() if app_init is not None else None)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().nldpc_boosted_forward(g.ptr, ctypes.byref(cfg), _ptr(xa), _ptr(vn_w), _ptr(cn_w), _ptr(ucn_w), B, T,
+                                              _lib.NLDPC_OUT_ALL, _ptr(soft), _lib.NLDPC_OUT_NONE, _vp(0),
+                                              _ptr(llr_last) if want_llr else _vp(0), _stream(xa))
+    _lib.check(rc, "nldpc_boosted_forward")
+    return soft, llr_last, xin_out
+
+
+@boosted_forward.register_fake
+def _(xa, vn_w, cn_w, ucn_w, graph_id, T, decoder_type, qbit, llr_lo, llr_hi, compute_ucn, ucn_mix, llr_init, xin_init, app_init,
+      want_llr, want_xin):
+    g = _lib.graph_by_id(graph_id)
+    B = xa.shape[0]
+    return (xa.new_empty((T, B, g.NZ)), xa.new_empty((B, g.Z, g.E) if want_llr else (0,)),
+            xa.new_empty((B, g.N, g.Z) if want_xin else (0,)))
