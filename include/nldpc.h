@@ -87,12 +87,16 @@ int nldpc_neural_decode_host(const nldpc_graph_t *g, const float *xa_host, const
                              int B, int T, int soft_mode, float *soft_host, int hard_mode, uint8_t *hard_host);
 
 /* Backward of nldpc_neural_forward w.r.t. w and b (closed form of autograd through
- * NeuralLDPCDecoder.py:54-98): recomputes the forward per codeword tile
- * keeping the c2v history on chip, then walks the iterations backwards.
+ * NeuralLDPCDecoder.py:54-98).  The forward is re-run in a training-dump mode that
+ * spills the per-iteration v2c to `workspace_dev` (HBM is idle in this kernel), then the iterations are
+ * walked backwards with the gradient messages in shared memory.
  *   gout_dev : [T][B][N*Z] upstream gradients dL/dout_t (zeros where an iteration is unused)
- *   gw_dev, gb_dev : [T][E] fp32, OVERWRITTEN with the batch-summed gradients. */
+ *   gw_dev, gb_dev : [T][E] fp32, OVERWRITTEN with the batch-summed gradients
+ *   workspace_dev  : at least nldpc_backward_workspace_bytes(g, B, T, 0) bytes */
+size_t nldpc_backward_workspace_bytes(const nldpc_graph_t *g, int B, int T, int boosted);
 int nldpc_neural_backward(const nldpc_graph_t *g, const float *xa_dev, const float *w_dev, const float *b_dev,
-                          const float *gout_dev, int B, int T, float *gw_dev, float *gb_dev, void *stream);
+                          const float *gout_dev, int B, int T, float *gw_dev, float *gb_dev, void *workspace_dev,
+                          size_t workspace_bytes, void *stream);
 
 /* Configuration of the Boosted decoder loop body, sharing types already folded by the caller into
  * per-iteration rows (NULL = "no weight of that kind"):
@@ -122,6 +126,16 @@ int nldpc_boosted_forward(const nldpc_graph_t *g, const nldpc_boosted_cfg_t *cfg
                           const float *vn_w_dev, const float *cn_w_dev, const float *ucn_w_dev,
                           int B, int T, int soft_mode, float *soft_dev, int hard_mode, uint8_t *hard_dev,
                           float *llr_last_dev, void *stream);
+
+/* Backward of nldpc_boosted_forward (MS / QMS decoders, runs from the zero state) w.r.t. the folded weight rows:
+ * autograd through BoostedNeuralLDPCDecoder.py:320-531 incl. the straight-through quantisers (:202-214), the
+ * +-range clamps and the compounding VN-weight chain (:325-337).
+ *   gvn_dev [T][N], gcn_dev [T][E], gucn_dev [T][E]: OVERWRITTEN (pass NULL where the weight kind is absent)
+ *   workspace_dev: at least nldpc_backward_workspace_bytes(g, B, T, 1) bytes */
+int nldpc_boosted_backward(const nldpc_graph_t *g, const nldpc_boosted_cfg_t *cfg, const float *xa_dev,
+                           const float *vn_w_dev, const float *cn_w_dev, const float *ucn_w_dev, const float *gout_dev,
+                           int B, int T, float *gvn_dev, float *gcn_dev, float *gucn_dev, void *workspace_dev,
+                           size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -62,8 +62,13 @@ def lib():
             L.nldpc_neural_forward.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, ci, vp, vp]
             L.nldpc_neural_decode_host.restype = ci
             L.nldpc_neural_decode_host.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, ci, vp]
+            L.nldpc_backward_workspace_bytes.restype = ctypes.c_size_t
+            L.nldpc_backward_workspace_bytes.argtypes = [vp, ci, ci, ci]
             L.nldpc_neural_backward.restype = ci
-            L.nldpc_neural_backward.argtypes = [vp, vp, vp, vp, vp, ci, ci, vp, vp, vp]
+            L.nldpc_neural_backward.argtypes = [vp, vp, vp, vp, vp, ci, ci, vp, vp, vp, ctypes.c_size_t, vp]
+            L.nldpc_boosted_backward.restype = ci
+            L.nldpc_boosted_backward.argtypes = [vp, ctypes.POINTER(BoostedCfg), vp, vp, vp, vp, vp, ci, ci, vp, vp, vp, vp,
+                                                 ctypes.c_size_t, vp]
             L.nldpc_boosted_forward.restype = ci
             L.nldpc_boosted_forward.argtypes = [vp, ctypes.POINTER(BoostedCfg), vp, vp, vp, vp, ci, ci, ci, vp, ci, vp, vp, vp]
             _lib = L

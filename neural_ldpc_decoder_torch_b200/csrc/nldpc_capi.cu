@@ -142,6 +142,7 @@ extern "C" int nldpc_graph_create(const int32_t *basegraph, int M, int N, int Z,
 
     ce = (cudaError_t)generic_prepare(g->smem_bytes);
     if (ce == cudaSuccess) ce = (cudaError_t)generic_boosted_prepare();
+    if (ce == cudaSuccess) ce = (cudaError_t)backward_prepare();
     if (ce != cudaSuccess) {
         cudaGetLastError();
         cudaFree(g->tables);
@@ -299,10 +300,99 @@ extern "C" int nldpc_neural_decode_host(const nldpc_graph_t *gc, const float *xa
     return NLDPC_OK;
 }
 
+// ---- backward ------------------------------------------------------------------------------------------------
+struct WsLayout { size_t v2c, xin, mask, ucn, total; };
+static WsLayout ws_layout(const nldpc_graph *g, int B, int T, int boosted) {
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    WsLayout l{};
+    size_t off = 0;
+    l.v2c = off; off = up(off + (size_t)T * B * g->S * g->Z * 4);
+    if (boosted) {
+        l.xin = off; off = up(off + (size_t)(T + 1) * B * g->N * g->Z * 4);
+        l.mask = off; off = up(off + (size_t)T * B * g->N * g->Z);
+        l.ucn = off; off = up(off + (size_t)T * B * g->M * g->Z);
+    }
+    l.total = off;
+    return l;
+}
+
+extern "C" size_t nldpc_backward_workspace_bytes(const nldpc_graph_t *g, int B, int T, int boosted) {
+    if (!g || B <= 0 || T <= 0) return 0;
+    return ws_layout(g, B, T, boosted).total;
+}
+
 extern "C" int nldpc_neural_backward(const nldpc_graph_t *g, const float *xa_dev, const float *w_dev, const float *b_dev,
-                                     const float *gout_dev, int B, int T, float *gw_dev, float *gb_dev, void *stream) {
-    (void)g; (void)xa_dev; (void)w_dev; (void)b_dev; (void)gout_dev; (void)B; (void)T; (void)gw_dev; (void)gb_dev; (void)stream;
-    return fail(NLDPC_E_UNSUPPORTED, "nldpc_neural_backward: not implemented yet");
+                                     const float *gout_dev, int B, int T, float *gw_dev, float *gb_dev, void *workspace_dev,
+                                     size_t workspace_bytes, void *stream) {
+    if (!g || B < 0 || T <= 0 || !gw_dev || !gb_dev) return fail(NLDPC_E_INVALID, "nldpc_neural_backward: bad argument");
+    CUDA_TRY(cudaSetDevice(g->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(gw_dev, 0, (size_t)T * g->E * 4, st));
+    CUDA_TRY(cudaMemsetAsync(gb_dev, 0, (size_t)T * g->E * 4, st));
+    if (B == 0) return NLDPC_OK;
+    if (!xa_dev || !w_dev || !b_dev || !gout_dev) return fail(NLDPC_E_INVALID, "nldpc_neural_backward: NULL input pointer");
+    const WsLayout l = ws_layout(g, B, T, 0);
+    if (!workspace_dev || workspace_bytes < l.total)
+        return fail(NLDPC_E_INVALID, "nldpc_neural_backward: workspace too small (see nldpc_backward_workspace_bytes)");
+    // (A) forward re-run in training-dump mode
+    DecodeArgs a{};
+    a.xa = xa_dev; a.w = w_dev; a.b = b_dev; a.B = B; a.T = T; a.wb_off = -1;
+    a.hist_v2c = reinterpret_cast<float *>((char *)workspace_dev + l.v2c);
+    const int n_tiles = (B + g->cw_per_cta - 1) / g->cw_per_cta;
+    const int ctas_per_sm = std::max(1, (int)((size_t)kSmemBudget / (g->smem_bytes + 1024)));
+    const int grid = std::min(n_tiles, g->sm_count * ctas_per_sm);
+    CUDA_TRY((cudaError_t)generic_launch_neural(g->dev, a, g->cw_per_cta, g->threads, g->smem_bytes, g->use_tma, grid, st));
+    // (B) backward sweep
+    BwdArgs ba{};
+    ba.xa = xa_dev; ba.w = w_dev; ba.b = b_dev; ba.gout = gout_dev; ba.hist_v2c = a.hist_v2c;
+    ba.gw = gw_dev; ba.gb = gb_dev; ba.B = B; ba.T = T; ba.mode = 0;
+    const int rc = backward_launch(g->dev, ba, g->sm_count, st);
+    if (rc == -2) return fail(NLDPC_E_UNSUPPORTED, "nldpc_neural_backward: graph does not fit on chip");
+    if (rc != 0) return fail(rc, std::string("nldpc_neural_backward: ") + cudaGetErrorString((cudaError_t)rc));
+    return NLDPC_OK;
+}
+
+extern "C" int nldpc_boosted_backward(const nldpc_graph_t *g, const nldpc_boosted_cfg_t *cfg, const float *xa_dev,
+                                      const float *vn_w_dev, const float *cn_w_dev, const float *ucn_w_dev, const float *gout_dev,
+                                      int B, int T, float *gvn_dev, float *gcn_dev, float *gucn_dev, void *workspace_dev,
+                                      size_t workspace_bytes, void *stream) {
+    if (!g || !cfg || B < 0 || T <= 0) return fail(NLDPC_E_INVALID, "nldpc_boosted_backward: bad argument");
+    if (cfg->decoder_type != NLDPC_DEC_MS && cfg->decoder_type != NLDPC_DEC_QMS)
+        return fail(NLDPC_E_UNSUPPORTED, "nldpc_boosted_backward: only the MS and QMS decoders have a backward");
+    if (cfg->llr_init_dev || cfg->xin_init_dev || cfg->app_init_dev)
+        return fail(NLDPC_E_UNSUPPORTED, "nldpc_boosted_backward: runs that continue from stored state are forward-only");
+    if ((vn_w_dev && !gvn_dev) || (cn_w_dev && !gcn_dev) || (cfg->ucn_mix && !gucn_dev))
+        return fail(NLDPC_E_INVALID, "nldpc_boosted_backward: missing gradient output");
+    CUDA_TRY(cudaSetDevice(g->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (gvn_dev) CUDA_TRY(cudaMemsetAsync(gvn_dev, 0, (size_t)T * g->N * 4, st));
+    if (gcn_dev) CUDA_TRY(cudaMemsetAsync(gcn_dev, 0, (size_t)T * g->E * 4, st));
+    if (gucn_dev) CUDA_TRY(cudaMemsetAsync(gucn_dev, 0, (size_t)T * g->E * 4, st));
+    if (B == 0) return NLDPC_OK;
+    if (!xa_dev || !gout_dev) return fail(NLDPC_E_INVALID, "nldpc_boosted_backward: NULL input pointer");
+    const WsLayout l = ws_layout(g, B, T, 1);
+    if (!workspace_dev || workspace_bytes < l.total)
+        return fail(NLDPC_E_INVALID, "nldpc_boosted_backward: workspace too small (see nldpc_backward_workspace_bytes)");
+    char *ws = (char *)workspace_dev;
+    DecodeArgs a{};
+    a.xa = xa_dev; a.w = cn_w_dev; a.b = ucn_w_dev; a.vn_w = vn_w_dev; a.B = B; a.T = T; a.wb_off = -1;
+    a.decoder_type = cfg->decoder_type; a.qbit = cfg->qbit; a.compute_ucn = cfg->compute_ucn; a.ucn_mix = cfg->ucn_mix;
+    a.llr_lo = cfg->llr_lo; a.llr_hi = cfg->llr_hi;
+    a.hist_v2c = reinterpret_cast<float *>(ws + l.v2c); a.hist_xin = reinterpret_cast<float *>(ws + l.xin);
+    a.hist_mask = reinterpret_cast<uint8_t *>(ws + l.mask); a.hist_ucn = reinterpret_cast<uint8_t *>(ws + l.ucn);
+    int rc = generic_launch_boosted(g->dev, a, g->sm_count, st);
+    if (rc == -2) return fail(NLDPC_E_UNSUPPORTED, "nldpc_boosted_backward: graph does not fit on chip");
+    if (rc != 0) return fail(rc, std::string("nldpc_boosted_backward (forward dump): ") + cudaGetErrorString((cudaError_t)rc));
+    BwdArgs ba{};
+    ba.xa = xa_dev; ba.w = cn_w_dev; ba.b = cfg->ucn_mix ? ucn_w_dev : nullptr; ba.vn_w = vn_w_dev; ba.gout = gout_dev;
+    ba.hist_v2c = a.hist_v2c; ba.hist_xin = a.hist_xin; ba.hist_mask = a.hist_mask; ba.hist_ucn = cfg->ucn_mix ? a.hist_ucn : nullptr;
+    ba.gw = gcn_dev; ba.gb = cfg->ucn_mix ? gucn_dev : nullptr; ba.gvn = vn_w_dev ? gvn_dev : nullptr;
+    ba.B = B; ba.T = T; ba.mode = cfg->decoder_type == NLDPC_DEC_QMS ? 2 : 1; ba.qbit = cfg->qbit; ba.lo = cfg->llr_lo; ba.hi = cfg->llr_hi;
+    ba.ucn_mix = cfg->ucn_mix;
+    rc = backward_launch(g->dev, ba, g->sm_count, st);
+    if (rc == -2) return fail(NLDPC_E_UNSUPPORTED, "nldpc_boosted_backward: graph does not fit on chip");
+    if (rc != 0) return fail(rc, std::string("nldpc_boosted_backward: ") + cudaGetErrorString((cudaError_t)rc));
+    return NLDPC_OK;
 }
 
 extern "C" int nldpc_boosted_forward(const nldpc_graph_t *g, const nldpc_boosted_cfg_t *cfg, const float *xa_dev,

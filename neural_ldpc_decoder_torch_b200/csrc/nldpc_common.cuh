@@ -48,12 +48,37 @@ struct DecodeArgs {
     const float *xin_init;   // [B][N][Z] compounding channel input entering the first executed iteration
     float *xin_out;          // [B][N][Z] receives it after the last one
     const float *app_init;   // [B][N*Z] previous output for the UCN indicator of the first executed iteration
+    // training dump for the backward kernel (nullptr = off), see nldpc_backward.cu
+    float *hist_v2c;         // [T][B][S][Z]
+    float *hist_xin;         // [T+1][B][N][Z] (Boosted)
+    uint8_t *hist_mask;      // [T][B][N*Z]   (Boosted)
+    uint8_t *hist_ucn;       // [T][B][M][Z]  (Boosted, UCN)
 };
 
 // host-side launch helpers of the table-driven kernel (nldpc_generic.cu)
 int generic_prepare(size_t smem_bytes);
 int generic_launch_neural(const GraphDev &g, const DecodeArgs &a, int cw_per_cta, int threads, size_t smem_bytes, int use_tma,
                           int grid, cudaStream_t st);
+// launch arguments of the backward kernel (nldpc_backward.cu)
+struct BwdArgs {
+    const float *xa;        // [B][N][Z]
+    const float *w, *b;     // Neural: w/b [T][E];  Boosted: cn_w / ucn_w [T][E] or nullptr
+    const float *vn_w;      // Boosted: [T][N] or nullptr
+    const float *gout;      // [T][B][N*Z]
+    const float *hist_v2c;  // [T][B][S][Z]   v2c of the stored edges entering the CN phase of iteration t
+    const float *hist_xin;  // [T+1][B][N][Z] channel-input state: [0] = before iteration 0, [t+1] = after iteration t's update (Boosted)
+    const uint8_t *hist_mask;   // [T][B][N*Z] 1 where the output clamp passed the gradient (Boosted)
+    const uint8_t *hist_ucn;    // [T][B][M][Z] unsatisfied-check indicator (Boosted, ucn_mix) or nullptr
+    float *gw, *gb;         // [T][E] (+=)   Neural: weights/biases;  Boosted: cn_w / ucn_w rows
+    float *gvn;             // [T][N] (+=)   Boosted VN weights or nullptr
+    int B, T;
+    int mode;               // 0 Neural, 1 Boosted MS, 2 Boosted QMS
+    int qbit;
+    float lo, hi;
+    int ucn_mix;
+};
+int backward_prepare();
+int backward_launch(const GraphDev &g, const BwdArgs &a, int sm_count, cudaStream_t st);   // -2: does not fit
 int generic_boosted_prepare();
 int generic_launch_boosted(const GraphDev &g, const DecodeArgs &a, int sm_count, cudaStream_t st);   // -2: does not fit
 

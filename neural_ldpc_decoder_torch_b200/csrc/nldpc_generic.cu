@@ -131,6 +131,10 @@ nldpc_generic_neural_kernel(const GraphDev g, const DecodeArgs a, const int cw_p
 #undef NLDPC_VN_CASE
                         if (soft_prev || hard_prev) emit(ec, j * g.Z + z, addf(x, tot));   // out = xa + tot (:96)
                     }
+                    if (a.hist_v2c) {   // training dump: the v2c every CN phase reads (nldpc_backward.cu)
+                        float *hv = a.hist_v2c + (((size_t)t * a.B + (b0 + cw)) * g.S) * g.Z + z;
+                        for (int s = 0; s < g.S; s++) hv[(size_t)s * g.Z] = slab[(g.N + s) * g.Z + z];
+                    }
                 }
                 __syncthreads();
                 if (hard_prev) {   // flush iteration t-1's packed decisions, then clear for iteration t

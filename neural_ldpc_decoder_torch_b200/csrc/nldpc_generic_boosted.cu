@@ -39,18 +39,22 @@ struct BoostedCtx {
     bool want_c2v1;              // compute the c2v of degree-1 edges even when nothing is emitted (llr_last)
     float *llr_last;             // &llr_last[b][z][0] (stride E per lane) or nullptr
     int E;
+    uint8_t *mask_out;           // training dump: &hist_mask[t][b][0] of the iteration being emitted, or nullptr
+    uint8_t *ucn_out;            // training dump: &hist_ucn[t][b][0] ([M][Z]) or nullptr
 };
 
 // out = clamp(xo + tot, range) (:520-521) -> soft/hard outputs and, when tracked, the APP rows
 __device__ __forceinline__ void emit_boosted(const EmitCtx &ec, const BoostedCtx &bc, float *__restrict__ slab, int Z, int q, float tot) {
-    const float v = clampf(addf(slab[bc.xo_row0 * Z + q], tot), bc.lo, bc.hi);
+    const float sum = addf(slab[bc.xo_row0 * Z + q], tot);
+    const float v = clampf(sum, bc.lo, bc.hi);
+    if (bc.mask_out) bc.mask_out[q] = (sum >= bc.lo && sum <= bc.hi) ? 1 : 0;
     emit(ec, q, v);
     if (bc.app_store_row0 >= 0) slab[bc.app_store_row0 * Z + q] = v;
 }
 
 template <int D>
-__device__ __forceinline__ void cn_check_boosted(float *__restrict__ slab, int h, const GraphDev &g, int e0, const BoostedCtx &bc,
-                                                 const EmitCtx &ec, bool emit_now) {
+__device__ __forceinline__ void cn_check_boosted(float *__restrict__ slab, int h, const GraphDev &g, int e0, int row_i,
+                                                 const BoostedCtx &bc, const EmitCtx &ec, bool emit_now) {
     const bool is_qms = bc.decoder_type == 2, is_sp = bc.decoder_type == 0;
     float u[D];
     int addr[D], zz[D];
@@ -73,6 +77,7 @@ __device__ __forceinline__ void cn_check_boosted(float *__restrict__ slab, int h
         }
     }
     const float s_ucn = ucn_par ? 1.0f : 0.0f;
+    if (bc.ucn_out) bc.ucn_out[row_i * g.Z + h] = (uint8_t)ucn_par;
     float o[D];
     if (is_sp) {                                                  // (:400-408) product of tanh(-u/2) over the others
         float th[D];
@@ -189,7 +194,11 @@ nldpc_generic_boosted_kernel(const GraphDev g, const DecodeArgs a, const Boosted
                 BoostedCtx bc{};
                 bc.lo = a.llr_lo; bc.hi = a.llr_hi; bc.xo_row0 = lay.xo_row0;
                 bc.app_store_row0 = app_prev ? lay.app_row0 : -1;
+                const bool dump_prev = t > 0 && a.hist_mask != nullptr;
+                bc.mask_out = dump_prev ? a.hist_mask + ((size_t)(t - 1) * a.B + b) * NZ : nullptr;
                 if (active) {
+                    if (a.hist_xin && t == 0)
+                        for (int j = 0; j < g.N; j++) a.hist_xin[((size_t)b * g.N + j) * Z + z] = slab[j * Z + z];
                     // marginal of the previous iteration must read the OLD c2v: do it inside the block loop before the
                     // in-place v2c overwrite (vn_block returns the column total of the c2v it loaded)
                     const float *vw = a.vn_w ? a.vn_w + (size_t)t * g.N : nullptr;
@@ -198,6 +207,7 @@ nldpc_generic_boosted_kernel(const GraphDev g, const DecodeArgs a, const Boosted
                         if (vw) x = mulf(x, __ldg(vw + j));
                         if (is_qms) x = quantf(x, a.qbit);
                         slab[j * Z + z] = x;
+                        if (a.hist_xin) a.hist_xin[(((size_t)(t + 1) * a.B + b) * g.N + j) * Z + z] = x;
                     }
                     for (int c = 0; c < g.n_vcols; c++) {
                         const int j = __ldg(g.vcol_j + c);
@@ -208,7 +218,11 @@ nldpc_generic_boosted_kernel(const GraphDev g, const DecodeArgs a, const Boosted
 #define NLDPC_VN_CASE(D) tot = vn_block<D>(slab + z, Z, g.vcol_row + p0, x)
                         NLDPC_DEG_SWITCH(d, NLDPC_VN_CASE)
 #undef NLDPC_VN_CASE
-                        if (soft_prev || hard_prev || app_prev) emit_boosted(ec, bc, slab, Z, j * Z + z, tot);
+                        if (soft_prev || hard_prev || app_prev || dump_prev) emit_boosted(ec, bc, slab, Z, j * Z + z, tot);
+                    }
+                    if (a.hist_v2c) {
+                        float *hv = a.hist_v2c + (((size_t)t * a.B + b) * g.S) * Z + z;
+                        for (int s = 0; s < g.S; s++) hv[(size_t)s * Z] = slab[(g.N + s) * Z + z];
                     }
                 }
                 __syncthreads();
@@ -245,12 +259,14 @@ nldpc_generic_boosted_kernel(const GraphDev g, const DecodeArgs a, const Boosted
                 bc.want_c2v1 = last && a.llr_last != nullptr;
                 bc.llr_last = (last && a.llr_last) ? a.llr_last + (size_t)b * Z * g.E : nullptr;
                 bc.E = g.E;
-                const bool emit_now = soft_now || hard_now || track_app;
+                bc.mask_out = a.hist_mask ? a.hist_mask + ((size_t)t * a.B + b) * NZ : nullptr;
+                bc.ucn_out = (a.hist_ucn && track_app) ? a.hist_ucn + ((size_t)t * a.B + b) * g.M * Z : nullptr;
+                const bool emit_now = soft_now || hard_now || track_app || a.hist_mask != nullptr;
                 if (active) {
                     for (int i = 0; i < g.M; i++) {
                         const int e0 = __ldg(g.row_ptr + i);
                         const int d = __ldg(g.row_ptr + i + 1) - e0;
-#define NLDPC_CN_CASE(D) cn_check_boosted<D>(slab, z, g, e0, bc, ec, emit_now)
+#define NLDPC_CN_CASE(D) cn_check_boosted<D>(slab, z, g, e0, i, bc, ec, emit_now)
                         NLDPC_DEG_SWITCH(d, NLDPC_CN_CASE)
 #undef NLDPC_CN_CASE
                     }
@@ -267,8 +283,9 @@ nldpc_generic_boosted_kernel(const GraphDev g, const DecodeArgs a, const Boosted
             ec.cw_off = (size_t)b * NZ;
             BoostedCtx bc{};
             bc.lo = a.llr_lo; bc.hi = a.llr_hi; bc.xo_row0 = lay.xo_row0; bc.app_store_row0 = -1;
+            bc.mask_out = a.hist_mask ? a.hist_mask + ((size_t)(a.T - 1) * a.B + b) * NZ : nullptr;
             if (active) {
-                if (soft_now || hard_now) {
+                if (soft_now || hard_now || a.hist_mask) {
                     for (int c = 0; c < g.n_vcols; c++) {
                         const int j = __ldg(g.vcol_j + c);
                         const int p0 = __ldg(g.vcol_ptr + c), p1 = __ldg(g.vcol_ptr + c + 1);

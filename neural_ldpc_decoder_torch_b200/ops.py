@@ -94,9 +94,11 @@ def neural_backward(xa: torch.Tensor, w: torch.Tensor, b: torch.Tensor, gout: to
     gout = gout.contiguous()
     gw = torch.empty_like(w)
     gb = torch.empty_like(b)
+    nbytes = int(_lib.lib().nldpc_backward_workspace_bytes(g.ptr, B, T, 0))
+    ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=xa.device)     # per-iteration v2c dump (HBM)
     with torch.cuda.device(xa.device):
         rc = _lib.lib().nldpc_neural_backward(g.ptr, _ptr(xa), _ptr(w), _ptr(b), _ptr(gout), B, T, _ptr(gw), _ptr(gb),
-                                              _stream(xa))
+                                              _ptr(ws), nbytes, _stream(xa))
     _lib.check(rc, "nldpc_neural_backward")
     return gw, gb
 
@@ -203,3 +205,62 @@ def _(xa, vn_w, cn_w, ucn_w, graph_id, T, decoder_type, qbit, llr_lo, llr_hi, co
     B = xa.shape[0]
     return (xa.new_empty((T, B, g.NZ)), xa.new_empty((B, g.Z, g.E) if want_llr else (0,)),
             xa.new_empty((B, g.N, g.Z) if want_xin else (0,)))
+
+
+@torch.library.custom_op("nldpc::boosted_backward", mutates_args=())
+def boosted_backward(xa: torch.Tensor, vn_w: Optional[torch.Tensor], cn_w: Optional[torch.Tensor], ucn_w: Optional[torch.Tensor],
+                     gout: torch.Tensor, graph_id: int, T: int, decoder_type: int, qbit: int, llr_lo: float, llr_hi: float,
+                     compute_ucn: bool, ucn_mix: bool) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """gradients w.r.t. the folded weight rows (vn [T,N], cn [T,E], ucn [T,E]; empty where absent)"""
+    g = _lib.graph_by_id(graph_id)
+    _check_cuda_f32("xa", xa)
+    _check_cuda_f32("gout", gout)
+    B, dev = xa.shape[0], xa.device
+    if tuple(gout.shape) != (T, B, g.NZ):
+        raise ValueError("gout must be [T, B, N*Z]")
+    xa, gout = xa.contiguous(), gout.contiguous()
+    vn_w = _opt_f32("vn_w", vn_w, (T, g.N), dev)
+    cn_w = _opt_f32("cn_w", cn_w, (T, g.E), dev)
+    ucn_w = _opt_f32("ucn_w", ucn_w, (T, g.E), dev)
+    gvn = torch.empty((T, g.N) if vn_w is not None else (0,), dtype=torch.float32, device=dev)
+    gcn = torch.empty((T, g.E) if cn_w is not None else (0,), dtype=torch.float32, device=dev)
+    gucn = torch.empty((T, g.E) if (ucn_w is not None and ucn_mix) else (0,), dtype=torch.float32, device=dev)
+    nbytes = int(_lib.lib().nldpc_backward_workspace_bytes(g.ptr, B, T, 1))
+    ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=dev)
+    cfg = _lib.BoostedCfg(decoder_type, qbit, llr_lo, llr_hi, int(compute_ucn), int(ucn_mix), None, None, None, None)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().nldpc_boosted_backward(g.ptr, ctypes.byref(cfg), _ptr(xa), _ptr(vn_w), _ptr(cn_w), _ptr(ucn_w), _ptr(gout), B, T,
+                                               _ptr(gvn) if gvn.numel() else _vp(0), _ptr(gcn) if gcn.numel() else _vp(0),
+                                               _ptr(gucn) if gucn.numel() else _vp(0), _ptr(ws), nbytes, _stream(xa))
+    _lib.check(rc, "nldpc_boosted_backward")
+    return gvn, gcn, gucn
+
+
+@boosted_backward.register_fake
+def _(xa, vn_w, cn_w, ucn_w, gout, graph_id, T, decoder_type, qbit, llr_lo, llr_hi, compute_ucn, ucn_mix):
+    g = _lib.graph_by_id(graph_id)
+    return (xa.new_empty((T, g.N) if vn_w is not None else (0,)), xa.new_empty((T, g.E) if cn_w is not None else (0,)),
+            xa.new_empty((T, g.E) if (ucn_w is not None and ucn_mix) else (0,)))
+
+
+def _boosted_setup_ctx(ctx, inputs, output):
+    (xa, vn_w, cn_w, ucn_w, graph_id, T, dec, qbit, lo, hi, compute_ucn, ucn_mix, llr_init, xin_init, app_init, want_llr,
+     want_xin) = inputs
+    ctx.save_for_backward(xa, vn_w, cn_w, ucn_w)
+    ctx.cfg = (graph_id, T, dec, qbit, lo, hi, compute_ucn, ucn_mix)
+    ctx.stateful = llr_init is not None or xin_init is not None or app_init is not None
+
+
+def _boosted_bwd(ctx, gsoft, gllr, gxin):
+    xa, vn_w, cn_w, ucn_w = ctx.saved_tensors
+    graph_id, T, dec, qbit, lo, hi, compute_ucn, ucn_mix = ctx.cfg
+    if ctx.stateful:
+        raise _lib.NldpcError("backward through a run that continues from stored state (partial target_iter after an earlier "
+                              "call) is not supported: run the trained iterations in one forward call starting at iteration 0")
+    gvn, gcn, gucn = torch.ops.nldpc.boosted_backward(xa, vn_w, cn_w, ucn_w, gsoft.contiguous(), graph_id, T, dec, qbit, lo, hi,
+                                                      compute_ucn, ucn_mix)
+    return (None, gvn if vn_w is not None else None, gcn if cn_w is not None else None,
+            gucn if (ucn_w is not None and ucn_mix) else None) + (None,) * 13
+
+
+boosted_forward.register_autograd(_boosted_bwd, setup_context=_boosted_setup_ctx)
