@@ -322,10 +322,10 @@ class BoostedNeuralLDPCDecoder(nn.Module):
             app_init = self.outputs[t0 - 1].to(device) if (compute_ucn and t0 > 0) else None
             want_llr = self.store_llr != "none"
             want_xin = len(runs) > 1 and not is_input_iterable
-            soft, llr_last, xin_out = torch.ops.nldpc.boosted_forward(
+            soft, llr_last, xin_out, _ = torch.ops.nldpc.boosted_forward(
                 x_run, vn_w, cn_w, ucn_w, gid, len(run), dec, int(self.decoder_qms_qbit),
                 float(self.allowed_llr_range.start), float(self.allowed_llr_range.end), bool(compute_ucn), bool(ucn_mix),
-                llr_init, xin_state, app_init, want_llr, want_xin)
+                llr_init, xin_state, app_init, want_llr, want_xin, 1, 0)
             for k, t in enumerate(run):
                 self.outputs[t] = soft[k]
             if want_llr:
@@ -339,6 +339,36 @@ class BoostedNeuralLDPCDecoder(nn.Module):
         elif isinstance(target_iter, list):
             return [self.outputs[i] for i in target_iter]
         return self.outputs
+
+
+def _decode(self, xa, n_iters, soft_mode, hard_mode):
+    from .. import _lib  # noqa: F401
+    T = self.iter_node_counts if n_iters is None else n_iters
+    device = xa.device
+    gid = self.conn_mat.graph_id(device)
+    vn_w, cn_w, ucn_w, compute_ucn, ucn_mix = self.fold_weights(list(range(T)), device)
+    dec = {DecoderType.SP: 0, DecoderType.MS: 1, DecoderType.QMS: 2}[self.decoding_type]
+    soft, _, _, hard = torch.ops.nldpc.boosted_forward(
+        xa, vn_w, cn_w, ucn_w, gid, T, dec, int(self.decoder_qms_qbit), float(self.allowed_llr_range.start),
+        float(self.allowed_llr_range.end), bool(compute_ucn), bool(ucn_mix), None, None, None, False, False, soft_mode, hard_mode)
+    return soft, hard
+
+
+@torch.no_grad()
+def decode_hard(self, xa, n_iters=None, all_iters=False):
+    """Stateless throughput mode (any batch size): packed hard decisions `(out < 0)` (Functions.py:90 predicate) after
+    `n_iters` iterations from the zero state; uint8 [B, ceil(N*Z/8)] or [T, B, ...] with all_iters."""
+    return _decode(self, xa, n_iters, 0, 1 if all_iters else 2)[1]
+
+
+@torch.no_grad()
+def decode_soft_last(self, xa, n_iters=None):
+    """Stateless: the soft output of the last iteration only, [B, N*Z]."""
+    return _decode(self, xa, n_iters, 2, 0)[0]
+
+
+BoostedNeuralLDPCDecoder.decode_hard = decode_hard
+BoostedNeuralLDPCDecoder.decode_soft_last = decode_soft_last
 
 
 def _add_dense_buffers(module, state_dict, prefix, local_metadata):

@@ -149,6 +149,10 @@ def neural_decode_host(graph_id, xa_host, w_host, b_host, soft_mode=_lib.NLDPC_O
 from typing import Optional  # noqa: E402
 
 
+def _out_shape(mode, T, B, last):
+    return (T, B, last) if mode == _lib.NLDPC_OUT_ALL else ((B, last) if mode == _lib.NLDPC_OUT_LAST else (0,))
+
+
 def _opt_f32(name, t, shape, device):
     if t is None:
         return None
@@ -164,10 +168,11 @@ def _opt_f32(name, t, shape, device):
 def boosted_forward(xa: torch.Tensor, vn_w: Optional[torch.Tensor], cn_w: Optional[torch.Tensor], ucn_w: Optional[torch.Tensor],
                     graph_id: int, T: int, decoder_type: int, qbit: int, llr_lo: float, llr_hi: float, compute_ucn: bool,
                     ucn_mix: bool, llr_init: Optional[torch.Tensor], xin_init: Optional[torch.Tensor],
-                    app_init: Optional[torch.Tensor], want_llr: bool,
-                    want_xin: bool) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """T consecutive iterations of the Boosted loop body.  Returns (soft [T,B,N*Z], llr_last [B,Z,E] | empty,
-    xin_out [B,N,Z] | empty).  Weight rows are indexed by executed iteration."""
+                    app_init: Optional[torch.Tensor], want_llr: bool, want_xin: bool, soft_mode: int,
+                    hard_mode: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """T consecutive iterations of the Boosted loop body.  Returns (soft [T,B,N*Z] | [B,N*Z] | empty per soft_mode,
+    llr_last [B,Z,E] | empty, xin_out [B,N,Z] | empty, packed hard decisions per hard_mode | empty).
+    Weight rows are indexed by executed iteration."""
     g = _lib.graph_by_id(graph_id)
     _check_cuda_f32("xa", xa)
     if xa.dim() != 3 or xa.shape[1] != g.N or xa.shape[2] != g.Z:
@@ -182,7 +187,8 @@ def boosted_forward(xa: torch.Tensor, vn_w: Optional[torch.Tensor], cn_w: Option
     llr_init = _opt_f32("llr_init", llr_init, (B, g.Z, g.E), dev)
     xin_init = _opt_f32("xin_init", xin_init, (B, g.N, g.Z), dev)
     app_init = _opt_f32("app_init", app_init, (B, g.NZ), dev)
-    soft = torch.empty((T, B, g.NZ), dtype=torch.float32, device=dev)
+    soft = torch.empty(_out_shape(soft_mode, T, B, g.NZ), dtype=torch.float32, device=dev)
+    hard = torch.empty(_out_shape(hard_mode, T, B, g.hard_bytes), dtype=torch.uint8, device=dev)
     llr_last = torch.empty((B, g.Z, g.E) if want_llr else (0,), dtype=torch.float32, device=dev)
     xin_out = torch.empty((B, g.N, g.Z) if want_xin else (0,), dtype=torch.float32, device=dev)
     cfg = _lib.BoostedCfg(decoder_type, qbit, llr_lo, llr_hi, int(compute_ucn), int(ucn_mix),
@@ -192,19 +198,21 @@ def boosted_forward(xa: torch.Tensor, vn_w: Optional[torch.Tensor], cn_w: Option
                           app_init.data_ptr() if app_init is not None else None)
     with torch.cuda.device(dev):
         rc = _lib.lib().nldpc_boosted_forward(g.ptr, ctypes.byref(cfg), _ptr(xa), _ptr(vn_w), _ptr(cn_w), _ptr(ucn_w), B, T,
-                                              _lib.NLDPC_OUT_ALL, _ptr(soft), _lib.NLDPC_OUT_NONE, _vp(0),
+                                              soft_mode, _ptr(soft) if soft_mode else _vp(0), hard_mode,
+                                              _ptr(hard) if hard_mode else _vp(0),
                                               _ptr(llr_last) if want_llr else _vp(0), _stream(xa))
     _lib.check(rc, "nldpc_boosted_forward")
-    return soft, llr_last, xin_out
+    return soft, llr_last, xin_out, hard
 
 
 @boosted_forward.register_fake
 def _(xa, vn_w, cn_w, ucn_w, graph_id, T, decoder_type, qbit, llr_lo, llr_hi, compute_ucn, ucn_mix, llr_init, xin_init, app_init,
-      want_llr, want_xin):
+      want_llr, want_xin, soft_mode, hard_mode):
     g = _lib.graph_by_id(graph_id)
     B = xa.shape[0]
-    return (xa.new_empty((T, B, g.NZ)), xa.new_empty((B, g.Z, g.E) if want_llr else (0,)),
-            xa.new_empty((B, g.N, g.Z) if want_xin else (0,)))
+    return (xa.new_empty(_out_shape(soft_mode, T, B, g.NZ)), xa.new_empty((B, g.Z, g.E) if want_llr else (0,)),
+            xa.new_empty((B, g.N, g.Z) if want_xin else (0,)),
+            xa.new_empty(_out_shape(hard_mode, T, B, g.hard_bytes), dtype=torch.uint8))
 
 
 @torch.library.custom_op("nldpc::boosted_backward", mutates_args=())
@@ -245,22 +253,25 @@ def _(xa, vn_w, cn_w, ucn_w, gout, graph_id, T, decoder_type, qbit, llr_lo, llr_
 
 def _boosted_setup_ctx(ctx, inputs, output):
     (xa, vn_w, cn_w, ucn_w, graph_id, T, dec, qbit, lo, hi, compute_ucn, ucn_mix, llr_init, xin_init, app_init, want_llr,
-     want_xin) = inputs
+     want_xin, soft_mode, hard_mode) = inputs
     ctx.save_for_backward(xa, vn_w, cn_w, ucn_w)
     ctx.cfg = (graph_id, T, dec, qbit, lo, hi, compute_ucn, ucn_mix)
     ctx.stateful = llr_init is not None or xin_init is not None or app_init is not None
+    ctx.soft_all = soft_mode == _lib.NLDPC_OUT_ALL
 
 
-def _boosted_bwd(ctx, gsoft, gllr, gxin):
+def _boosted_bwd(ctx, gsoft, gllr, gxin, ghard):
     xa, vn_w, cn_w, ucn_w = ctx.saved_tensors
     graph_id, T, dec, qbit, lo, hi, compute_ucn, ucn_mix = ctx.cfg
+    if not ctx.soft_all:
+        raise _lib.NldpcError("backward needs the per-iteration soft outputs (soft_mode = ALL)")
     if ctx.stateful:
         raise _lib.NldpcError("backward through a run that continues from stored state (partial target_iter after an earlier "
                               "call) is not supported: run the trained iterations in one forward call starting at iteration 0")
     gvn, gcn, gucn = torch.ops.nldpc.boosted_backward(xa, vn_w, cn_w, ucn_w, gsoft.contiguous(), graph_id, T, dec, qbit, lo, hi,
                                                       compute_ucn, ucn_mix)
     return (None, gvn if vn_w is not None else None, gcn if cn_w is not None else None,
-            gucn if (ucn_w is not None and ucn_mix) else None) + (None,) * 13
+            gucn if (ucn_w is not None and ucn_mix) else None) + (None,) * 15
 
 
 boosted_forward.register_autograd(_boosted_bwd, setup_context=_boosted_setup_ctx)

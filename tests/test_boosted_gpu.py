@@ -80,8 +80,9 @@ def test_boosted_stateful_staged_runs_match_one_shot(graphs):
         llr, o = oracle.boosted_step(d["basegraph"], m.Z, 2, 5, (-20.0, 20.0), xin, xo, llr, vn_w[t].numpy(), cn_w[t].numpy(),
                                      ucn_w[t].numpy(), cu, mix, None if t == 0 else outs[-1])
         outs.append(o)
-    xin, xo = d["xa"].copy(), d["xa"].copy()                 # new forward() call: the scaling restarts from xa
     for t in range(3, T):
+        if t in (3, T - 1):                                   # a new forward() call: the VN scaling restarts from xa
+            xin, xo = d["xa"].copy(), d["xa"].copy()
         llr, o = oracle.boosted_step(d["basegraph"], m.Z, 2, 5, (-20.0, 20.0), xin, xo, llr, vn_w[t].numpy(), cn_w[t].numpy(),
                                      ucn_w[t].numpy(), cu, mix, outs[-1])
         outs.append(o)
@@ -114,3 +115,16 @@ def test_boosted_cpu_input_fails_loudly(graphs):
     m = build_module(d, device="cuda")
     with pytest.raises(NldpcError):
         m(torch.from_numpy(d["xa"]))
+
+
+def test_boosted_stateless_decode_methods(graphs):
+    d = load_golden(CASES[3])           # WiMAX QMS (3,0,3), T=20, B=8
+    m = build_module(d, device="cuda", batch=3)          # constructor batch differs: the stateless methods take any batch
+    xa = torch.from_numpy(d["xa"]).cuda()
+    hard = m.decode_hard(xa).cpu().numpy()
+    assert np.array_equal(hard, np.packbits(d["out"][-1] < 0, axis=1, bitorder="little"))
+    hall = m.decode_hard(xa, all_iters=True).cpu().numpy()
+    for t in range(int(d["T"])):
+        assert np.array_equal(hall[t], np.packbits(d["out"][t] < 0, axis=1, bitorder="little"))
+    assert np.array_equal(m.decode_soft_last(xa).cpu().numpy(), d["out"][-1])
+    assert np.array_equal(m.decode_soft_last(xa, n_iters=5).cpu().numpy(), d["out"][4])

@@ -52,8 +52,7 @@ def main():
         t0 = time.perf_counter()
         while n < args.codewords:
             x, y = gen(B)
-            with torch.no_grad():
-                out = model(x, target_iter=T - 1)
+            out = model.decode_soft_last(x)
             wrong = ((out < 0).float() != y)                      # reference predicate (inverted w.r.t. the true decision)
             per = wrong.sum(dim=1)
             bit_err += int(per.sum()); frame_err += int((per > 0).sum())
