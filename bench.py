@@ -284,7 +284,7 @@ def main():
                        "codewords_per_gpu_per_step": B, "iterations": T, "output": "packed hard decisions (out<0), last iteration",
                        "l2_policy": "inputs (218 MB per step) larger than the 126 MB L2",
                        "specialised_kernel": bool(gh.specialised), "codewords_per_cta": gh.cw_per_cta},
-            "gpu_launches": args.steps,
+            "gpu_launches": 2 * args.steps,   # per step: pack_wb_kernel (weights -> constant arena) + the decode kernel
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback",
