@@ -416,6 +416,12 @@ extern "C" int nldpc_boosted_forward(const nldpc_graph_t *g, const nldpc_boosted
     a.llr_lo = cfg->llr_lo; a.llr_hi = cfg->llr_hi;
     a.llr_init = cfg->llr_init_dev; a.xin_init = cfg->xin_init_dev; a.xin_out = cfg->xin_out_dev; a.app_init = cfg->app_init_dev;
     cudaStream_t st = (cudaStream_t)stream;
+    if (g->spec_id >= 0 && !force_generic()) {
+        const int src = spec_launch_boosted(g->spec_id, a, g->sm_count, st);
+        if (src > 0) return fail(src, std::string("nldpc_boosted_forward (specialised): ") + cudaGetErrorString((cudaError_t)src));
+        if (src == 0) return NLDPC_OK;
+        // src < 0: configuration not covered by the specialised kernels (SP, other q-bit grids, UCN, stateful runs)
+    }
     const int rc = generic_launch_boosted(g->dev, a, g->sm_count, st);
     if (rc == -2) return fail(NLDPC_E_UNSUPPORTED, "nldpc_boosted_forward: one codeword's boosted state does not fit in shared memory");
     if (rc != 0) return fail(rc, std::string("nldpc_boosted_forward: ") + cudaGetErrorString((cudaError_t)rc));

@@ -7,82 +7,11 @@
 #include "generated/nldpc_graph_bg2z16.cuh"
 #include "generated/nldpc_graph_wimaxz24.cuh"
 
-#include <mutex>
-#include <vector>
+#include "nldpc_spec_host.cuh"
 
 namespace nldpc {
 
-
 namespace {
-
-// {w[i], b[i]} -> constant arena (written through its global address; visible to the launches that follow
-// on the same stream: the constant cache is invalidated at kernel boundaries)
-__global__ void pack_wb_kernel(const float *__restrict__ w, const float *__restrict__ b, float2 *__restrict__ dst, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = make_float2(w[i], b ? b[i] : 0.0f);
-}
-
-// Ring allocator over the constant arena, per device.  A range is reused only after the launch that read it
-// has finished: a launch on another stream that wants an overlapping range first waits on that launch's event.
-struct ConstArena {
-    struct Pending { int off, len; cudaEvent_t ev; cudaStream_t st; };
-    std::mutex mu;
-    int head = 0;
-    std::vector<Pending> pend;
-    std::vector<cudaEvent_t> pool;
-    float2 *base = nullptr;
-
-    // returns offset (float2 units) or -1 when `len` does not fit at all
-    int acquire(int len, cudaStream_t st, cudaError_t *err) {
-        *err = cudaSuccess;
-        if (len > kConstFloat2) return -1;
-        std::lock_guard<std::mutex> lk(mu);
-        if (!base) {
-            *err = cudaGetSymbolAddress((void **)&base, c_wb);
-            if (*err != cudaSuccess) return -1;
-        }
-        if (head + len > kConstFloat2) head = 0;
-        const int off = head;
-        head += (len + 1) & ~1;   // keep 16-byte alignment
-        for (size_t i = 0; i < pend.size();) {
-            Pending &p = pend[i];
-            const bool overlap = p.off < off + len && off < p.off + p.len;
-            if (overlap) {
-                if (p.st != st) {
-                    *err = cudaStreamWaitEvent(st, p.ev, 0);
-                    if (*err != cudaSuccess) return -1;
-                }
-                pool.push_back(p.ev);
-                pend[i] = pend.back();
-                pend.pop_back();
-            } else {
-                i++;
-            }
-        }
-        return off;
-    }
-    // call after the consumer kernel has been enqueued on `st`
-    cudaError_t release_after(int off, int len, cudaStream_t st) {
-        std::lock_guard<std::mutex> lk(mu);
-        cudaEvent_t ev;
-        if (!pool.empty()) { ev = pool.back(); pool.pop_back(); }
-        else {
-            cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-            if (e != cudaSuccess) return e;
-        }
-        cudaError_t e = cudaEventRecord(ev, st);
-        if (e != cudaSuccess) return e;
-        pend.push_back({off, len, ev, st});
-        return cudaSuccess;
-    }
-};
-
-ConstArena &arena_for_current_device() {
-    static ConstArena arenas[64];
-    int dev = 0;
-    cudaGetDevice(&dev);
-    return arenas[dev & 63];
-}
 
 template <class G>
 bool graph_matches(const int32_t *bg, int M, int N, int Z) {
@@ -94,11 +23,6 @@ bool graph_matches(const int32_t *bg, int M, int N, int Z) {
         if (!a && (bg[i] % Z) != (ref[i] % Z)) return false;
     }
     return true;
-}
-
-template <class K>
-cudaError_t set_smem(K kernel, size_t bytes) {
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
 template <class G>
@@ -149,8 +73,8 @@ int spec_find(const int32_t *bg, int M, int N, int Z) {
 
 int spec_prepare(int id) {
     switch (id) {
-        case 0: return prepare<gen::Bg2Z16>();
-        case 1: return prepare<gen::WimaxZ24>();
+        case 0: { int rc = prepare<gen::Bg2Z16>(); return rc ? rc : spec_boosted_prepare_bg2(); }
+        case 1: { int rc = prepare<gen::WimaxZ24>(); return rc ? rc : spec_boosted_prepare_wimax(); }
         default: return -1;
     }
 }
@@ -162,6 +86,14 @@ int spec_launch_neural(int id, const DecodeArgs &a, int sm_count, cudaStream_t s
     switch (id) {
         case 0: return launch_neural<gen::Bg2Z16>(a, sm_count, st);
         case 1: return launch_neural<gen::WimaxZ24>(a, sm_count, st);
+        default: return -1;
+    }
+}
+
+int spec_launch_boosted(int id, const DecodeArgs &a, int sm_count, cudaStream_t st) {
+    switch (id) {
+        case 0: return spec_boosted_launch_bg2(a, sm_count, st);
+        case 1: return spec_boosted_launch_wimax(a, sm_count, st);
         default: return -1;
     }
 }

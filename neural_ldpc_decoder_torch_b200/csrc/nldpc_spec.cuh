@@ -10,4 +10,10 @@ int spec_cw_per_cta(int id);
 int spec_threads(int id);
 // 0 = launched, >0 = cudaError_t, <0 = configuration not covered (caller falls back to the generic kernel)
 int spec_launch_neural(int id, const DecodeArgs &a, int sm_count, cudaStream_t st);
+int spec_launch_boosted(int id, const DecodeArgs &a, int sm_count, cudaStream_t st);
+// per-code translation units
+int spec_boosted_prepare_bg2();
+int spec_boosted_launch_bg2(const DecodeArgs &a, int sm_count, cudaStream_t st);
+int spec_boosted_prepare_wimax();
+int spec_boosted_launch_wimax(const DecodeArgs &a, int sm_count, cudaStream_t st);
 }  // namespace nldpc

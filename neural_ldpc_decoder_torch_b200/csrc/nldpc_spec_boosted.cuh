@@ -1,0 +1,63 @@
+// nldpc_spec_boosted.cuh — instantiation helper for the specialised Boosted (MS / QMS q=5, no UCN) kernels of one code.
+// Included by one translation unit per code so the 8 variants of each compile in parallel.
+#pragma once
+#include <algorithm>
+
+#include "nldpc_spec_host.cuh"
+
+namespace nldpc {
+namespace {
+
+template <class G, int MODE, bool kXo>
+int boosted_prepare_one() {
+    cudaError_t e;
+    if ((e = set_smem(nldpc_spec_neural_kernel<G, true, true, MODE, kXo>, SpecCfg<G, kXo>::kSmemBytes)) != cudaSuccess) return (int)e;
+    if ((e = set_smem(nldpc_spec_neural_kernel<G, false, true, MODE, kXo>, SpecCfg<G, kXo>::kSmemBytes)) != cudaSuccess) return (int)e;
+    return 0;
+}
+
+template <class G>
+int boosted_prepare() {
+    int rc;
+    if ((rc = boosted_prepare_one<G, 1, false>())) return rc;
+    if ((rc = boosted_prepare_one<G, 1, true>())) return rc;
+    if ((rc = boosted_prepare_one<G, 2, false>())) return rc;
+    if ((rc = boosted_prepare_one<G, 2, true>())) return rc;
+    return 0;
+}
+
+template <class G, int MODE, bool kXo>
+int boosted_launch_one(const DecodeArgs &args, int sm_count, cudaStream_t st) {
+    using Cfg = SpecCfg<G, kXo>;
+    const int n_units = (args.B + Cfg::Shape::kCw - 1) / Cfg::Shape::kCw;
+    const int ctas = (n_units + Cfg::kGroups - 1) / Cfg::kGroups;
+    const int grid = std::min(ctas, sm_count * 2);
+    const bool every = args.soft_mode == 1 || args.hard_mode == 1;
+    if (every) nldpc_spec_neural_kernel<G, true, true, MODE, kXo><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(args);
+    else nldpc_spec_neural_kernel<G, false, true, MODE, kXo><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(args);
+    return (int)cudaGetLastError();
+}
+
+// 0 launched, >0 cudaError_t, -1 configuration not covered (caller uses the table-driven kernel)
+template <class G>
+int boosted_launch(const DecodeArgs &a, int sm_count, cudaStream_t st) {
+    const bool qms5 = a.decoder_type == 2 && a.qbit == 5, ms = a.decoder_type == 1;
+    if (!(qms5 || ms) || a.compute_ucn || a.llr_init || a.xin_init || a.xin_out || a.app_init || a.hist_v2c) return -1;
+    ConstArena &arena = arena_for_current_device();
+    const int len = a.T * G::E;
+    cudaError_t err;
+    const int off = arena.acquire(len, st, &err);
+    if (err != cudaSuccess) return (int)err;
+    if (off < 0) return -1;
+    DecodeArgs args = a;
+    args.wb_off = off;
+    pack_wb_kernel<<<(len + 255) / 256, 256, 0, st>>>(a.w, nullptr, arena.base + off, len);   // cn_w (or 1.0), no bias
+    int rc;
+    if (ms) rc = a.vn_w ? boosted_launch_one<G, 1, true>(args, sm_count, st) : boosted_launch_one<G, 1, false>(args, sm_count, st);
+    else rc = a.vn_w ? boosted_launch_one<G, 2, true>(args, sm_count, st) : boosted_launch_one<G, 2, false>(args, sm_count, st);
+    if (rc != 0) return rc;
+    return (int)arena.release_after(off, len, st);
+}
+
+}  // namespace
+}  // namespace nldpc

@@ -16,6 +16,8 @@
 //
 // Exactness contract: see nldpc_generic.cu / oracle/nldpc_oracle.c.
 #pragma once
+#include <type_traits>
+
 #include "nldpc_common.cuh"
 
 namespace nldpc {
@@ -58,6 +60,16 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
     return d;
 }
 
+// decoder arithmetic selected at compile time: 0 = NeuralLDPCDecoder, 1 = Boosted MS, 2 = Boosted QMS with q_bit = 5
+// (other q-bit grids, SP and the UCN indicator run on the table-driven kernel)
+__device__ __forceinline__ float clamp_rng(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+__device__ __forceinline__ float quant5(float x) { return clamp_rng(mulf(rintf(mulf(x, 2.0f)), 0.5f), -7.5f, 7.5f); }   // (:190-191)
+template <int MODE>
+__device__ __forceinline__ float condition(float x, float lo, float hi) {        // QMS: quantise, MS: clamp (:386-389, :507-510)
+    if constexpr (MODE == 2) return quant5(x);
+    else return clamp_rng(x, lo, hi);
+}
+
 template <int Z>
 struct GroupShape {
     static constexpr int kLanes = (Z == 16 || Z == 32) ? 32 : (Z == 24 ? 96 : 0);
@@ -89,6 +101,10 @@ struct NeuralLane {
     int z;
     bool valid;
     float zmin;              // min |v2c| written by this lane in the current VN phase (0 => the zero-safe CN phase is needed)
+    // Boosted decoder (MODE != 0)
+    int xo_off;              // float offset from the xin rows to the xo rows (0: xa_origin and xa_input are the same rows)
+    float lo, hi;            // allowed_llr_range
+    float *llr_last;         // &llr_last[b][0][0] ([Z][E]) while the last iteration's CN phase runs, else nullptr
 
     // ---- emission of one marginal value -------------------------------------------------------------------
     // un-rotated: this lane holds bit (J, z)
@@ -138,13 +154,13 @@ struct VnFirst {
     template <int J, int... R>
     __device__ __forceinline__ void col() {
         const float v = addf(c.lane[J * G::Z], 0.0f);
-        c.zmin = fminf(c.zmin, fabsf(v));
+        c.zmin = fminf(c.zmin, fabsf(v));       // (only read by the Neural CN dispatch)
         ((c.lane[R * G::Z] = v), ...);
     }
 };
 
 // iterations >= 1: v2c[k] = x + (((0 + c[0]) + c[1]) + ... skipping k); kEmit: marginal of the previous iteration
-template <class G, bool kEmit>
+template <class G, bool kEmit, int MODE = 0>
 struct VnStep {
     NeuralLane<G> &c;
     template <int J, int... R>
@@ -169,28 +185,32 @@ struct VnStep {
 #pragma unroll
             for (int q = k + 2; q < D; q++) s = add2(s, pack2(m[q], m[q]));
             s = add2(pack2(x, x), s);
-            c.zmin = fmin3(c.zmin, fabsf(lo(s)), fabsf(hi(s)));
+            if constexpr (MODE == 0) c.zmin = fmin3(c.zmin, fabsf(lo(s)), fabsf(hi(s)));
             c.lane[rows[k] * G::Z] = lo(s);
             c.lane[rows[k + 1] * G::Z] = hi(s);
         }
         if constexpr (D & 1) {
             const float v = addf(x, pre[D - 1]);
-            c.zmin = fminf(c.zmin, fabsf(v));
+            if constexpr (MODE == 0) c.zmin = fminf(c.zmin, fabsf(v));
             c.lane[rows[D - 1] * G::Z] = v;
         }
-        if constexpr (kEmit) c.template emit<J>(addf(x, p));       // out = xa + llr @ W_output (:94-96)
+        if constexpr (kEmit) {
+            if constexpr (MODE == 0) c.template emit<J>(addf(x, p));       // out = xa + llr @ W_output (:94-96)
+            else c.template emit<J>(clamp_rng(addf(c.lane[c.xo_off + J * G::Z], p), c.lo, c.hi));   // Boosted :520-521
+        }
     }
 };
 
 // marginal only (after the last CN phase)
-template <class G>
+template <class G, int MODE = 0>
 struct Marginal {
     NeuralLane<G> &c;
     template <int J, int... R>
     __device__ __forceinline__ void col() {
         float p = 0.0f;
         ((p = addf(p, c.lane[R * G::Z])), ...);
-        c.template emit<J>(addf(c.lane[J * G::Z], p));
+        if constexpr (MODE == 0) c.template emit<J>(addf(c.lane[J * G::Z], p));
+        else c.template emit<J>(clamp_rng(addf(c.lane[c.xo_off + J * G::Z], p), c.lo, c.hi));
     }
 };
 
@@ -260,6 +280,76 @@ __device__ __forceinline__ void cn_check_core(NeuralLane<G> &c) {
     }
 }
 
+// Boosted MS / QMS check update, BoostedNeuralLDPCDecoder.py:380-526 (no UCN mixing): condition the inputs (quantise or
+// clamp), nudge exact zeros to +1e-4, min over the others, mag - 1e-4 [mag <= 1e-4], o = mag * sgn, |o| * W_cn, ReLU,
+// condition again, * sign(o) (sign(0) = 0).  kXo: xa_origin lives in its own rows (VN weights make xa_input drift).
+template <class G, bool kEmit, int MODE, bool kXo, class... Es>
+__device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c) {
+    constexpr int D = sizeof...(Es);
+    constexpr int rows[D] = {Es::row...};
+    constexpr int shf[D] = {Es::shift...};
+    constexpr int eix[D] = {Es::e...};
+    constexpr int col1[D] = {Es::col1...};
+    float u[D], raw[D];
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        raw[k] = c.rot[shf[k]][rows[k] * G::Z];                          // gather (:380-384)
+        const float v = condition<MODE>(raw[k], c.lo, c.hi);
+        u[k] = (v == 0.0f) ? 0.0001f : v;                                // x + 1e-4 * [x == 0] (:391-393)
+    }
+    constexpr int H = (D + 1) / 2;
+    float se[H + 1];
+    se[H] = 10000.0f;
+#pragma unroll
+    for (int q = H - 1; q >= 0; q--) {
+        if (2 * q + 1 < D) se[q] = fmin3(fabsf(u[2 * q]), fabsf(u[2 * q + 1]), se[q + 1]);
+        else se[q] = fminf(fabsf(u[2 * q]), se[q + 1]);
+    }
+    unsigned x = (D & 1) ? 0x80000000u : 0u;
+#pragma unroll
+    for (int k = 0; k < D; k++) x ^= __float_as_uint(u[k]);
+    float pe = 10000.0f;
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        const int q = k >> 1;
+        float mag;
+        if ((k & 1) == 0) {
+            if (k + 1 < D) mag = fmin3(pe, fabsf(u[k + 1]), se[q + 1]);
+            else mag = fminf(pe, se[q + 1]);
+        } else {
+            mag = fmin3(pe, fabsf(u[k - 1]), se[q + 1]);
+            pe = fmin3(pe, fabsf(u[k - 1]), fabsf(u[k]));
+        }
+        if (col1[k] >= 0 && !kEmit) continue;
+        const float madj = (mag > 0.0001f) ? mag : addf(mag, -0.0001f);   // (:416)
+        const float wk = c_wb[c.wb_base + eix[k]].x;
+        float m = fmaxf(mulf(fabsf(madj), wk), 0.0f);                     // |o| * W, ReLU (:431-505)
+        m = condition<MODE>(m, c.lo, c.hi);                               // (:507-510)
+        // sign(o) = sign(madj) * sgn;  sgn is negative iff the number of positive OTHER inputs is even (:417-423)
+        const unsigned sb = (x ^ __float_as_uint(u[k]) ^ __float_as_uint(madj)) & 0x80000000u;
+        float c2v = __uint_as_float(__float_as_uint(m) | sb);
+        c2v = (madj == 0.0f) ? 0.0f : c2v;                                // m * sign(0) (:512)
+        if constexpr (kEmit) {
+            if (c.llr_last) c.llr_last[(size_t)(c.rot[shf[k]] - (c.lane - c.z)) * G::E + eix[k]] = c2v;   // self.llr[T][b][z][e]
+        }
+        if (col1[k] < 0) {
+            c.rot[shf[k]][rows[k] * G::Z] = c2v;
+        } else if constexpr (kEmit) {
+            const float xo = kXo ? c.rot[shf[k]][c.xo_off + col1[k] * G::Z] : raw[k];
+            c.emit_rot(col1[k], shf[k], clamp_rng(addf(xo, addf(0.0f, c2v)), c.lo, c.hi));   // (:513-526)
+        }
+    }
+}
+
+template <class G, bool kEmit, int MODE, bool kXo>
+struct CnBoosted {
+    NeuralLane<G> &c;
+    template <class... Es>
+    __device__ __forceinline__ void chk() {
+        cn_check_boosted_core<G, kEmit, MODE, kXo, Es...>(c);
+    }
+};
+
 template <class G, bool kEmit, bool kConstW, bool kZeroSafe>
 struct CnNeural {
     NeuralLane<G> &c;
@@ -295,12 +385,20 @@ __device__ __forceinline__ void cn_phase(NeuralLane<G> &c, bool xa_zero) {
 }
 
 // -----------------------------------------------------------------------------------------------------------
-template <class G>
+constexpr int slab_with_xo(int slab, int nz, int z) {
+    int s = slab + nz;
+    while ((s % 32) != (z % 32) || (s % 4)) s++;
+    return s;
+}
+
+template <class G, bool kXo = false>
 struct SpecCfg {
     using Shape = GroupShape<G::Z>;
+    static constexpr int kSlabF = kXo ? slab_with_xo(G::kSlab, G::N * G::Z, G::Z) : G::kSlab;   // floats per codeword slab
+    static constexpr int kXoOff = kXo ? (G::N + G::S) * G::Z : 0;        // xo rows follow the message rows
     static constexpr int kHardBytes = (G::N * G::Z + 7) / 8;
     static constexpr int kHardStride = (kHardBytes + 15) & ~15;           // per-codeword staging, 16 B multiple
-    static constexpr int kPerCw = G::kSlab * 4 + kHardStride;            // shared bytes per codeword
+    static constexpr int kPerCw = kSlabF * 4 + kHardStride;              // shared bytes per codeword
     // groups per CTA so that two CTAs fit one SM (227 KB), threads <= 384
     static constexpr int kBudget = (kSmemBudget - 2 * 1024) / 2 - 256;
     static constexpr int kGroupsRaw = kBudget / (kPerCw * Shape::kCw);
@@ -312,14 +410,16 @@ struct SpecCfg {
 
 // kEvery: outputs are produced after every iteration (drop-in list mode / per-iteration hard decisions);
 // otherwise only after the last one (throughput mode) and the loop body carries no output code at all.
-template <class G, bool kEvery, bool kConstW>
-__global__ void __launch_bounds__(SpecCfg<G>::kThreads, 2) nldpc_spec_neural_kernel(const DecodeArgs a) {
-    using Cfg = SpecCfg<G>;
+template <class G, bool kEvery, bool kConstW, int MODE = 0, bool kXo = false>
+__global__ void __launch_bounds__(SpecCfg<G, kXo>::kThreads, 2) nldpc_spec_neural_kernel(const DecodeArgs a) {
+    using Cfg = SpecCfg<G, kXo>;
+    static_assert(MODE == 0 || kConstW, "the Boosted variants read their weights from the constant arena");
+    static_assert(MODE != 0 || !kXo, "xo rows only exist for the Boosted decoder with VN weights");
     using Shape = typename Cfg::Shape;
     constexpr int Z = G::Z, NZ = G::N * G::Z;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *slabs = reinterpret_cast<float *>(smem_raw);
-    uint8_t *hstage = smem_raw + (size_t)Cfg::kCwPerCta * G::kSlab * 4;
+    uint8_t *hstage = smem_raw + (size_t)Cfg::kCwPerCta * Cfg::kSlabF * 4;
     uint64_t *bars = reinterpret_cast<uint64_t *>(hstage + (size_t)Cfg::kCwPerCta * Cfg::kHardStride);
 
     const int grp = threadIdx.x / Shape::kLanes;            // group within the CTA
@@ -327,7 +427,7 @@ __global__ void __launch_bounds__(SpecCfg<G>::kThreads, 2) nldpc_spec_neural_ker
     const int cwl = gl / Z;                                 // codeword within the group
     const int z = gl - cwl * Z;
     const int cw_in_cta = grp * Shape::kCw + cwl;
-    float *slab = slabs + (size_t)cw_in_cta * G::kSlab;
+    float *slab = slabs + (size_t)cw_in_cta * Cfg::kSlabF;
     uint64_t *bar = bars + grp;
 
     if (gl == 0) {
@@ -339,6 +439,10 @@ __global__ void __launch_bounds__(SpecCfg<G>::kThreads, 2) nldpc_spec_neural_ker
     NeuralLane<G> c;
     c.lane = slab + z;
     c.z = z;
+    c.xo_off = Cfg::kXoOff;
+    c.lo = a.llr_lo;
+    c.hi = a.llr_hi;
+    c.llr_last = nullptr;
 #pragma unroll
     for (int s = 0; s < Z; s++) c.rot[s] = slab + ((z + s) % Z);
     uint8_t *hb_mine = hstage + (size_t)cw_in_cta * Cfg::kHardStride;
@@ -366,7 +470,7 @@ __global__ void __launch_bounds__(SpecCfg<G>::kThreads, 2) nldpc_spec_neural_ker
             fence_proxy_async();
             mbar_arrive_expect_tx(bar, (uint32_t)(ncw * NZ * sizeof(float)));
             for (int q = 0; q < ncw; q++)
-                tma_load_1d(slabs + (size_t)(grp * Shape::kCw + q) * G::kSlab, a.xa + (size_t)(b0 + q) * NZ,
+                tma_load_1d(slabs + (size_t)(grp * Shape::kCw + q) * Cfg::kSlabF, a.xa + (size_t)(b0 + q) * NZ,
                             (uint32_t)(NZ * sizeof(float)), bar);
         }
         if constexpr (Z != 16 && Z != 32) {   // atomicOr staging must start from zero
@@ -377,14 +481,43 @@ __global__ void __launch_bounds__(SpecCfg<G>::kThreads, 2) nldpc_spec_neural_ker
             phase ^= 1;
         }
 
-        // screen the channel LLRs of this lane for exact zeros once (degree-1 blocks feed the CN phase directly)
         bool xa_zero = false;
-        {
+        if constexpr (MODE == 0) {
+            // screen the channel LLRs of this lane for exact zeros once (degree-1 blocks feed the CN phase directly)
             float zm = 1.0f;
             for (int j = 0; j < G::N; j++) zm = fminf(zm, fabsf(c.lane[j * Z]));
             xa_zero = (zm == 0.0f);
+        } else {
+            // Boosted: xa_origin is quantised once if QMS (:517-518, idempotent).  Without VN weights xa_input == xa_origin
+            // live in the same rows; with VN weights xa_input starts as the raw xa and is rescaled every iteration.
+            for (int j = 0; j < G::N; j++) {
+                const float x = c.lane[j * Z];
+                const float xq = (MODE == 2) ? quant5(x) : x;
+                if constexpr (kXo) c.lane[Cfg::kXoOff + j * Z] = xq;
+                else c.lane[j * Z] = xq;
+            }
         }
         c.zmin = 10000.0f;
+        // per-iteration pieces shared by both output modes
+        auto xin_update = [&](int t) {
+            if constexpr (kXo) {   // xa_input *= w_VN(t), re-quantised if QMS (:325-337); own lane only, no hazard
+                const float *vw = a.vn_w + (size_t)t * G::N;
+                for (int j = 0; j < G::N; j++) {
+                    float x = mulf(c.lane[j * Z], __ldg(vw + j));
+                    if constexpr (MODE == 2) x = quant5(x);
+                    c.lane[j * Z] = x;
+                }
+            }
+        };
+        auto cn_run = [&](auto emit_tag) {
+            constexpr bool kEmitNow = decltype(emit_tag)::value;
+            if constexpr (MODE == 0) {
+                cn_phase<G, kEmitNow, kConstW>(c, xa_zero);
+            } else {
+                CnBoosted<G, kEmitNow, MODE, kXo> f{c};
+                G::checks(f);
+            }
+        };
         float *soft_cw = (soft_any && c.valid) ? a.soft + (size_t)b * NZ : nullptr;     // + t*B*NZ in ALL mode
         const size_t soft_iter = (size_t)a.B * NZ;
         uint8_t *hb_cw = hard_any ? hb_mine : nullptr;
@@ -418,13 +551,14 @@ __global__ void __launch_bounds__(SpecCfg<G>::kThreads, 2) nldpc_spec_neural_ker
                 c.wt = a.w + (size_t)t * G::E;
                 c.bt = a.b + (size_t)t * G::E;
                 c.wb_base = a.wb_off + t * G::E;
+                xin_update(t);
                 if (t == 0) {
                     VnFirst<G> f{c};
                     G::vcols(f);
                 } else {
                     c.soft = (soft_all && soft_cw) ? soft_cw + (size_t)(t - 1) * soft_iter : nullptr;
                     c.hb = hard_all ? hb_cw : nullptr;
-                    VnStep<G, true> f{c};
+                    VnStep<G, true, MODE> f{c};
                     G::vcols(f);
                     if (hard_all) flush_hard(t - 1);
                 }
@@ -432,7 +566,8 @@ __global__ void __launch_bounds__(SpecCfg<G>::kThreads, 2) nldpc_spec_neural_ker
                 const bool last = t == a.T - 1;
                 c.soft = (soft_cw && (soft_all || last)) ? soft_cw + (soft_all ? (size_t)t * soft_iter : 0) : nullptr;
                 c.hb = (hard_all || last) ? hb_cw : nullptr;
-                cn_phase<G, true, kConstW>(c, xa_zero);
+                c.llr_last = (last && a.llr_last && c.valid) ? a.llr_last + (size_t)b * Z * G::E : nullptr;
+                cn_run(std::true_type{});
                 phase_sync();
             }
         } else {
@@ -440,20 +575,22 @@ __global__ void __launch_bounds__(SpecCfg<G>::kThreads, 2) nldpc_spec_neural_ker
                 c.wt = a.w + (size_t)t * G::E;
                 c.bt = a.b + (size_t)t * G::E;
                 c.wb_base = a.wb_off + t * G::E;
+                xin_update(t);
                 if (t == 0) {
                     VnFirst<G> f{c};
                     G::vcols(f);
                 } else {
-                    VnStep<G, false> f{c};
+                    VnStep<G, false, MODE> f{c};
                     G::vcols(f);
                 }
                 phase_sync();
                 if (t < a.T - 1) {
-                    cn_phase<G, false, kConstW>(c, xa_zero);
+                    cn_run(std::false_type{});
                 } else {
                     c.soft = soft_cw;
                     c.hb = hb_cw;
-                    cn_phase<G, true, kConstW>(c, xa_zero);
+                    c.llr_last = (a.llr_last && c.valid) ? a.llr_last + (size_t)b * Z * G::E : nullptr;
+                    cn_run(std::true_type{});
                 }
                 phase_sync();
             }
@@ -462,7 +599,7 @@ __global__ void __launch_bounds__(SpecCfg<G>::kThreads, 2) nldpc_spec_neural_ker
         {
             c.soft = soft_cw ? soft_cw + (soft_all ? (size_t)(a.T - 1) * soft_iter : 0) : nullptr;
             c.hb = hb_cw;
-            Marginal<G> f{c};
+            Marginal<G, MODE> f{c};
             G::vcols(f);
             if (hard_any) flush_hard(a.T - 1);
         }
