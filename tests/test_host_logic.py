@@ -120,3 +120,34 @@ def test_product_package_never_imports_oracle():
                 for line in open(path):
                     assert not re.search(r"#\s*include.*oracle", line), (f, line)
                     assert "dlopen" not in line, (f, line)
+
+
+def test_checkpoint_utils_roundtrip_and_reference_layout(tmp_path, graphs):
+    from neural_ldpc_decoder_torch_b200.checkpoint_utils import CheckPointUtil, MetricsLogger
+    from neural_ldpc_decoder_torch_b200.neural_ldpc_decoder import ConnectingMatrix, ConnectingMatrixTorch, NeuralLDPCDecoder
+    bg, Z = graphs["wimax"]
+    cm = ConnectingMatrixTorch(ConnectingMatrix(Z=Z, basegraph=bg))
+    m = NeuralLDPCDecoder(2, 4, cm)
+    with torch.no_grad():
+        m.weights_var[1].fill_(0.7)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    ck = CheckPointUtil(checkpoint_dir=str(tmp_path))
+    path = ck.save("c.pth", m, optimizer=opt, epoch=3, metrics={"loss": 0.5, "ber_last_iter": 1e-3}, config={"T": 2})
+    raw = torch.load(path)
+    assert set(raw.keys()) == {"model_state_dict", "optimizer_state_dict", "epoch", "loss", "ber_last_iter", "config"}
+    assert "Lift_Matrix1" in raw["model_state_dict"] and "weights_var.1" in raw["model_state_dict"]     # reference key set
+    m2 = NeuralLDPCDecoder(2, 4, cm)
+    got = ck.load("c.pth", m2, optimizer=torch.optim.Adam(m2.parameters()))
+    assert got["epoch"] == 3 and torch.equal(m2.weights_var[1], m.weights_var[1])
+    wpath = ck.save_weights("w_epoch_1", m, as_txt=True)
+    assert wpath.endswith("w_epoch_1.pth") and os.path.exists(wpath)
+    txt = os.path.join(str(tmp_path), "w_epoch_1_weights_txt")
+    assert os.path.exists(os.path.join(txt, "weights_var_1.txt")) and not os.path.exists(os.path.join(txt, "Lift_Matrix1.txt"))
+    assert np.allclose(np.loadtxt(os.path.join(txt, "weights_var_1.txt")), 0.7)
+    log = MetricsLogger(log_dir=str(tmp_path))
+    log.log(0, {"loss": 0.25, "ber_last_iter": 1.5e-3}, "c.pth", config={"T": 2})
+    log.log(1, {"loss": 0.2, "ber_last_iter": 1.0e-3}, "c2.pth")
+    lines = open(log.log_file).read().splitlines()
+    assert lines[0].startswith("# Training started") and lines[2].startswith("# Columns: Epoch, Timestamp, loss, ber_last_iter")
+    assert lines[-1].endswith("0.200000, 1.000000e-03, c2.pth")
+    assert log.is_best(1e-3) and not log.is_best(2e-3) and log.is_best(5e-4)
