@@ -137,6 +137,14 @@ int nldpc_boosted_backward(const nldpc_graph_t *g, const nldpc_boosted_cfg_t *cf
                            int B, int T, float *gvn_dev, float *gcn_dev, float *gucn_dev, void *workspace_dev,
                            size_t workspace_bytes, void *stream);
 
+/* Fused multi-iteration BCE-with-logits loss and gradient: replaces the loop of LDPCDecoderLoss.forward
+ * (LDPCDecoderLoss.py:73-108, BCE branch) over the T iteration outputs.
+ *   soft_dev [T][n] logits (n = B*N*Z), y_dev [n] labels, coef_dev [T] = etha^{c_t} / sum_t etha^{c_t}
+ *   loss_dev: 1 float, OVERWRITTEN with sum_t coef_t * mean_i bce(soft[t][i], y[i])
+ *   gout_dev: [T][n] or NULL, receives dL/dsoft = coef_t * (sigmoid(x) - y) / n   (current device, asynchronous) */
+int nldpc_multi_iter_bce(const float *soft_dev, const float *y_dev, const float *coef_dev, int T, size_t n_per_iter,
+                         float *loss_dev, float *gout_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,7 @@ class LDPCDecoderLoss(nn.Module):
         super(LDPCDecoderLoss, self).__init__()
         self.loss_type = loss_type
         self.etha = etha
+        self.fused = True      # use the fused CUDA loss kernel when the outputs come from the CUDA decoder
 
     def forward(self, outputs: Optional[list | torch.Tensor], expected: Optional[list | torch.Tensor],
                 coeff_param: Optional[list | int] = 1) -> torch.Tensor:
@@ -30,6 +31,13 @@ class LDPCDecoderLoss(nn.Module):
             raise ValueError("Invalid types for outputs and expected in LDPCDecoderLoss. Outputs must be either a torch.Tensor or a "
                              "list of torch.Tensor. expected must be either a torch.Tensor or a list of torch.Tensor with matching "
                              "length to outputs.")
+        if (self.loss_type == LossType.BCE and self.fused and isinstance(outputs, list) and isinstance(expected, torch.Tensor)
+                and expected.is_cuda):
+            # all iteration outputs are views of one [T, B, N*Z] tensor produced by the CUDA decoder: one fused kernel
+            from ..ops import fused_multi_iter_bce
+            fused = fused_multi_iter_bce(outputs, expected, self.etha, coeff_param)
+            if fused is not None:
+                return fused
         total, norm = 0, 0
         for t in range(len(outs) - 1, -1, -1):
             coeff = 1

@@ -275,3 +275,67 @@ def _boosted_bwd(ctx, gsoft, gllr, gxin, ghard):
 
 
 boosted_forward.register_autograd(_boosted_bwd, setup_context=_boosted_setup_ctx)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fused multi-iteration BCE (LDPCDecoderLoss.py:73-108, BCE branch)
+@torch.library.custom_op("nldpc::multi_iter_bce", mutates_args=())
+def multi_iter_bce(soft: torch.Tensor, y: torch.Tensor, coef: torch.Tensor, want_grad: bool) -> tuple[torch.Tensor, torch.Tensor]:
+    """soft [T, ...] logits, y [...] labels, coef [T] normalised iteration weights -> (loss scalar, dL/dsoft or empty)"""
+    _check_cuda_f32("soft", soft)
+    _check_cuda_f32("y", y)
+    _check_cuda_f32("coef", coef)
+    T = soft.shape[0]
+    n = y.numel()
+    if soft.numel() != T * n or coef.numel() != T:
+        raise ValueError("soft must be [T, *y.shape] and coef [T]")
+    soft, y, coef = soft.contiguous(), y.contiguous(), coef.contiguous()
+    loss = torch.empty((), dtype=torch.float32, device=soft.device)
+    gout = torch.empty_like(soft) if want_grad else torch.empty((0,), dtype=torch.float32, device=soft.device)
+    with torch.cuda.device(soft.device):
+        rc = _lib.lib().nldpc_multi_iter_bce(_ptr(soft), _ptr(y), _ptr(coef), T, n, _ptr(loss), _ptr(gout) if want_grad else _vp(0),
+                                             _stream(soft))
+    _lib.check(rc, "nldpc_multi_iter_bce")
+    return loss, gout
+
+
+@multi_iter_bce.register_fake
+def _(soft, y, coef, want_grad):
+    return soft.new_empty(()), (torch.empty_like(soft) if want_grad else soft.new_empty((0,)))
+
+
+def _bce_setup_ctx(ctx, inputs, output):
+    ctx.save_for_backward(output[1])
+
+
+def _bce_bwd(ctx, gloss, ggout):
+    (gout,) = ctx.saved_tensors
+    return gout * gloss, None, None, None
+
+
+multi_iter_bce.register_autograd(_bce_bwd, setup_context=_bce_setup_ctx)
+
+
+def fused_multi_iter_bce(outputs, y, etha=1.0, coeff_param=None):
+    """Drop-in for LDPCDecoderLoss(BCE)(outputs, y, coeff_param) when `outputs` is the list a decoder's forward returned
+    (views of ONE [T, B, N*Z] tensor): a single fused kernel for the loss and its gradient.  Returns None when the list
+    is not such a set of views (caller falls back to the per-iteration torch ops)."""
+    if not isinstance(outputs, (list, tuple)) or len(outputs) == 0 or not all(isinstance(o, torch.Tensor) and o.is_cuda for o in outputs):
+        return None
+    base = outputs[0]._base
+    if base is None or base.dim() != outputs[0].dim() + 1 or base.shape[0] != len(outputs) or not base.is_contiguous():
+        return None
+    step = base.stride(0)
+    for t, o in enumerate(outputs):
+        if o._base is not base or o.storage_offset() != base.storage_offset() + t * step or tuple(o.shape) != tuple(base.shape[1:]):
+            return None
+    T = len(outputs)
+    if coeff_param is None:
+        coeffs = [1] * T
+    else:
+        coeffs = list(coeff_param) if isinstance(coeff_param, (list, tuple)) else [coeff_param] * T
+    w = [float(pow(etha, c)) for c in coeffs]
+    tot = sum(w)
+    coef = torch.tensor([v / tot if tot > 0 else v for v in w], dtype=torch.float32, device=base.device)
+    loss, _ = torch.ops.nldpc.multi_iter_bce(base, y.to(torch.float32), coef, base.requires_grad)
+    return 1.0 * loss

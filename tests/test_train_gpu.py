@@ -62,3 +62,27 @@ def test_boosted_train_step_matches_reference(tag):
         assert abs(float(m.weight_CN_1.grad) - 0.023220574483275414) < 1e-6
         gn = float(torch.sqrt(sum((p.grad.double() ** 2).sum() for p in m.parameters())))
         assert abs(gn - 0.046869996935129166) < 1e-6
+
+
+def test_fused_multi_iter_bce_matches_torch():
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.LDPCDecoderLoss import LDPCDecoderLoss
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.LossType import LossType
+    g = torch.Generator(device="cuda").manual_seed(1)
+    T, B, NZ = 7, 33, 832
+    base = (6.0 * torch.randn((T, B, NZ), generator=g, device="cuda")).requires_grad_(True)
+    y = (torch.rand((B, NZ), generator=g, device="cuda") > 0.5).float()
+    outs = list(base.unbind(0))
+    crit = LDPCDecoderLoss(LossType.BCE, etha=1.3)
+    fused = crit(outs, y, coeff_param=list(range(T)))
+    fused.backward()
+    gf = base.grad.clone()
+    base.grad = None
+    crit.fused = False
+    plain = crit(list(base.unbind(0)), y, coeff_param=list(range(T)))
+    plain.backward()
+    assert abs(fused.item() - plain.item()) < 2e-6 * abs(plain.item())
+    assert float((gf - base.grad).abs().max()) < 1e-6 * float(base.grad.abs().max()) + 1e-12
+    # a list that is NOT a set of views of one tensor silently takes the per-iteration path
+    crit.fused = True
+    loose = [base[t].clone() for t in range(T)]
+    assert abs(crit(loose, y, coeff_param=list(range(T))).item() - plain.item()) < 2e-6 * abs(plain.item())
