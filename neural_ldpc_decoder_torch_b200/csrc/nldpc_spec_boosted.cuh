@@ -31,7 +31,7 @@ int boosted_launch_one(const DecodeArgs &args, int sm_count, cudaStream_t st) {
     using Cfg = SpecCfg<G, kXo>;
     const int n_units = (args.B + Cfg::Shape::kCw - 1) / Cfg::Shape::kCw;
     const int ctas = (n_units + Cfg::kGroups - 1) / Cfg::kGroups;
-    const int grid = std::min(ctas, sm_count * 2);
+    const int grid = std::min(ctas, sm_count * Cfg::kCtasPerSm);
     const bool every = args.soft_mode == 1 || args.hard_mode == 1;
     if (every) nldpc_spec_neural_kernel<G, true, true, MODE, kXo><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(args);
     else nldpc_spec_neural_kernel<G, false, true, MODE, kXo><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(args);

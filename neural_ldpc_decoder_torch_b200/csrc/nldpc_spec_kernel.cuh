@@ -98,6 +98,7 @@ struct NeuralLane {
     int wb_base;             // offset of {w,b}[t][0] in the constant arena (kConstW == true)
     float *soft;             // &soft_t[b][0] of the iteration being emitted, or nullptr (also when b >= B)
     uint8_t *hb;             // this codeword's hard-decision staging bytes in shared memory (N*Z/8), or nullptr
+    float xreg[G::kXRegs > 0 ? G::kXRegs : 1];   // channel LLRs of identity-circulant degree-1 blocks (lane-private)
     int z;
     bool valid;
     float zmin;              // min |v2c| written by this lane in the current VN phase (0 => the zero-safe CN phase is needed)
@@ -151,26 +152,26 @@ struct NeuralLane {
 template <class G>
 struct VnFirst {
     NeuralLane<G> &c;
-    template <int J, int... R>
+    template <int J, int XROW, int... R>
     __device__ __forceinline__ void col() {
-        const float v = addf(c.lane[J * G::Z], 0.0f);
+        const float v = addf(c.lane[XROW * G::Z], 0.0f);
         c.zmin = fminf(c.zmin, fabsf(v));       // (only read by the Neural CN dispatch)
         ((c.lane[R * G::Z] = v), ...);
     }
 };
 
 // iterations >= 1: v2c[k] = x + (((0 + c[0]) + c[1]) + ... skipping k); kEmit: marginal of the previous iteration
-template <class G, bool kEmit, int MODE = 0>
+template <class G, bool kEmit, int MODE = 0, bool kXo = false>
 struct VnStep {
     NeuralLane<G> &c;
-    template <int J, int... R>
+    template <int J, int XROW, int... R>
     __device__ __forceinline__ void col() {
         constexpr int D = sizeof...(R);
         constexpr int rows[D] = {R...};
         float m[D], pre[D];
 #pragma unroll
         for (int k = 0; k < D; k++) m[k] = c.lane[rows[k] * G::Z];
-        const float x = c.lane[J * G::Z];
+        const float x = c.lane[XROW * G::Z];
         float p = 0.0f;                       // running prefix ((0 + m0) + m1) + ...
 #pragma unroll
         for (int k = 0; k < D; k++) {
@@ -196,21 +197,78 @@ struct VnStep {
         }
         if constexpr (kEmit) {
             if constexpr (MODE == 0) c.template emit<J>(addf(x, p));       // out = xa + llr @ W_output (:94-96)
-            else c.template emit<J>(clamp_rng(addf(c.lane[c.xo_off + J * G::Z], p), c.lo, c.hi));   // Boosted :520-521
+            else c.template emit<J>(clamp_rng(addf(kXo ? c.lane[c.xo_off + J * G::Z] : x, p), c.lo, c.hi));   // Boosted :520-521
         }
     }
 };
 
 // marginal only (after the last CN phase)
-template <class G, int MODE = 0>
+template <class G, int MODE = 0, bool kXo = false>
 struct Marginal {
     NeuralLane<G> &c;
-    template <int J, int... R>
+    template <int J, int XROW, int... R>
     __device__ __forceinline__ void col() {
         float p = 0.0f;
         ((p = addf(p, c.lane[R * G::Z])), ...);
-        if constexpr (MODE == 0) c.template emit<J>(addf(c.lane[J * G::Z], p));
-        else c.template emit<J>(clamp_rng(addf(c.lane[c.xo_off + J * G::Z], p), c.lo, c.hi));
+        if constexpr (MODE == 0) c.template emit<J>(addf(c.lane[XROW * G::Z], p));
+        else c.template emit<J>(clamp_rng(addf(c.lane[(kXo ? c.xo_off + J * G::Z : XROW * G::Z)], p), c.lo, c.hi));
+    }
+};
+
+// where each block's channel LLR lives: shared row DEST >= 0 or lane register -(1 + DEST)
+template <class G, int DEST>
+__device__ __forceinline__ float &xa_ref(NeuralLane<G> &c) {
+    if constexpr (DEST >= 0) return c.lane[DEST * G::Z];
+    else return c.xreg[-DEST - 1];
+}
+
+// after the bulk-TMA load: move this lane's raw channel LLRs from the staging area (message rows) to their places.
+// MODE 0 also screens for exact zeros; Boosted quantises xa_origin once if QMS (:517-518) and, with VN weights (kXo),
+// keeps it in its own rows while xa_input starts as the raw value.
+template <class G, int MODE, bool kXo>
+struct PlaceXa {
+    NeuralLane<G> &c;
+    const float *stage;      // &staging[z]
+    float zm;
+    template <int J, int DEST>
+    __device__ __forceinline__ void put() {
+        const float v = stage[J * G::Z];
+        if constexpr (MODE == 0) {
+            zm = fminf(zm, fabsf(v));
+            xa_ref<G, DEST>(c) = v;
+        } else {
+            const float xq = (MODE == 2) ? quant5(v) : v;
+            if constexpr (kXo) {
+                c.lane[c.xo_off + J * G::Z] = xq;
+                xa_ref<G, DEST>(c) = v;
+            } else {
+                xa_ref<G, DEST>(c) = xq;
+            }
+        }
+    }
+};
+
+// xa_input *= w_VN(t), re-quantised if QMS (:325-337); every element is private to its lane
+template <class G, int MODE>
+struct ScaleXin {
+    NeuralLane<G> &c;
+    const float *vw;
+    template <int J, int DEST>
+    __device__ __forceinline__ void put() {
+        float x = mulf(xa_ref<G, DEST>(c), __ldg(vw + J));
+        if constexpr (MODE == 2) x = quant5(x);
+        xa_ref<G, DEST>(c) = x;
+    }
+};
+
+// refill the lane registers from global memory (out-of-line paths that cannot receive them by value)
+template <class G>
+struct ReloadXreg {
+    NeuralLane<G> &c;
+    const float *xa_lane;    // &xa[b][0][z]
+    template <int J, int DEST>
+    __device__ __forceinline__ void put() {
+        if constexpr (DEST < 0) c.xreg[-DEST - 1] = __ldg(xa_lane + J * G::Z);
     }
 };
 
@@ -231,7 +289,7 @@ __device__ __forceinline__ void cn_check_core(NeuralLane<G> &c) {
     float u[D], raw[D];
 #pragma unroll
     for (int k = 0; k < D; k++) {
-        raw[k] = c.rot[shf[k]][rows[k] * G::Z];                          // gather u[h] = v2c[(h+s) mod Z] (:59-63)
+        raw[k] = rows[k] >= 0 ? c.rot[shf[k]][rows[k] * G::Z] : c.xreg[rows[k] < 0 ? -rows[k] - 1 : 0];   // gather (:59-63)
         u[k] = (kZeroSafe && raw[k] == 0.0f) ? -10000.0f : raw[k];
     }
     // min over the other edges, capped at 10000 (:74-75): pairwise prefix/suffix minima with 3-input FMNMX
@@ -293,7 +351,7 @@ __device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c) {
     float u[D], raw[D];
 #pragma unroll
     for (int k = 0; k < D; k++) {
-        raw[k] = c.rot[shf[k]][rows[k] * G::Z];                          // gather (:380-384)
+        raw[k] = rows[k] >= 0 ? c.rot[shf[k]][rows[k] * G::Z] : c.xreg[rows[k] < 0 ? -rows[k] - 1 : 0];   // gather (:380-384)
         const float v = condition<MODE>(raw[k], c.lo, c.hi);
         u[k] = (v == 0.0f) ? 0.0001f : v;                                // x + 1e-4 * [x == 0] (:391-393)
     }
@@ -362,22 +420,26 @@ struct CnNeural {
 // out-of-line zero-safe CN phase; takes the lane state by value (a pointer to it would force it into local memory)
 template <class G, bool kEmit, bool kConstW>
 __device__ __noinline__ void cn_phase_zero_safe(float *lane, int z, const float *wt, const float *bt, int wb_base, float *soft,
-                                                uint8_t *hb) {
+                                                uint8_t *hb, const float *xa_lane) {
     NeuralLane<G> c;
     c.lane = lane; c.z = z; c.wt = wt; c.bt = bt; c.wb_base = wb_base; c.soft = soft; c.hb = hb; c.valid = true; c.zmin = 1.0f;
 #pragma unroll
     for (int s = 0; s < G::Z; s++) c.rot[s] = (lane - z) + ((z + s) % G::Z);
+    if constexpr (G::kXRegs > 0) {
+        ReloadXreg<G> r{c, xa_lane};
+        G::blocks(r);
+    }
     CnNeural<G, kEmit, kConstW, true> f{c};
     G::checks(f);
 }
 
 // CN phase dispatch: warp-uniform choice between the inlined fast phase and the out-of-line zero-safe phase
 template <class G, bool kEmit, bool kConstW>
-__device__ __forceinline__ void cn_phase(NeuralLane<G> &c, bool xa_zero) {
+__device__ __forceinline__ void cn_phase(NeuralLane<G> &c, bool xa_zero, const float *xa_lane) {
     const bool need_safe = __any_sync(0xffffffffu, xa_zero || c.zmin == 0.0f);
     c.zmin = 10000.0f;
     if (need_safe) {
-        cn_phase_zero_safe<G, kEmit, kConstW>(c.lane, c.z, c.wt, c.bt, c.wb_base, c.soft, c.hb);
+        cn_phase_zero_safe<G, kEmit, kConstW>(c.lane, c.z, c.wt, c.bt, c.wb_base, c.soft, c.hb, xa_lane);
     } else {
         CnNeural<G, kEmit, kConstW, false> f{c};
         G::checks(f);
@@ -395,23 +457,43 @@ template <class G, bool kXo = false>
 struct SpecCfg {
     using Shape = GroupShape<G::Z>;
     static constexpr int kSlabF = kXo ? slab_with_xo(G::kSlab, G::N * G::Z, G::Z) : G::kSlab;   // floats per codeword slab
-    static constexpr int kXoOff = kXo ? (G::N + G::S) * G::Z : 0;        // xo rows follow the message rows
+    static constexpr int kXoOff = kXo ? (G::kXRows + G::S) * G::Z : 0;   // N xo rows follow the message rows
     static constexpr int kHardBytes = (G::N * G::Z + 7) / 8;
     static constexpr int kHardStride = (kHardBytes + 15) & ~15;           // per-codeword staging, 16 B multiple
     static constexpr int kPerCw = kSlabF * 4 + kHardStride;              // shared bytes per codeword
-    // groups per CTA so that two CTAs fit one SM (227 KB), threads <= 384
-    static constexpr int kBudget = (kSmemBudget - 2 * 1024) / 2 - 256;
-    static constexpr int kGroupsRaw = kBudget / (kPerCw * Shape::kCw);
-    static constexpr int kGroups = kGroupsRaw < 1 ? 1 : (kGroupsRaw * Shape::kLanes > 384 ? 384 / Shape::kLanes : kGroupsRaw);
+    // CTA shape.  Warp k of a CTA runs on SM sub-partition k mod 4 and the kernel is issue-bound per sub-partition, so what
+    // counts is how evenly the resident warps spread over the four of them, not how many there are (measured on BG2:
+    // 2 CTAs x 5 warps put 4/2/2/2 warps on the sub-partitions and ran 20 % SLOWER than 2 x 4 warps although 25 % more
+    // codewords were resident).  Score a configuration (c CTAs per SM, g groups per CTA) as
+    //     resident warps * u(m) / m,   m = warps on the busiest sub-partition,  u = measured issue utilisation at m warps
+    // and take the best one that fits shared memory.
+    static constexpr int kMaxCwSm = (kSmemBudget - 2 * 1024 - 512) / kPerCw;
+    static constexpr int score(int ctas, int g) {
+        if (g <= 0 || ctas * g * Shape::kCw > kMaxCwSm || g * Shape::kLanes > 512) return -1;
+        const int w = g * Shape::kWarps;
+        const int m = ctas * ((w + 3) / 4);
+        const int u = m <= 1 ? 35 : (m == 2 ? 59 : (m == 3 ? 68 : 72));      // percent
+        return ctas * w * u * 12 / m;
+    }
+    static constexpr int best(bool want_groups) {
+        int bs = -1, bc = 1, bg = 1;
+        for (int c = 1; c <= 2; c++)
+            for (int g = 1; g <= 16; g++)
+                if (score(c, g) > bs) { bs = score(c, g); bc = c; bg = g; }
+        return want_groups ? bg : bc;
+    }
+    static constexpr int kCtasPerSm = best(false);
+    static constexpr int kGroups = best(true);
     static constexpr int kThreads = kGroups * Shape::kLanes;
     static constexpr int kCwPerCta = kGroups * Shape::kCw;
     static constexpr size_t kSmemBytes = (size_t)kCwPerCta * kPerCw + (size_t)kGroups * 8 + 16;
+    static_assert(G::S >= G::N, "the raw codeword is staged in the message rows");
 };
 
 // kEvery: outputs are produced after every iteration (drop-in list mode / per-iteration hard decisions);
 // otherwise only after the last one (throughput mode) and the loop body carries no output code at all.
 template <class G, bool kEvery, bool kConstW, int MODE = 0, bool kXo = false>
-__global__ void __launch_bounds__(SpecCfg<G, kXo>::kThreads, 2) nldpc_spec_neural_kernel(const DecodeArgs a) {
+__global__ void __launch_bounds__(SpecCfg<G, kXo>::kThreads, SpecCfg<G, kXo>::kCtasPerSm) nldpc_spec_neural_kernel(const DecodeArgs a) {
     using Cfg = SpecCfg<G, kXo>;
     static_assert(MODE == 0 || kConstW, "the Boosted variants read their weights from the constant arena");
     static_assert(MODE != 0 || !kXo, "xo rows only exist for the Boosted decoder with VN weights");
@@ -470,7 +552,7 @@ __global__ void __launch_bounds__(SpecCfg<G, kXo>::kThreads, 2) nldpc_spec_neura
             fence_proxy_async();
             mbar_arrive_expect_tx(bar, (uint32_t)(ncw * NZ * sizeof(float)));
             for (int q = 0; q < ncw; q++)
-                tma_load_1d(slabs + (size_t)(grp * Shape::kCw + q) * Cfg::kSlabF, a.xa + (size_t)(b0 + q) * NZ,
+                tma_load_1d(slabs + (size_t)(grp * Shape::kCw + q) * Cfg::kSlabF + G::kXRows * Z, a.xa + (size_t)(b0 + q) * NZ,
                             (uint32_t)(NZ * sizeof(float)), bar);
         }
         if constexpr (Z != 16 && Z != 32) {   // atomicOr staging must start from zero
@@ -481,38 +563,27 @@ __global__ void __launch_bounds__(SpecCfg<G, kXo>::kThreads, 2) nldpc_spec_neura
             phase ^= 1;
         }
 
+        // the raw codeword sits in the message rows (staging); every lane moves its own elements to their places
+        // (shared rows / registers).  Lane z only ever touches element z of a row in the VN phase, so no barrier is needed
+        // before iteration 0 overwrites the staging area.
         bool xa_zero = false;
-        if constexpr (MODE == 0) {
-            // screen the channel LLRs of this lane for exact zeros once (degree-1 blocks feed the CN phase directly)
-            float zm = 1.0f;
-            for (int j = 0; j < G::N; j++) zm = fminf(zm, fabsf(c.lane[j * Z]));
-            xa_zero = (zm == 0.0f);
-        } else {
-            // Boosted: xa_origin is quantised once if QMS (:517-518, idempotent).  Without VN weights xa_input == xa_origin
-            // live in the same rows; with VN weights xa_input starts as the raw xa and is rescaled every iteration.
-            for (int j = 0; j < G::N; j++) {
-                const float x = c.lane[j * Z];
-                const float xq = (MODE == 2) ? quant5(x) : x;
-                if constexpr (kXo) c.lane[Cfg::kXoOff + j * Z] = xq;
-                else c.lane[j * Z] = xq;
-            }
+        {
+            PlaceXa<G, MODE, kXo> pl{c, c.lane + G::kXRows * Z, 1.0f};
+            G::blocks(pl);
+            xa_zero = (pl.zm == 0.0f);
         }
         c.zmin = 10000.0f;
         // per-iteration pieces shared by both output modes
         auto xin_update = [&](int t) {
-            if constexpr (kXo) {   // xa_input *= w_VN(t), re-quantised if QMS (:325-337); own lane only, no hazard
-                const float *vw = a.vn_w + (size_t)t * G::N;
-                for (int j = 0; j < G::N; j++) {
-                    float x = mulf(c.lane[j * Z], __ldg(vw + j));
-                    if constexpr (MODE == 2) x = quant5(x);
-                    c.lane[j * Z] = x;
-                }
+            if constexpr (kXo) {
+                ScaleXin<G, MODE> sc{c, a.vn_w + (size_t)t * G::N};
+                G::blocks(sc);
             }
         };
         auto cn_run = [&](auto emit_tag) {
             constexpr bool kEmitNow = decltype(emit_tag)::value;
             if constexpr (MODE == 0) {
-                cn_phase<G, kEmitNow, kConstW>(c, xa_zero);
+                cn_phase<G, kEmitNow, kConstW>(c, xa_zero, a.xa + (size_t)min(b, a.B - 1) * NZ + z);
             } else {
                 CnBoosted<G, kEmitNow, MODE, kXo> f{c};
                 G::checks(f);
@@ -558,7 +629,7 @@ __global__ void __launch_bounds__(SpecCfg<G, kXo>::kThreads, 2) nldpc_spec_neura
                 } else {
                     c.soft = (soft_all && soft_cw) ? soft_cw + (size_t)(t - 1) * soft_iter : nullptr;
                     c.hb = hard_all ? hb_cw : nullptr;
-                    VnStep<G, true, MODE> f{c};
+                    VnStep<G, true, MODE, kXo> f{c};
                     G::vcols(f);
                     if (hard_all) flush_hard(t - 1);
                 }
@@ -580,7 +651,7 @@ __global__ void __launch_bounds__(SpecCfg<G, kXo>::kThreads, 2) nldpc_spec_neura
                     VnFirst<G> f{c};
                     G::vcols(f);
                 } else {
-                    VnStep<G, false, MODE> f{c};
+                    VnStep<G, false, MODE, kXo> f{c};
                     G::vcols(f);
                 }
                 phase_sync();
@@ -599,7 +670,7 @@ __global__ void __launch_bounds__(SpecCfg<G, kXo>::kThreads, 2) nldpc_spec_neura
         {
             c.soft = soft_cw ? soft_cw + (soft_all ? (size_t)(a.T - 1) * soft_iter : 0) : nullptr;
             c.hb = hb_cw;
-            Marginal<G, MODE> f{c};
+            Marginal<G, MODE, kXo> f{c};
             G::vcols(f);
             if (hard_any) flush_hard(a.T - 1);
         }
