@@ -465,14 +465,16 @@ struct SpecCfg {
     // counts is how evenly the resident warps spread over the four of them, not how many there are (measured on BG2:
     // 2 CTAs x 5 warps put 4/2/2/2 warps on the sub-partitions and ran 20 % SLOWER than 2 x 4 warps although 25 % more
     // codewords were resident).  Score a configuration (c CTAs per SM, g groups per CTA) as
-    //     resident warps * u(m) / m,   m = warps on the busiest sub-partition,  u = measured issue utilisation at m warps
-    // and take the best one that fits shared memory.
+    //     resident warps * u(m) / m,   m = warps on the busiest sub-partition,  u = issue utilisation at m warps
+    // and take the best one that fits shared memory.  More than 2 warps per sub-partition do NOT pay off here: every warp
+    // streams through ~60 KB of unrolled code and more resident warps mean more instruction-cache pressure (BG2: 1 CTA x
+    // 10 warps 36.3 M cw/s vs 8 warps 43.2 M; WiMAX: 15 warps 57.2 M vs 12 warps 59.2 M vs 2 x 6 warps 55.4 M).
     static constexpr int kMaxCwSm = (kSmemBudget - 2 * 1024 - 512) / kPerCw;
     static constexpr int score(int ctas, int g) {
         if (g <= 0 || ctas * g * Shape::kCw > kMaxCwSm || g * Shape::kLanes > 512) return -1;
         const int w = g * Shape::kWarps;
         const int m = ctas * ((w + 3) / 4);
-        const int u = m <= 1 ? 35 : (m == 2 ? 59 : (m == 3 ? 68 : 72));      // percent
+        const int u = m <= 1 ? 35 : (m == 2 ? 59 : (m == 3 ? 50 : 45));      // percent, from the measurements below
         return ctas * w * u * 12 / m;
     }
     static constexpr int best(bool want_groups) {
