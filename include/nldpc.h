@@ -92,11 +92,16 @@ int nldpc_neural_decode_host(const nldpc_graph_t *g, const float *xa_host, const
  * walked backwards with the gradient messages in shared memory.
  *   gout_dev : [T][B][N*Z] upstream gradients dL/dout_t (zeros where an iteration is unused)
  *   gw_dev, gb_dev : [T][E] fp32, OVERWRITTEN with the batch-summed gradients
- *   workspace_dev  : at least nldpc_backward_workspace_bytes(g, B, T, 0) bytes */
+ *   workspace_dev  : at least nldpc_backward_workspace_bytes(g, B, T, 0) bytes
+ *   have_dump      : non-zero when nldpc_neural_forward_train already filled the workspace for these inputs
+ *                    (the forward re-run is then skipped) */
 size_t nldpc_backward_workspace_bytes(const nldpc_graph_t *g, int B, int T, int boosted);
 int nldpc_neural_backward(const nldpc_graph_t *g, const float *xa_dev, const float *w_dev, const float *b_dev,
                           const float *gout_dev, int B, int T, float *gw_dev, float *gb_dev, void *workspace_dev,
-                          size_t workspace_bytes, void *stream);
+                          size_t workspace_bytes, int have_dump, void *stream);
+/* nldpc_neural_forward with every-iteration soft outputs [T][B][N*Z] that also writes the training dump. */
+int nldpc_neural_forward_train(const nldpc_graph_t *g, const float *xa_dev, const float *w_dev, const float *b_dev, int B,
+                               int T, float *soft_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
 
 /* Configuration of the Boosted decoder loop body, sharing types already folded by the caller into
  * per-iteration rows (NULL = "no weight of that kind"):
@@ -116,6 +121,10 @@ typedef struct nldpc_boosted_cfg {
     float *xin_out_dev;        /* [B][N][Z] receives it after the last executed iteration; NULL = not wanted */
     const float *app_init_dev; /* [B][N*Z] previous output used by the UCN indicator of the first executed iteration;
                                   NULL = use the channel input (the curr_iter == 0 rule, :340-341) */
+    /* Training: when non-NULL (forward only, soft_mode = ALL) the kernel also spills what nldpc_boosted_backward needs;
+     * at least nldpc_backward_workspace_bytes(g, B, T, 1) bytes.  Pass the same buffer with have_dump = 1 to the backward. */
+    void *train_dump_dev;
+    size_t train_dump_bytes;
 } nldpc_boosted_cfg_t;
 
 /* Replaces the loop of BoostedNeuralLDPCDecoder.forward (:320-531) for iterations 0..T-1 from a
@@ -135,7 +144,7 @@ int nldpc_boosted_forward(const nldpc_graph_t *g, const nldpc_boosted_cfg_t *cfg
 int nldpc_boosted_backward(const nldpc_graph_t *g, const nldpc_boosted_cfg_t *cfg, const float *xa_dev,
                            const float *vn_w_dev, const float *cn_w_dev, const float *ucn_w_dev, const float *gout_dev,
                            int B, int T, float *gvn_dev, float *gcn_dev, float *gucn_dev, void *workspace_dev,
-                           size_t workspace_bytes, void *stream);
+                           size_t workspace_bytes, int have_dump, void *stream);
 
 /* Fused multi-iteration BCE-with-logits loss and gradient: replaces the loop of LDPCDecoderLoss.forward
  * (LDPCDecoderLoss.py:73-108, BCE branch) over the T iteration outputs.

@@ -26,7 +26,7 @@ class BoostedCfg(ctypes.Structure):
     _fields_ = [("decoder_type", ctypes.c_int32), ("qbit", ctypes.c_int32), ("llr_lo", ctypes.c_float),
                 ("llr_hi", ctypes.c_float), ("compute_ucn", ctypes.c_int32), ("ucn_mix", ctypes.c_int32),
                 ("llr_init", ctypes.c_void_p), ("xin_init", ctypes.c_void_p), ("xin_out", ctypes.c_void_p),
-                ("app_init", ctypes.c_void_p)]
+                ("app_init", ctypes.c_void_p), ("train_dump", ctypes.c_void_p), ("train_dump_bytes", ctypes.c_size_t)]
 
 
 def build(verbose=False):
@@ -65,10 +65,12 @@ def lib():
             L.nldpc_backward_workspace_bytes.restype = ctypes.c_size_t
             L.nldpc_backward_workspace_bytes.argtypes = [vp, ci, ci, ci]
             L.nldpc_neural_backward.restype = ci
-            L.nldpc_neural_backward.argtypes = [vp, vp, vp, vp, vp, ci, ci, vp, vp, vp, ctypes.c_size_t, vp]
+            L.nldpc_neural_backward.argtypes = [vp, vp, vp, vp, vp, ci, ci, vp, vp, vp, ctypes.c_size_t, ci, vp]
+            L.nldpc_neural_forward_train.restype = ci
+            L.nldpc_neural_forward_train.argtypes = [vp, vp, vp, vp, ci, ci, vp, vp, ctypes.c_size_t, vp]
             L.nldpc_boosted_backward.restype = ci
             L.nldpc_boosted_backward.argtypes = [vp, ctypes.POINTER(BoostedCfg), vp, vp, vp, vp, vp, ci, ci, vp, vp, vp, vp,
-                                                 ctypes.c_size_t, vp]
+                                                 ctypes.c_size_t, ci, vp]
             L.nldpc_boosted_forward.restype = ci
             L.nldpc_boosted_forward.argtypes = [vp, ctypes.POINTER(BoostedCfg), vp, vp, vp, vp, ci, ci, ci, vp, ci, vp, vp, vp]
             L.nldpc_multi_iter_bce.restype = ci

@@ -322,10 +322,13 @@ class BoostedNeuralLDPCDecoder(nn.Module):
             app_init = self.outputs[t0 - 1].to(device) if (compute_ucn and t0 > 0) else None
             want_llr = self.store_llr != "none"
             want_xin = len(runs) > 1 and not is_input_iterable
-            soft, llr_last, xin_out, _ = torch.ops.nldpc.boosted_forward(
+            needs_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (vn_w, cn_w, ucn_w))
+            want_dump = (needs_grad and llr_init is None and xin_state is None and app_init is None
+                         and self.decoding_type != DecoderType.SP)
+            soft, llr_last, xin_out, _, _ = torch.ops.nldpc.boosted_forward(
                 x_run, vn_w, cn_w, ucn_w, gid, len(run), dec, int(self.decoder_qms_qbit),
                 float(self.allowed_llr_range.start), float(self.allowed_llr_range.end), bool(compute_ucn), bool(ucn_mix),
-                llr_init, xin_state, app_init, want_llr, want_xin, 1, 0)
+                llr_init, xin_state, app_init, want_llr, want_xin, 1, 0, want_dump)
             for k, t in enumerate(run):
                 self.outputs[t] = soft[k]
             if want_llr:
@@ -348,9 +351,10 @@ def _decode(self, xa, n_iters, soft_mode, hard_mode):
     gid = self.conn_mat.graph_id(device)
     vn_w, cn_w, ucn_w, compute_ucn, ucn_mix = self.fold_weights(list(range(T)), device)
     dec = {DecoderType.SP: 0, DecoderType.MS: 1, DecoderType.QMS: 2}[self.decoding_type]
-    soft, _, _, hard = torch.ops.nldpc.boosted_forward(
+    soft, _, _, hard, _ = torch.ops.nldpc.boosted_forward(
         xa, vn_w, cn_w, ucn_w, gid, T, dec, int(self.decoder_qms_qbit), float(self.allowed_llr_range.start),
-        float(self.allowed_llr_range.end), bool(compute_ucn), bool(ucn_mix), None, None, None, False, False, soft_mode, hard_mode)
+        float(self.allowed_llr_range.end), bool(compute_ucn), bool(ucn_mix), None, None, None, False, False, soft_mode, hard_mode,
+        False)
     return soft, hard
 
 

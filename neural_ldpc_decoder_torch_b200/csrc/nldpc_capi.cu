@@ -48,6 +48,22 @@ struct nldpc_graph {
     size_t ws_wb_bytes = 0;
 };
 
+struct WsLayout { size_t v2c, xin, mask, ucn, total; };
+static WsLayout ws_layout(const nldpc_graph *g, int B, int T, int boosted) {
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    WsLayout l{};
+    size_t off = 0;
+    l.v2c = off; off = up(off + (size_t)T * B * g->S * g->Z * 4);
+    if (boosted) {
+        l.xin = off; off = up(off + (size_t)(T + 1) * B * g->N * g->Z * 4);
+        l.mask = off; off = up(off + (size_t)T * B * g->N * g->Z);
+        l.ucn = off; off = up(off + (size_t)T * B * g->M * g->Z);
+    }
+    l.total = off;
+    return l;
+}
+static int boosted_dispatch(const nldpc_graph *g, const DecodeArgs &a, cudaStream_t st);
+
 extern "C" const char *nldpc_last_error(void) { return g_err.c_str(); }
 extern "C" int nldpc_abi_version(void) { return NLDPC_ABI_VERSION; }
 
@@ -194,6 +210,9 @@ static bool force_generic() {
     return e && e[0] == '1';
 }
 
+// Neural forward dispatch: specialised kernel when the graph has one, else the table-driven kernel
+static int neural_dispatch(const nldpc_graph *g, const DecodeArgs &a, cudaStream_t st);
+
 extern "C" int nldpc_neural_forward(const nldpc_graph_t *g, const float *xa_dev, const float *w_dev, const float *b_dev,
                                     int B, int T, int soft_mode, float *soft_dev, int hard_mode, uint8_t *hard_dev,
                                     void *stream) {
@@ -205,7 +224,11 @@ extern "C" int nldpc_neural_forward(const nldpc_graph_t *g, const float *xa_dev,
     DecodeArgs a{};
     a.xa = xa_dev; a.w = w_dev; a.b = b_dev; a.B = B; a.T = T;
     a.soft_mode = soft_mode; a.soft = soft_dev; a.hard_mode = hard_mode; a.hard = hard_dev;
-    cudaStream_t st = (cudaStream_t)stream;
+    return neural_dispatch(g, a, (cudaStream_t)stream);
+}
+
+static int neural_dispatch(const nldpc_graph *g, const DecodeArgs &a, cudaStream_t st) {
+    const int B = a.B;
     if (g->spec_id >= 0 && !force_generic()) {
         int rc = spec_launch_neural(g->spec_id, a, g->sm_count, st);
         if (rc > 0) return fail(rc, std::string("nldpc_neural_forward (specialised): ") + cudaGetErrorString((cudaError_t)rc));
@@ -301,21 +324,6 @@ extern "C" int nldpc_neural_decode_host(const nldpc_graph_t *gc, const float *xa
 }
 
 // ---- backward ------------------------------------------------------------------------------------------------
-struct WsLayout { size_t v2c, xin, mask, ucn, total; };
-static WsLayout ws_layout(const nldpc_graph *g, int B, int T, int boosted) {
-    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    WsLayout l{};
-    size_t off = 0;
-    l.v2c = off; off = up(off + (size_t)T * B * g->S * g->Z * 4);
-    if (boosted) {
-        l.xin = off; off = up(off + (size_t)(T + 1) * B * g->N * g->Z * 4);
-        l.mask = off; off = up(off + (size_t)T * B * g->N * g->Z);
-        l.ucn = off; off = up(off + (size_t)T * B * g->M * g->Z);
-    }
-    l.total = off;
-    return l;
-}
-
 extern "C" size_t nldpc_backward_workspace_bytes(const nldpc_graph_t *g, int B, int T, int boosted) {
     if (!g || B <= 0 || T <= 0) return 0;
     return ws_layout(g, B, T, boosted).total;
@@ -323,7 +331,7 @@ extern "C" size_t nldpc_backward_workspace_bytes(const nldpc_graph_t *g, int B, 
 
 extern "C" int nldpc_neural_backward(const nldpc_graph_t *g, const float *xa_dev, const float *w_dev, const float *b_dev,
                                      const float *gout_dev, int B, int T, float *gw_dev, float *gb_dev, void *workspace_dev,
-                                     size_t workspace_bytes, void *stream) {
+                                     size_t workspace_bytes, int have_dump, void *stream) {
     if (!g || B < 0 || T <= 0 || !gw_dev || !gb_dev) return fail(NLDPC_E_INVALID, "nldpc_neural_backward: bad argument");
     CUDA_TRY(cudaSetDevice(g->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -334,14 +342,12 @@ extern "C" int nldpc_neural_backward(const nldpc_graph_t *g, const float *xa_dev
     const WsLayout l = ws_layout(g, B, T, 0);
     if (!workspace_dev || workspace_bytes < l.total)
         return fail(NLDPC_E_INVALID, "nldpc_neural_backward: workspace too small (see nldpc_backward_workspace_bytes)");
-    // (A) forward re-run in training-dump mode
+    // (A) forward re-run in training-dump mode, unless the forward pass already wrote the dump (nldpc_neural_forward_train)
     DecodeArgs a{};
     a.xa = xa_dev; a.w = w_dev; a.b = b_dev; a.B = B; a.T = T; a.wb_off = -1;
     a.hist_v2c = reinterpret_cast<float *>((char *)workspace_dev + l.v2c);
-    const int n_tiles = (B + g->cw_per_cta - 1) / g->cw_per_cta;
-    const int ctas_per_sm = std::max(1, (int)((size_t)kSmemBudget / (g->smem_bytes + 1024)));
-    const int grid = std::min(n_tiles, g->sm_count * ctas_per_sm);
-    CUDA_TRY((cudaError_t)generic_launch_neural(g->dev, a, g->cw_per_cta, g->threads, g->smem_bytes, g->use_tma, grid, st));
+    if (!have_dump)
+        if (int rc = neural_dispatch(g, a, st)) return rc;
     // (B) backward sweep
     BwdArgs ba{};
     ba.xa = xa_dev; ba.w = w_dev; ba.b = b_dev; ba.gout = gout_dev; ba.hist_v2c = a.hist_v2c;
@@ -352,10 +358,25 @@ extern "C" int nldpc_neural_backward(const nldpc_graph_t *g, const float *xa_dev
     return NLDPC_OK;
 }
 
+extern "C" int nldpc_neural_forward_train(const nldpc_graph_t *g, const float *xa_dev, const float *w_dev, const float *b_dev, int B,
+                                          int T, float *soft_dev, void *workspace_dev, size_t workspace_bytes, void *stream) {
+    if (!g || B < 0 || T <= 0) return fail(NLDPC_E_INVALID, "nldpc_neural_forward_train: bad argument");
+    if (B == 0) return NLDPC_OK;
+    if (!xa_dev || !w_dev || !b_dev || !soft_dev) return fail(NLDPC_E_INVALID, "nldpc_neural_forward_train: NULL pointer");
+    const WsLayout l = ws_layout(g, B, T, 0);
+    if (!workspace_dev || workspace_bytes < l.total)
+        return fail(NLDPC_E_INVALID, "nldpc_neural_forward_train: workspace too small (see nldpc_backward_workspace_bytes)");
+    CUDA_TRY(cudaSetDevice(g->device));
+    DecodeArgs a{};
+    a.xa = xa_dev; a.w = w_dev; a.b = b_dev; a.B = B; a.T = T; a.soft_mode = NLDPC_OUT_ALL; a.soft = soft_dev;
+    a.hist_v2c = reinterpret_cast<float *>((char *)workspace_dev + l.v2c);
+    return neural_dispatch(g, a, (cudaStream_t)stream);
+}
+
 extern "C" int nldpc_boosted_backward(const nldpc_graph_t *g, const nldpc_boosted_cfg_t *cfg, const float *xa_dev,
                                       const float *vn_w_dev, const float *cn_w_dev, const float *ucn_w_dev, const float *gout_dev,
                                       int B, int T, float *gvn_dev, float *gcn_dev, float *gucn_dev, void *workspace_dev,
-                                      size_t workspace_bytes, void *stream) {
+                                      size_t workspace_bytes, int have_dump, void *stream) {
     if (!g || !cfg || B < 0 || T <= 0) return fail(NLDPC_E_INVALID, "nldpc_boosted_backward: bad argument");
     if (cfg->decoder_type != NLDPC_DEC_MS && cfg->decoder_type != NLDPC_DEC_QMS)
         return fail(NLDPC_E_UNSUPPORTED, "nldpc_boosted_backward: only the MS and QMS decoders have a backward");
@@ -380,9 +401,9 @@ extern "C" int nldpc_boosted_backward(const nldpc_graph_t *g, const nldpc_booste
     a.llr_lo = cfg->llr_lo; a.llr_hi = cfg->llr_hi;
     a.hist_v2c = reinterpret_cast<float *>(ws + l.v2c); a.hist_xin = reinterpret_cast<float *>(ws + l.xin);
     a.hist_mask = reinterpret_cast<uint8_t *>(ws + l.mask); a.hist_ucn = reinterpret_cast<uint8_t *>(ws + l.ucn);
-    int rc = generic_launch_boosted(g->dev, a, g->sm_count, st);
-    if (rc == -2) return fail(NLDPC_E_UNSUPPORTED, "nldpc_boosted_backward: graph does not fit on chip");
-    if (rc != 0) return fail(rc, std::string("nldpc_boosted_backward (forward dump): ") + cudaGetErrorString((cudaError_t)rc));
+    int rc = 0;
+    if (!have_dump)
+        if ((rc = boosted_dispatch(g, a, st))) return rc;
     BwdArgs ba{};
     ba.xa = xa_dev; ba.w = cn_w_dev; ba.b = cfg->ucn_mix ? ucn_w_dev : nullptr; ba.vn_w = vn_w_dev; ba.gout = gout_dev;
     ba.hist_v2c = a.hist_v2c; ba.hist_xin = a.hist_xin; ba.hist_mask = a.hist_mask; ba.hist_ucn = cfg->ucn_mix ? a.hist_ucn : nullptr;
@@ -415,7 +436,18 @@ extern "C" int nldpc_boosted_forward(const nldpc_graph_t *g, const nldpc_boosted
     a.decoder_type = cfg->decoder_type; a.qbit = cfg->qbit; a.compute_ucn = cfg->compute_ucn; a.ucn_mix = cfg->ucn_mix;
     a.llr_lo = cfg->llr_lo; a.llr_hi = cfg->llr_hi;
     a.llr_init = cfg->llr_init_dev; a.xin_init = cfg->xin_init_dev; a.xin_out = cfg->xin_out_dev; a.app_init = cfg->app_init_dev;
-    cudaStream_t st = (cudaStream_t)stream;
+    if (cfg->train_dump_dev) {   // training mode: spill what the backward kernel needs (nldpc_backward_workspace_bytes(.., 1))
+        if (soft_mode != NLDPC_OUT_ALL) return fail(NLDPC_E_INVALID, "nldpc_boosted_forward: the training dump needs soft_mode = ALL");
+        const WsLayout l = ws_layout(g, B, T, 1);
+        if (cfg->train_dump_bytes < l.total) return fail(NLDPC_E_INVALID, "nldpc_boosted_forward: training dump buffer too small");
+        char *ws = (char *)cfg->train_dump_dev;
+        a.hist_v2c = reinterpret_cast<float *>(ws + l.v2c); a.hist_xin = reinterpret_cast<float *>(ws + l.xin);
+        a.hist_mask = reinterpret_cast<uint8_t *>(ws + l.mask); a.hist_ucn = reinterpret_cast<uint8_t *>(ws + l.ucn);
+    }
+    return boosted_dispatch(g, a, (cudaStream_t)stream);
+}
+
+static int boosted_dispatch(const nldpc_graph *g, const DecodeArgs &a, cudaStream_t st) {
     if (g->spec_id >= 0 && !force_generic()) {
         const int src = spec_launch_boosted(g->spec_id, a, g->sm_count, st);
         if (src > 0) return fail(src, std::string("nldpc_boosted_forward (specialised): ") + cudaGetErrorString((cudaError_t)src));

@@ -41,7 +41,7 @@ int launch_neural(const DecodeArgs &a, int sm_count, cudaStream_t st) {
     const int n_units = (a.B + Cfg::Shape::kCw - 1) / Cfg::Shape::kCw;
     const int ctas = (n_units + Cfg::kGroups - 1) / Cfg::kGroups;
     const int grid = std::min(ctas, sm_count * Cfg::kCtasPerSm);
-    const bool every = a.soft_mode == 1 || a.hard_mode == 1;
+    const bool every = a.soft_mode == 1 || a.hard_mode == 1 || a.hist_v2c != nullptr;
     DecodeArgs args = a;
     // weights -> constant arena (uniform-datapath reads in the kernel); LDG variant if they do not fit
     ConstArena &arena = arena_for_current_device();

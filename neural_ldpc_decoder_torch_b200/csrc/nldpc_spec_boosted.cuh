@@ -42,7 +42,8 @@ int boosted_launch_one(const DecodeArgs &args, int sm_count, cudaStream_t st) {
 template <class G>
 int boosted_launch(const DecodeArgs &a, int sm_count, cudaStream_t st) {
     const bool qms5 = a.decoder_type == 2 && a.qbit == 5, ms = a.decoder_type == 1;
-    if (!(qms5 || ms) || a.compute_ucn || a.llr_init || a.xin_init || a.xin_out || a.app_init || a.hist_v2c) return -1;
+    if (!(qms5 || ms) || a.compute_ucn || a.llr_init || a.xin_init || a.xin_out || a.app_init) return -1;
+    if (a.hist_v2c && a.soft_mode != 1) return -1;      // the training dump rides on the every-iteration variant
     ConstArena &arena = arena_for_current_device();
     const int len = a.T * G::E;
     cudaError_t err;

@@ -70,6 +70,14 @@ __device__ __forceinline__ float condition(float x, float lo, float hi) {       
     else return clamp_rng(x, lo, hi);
 }
 
+// Boosted output: clamp(xa_origin + total, range) (:520-521); the training dump records whether the clamp passes gradient
+template <class L>
+__device__ __forceinline__ float boosted_out(L &c, int q, float xo, float tot) {
+    const float sum = addf(xo, tot);
+    if (c.mask) c.mask[q] = (sum >= c.lo && sum <= c.hi) ? 1 : 0;
+    return clamp_rng(sum, c.lo, c.hi);
+}
+
 template <int Z>
 struct GroupShape {
     static constexpr int kLanes = (Z == 16 || Z == 32) ? 32 : (Z == 24 ? 96 : 0);
@@ -106,6 +114,7 @@ struct NeuralLane {
     int xo_off;              // float offset from the xin rows to the xo rows (0: xa_origin and xa_input are the same rows)
     float lo, hi;            // allowed_llr_range
     float *llr_last;         // &llr_last[b][0][0] ([Z][E]) while the last iteration's CN phase runs, else nullptr
+    uint8_t *mask;           // training dump: &hist_mask[t_emit][b][0] of the iteration being emitted, or nullptr
 
     // ---- emission of one marginal value -------------------------------------------------------------------
     // un-rotated: this lane holds bit (J, z)
@@ -197,7 +206,7 @@ struct VnStep {
         }
         if constexpr (kEmit) {
             if constexpr (MODE == 0) c.template emit<J>(addf(x, p));       // out = xa + llr @ W_output (:94-96)
-            else c.template emit<J>(clamp_rng(addf(kXo ? c.lane[c.xo_off + J * G::Z] : x, p), c.lo, c.hi));   // Boosted :520-521
+            else c.template emit<J>(boosted_out(c, J * G::Z + c.z, kXo ? c.lane[c.xo_off + J * G::Z] : x, p));   // Boosted :520-521
         }
     }
 };
@@ -211,7 +220,7 @@ struct Marginal {
         float p = 0.0f;
         ((p = addf(p, c.lane[R * G::Z])), ...);
         if constexpr (MODE == 0) c.template emit<J>(addf(c.lane[XROW * G::Z], p));
-        else c.template emit<J>(clamp_rng(addf(c.lane[(kXo ? c.xo_off + J * G::Z : XROW * G::Z)], p), c.lo, c.hi));
+        else c.template emit<J>(boosted_out(c, J * G::Z + c.z, c.lane[(kXo ? c.xo_off + J * G::Z : XROW * G::Z)], p));
     }
 };
 
@@ -258,6 +267,17 @@ struct ScaleXin {
         float x = mulf(xa_ref<G, DEST>(c), __ldg(vw + J));
         if constexpr (MODE == 2) x = quant5(x);
         xa_ref<G, DEST>(c) = x;
+    }
+};
+
+// training dump of the channel-input state (hist_xin[.][b][J][z])
+template <class G>
+struct DumpXin {
+    NeuralLane<G> &c;
+    float *dst;              // &hist_xin[t][b][0][z]
+    template <int J, int DEST>
+    __device__ __forceinline__ void put() {
+        dst[J * G::Z] = xa_ref<G, DEST>(c);
     }
 };
 
@@ -394,7 +414,7 @@ __device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c) {
             c.rot[shf[k]][rows[k] * G::Z] = c2v;
         } else if constexpr (kEmit) {
             const float xo = kXo ? c.rot[shf[k]][c.xo_off + col1[k] * G::Z] : raw[k];
-            c.emit_rot(col1[k], shf[k], clamp_rng(addf(xo, addf(0.0f, c2v)), c.lo, c.hi));   // (:513-526)
+            c.emit_rot(col1[k], shf[k], boosted_out(c, col1[k] * G::Z + (int)(c.rot[shf[k]] - (c.lane - c.z)), xo, addf(0.0f, c2v)));   // (:513-526)
         }
     }
 }
@@ -527,6 +547,7 @@ __global__ void __launch_bounds__(SpecCfg<G, kXo>::kThreads, SpecCfg<G, kXo>::kC
     c.lo = a.llr_lo;
     c.hi = a.llr_hi;
     c.llr_last = nullptr;
+    c.mask = nullptr;
 #pragma unroll
     for (int s = 0; s < Z; s++) c.rot[s] = slab + ((z + s) % Z);
     uint8_t *hb_mine = hstage + (size_t)cw_in_cta * Cfg::kHardStride;
@@ -624,21 +645,36 @@ __global__ void __launch_bounds__(SpecCfg<G, kXo>::kThreads, SpecCfg<G, kXo>::kC
                 c.wt = a.w + (size_t)t * G::E;
                 c.bt = a.b + (size_t)t * G::E;
                 c.wb_base = a.wb_off + t * G::E;
+                const bool dump = a.hist_v2c != nullptr && c.valid;     // training dump for the backward kernel
+                if (MODE != 0 && dump && t == 0) {
+                    DumpXin<G> d{c, a.hist_xin + (size_t)b * NZ + z};
+                    G::blocks(d);
+                }
                 xin_update(t);
+                if (MODE != 0 && dump) {
+                    DumpXin<G> d{c, a.hist_xin + ((size_t)(t + 1) * a.B + b) * NZ + z};
+                    G::blocks(d);
+                }
                 if (t == 0) {
                     VnFirst<G> f{c};
                     G::vcols(f);
                 } else {
                     c.soft = (soft_all && soft_cw) ? soft_cw + (size_t)(t - 1) * soft_iter : nullptr;
                     c.hb = hard_all ? hb_cw : nullptr;
+                    c.mask = (MODE != 0 && dump) ? a.hist_mask + ((size_t)(t - 1) * a.B + b) * NZ : nullptr;
                     VnStep<G, true, MODE, kXo> f{c};
                     G::vcols(f);
                     if (hard_all) flush_hard(t - 1);
+                }
+                if (dump) {   // the v2c every CN phase reads, slot-major (same slot order as the table-driven kernels)
+                    float *hv = a.hist_v2c + (((size_t)t * a.B + b) * G::S) * Z + z;
+                    for (int q = 0; q < G::S; q++) hv[(size_t)q * Z] = c.lane[(G::kXRows + q) * Z];
                 }
                 phase_sync();
                 const bool last = t == a.T - 1;
                 c.soft = (soft_cw && (soft_all || last)) ? soft_cw + (soft_all ? (size_t)t * soft_iter : 0) : nullptr;
                 c.hb = (hard_all || last) ? hb_cw : nullptr;
+                c.mask = (MODE != 0 && dump) ? a.hist_mask + ((size_t)t * a.B + b) * NZ : nullptr;
                 c.llr_last = (last && a.llr_last && c.valid) ? a.llr_last + (size_t)b * Z * G::E : nullptr;
                 cn_run(std::true_type{});
                 phase_sync();
@@ -672,6 +708,7 @@ __global__ void __launch_bounds__(SpecCfg<G, kXo>::kThreads, SpecCfg<G, kXo>::kC
         {
             c.soft = soft_cw ? soft_cw + (soft_all ? (size_t)(a.T - 1) * soft_iter : 0) : nullptr;
             c.hb = hb_cw;
+            c.mask = (MODE != 0 && kEvery && a.hist_mask && c.valid) ? a.hist_mask + ((size_t)(a.T - 1) * a.B + b) * NZ : nullptr;
             Marginal<G, MODE, kXo> f{c};
             G::vcols(f);
             if (hard_any) flush_hard(a.T - 1);

@@ -70,7 +70,11 @@ class NeuralLDPCDecoder(nn.Module):
         gid = self.conn_mat.graph_id(xa.device)
         if w.device != xa.device:
             w, b = w.to(xa.device), b.to(xa.device)
-        out = torch.ops.nldpc.neural_forward(xa, w, b, gid)
+        if torch.is_grad_enabled() and (w.requires_grad or b.requires_grad):
+            # training: the forward also spills the per-iteration v2c the backward kernel needs (no forward re-run)
+            out, _ = torch.ops.nldpc.neural_forward_train(xa, w, b, gid)
+        else:
+            out = torch.ops.nldpc.neural_forward(xa, w, b, gid)
         return list(out.unbind(0))
 
     @torch.no_grad()

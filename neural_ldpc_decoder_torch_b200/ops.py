@@ -6,6 +6,7 @@ device memory and the current stream; the arithmetic is in libnldpc_b200.so (han
   nldpc::neural_backward(xa, w, b, gout, graph_id) -> (gw, gb)       autograd of the above (SURVEY App. B)
 """
 import ctypes
+from typing import Optional
 
 import torch
 
@@ -84,8 +85,9 @@ def _(xa, w, b, graph_id, all_iters):
 
 
 @torch.library.custom_op("nldpc::neural_backward", mutates_args=())
-def neural_backward(xa: torch.Tensor, w: torch.Tensor, b: torch.Tensor, gout: torch.Tensor,
-                    graph_id: int) -> tuple[torch.Tensor, torch.Tensor]:
+def neural_backward(xa: torch.Tensor, w: torch.Tensor, b: torch.Tensor, gout: torch.Tensor, graph_id: int,
+                    dump: Optional[torch.Tensor] = None) -> tuple[torch.Tensor, torch.Tensor]:
+    """`dump`: the training dump written by nldpc::neural_forward_train for the same inputs (skips the forward re-run)"""
     g, xa, w, b = _prep(xa, w, b, graph_id)
     _check_cuda_f32("gout", gout)
     B, T = xa.shape[0], w.shape[0]
@@ -95,17 +97,53 @@ def neural_backward(xa: torch.Tensor, w: torch.Tensor, b: torch.Tensor, gout: to
     gw = torch.empty_like(w)
     gb = torch.empty_like(b)
     nbytes = int(_lib.lib().nldpc_backward_workspace_bytes(g.ptr, B, T, 0))
-    ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=xa.device)     # per-iteration v2c dump (HBM)
+    have_dump = dump is not None and dump.numel() >= nbytes
+    ws = dump if have_dump else torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=xa.device)   # per-iteration v2c dump (HBM)
     with torch.cuda.device(xa.device):
         rc = _lib.lib().nldpc_neural_backward(g.ptr, _ptr(xa), _ptr(w), _ptr(b), _ptr(gout), B, T, _ptr(gw), _ptr(gb),
-                                              _ptr(ws), nbytes, _stream(xa))
+                                              _ptr(ws), nbytes, int(have_dump), _stream(xa))
     _lib.check(rc, "nldpc_neural_backward")
     return gw, gb
 
 
 @neural_backward.register_fake
-def _(xa, w, b, gout, graph_id):
+def _(xa, w, b, gout, graph_id, dump=None):
     return torch.empty_like(w), torch.empty_like(b)
+
+
+@torch.library.custom_op("nldpc::neural_forward_train", mutates_args=())
+def neural_forward_train(xa: torch.Tensor, w: torch.Tensor, b: torch.Tensor, graph_id: int) -> tuple[torch.Tensor, torch.Tensor]:
+    """training-mode forward: out [T, B, N*Z] plus the per-iteration dump the backward kernel reads (uint8 workspace)"""
+    g, xa, w, b = _prep(xa, w, b, graph_id)
+    B, T = xa.shape[0], w.shape[0]
+    out = torch.empty((T, B, g.NZ), dtype=torch.float32, device=xa.device)
+    nbytes = int(_lib.lib().nldpc_backward_workspace_bytes(g.ptr, B, T, 0))
+    ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=xa.device)
+    with torch.cuda.device(xa.device):
+        rc = _lib.lib().nldpc_neural_forward_train(g.ptr, _ptr(xa), _ptr(w), _ptr(b), B, T, _ptr(out), _ptr(ws), nbytes, _stream(xa))
+    _lib.check(rc, "nldpc_neural_forward_train")
+    return out, ws
+
+
+@neural_forward_train.register_fake
+def _(xa, w, b, graph_id):
+    g = _lib.graph_by_id(graph_id)
+    return xa.new_empty((w.shape[0], xa.shape[0], g.NZ)), xa.new_empty((1,), dtype=torch.uint8)
+
+
+def _neural_train_setup_ctx(ctx, inputs, output):
+    xa, w, b, graph_id = inputs
+    ctx.save_for_backward(xa, w, b, output[1])
+    ctx.graph_id = graph_id
+
+
+def _neural_train_bwd(ctx, gout, gws):
+    xa, w, b, ws = ctx.saved_tensors
+    gw, gb = torch.ops.nldpc.neural_backward(xa, w, b, gout.contiguous(), ctx.graph_id, ws)
+    return None, gw, gb, None
+
+
+neural_forward_train.register_autograd(_neural_train_bwd, setup_context=_neural_train_setup_ctx)
 
 
 def _neural_setup_ctx(ctx, inputs, output):
@@ -116,7 +154,7 @@ def _neural_setup_ctx(ctx, inputs, output):
 
 def _neural_bwd(ctx, gout):
     xa, w, b = ctx.saved_tensors
-    gw, gb = torch.ops.nldpc.neural_backward(xa, w, b, gout.contiguous(), ctx.graph_id)
+    gw, gb = torch.ops.nldpc.neural_backward(xa, w, b, gout.contiguous(), ctx.graph_id, None)
     return None, gw, gb, None
 
 
@@ -146,7 +184,6 @@ def neural_decode_host(graph_id, xa_host, w_host, b_host, soft_mode=_lib.NLDPC_O
 
 # ---------------------------------------------------------------------------------------------------------------
 # Boosted decoder (BoostedNeuralLDPCDecoder.py:320-531)
-from typing import Optional  # noqa: E402
 
 
 def _out_shape(mode, T, B, last):
@@ -169,7 +206,7 @@ def boosted_forward(xa: torch.Tensor, vn_w: Optional[torch.Tensor], cn_w: Option
                     graph_id: int, T: int, decoder_type: int, qbit: int, llr_lo: float, llr_hi: float, compute_ucn: bool,
                     ucn_mix: bool, llr_init: Optional[torch.Tensor], xin_init: Optional[torch.Tensor],
                     app_init: Optional[torch.Tensor], want_llr: bool, want_xin: bool, soft_mode: int,
-                    hard_mode: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+                    hard_mode: int, want_dump: bool = False) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """T consecutive iterations of the Boosted loop body.  Returns (soft [T,B,N*Z] | [B,N*Z] | empty per soft_mode,
     llr_last [B,Z,E] | empty, xin_out [B,N,Z] | empty, packed hard decisions per hard_mode | empty).
     Weight rows are indexed by executed iteration."""
@@ -191,34 +228,37 @@ def boosted_forward(xa: torch.Tensor, vn_w: Optional[torch.Tensor], cn_w: Option
     hard = torch.empty(_out_shape(hard_mode, T, B, g.hard_bytes), dtype=torch.uint8, device=dev)
     llr_last = torch.empty((B, g.Z, g.E) if want_llr else (0,), dtype=torch.float32, device=dev)
     xin_out = torch.empty((B, g.N, g.Z) if want_xin else (0,), dtype=torch.float32, device=dev)
+    nbytes = int(_lib.lib().nldpc_backward_workspace_bytes(g.ptr, B, T, 1)) if want_dump else 0
+    dump = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=dev)
     cfg = _lib.BoostedCfg(decoder_type, qbit, llr_lo, llr_hi, int(compute_ucn), int(ucn_mix),
                           llr_init.data_ptr() if llr_init is not None else None,
                           xin_init.data_ptr() if xin_init is not None else None,
                           xin_out.data_ptr() if want_xin else None,
-                          app_init.data_ptr() if app_init is not None else None)
+                          app_init.data_ptr() if app_init is not None else None,
+                          dump.data_ptr() if want_dump else None, nbytes)
     with torch.cuda.device(dev):
         rc = _lib.lib().nldpc_boosted_forward(g.ptr, ctypes.byref(cfg), _ptr(xa), _ptr(vn_w), _ptr(cn_w), _ptr(ucn_w), B, T,
                                               soft_mode, _ptr(soft) if soft_mode else _vp(0), hard_mode,
                                               _ptr(hard) if hard_mode else _vp(0),
                                               _ptr(llr_last) if want_llr else _vp(0), _stream(xa))
     _lib.check(rc, "nldpc_boosted_forward")
-    return soft, llr_last, xin_out, hard
+    return soft, llr_last, xin_out, hard, dump
 
 
 @boosted_forward.register_fake
 def _(xa, vn_w, cn_w, ucn_w, graph_id, T, decoder_type, qbit, llr_lo, llr_hi, compute_ucn, ucn_mix, llr_init, xin_init, app_init,
-      want_llr, want_xin, soft_mode, hard_mode):
+      want_llr, want_xin, soft_mode, hard_mode, want_dump=False):
     g = _lib.graph_by_id(graph_id)
     B = xa.shape[0]
     return (xa.new_empty(_out_shape(soft_mode, T, B, g.NZ)), xa.new_empty((B, g.Z, g.E) if want_llr else (0,)),
             xa.new_empty((B, g.N, g.Z) if want_xin else (0,)),
-            xa.new_empty(_out_shape(hard_mode, T, B, g.hard_bytes), dtype=torch.uint8))
+            xa.new_empty(_out_shape(hard_mode, T, B, g.hard_bytes), dtype=torch.uint8), xa.new_empty((1,), dtype=torch.uint8))
 
 
 @torch.library.custom_op("nldpc::boosted_backward", mutates_args=())
 def boosted_backward(xa: torch.Tensor, vn_w: Optional[torch.Tensor], cn_w: Optional[torch.Tensor], ucn_w: Optional[torch.Tensor],
                      gout: torch.Tensor, graph_id: int, T: int, decoder_type: int, qbit: int, llr_lo: float, llr_hi: float,
-                     compute_ucn: bool, ucn_mix: bool) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+                     compute_ucn: bool, ucn_mix: bool, dump: Optional[torch.Tensor] = None) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """gradients w.r.t. the folded weight rows (vn [T,N], cn [T,E], ucn [T,E]; empty where absent)"""
     g = _lib.graph_by_id(graph_id)
     _check_cuda_f32("xa", xa)
@@ -234,18 +274,19 @@ def boosted_backward(xa: torch.Tensor, vn_w: Optional[torch.Tensor], cn_w: Optio
     gcn = torch.empty((T, g.E) if cn_w is not None else (0,), dtype=torch.float32, device=dev)
     gucn = torch.empty((T, g.E) if (ucn_w is not None and ucn_mix) else (0,), dtype=torch.float32, device=dev)
     nbytes = int(_lib.lib().nldpc_backward_workspace_bytes(g.ptr, B, T, 1))
-    ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=dev)
-    cfg = _lib.BoostedCfg(decoder_type, qbit, llr_lo, llr_hi, int(compute_ucn), int(ucn_mix), None, None, None, None)
+    have_dump = dump is not None and dump.numel() >= nbytes
+    ws = dump if have_dump else torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=dev)
+    cfg = _lib.BoostedCfg(decoder_type, qbit, llr_lo, llr_hi, int(compute_ucn), int(ucn_mix), None, None, None, None, None, 0)
     with torch.cuda.device(dev):
         rc = _lib.lib().nldpc_boosted_backward(g.ptr, ctypes.byref(cfg), _ptr(xa), _ptr(vn_w), _ptr(cn_w), _ptr(ucn_w), _ptr(gout), B, T,
                                                _ptr(gvn) if gvn.numel() else _vp(0), _ptr(gcn) if gcn.numel() else _vp(0),
-                                               _ptr(gucn) if gucn.numel() else _vp(0), _ptr(ws), nbytes, _stream(xa))
+                                               _ptr(gucn) if gucn.numel() else _vp(0), _ptr(ws), nbytes, int(have_dump), _stream(xa))
     _lib.check(rc, "nldpc_boosted_backward")
     return gvn, gcn, gucn
 
 
 @boosted_backward.register_fake
-def _(xa, vn_w, cn_w, ucn_w, gout, graph_id, T, decoder_type, qbit, llr_lo, llr_hi, compute_ucn, ucn_mix):
+def _(xa, vn_w, cn_w, ucn_w, gout, graph_id, T, decoder_type, qbit, llr_lo, llr_hi, compute_ucn, ucn_mix, dump=None):
     g = _lib.graph_by_id(graph_id)
     return (xa.new_empty((T, g.N) if vn_w is not None else (0,)), xa.new_empty((T, g.E) if cn_w is not None else (0,)),
             xa.new_empty((T, g.E) if (ucn_w is not None and ucn_mix) else (0,)))
@@ -253,15 +294,15 @@ def _(xa, vn_w, cn_w, ucn_w, gout, graph_id, T, decoder_type, qbit, llr_lo, llr_
 
 def _boosted_setup_ctx(ctx, inputs, output):
     (xa, vn_w, cn_w, ucn_w, graph_id, T, dec, qbit, lo, hi, compute_ucn, ucn_mix, llr_init, xin_init, app_init, want_llr,
-     want_xin, soft_mode, hard_mode) = inputs
-    ctx.save_for_backward(xa, vn_w, cn_w, ucn_w)
+     want_xin, soft_mode, hard_mode, want_dump) = inputs
+    ctx.save_for_backward(xa, vn_w, cn_w, ucn_w, output[4] if want_dump else None)
     ctx.cfg = (graph_id, T, dec, qbit, lo, hi, compute_ucn, ucn_mix)
     ctx.stateful = llr_init is not None or xin_init is not None or app_init is not None
     ctx.soft_all = soft_mode == _lib.NLDPC_OUT_ALL
 
 
-def _boosted_bwd(ctx, gsoft, gllr, gxin, ghard):
-    xa, vn_w, cn_w, ucn_w = ctx.saved_tensors
+def _boosted_bwd(ctx, gsoft, gllr, gxin, ghard, gdump):
+    xa, vn_w, cn_w, ucn_w, dump = ctx.saved_tensors
     graph_id, T, dec, qbit, lo, hi, compute_ucn, ucn_mix = ctx.cfg
     if not ctx.soft_all:
         raise _lib.NldpcError("backward needs the per-iteration soft outputs (soft_mode = ALL)")
@@ -269,9 +310,9 @@ def _boosted_bwd(ctx, gsoft, gllr, gxin, ghard):
         raise _lib.NldpcError("backward through a run that continues from stored state (partial target_iter after an earlier "
                               "call) is not supported: run the trained iterations in one forward call starting at iteration 0")
     gvn, gcn, gucn = torch.ops.nldpc.boosted_backward(xa, vn_w, cn_w, ucn_w, gsoft.contiguous(), graph_id, T, dec, qbit, lo, hi,
-                                                      compute_ucn, ucn_mix)
+                                                      compute_ucn, ucn_mix, dump)
     return (None, gvn if vn_w is not None else None, gcn if cn_w is not None else None,
-            gucn if (ucn_w is not None and ucn_mix) else None) + (None,) * 15
+            gucn if (ucn_w is not None and ucn_mix) else None) + (None,) * 16
 
 
 boosted_forward.register_autograd(_boosted_bwd, setup_context=_boosted_setup_ctx)
