@@ -48,7 +48,7 @@ struct nldpc_graph {
     size_t ws_wb_bytes = 0;
 };
 
-struct WsLayout { size_t v2c, xin, mask, ucn, total; };
+struct WsLayout { size_t v2c, xin, mask, ucn, scratch, total; };
 static WsLayout ws_layout(const nldpc_graph *g, int B, int T, int boosted) {
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     WsLayout l{};
@@ -58,6 +58,10 @@ static WsLayout ws_layout(const nldpc_graph *g, int B, int T, int boosted) {
         l.xin = off; off = up(off + (size_t)(T + 1) * B * g->N * g->Z * 4);
         l.mask = off; off = up(off + (size_t)T * B * g->N * g->Z);
         l.ucn = off; off = up(off + (size_t)T * B * g->M * g->Z);
+    }
+    if (g->spec_id >= 0) {   // partial-sum rows of the specialised backward sweep
+        l.scratch = off;
+        off = up(off + (size_t)g->sm_count * spec_backward_scratch_rows(g->spec_id) * kSpecBwdScratchLanes * 4);
     }
     l.total = off;
     return l;
@@ -352,6 +356,12 @@ extern "C" int nldpc_neural_backward(const nldpc_graph_t *g, const float *xa_dev
     BwdArgs ba{};
     ba.xa = xa_dev; ba.w = w_dev; ba.b = b_dev; ba.gout = gout_dev; ba.hist_v2c = a.hist_v2c;
     ba.gw = gw_dev; ba.gb = gb_dev; ba.B = B; ba.T = T; ba.mode = 0;
+    if (g->spec_id >= 0 && !force_generic()) {
+        ba.scratch = reinterpret_cast<float *>((char *)workspace_dev + l.scratch);
+        const int src = spec_launch_backward(g->spec_id, ba, g->sm_count, st);
+        if (src > 0) return fail(src, std::string("nldpc_neural_backward (specialised): ") + cudaGetErrorString((cudaError_t)src));
+        if (src == 0) return NLDPC_OK;
+    }
     const int rc = backward_launch(g->dev, ba, g->sm_count, st);
     if (rc == -2) return fail(NLDPC_E_UNSUPPORTED, "nldpc_neural_backward: graph does not fit on chip");
     if (rc != 0) return fail(rc, std::string("nldpc_neural_backward: ") + cudaGetErrorString((cudaError_t)rc));
@@ -410,6 +420,12 @@ extern "C" int nldpc_boosted_backward(const nldpc_graph_t *g, const nldpc_booste
     ba.gw = gcn_dev; ba.gb = cfg->ucn_mix ? gucn_dev : nullptr; ba.gvn = vn_w_dev ? gvn_dev : nullptr;
     ba.B = B; ba.T = T; ba.mode = cfg->decoder_type == NLDPC_DEC_QMS ? 2 : 1; ba.qbit = cfg->qbit; ba.lo = cfg->llr_lo; ba.hi = cfg->llr_hi;
     ba.ucn_mix = cfg->ucn_mix;
+    if (g->spec_id >= 0 && !force_generic()) {
+        ba.scratch = reinterpret_cast<float *>(ws + l.scratch);
+        const int src = spec_launch_backward(g->spec_id, ba, g->sm_count, st);
+        if (src > 0) return fail(src, std::string("nldpc_boosted_backward (specialised): ") + cudaGetErrorString((cudaError_t)src));
+        if (src == 0) return NLDPC_OK;
+    }
     rc = backward_launch(g->dev, ba, g->sm_count, st);
     if (rc == -2) return fail(NLDPC_E_UNSUPPORTED, "nldpc_boosted_backward: graph does not fit on chip");
     if (rc != 0) return fail(rc, std::string("nldpc_boosted_backward: ") + cudaGetErrorString((cudaError_t)rc));

@@ -71,6 +71,7 @@ struct BwdArgs {
     const uint8_t *hist_ucn;    // [T][B][M][Z] unsatisfied-check indicator (Boosted, ucn_mix) or nullptr
     float *gw, *gb;         // [T][E] (+=)   Neural: weights/biases;  Boosted: cn_w / ucn_w rows
     float *gvn;             // [T][N] (+=)   Boosted VN weights or nullptr
+    float *scratch;         // specialised kernel: [grid][rows][threads] per-iteration partial sums (L2-resident) or nullptr
     int B, T;
     int mode;               // 0 Neural, 1 Boosted MS, 2 Boosted QMS
     int qbit;

@@ -8,6 +8,7 @@
 #include "generated/nldpc_graph_wimaxz24.cuh"
 
 #include "nldpc_spec_host.cuh"
+#include "nldpc_spec_backward.cuh"
 
 namespace nldpc {
 
@@ -94,6 +95,29 @@ int spec_launch_boosted(int id, const DecodeArgs &a, int sm_count, cudaStream_t 
     switch (id) {
         case 0: return spec_boosted_launch_bg2(a, sm_count, st);
         case 1: return spec_boosted_launch_wimax(a, sm_count, st);
+        default: return -1;
+    }
+}
+
+int spec_backward_scratch_rows(int id) {
+    switch (id) {
+        case 0: return 2 * gen::Bg2Z16::E + gen::Bg2Z16::N;
+        case 1: return 2 * gen::WimaxZ24::E + gen::WimaxZ24::N;
+        default: return 0;
+    }
+}
+
+int spec_launch_backward(int id, const BwdArgs &a, int sm_count, cudaStream_t st) {
+    if (a.mode == 0) {
+        switch (id) {
+            case 0: return spec_bwd_launch<gen::Bg2Z16, false>(a, sm_count, st);
+            case 1: return spec_bwd_launch<gen::WimaxZ24, false>(a, sm_count, st);
+            default: return -1;
+        }
+    }
+    switch (id) {
+        case 0: return spec_boosted_backward_bg2(a, sm_count, st);
+        case 1: return spec_boosted_backward_wimax(a, sm_count, st);
         default: return -1;
     }
 }

@@ -11,9 +11,15 @@ int spec_threads(int id);
 // 0 = launched, >0 = cudaError_t, <0 = configuration not covered (caller falls back to the generic kernel)
 int spec_launch_neural(int id, const DecodeArgs &a, int sm_count, cudaStream_t st);
 int spec_launch_boosted(int id, const DecodeArgs &a, int sm_count, cudaStream_t st);
+// scratch the specialised backward needs: sm_count * spec_backward_scratch_rows(id) * kSpecBwdScratchLanes floats
+constexpr int kSpecBwdScratchLanes = 384;
+int spec_backward_scratch_rows(int id);   // 2E + N of the code, 0 if there is no specialised backward
+int spec_launch_backward(int id, const BwdArgs &a, int sm_count, cudaStream_t st);   // 0 / cudaError_t / -1 not covered
 // per-code translation units
 int spec_boosted_prepare_bg2();
 int spec_boosted_launch_bg2(const DecodeArgs &a, int sm_count, cudaStream_t st);
 int spec_boosted_prepare_wimax();
 int spec_boosted_launch_wimax(const DecodeArgs &a, int sm_count, cudaStream_t st);
+int spec_boosted_backward_bg2(const BwdArgs &a, int sm_count, cudaStream_t st);
+int spec_boosted_backward_wimax(const BwdArgs &a, int sm_count, cudaStream_t st);
 }  // namespace nldpc

@@ -1,0 +1,353 @@
+// nldpc_spec_backward.cuh — specialised (graph-as-immediates) version of the backward sweep of nldpc_backward.cu for the
+// built-in codes: Neural (weights + biases) and Boosted MS / QMS q=5 without UCN (CN rows, optional VN rows).
+//
+// Same closed form as the table-driven kernel; what changes is the machinery:
+//   * one thread per (codeword, lane z), gradient messages in the forward's slab layout (rotation = pointer choice),
+//   * the forward's per-iteration v2c / channel-input state / clamp mask come from the HBM dump the training-mode forward
+//     wrote (coalesced 64 B rows per codeword),
+//   * the CTA runs in lockstep over iterations so that per-edge weight gradients can be accumulated hierarchically and
+//     WITHOUT atomics in the inner loop (fp32 atomicAdd on shared memory is an ATOMS.CAST.SPIN loop on sm_100):
+//     every lane stores its per-edge term to a private slot of an L2-resident scratch row [row][thread] (one STG per
+//     edge, immediate offsets) -> after the phase each warp owns a few rows, reads them back as float4 (L2 hits),
+//     warp-reduces and adds into a per-CTA [T][rows] table in shared memory -> one global atomicAdd per (t, row) per
+//     CTA at the end of the kernel,
+//   * the VN-weight chain (d xa_input) is lane-private and lives in registers.
+#pragma once
+#include <algorithm>
+
+#include "nldpc_spec.cuh"
+#include "nldpc_spec_host.cuh"
+
+namespace nldpc {
+
+__device__ __forceinline__ float bwd_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <class G>
+struct BwdLane {
+    static constexpr int Z = G::Z;
+    float *lane;              // &slab[z]
+    float *rot[Z];            // &slab[(z + s) mod Z]
+    const float *hv;          // &hist_v2c[t][b][0][0]
+    const float *gt;          // &gout[t][b][0]
+    const uint8_t *mk;        // &hist_mask[t][b][0] or nullptr
+    const float *xin;         // CN inputs of the degree-1 blocks: &xa[b][0] (Neural) or &hist_xin[t+1][b][0]
+    int wb_base;              // constant-arena offset of {w,b}[t][0]
+    float *scr;               // &scratch[cta][0][tid]: this thread's slot of every scratch row
+    float lo, hi;
+    int z;
+    bool valid;
+    float dxr[G::kXRegs > 0 ? G::kXRegs : 1];      // d xa_input of the register-resident degree-1 blocks (this iteration)
+
+    __device__ __forceinline__ float g_at(int q) const {     // upstream gradient through the output clamp mask
+        if (!valid) return 0.0f;
+        const float gv = __ldg(gt + q);
+        return (mk && !mk[q]) ? 0.0f : gv;
+    }
+};
+
+// VN phase backwards: dc2v[e] = G[j] + (sum of the block's dv2c_{t+1} - own)
+template <class G>
+struct VnBwd {
+    BwdLane<G> &c;
+    template <int J, int XROW, int... R>
+    __device__ __forceinline__ void col() {
+        const float gj = c.g_at(J * G::Z + c.z);
+        float tot = 0.0f;
+        ((tot += c.lane[R * G::Z]), ...);
+        ((c.lane[R * G::Z] = gj + (tot - c.lane[R * G::Z])), ...);
+    }
+};
+
+// sum of the block's dv2c_t (after the CN phase) -> d xa_input contribution of the blocks of degree >= 2
+template <class G>
+struct VnChainSum {
+    BwdLane<G> &c;
+    float *dx;                // [N] per-thread, indexed by block
+    template <int J, int XROW, int... R>
+    __device__ __forceinline__ void col() {
+        float tot = 0.0f;
+        ((tot += c.lane[R * G::Z]), ...);
+        dx[J] = tot;
+    }
+};
+
+template <class G, int MODE, bool kVn, int kThreads, class... Es>
+__device__ __forceinline__ void cn_check_bwd_core(BwdLane<G> &c) {
+    constexpr int D = sizeof...(Es);
+    constexpr int rows[D] = {Es::row...};
+    constexpr int shf[D] = {Es::shift...};
+    constexpr int eix[D] = {Es::e...};
+    constexpr int col1[D] = {Es::col1...};
+    constexpr int Z = G::Z;
+    float u[D], dc[D], smask[D];
+    unsigned par = 0;
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        const int zz = (int)(c.rot[shf[k]] - (c.lane - c.z));
+        float v = 0.0f;
+        if (col1[k] < 0) {                                       // stored edge: message row
+            if (c.valid) v = __ldg(c.hv + (rows[k] - G::kXRows) * Z + zz);
+            dc[k] = c.rot[shf[k]][rows[k] * Z];
+        } else {                                                 // degree-1 block: channel input, upstream gradient
+            if (c.valid) v = __ldg(c.xin + col1[k] * Z + zz);
+            dc[k] = c.g_at(col1[k] * Z + zz);
+        }
+        float mkk = 1.0f;
+        if constexpr (MODE == 2) {
+            mkk = (fabsf(v) <= 7.5f) ? 1.0f : 0.0f;
+            v = quant5(v);
+        } else if constexpr (MODE == 1) {
+            mkk = (v >= c.lo && v <= c.hi) ? 1.0f : 0.0f;
+            v = clamp_rng(v, c.lo, c.hi);
+        }
+        if constexpr (MODE != 0) v = (v == 0.0f) ? 0.0001f : v;
+        u[k] = v;
+        smask[k] = mkk;
+        par ^= (v > 0.0f) ? 1u : 0u;
+    }
+    // two smallest magnitudes, FIRST-index tie rule (torch.min on CPU)
+    float m1 = 3.0e38f, m2 = 3.0e38f;
+    int i1 = -1, i2 = -1;
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        float av = fabsf(u[k]);
+        av = (av > 0.0f) ? av : 10000.0f;
+        if (av < m1) { m2 = m1; i2 = i1; m1 = av; i1 = k; }
+        else if (av < m2) { m2 = av; i2 = k; }
+    }
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        const float others_min = (k == i1) ? m2 : m1;
+        const bool from_cap = !(others_min < 10000.0f);
+        const float mag = fminf(others_min, 10000.0f);
+        const float sgn = (par ^ ((u[k] > 0.0f) ? 1u : 0u)) ? 1.0f : -1.0f;
+        const float2 wb = c_wb[c.wb_base + eix[k]];
+        float coef, dmag, gwv;
+        if constexpr (MODE == 0) {
+            const float pre = addf(mulf(mag, wb.x), wb.y);
+            coef = (pre > 0.0f) ? dc[k] * sgn : 0.0f;
+            gwv = coef * mag;
+            dmag = coef * wb.x;
+            __stcg(c.scr + (G::E + eix[k]) * kThreads, coef);
+        } else {
+            const float madj = (mag > 0.0001f) ? mag : addf(mag, -0.0001f);
+            const float o = mulf(madj, sgn);
+            const float ao = fabsf(o);
+            const float so = (o > 0.0f) ? 1.0f : ((o < 0.0f) ? -1.0f : 0.0f);
+            const float pre = mulf(ao, wb.x);
+            const float m0 = fmaxf(pre, 0.0f);
+            float pm;
+            if constexpr (MODE == 2) pm = (m0 <= 7.5f) ? 1.0f : 0.0f;
+            else pm = (m0 >= c.lo && m0 <= c.hi) ? 1.0f : 0.0f;
+            coef = (pre > 0.0f) ? dc[k] * so * pm : 0.0f;
+            gwv = coef * ao;
+            dmag = coef * wb.x * so * sgn;
+        }
+        __stcg(c.scr + eix[k] * kThreads, gwv);
+        if (!from_cap) {
+            if (k == i1) s2 += dmag; else s1 += dmag;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        float du = (k == i1) ? s1 : ((k == i2) ? s2 : 0.0f);
+        const float su = (u[k] > 0.0f) ? 1.0f : ((u[k] < 0.0f) ? -1.0f : 0.0f);
+        du = du * su * smask[k];
+        if (col1[k] < 0) c.rot[shf[k]][rows[k] * Z] = du;           // dv2c_t, variable-lane domain
+        else if constexpr (kVn) c.dxr[rows[k] < 0 ? -rows[k] - 1 : 0] = du;   // (register-resident: G::kDeg1Smem == 0)
+    }
+}
+
+template <class G, int MODE, bool kVn, int kThreads>
+struct CnBwd {
+    BwdLane<G> &c;
+    template <class... Es>
+    __device__ __forceinline__ void chk() {
+        cn_check_bwd_core<G, MODE, kVn, kThreads, Es...>(c);
+    }
+};
+
+// VN-weight chain per block: dx = chain_{t+1} + sum_e dv2c_t[e];  dz = dx * [|xin_{t-1} * w| <= 7.5] (QMS);
+// grad_wVN[t][j] += dz * xin_{t-1};  chain_t = dz * w   (BoostedNeuralLDPCDecoder.py:325-337)
+template <class G, int MODE, int kThreads>
+struct VnChainStep {
+    BwdLane<G> &c;
+    float *chain;             // [N] per-thread
+    const float *dx_blocks;   // [N] per-thread: sums for blocks of degree >= 2
+    const float *xprev;       // &hist_xin[t][b][0]
+    const float *vw;          // w_VN[t]
+    template <int J, int DEST>
+    __device__ __forceinline__ void put() {
+        float dx = chain[J] + (DEST < 0 ? c.dxr[DEST < 0 ? -DEST - 1 : 0] : dx_blocks[J]);
+        const float xp = c.valid ? __ldg(xprev + J * G::Z + c.z) : 0.0f;
+        const float w = __ldg(vw + J);
+        if constexpr (MODE == 2) {
+            if (!(fabsf(mulf(xp, w)) <= 7.5f)) dx = 0.0f;
+        }
+        __stcg(c.scr + (G::E + J) * kThreads, dx * xp);     // Boosted rows: [E] CN weights, then [N] VN weights
+        chain[J] = dx * w;
+    }
+};
+
+template <class G>
+struct SpecBwdCfg {
+    using Fwd = SpecCfg<G, false>;
+    using Shape = typename Fwd::Shape;
+    static constexpr int kGroups = Fwd::kGroups;            // same CTA shape as the forward
+    static constexpr int kThreads = kGroups * Shape::kLanes;
+    static constexpr int kWarps = kThreads / 32;
+    static constexpr int kCwPerCta = kGroups * Shape::kCw;
+    static_assert(kThreads % 128 == 0 && kThreads <= kSpecBwdScratchLanes, "scratch rows are read back as float4 per lane");
+    static constexpr size_t slab_bytes() { return (size_t)kCwPerCta * G::kSlab * 4; }
+    __host__ __device__ static constexpr int rows(int mode, bool vn) { return mode == 0 ? 2 * G::E : G::E + (vn ? G::N : 0); }
+    // message slabs + per-CTA totals [T][rows]
+    static constexpr size_t smem_bytes(int T, int mode, bool vn) { return slab_bytes() + (size_t)T * rows(mode, vn) * 4 + 64; }
+};
+
+template <class G, int MODE, bool kVn>
+__global__ void __launch_bounds__(SpecBwdCfg<G>::kThreads, 1) nldpc_spec_backward_kernel(const BwdArgs a, const int wb_off) {
+    using Cfg = SpecBwdCfg<G>;
+    using Shape = typename Cfg::Shape;
+    constexpr int Z = G::Z, NZ = G::N * G::Z, E = G::E, N = G::N;
+    constexpr int kThreads = Cfg::kThreads, kRows = Cfg::rows(MODE, kVn), kPer = kThreads / 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *slabs = reinterpret_cast<float *>(smem_raw);
+    float *tot = slabs + (size_t)Cfg::kCwPerCta * G::kSlab;        // [T][kRows]
+
+    const int tid = threadIdx.x, warp = tid >> 5, ln = tid & 31;
+    const int grp = tid / Shape::kLanes, gl = tid - grp * Shape::kLanes;
+    const int cwl = gl / Z, z = gl - cwl * Z;
+    const int cw_in_cta = grp * Shape::kCw + cwl;
+    float *slab = slabs + (size_t)cw_in_cta * G::kSlab;
+    float *scr_cta = a.scratch + (size_t)blockIdx.x * kRows * kThreads;
+
+    BwdLane<G> c;
+    c.lane = slab + z;
+    c.z = z;
+    c.lo = a.lo;
+    c.hi = a.hi;
+    c.scr = scr_cta + tid;
+#pragma unroll
+    for (int s = 0; s < Z; s++) c.rot[s] = slab + ((z + s) % Z);
+
+    for (int i = tid; i < a.T * kRows; i += kThreads) tot[i] = 0.0f;
+
+    const int n_tiles = (a.B + Cfg::kCwPerCta - 1) / Cfg::kCwPerCta;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int b = tile * Cfg::kCwPerCta + cw_in_cta;
+        c.valid = b < a.B;
+        const size_t bb = (size_t)(c.valid ? b : 0);
+        for (int q = G::kXRows; q < G::kXRows + G::S; q++) c.lane[q * Z] = 0.0f;      // dv2c_T = 0 (own lane)
+        float chain[kVn ? N : 1], dxb[kVn ? N : 1];
+        if constexpr (kVn) {
+#pragma unroll
+            for (int j = 0; j < N; j++) chain[j] = 0.0f;
+        }
+        __syncthreads();
+        for (int t = a.T - 1; t >= 0; t--) {
+            c.hv = a.hist_v2c + (((size_t)t * a.B + bb) * G::S) * Z;
+            c.gt = a.gout + ((size_t)t * a.B + bb) * NZ;
+            c.mk = (MODE != 0) ? a.hist_mask + ((size_t)t * a.B + bb) * NZ : nullptr;
+            c.xin = (MODE == 0) ? a.xa + bb * NZ : a.hist_xin + ((size_t)(t + 1) * a.B + bb) * NZ;
+            c.wb_base = wb_off + t * E;
+            {
+                VnBwd<G> f{c};
+                G::vcols(f);
+            }
+            __syncthreads();     // (also: the previous iteration's scratch rows have been folded by every warp)
+            {
+                CnBwd<G, MODE, kVn, kThreads> f{c};
+                G::checks(f);
+            }
+            __syncthreads();
+            if constexpr (kVn) {
+                VnChainSum<G> s{c, dxb};
+                G::vcols(s);
+                VnChainStep<G, MODE, kThreads> st{c, chain, dxb, a.hist_xin + ((size_t)t * a.B + bb) * NZ, a.vn_w + (size_t)t * N};
+                G::blocks(st);
+                __syncthreads();
+            }
+            // fold this iteration's scratch rows (written by this CTA only, read back through L2) into the per-CTA totals;
+            // row r always belongs to warp r % kWarps, lane 0 -> plain read-modify-write
+            for (int r = warp; r < kRows; r += Cfg::kWarps) {
+                const float4 *p = reinterpret_cast<const float4 *>(scr_cta + (size_t)r * kThreads + ln * kPer);
+                float s = 0.0f;
+#pragma unroll
+                for (int q = 0; q < kPer / 4; q++) {
+                    const float4 v = __ldcg(p + q);
+                    s += (v.x + v.y) + (v.z + v.w);
+                }
+                s = bwd_warp_sum(s);
+                if (ln == 0) tot[(size_t)t * kRows + r] += s;
+            }
+        }
+    }
+    __syncthreads();
+    // one global atomic per (t, row) per CTA
+    for (int i = tid; i < a.T * kRows; i += kThreads) {
+        const int t = i / kRows, r = i - t * kRows;
+        const float v = tot[i];
+        if (v == 0.0f) continue;
+        if (r < E) atomicAdd(a.gw + (size_t)t * E + r, v);
+        else if (MODE == 0) atomicAdd(a.gb + (size_t)t * E + (r - E), v);
+        else atomicAdd(a.gvn + (size_t)t * N + (r - E), v);
+    }
+}
+
+namespace {
+
+template <class G, int MODE, bool kVn>
+int spec_bwd_launch_one(const BwdArgs &a, int wb_off, int sm_count, cudaStream_t st) {
+    using Cfg = SpecBwdCfg<G>;
+    const size_t smem = Cfg::smem_bytes(a.T, MODE, kVn);
+    static bool prepared = false;    // per translation unit and variant; the attribute is idempotent
+    if (!prepared) {
+        cudaError_t e = set_smem(nldpc_spec_backward_kernel<G, MODE, kVn>, kSmemBudget);
+        if (e != cudaSuccess) return (int)e;
+        prepared = true;
+    }
+    const int n_tiles = (a.B + Cfg::kCwPerCta - 1) / Cfg::kCwPerCta;
+    const int grid = std::min(n_tiles, sm_count);
+    nldpc_spec_backward_kernel<G, MODE, kVn><<<grid, Cfg::kThreads, smem, st>>>(a, wb_off);
+    return (int)cudaGetLastError();
+}
+
+// 0 launched, >0 cudaError_t, -1 not covered (caller uses the table-driven kernel).
+// kBoosted selects which kernels this translation unit instantiates: every kernel must live in exactly ONE unit, because
+// it reads that unit's constant arena (a second instantiation elsewhere would be folded with this one by the linker and
+// read the other unit's, never written, arena).
+template <class G, bool kBoosted>
+int spec_bwd_launch(const BwdArgs &a, int sm_count, cudaStream_t st) {
+    if (G::kDeg1Smem != 0) return -1;                         // the lane-private chain assumes identity circulants on degree-1 blocks
+    if (!a.scratch || kBoosted != (a.mode != 0)) return -1;
+    if (a.mode != 0 && (a.ucn_mix || a.hist_ucn)) return -1;
+    if (a.mode == 2 && a.qbit != 5) return -1;
+    if (a.mode != 0 && !a.w) return -1;                       // no CN weights: nothing but VN rows to learn; keep it simple
+    using Cfg = SpecBwdCfg<G>;
+    if (Cfg::smem_bytes(a.T, a.mode, a.gvn != nullptr) > (size_t)kSmemBudget) return -1;
+    ConstArena &arena = arena_for_current_device();
+    const int len = a.T * G::E;
+    cudaError_t err;
+    const int off = arena.acquire(len, st, &err);
+    if (err != cudaSuccess) return (int)err;
+    if (off < 0) return -1;
+    pack_wb_kernel<<<(len + 255) / 256, 256, 0, st>>>(a.w, a.mode == 0 ? a.b : nullptr, arena.base + off, len);
+    int rc;
+    if constexpr (!kBoosted) {
+        rc = spec_bwd_launch_one<G, 0, false>(a, off, sm_count, st);
+    } else {
+        if (a.mode == 1) rc = a.gvn ? spec_bwd_launch_one<G, 1, true>(a, off, sm_count, st) : spec_bwd_launch_one<G, 1, false>(a, off, sm_count, st);
+        else rc = a.gvn ? spec_bwd_launch_one<G, 2, true>(a, off, sm_count, st) : spec_bwd_launch_one<G, 2, false>(a, off, sm_count, st);
+    }
+    const cudaError_t rel = arena.release_after(off, len, st);
+    if (rc != 0) return rc;
+    return (int)rel;
+}
+
+}  // namespace
+}  // namespace nldpc
