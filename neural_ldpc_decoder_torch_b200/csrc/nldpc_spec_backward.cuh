@@ -42,20 +42,34 @@ struct BwdLane {
     bool valid;
     float dxr[G::kXRegs > 0 ? G::kXRegs : 1];      // d xa_input of the register-resident degree-1 blocks (this iteration)
 
-    __device__ __forceinline__ float g_at(int q) const {     // upstream gradient through the output clamp mask
-        if (!valid) return 0.0f;
+    // upstream gradient through the output clamp mask.  Loads are unconditional (rows of codeword 0 stand in for the
+    // padding lanes of the last tile) so that they stay branch-free and can be hoisted; the select zeroes padding lanes.
+    __device__ __forceinline__ float g_at(int q) const {
         const float gv = __ldg(gt + q);
-        return (mk && !mk[q]) ? 0.0f : gv;
+        bool keep = valid;
+        if (mk) keep = keep && (__ldg(mk + q) != 0);
+        return keep ? gv : 0.0f;
     }
 };
 
-// VN phase backwards: dc2v[e] = G[j] + (sum of the block's dv2c_{t+1} - own)
+// VN phase backwards: dc2v[e] = G[j] + (sum of the block's dv2c_{t+1} - own).  The upstream gradients of all blocks are
+// fetched first (independent loads in flight together), then the lane-private row updates run.
+template <class G>
+struct VnBwdLoad {
+    BwdLane<G> &c;
+    float *g;                 // [N] per-thread (only the blocks of degree >= 2 are touched)
+    template <int J, int XROW, int... R>
+    __device__ __forceinline__ void col() {
+        g[J] = c.g_at(J * G::Z + c.z);
+    }
+};
 template <class G>
 struct VnBwd {
     BwdLane<G> &c;
+    const float *g;
     template <int J, int XROW, int... R>
     __device__ __forceinline__ void col() {
-        const float gj = c.g_at(J * G::Z + c.z);
+        const float gj = g[J];
         float tot = 0.0f;
         ((tot += c.lane[R * G::Z]), ...);
         ((c.lane[R * G::Z] = gj + (tot - c.lane[R * G::Z])), ...);
@@ -75,8 +89,31 @@ struct VnChainSum {
     }
 };
 
+// operands of one check: the forward's CN inputs (dumped v2c, or the channel-input state for degree-1 blocks) and, for
+// degree-1 blocks, the upstream gradient of the block (their dc2v)
+template <class G, class... Es>
+__device__ __forceinline__ void cn_check_bwd_load(const BwdLane<G> &c, float *pv, float *pg) {
+    constexpr int D = sizeof...(Es);
+    constexpr int rows[D] = {Es::row...};
+    constexpr int shf[D] = {Es::shift...};
+    constexpr int col1[D] = {Es::col1...};
+    constexpr int Z = G::Z;
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        const int zz = (int)(c.rot[shf[k]] - (c.lane - c.z));
+        float v = 0.0f;
+        if (col1[k] < 0) {                                       // stored edge: message row
+            v = __ldg(c.hv + (rows[k] - G::kXRows) * Z + zz);
+        } else {                                                 // degree-1 block: channel input, upstream gradient
+            v = __ldg(c.xin + col1[k] * Z + zz);
+            pg[k] = c.g_at(col1[k] * Z + zz);
+        }
+        pv[k] = v;     // (padding lanes carry codeword 0's values: harmless, every gradient they meet is zero)
+    }
+}
+
 template <class G, int MODE, bool kVn, int kThreads, class... Es>
-__device__ __forceinline__ void cn_check_bwd_core(BwdLane<G> &c) {
+__device__ __forceinline__ void cn_check_bwd_core(BwdLane<G> &c, const float *pv, const float *pg) {
     constexpr int D = sizeof...(Es);
     constexpr int rows[D] = {Es::row...};
     constexpr int shf[D] = {Es::shift...};
@@ -87,15 +124,9 @@ __device__ __forceinline__ void cn_check_bwd_core(BwdLane<G> &c) {
     unsigned par = 0;
 #pragma unroll
     for (int k = 0; k < D; k++) {
-        const int zz = (int)(c.rot[shf[k]] - (c.lane - c.z));
-        float v = 0.0f;
-        if (col1[k] < 0) {                                       // stored edge: message row
-            if (c.valid) v = __ldg(c.hv + (rows[k] - G::kXRows) * Z + zz);
-            dc[k] = c.rot[shf[k]][rows[k] * Z];
-        } else {                                                 // degree-1 block: channel input, upstream gradient
-            if (c.valid) v = __ldg(c.xin + col1[k] * Z + zz);
-            dc[k] = c.g_at(col1[k] * Z + zz);
-        }
+        float v = pv[k];
+        if (col1[k] < 0) dc[k] = c.rot[shf[k]][rows[k] * Z];
+        else dc[k] = pg[k];
         float mkk = 1.0f;
         if constexpr (MODE == 2) {
             mkk = (fabsf(v) <= 7.5f) ? 1.0f : 0.0f;
@@ -166,33 +197,63 @@ __device__ __forceinline__ void cn_check_bwd_core(BwdLane<G> &c) {
 template <class G, int MODE, bool kVn, int kThreads>
 struct CnBwd {
     BwdLane<G> &c;
-    template <class... Es>
+    float pv[2][G::kMaxRowDeg], pg[2][G::kMaxRowDeg];     // operand slots (G::checks_pipelined)
+    template <int SLOT, class... Es>
+    __device__ __forceinline__ void ld() {
+        cn_check_bwd_load<G, Es...>(c, pv[SLOT], pg[SLOT]);
+    }
+    template <int SLOT, class... Es>
     __device__ __forceinline__ void chk() {
-        cn_check_bwd_core<G, MODE, kVn, kThreads, Es...>(c);
+        cn_check_bwd_core<G, MODE, kVn, kThreads, Es...>(c, pv[SLOT], pg[SLOT]);
     }
 };
 
 // VN-weight chain per block: dx = chain_{t+1} + sum_e dv2c_t[e];  dz = dx * [|xin_{t-1} * w| <= 7.5] (QMS);
 // grad_wVN[t][j] += dz * xin_{t-1};  chain_t = dz * w   (BoostedNeuralLDPCDecoder.py:325-337)
-template <class G, int MODE, int kThreads>
+// Runs in batches of kChainBatch blocks: a batch's channel-input loads are issued together, then consumed.
+constexpr int kChainBatch = 13;
+template <class G, int BATCH>
+struct VnChainLoad {
+    BwdLane<G> &c;
+    const float *xprev;       // &hist_xin[t][b][0]
+    float *xp;                // [kChainBatch]
+    template <int J, int DEST>
+    __device__ __forceinline__ void put() {
+        if constexpr (J / kChainBatch == BATCH) xp[J % kChainBatch] = __ldg(xprev + J * G::Z + c.z);
+    }
+};
+template <class G, int MODE, int kThreads, int BATCH>
 struct VnChainStep {
     BwdLane<G> &c;
     float *chain;             // [N] per-thread
     const float *dx_blocks;   // [N] per-thread: sums for blocks of degree >= 2
-    const float *xprev;       // &hist_xin[t][b][0]
+    const float *xpb;         // [kChainBatch]
     const float *vw;          // w_VN[t]
     template <int J, int DEST>
     __device__ __forceinline__ void put() {
-        float dx = chain[J] + (DEST < 0 ? c.dxr[DEST < 0 ? -DEST - 1 : 0] : dx_blocks[J]);
-        const float xp = c.valid ? __ldg(xprev + J * G::Z + c.z) : 0.0f;
-        const float w = __ldg(vw + J);
-        if constexpr (MODE == 2) {
-            if (!(fabsf(mulf(xp, w)) <= 7.5f)) dx = 0.0f;
+        if constexpr (J / kChainBatch == BATCH) {
+            float dx = chain[J] + (DEST < 0 ? c.dxr[DEST < 0 ? -DEST - 1 : 0] : dx_blocks[J]);
+            const float xp = xpb[J % kChainBatch];
+            const float w = __ldg(vw + J);
+            if constexpr (MODE == 2) {
+                if (!(fabsf(mulf(xp, w)) <= 7.5f)) dx = 0.0f;
+            }
+            __stcg(c.scr + (G::E + J) * kThreads, dx * xp);     // Boosted rows: [E] CN weights, then [N] VN weights
+            chain[J] = dx * w;
         }
-        __stcg(c.scr + (G::E + J) * kThreads, dx * xp);     // Boosted rows: [E] CN weights, then [N] VN weights
-        chain[J] = dx * w;
     }
 };
+template <class G, int MODE, int kThreads, int BATCH>
+__device__ __forceinline__ void vn_chain_batches(BwdLane<G> &c, float *chain, const float *dxb, const float *xprev, const float *vw) {
+    if constexpr (BATCH * kChainBatch < G::N) {
+        float xp[kChainBatch];
+        VnChainLoad<G, BATCH> l{c, xprev, xp};
+        G::blocks(l);
+        VnChainStep<G, MODE, kThreads, BATCH> st{c, chain, dxb, xp, vw};
+        G::blocks(st);
+        vn_chain_batches<G, MODE, kThreads, BATCH + 1>(c, chain, dxb, xprev, vw);
+    }
+}
 
 template <class G>
 struct SpecBwdCfg {
@@ -256,20 +317,22 @@ __global__ void __launch_bounds__(SpecBwdCfg<G>::kThreads, 1) nldpc_spec_backwar
             c.xin = (MODE == 0) ? a.xa + bb * NZ : a.hist_xin + ((size_t)(t + 1) * a.B + bb) * NZ;
             c.wb_base = wb_off + t * E;
             {
-                VnBwd<G> f{c};
+                float g[N];
+                VnBwdLoad<G> l{c, g};
+                G::vcols(l);
+                VnBwd<G> f{c, g};
                 G::vcols(f);
             }
             __syncthreads();     // (also: the previous iteration's scratch rows have been folded by every warp)
             {
                 CnBwd<G, MODE, kVn, kThreads> f{c};
-                G::checks(f);
+                G::checks_pipelined(f);
             }
             __syncthreads();
             if constexpr (kVn) {
                 VnChainSum<G> s{c, dxb};
                 G::vcols(s);
-                VnChainStep<G, MODE, kThreads> st{c, chain, dxb, a.hist_xin + ((size_t)t * a.B + bb) * NZ, a.vn_w + (size_t)t * N};
-                G::blocks(st);
+                vn_chain_batches<G, MODE, kThreads, 0>(c, chain, dxb, a.hist_xin + ((size_t)t * a.B + bb) * NZ, a.vn_w + (size_t)t * N);
                 __syncthreads();
             }
             // fold this iteration's scratch rows (written by this CTA only, read back through L2) into the per-CTA totals;
