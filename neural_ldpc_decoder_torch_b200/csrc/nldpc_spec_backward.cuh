@@ -26,8 +26,9 @@ __device__ __forceinline__ float bwd_warp_sum(float v) {
     return v;
 }
 
-template <class G>
+template <class G, int MODE>
 struct BwdLane {
+    static constexpr bool kMask = MODE != 0;     // Boosted: the output clamp mask gates the upstream gradient
     static constexpr int Z = G::Z;
     float *lane;              // &slab[z]
     float *rot[Z];            // &slab[(z + s) mod Z]
@@ -47,25 +48,25 @@ struct BwdLane {
     __device__ __forceinline__ float g_at(int q) const {
         const float gv = __ldg(gt + q);
         bool keep = valid;
-        if (mk) keep = keep && (__ldg(mk + q) != 0);
+        if constexpr (kMask) keep = keep && (__ldg(mk + q) != 0);
         return keep ? gv : 0.0f;
     }
 };
 
 // VN phase backwards: dc2v[e] = G[j] + (sum of the block's dv2c_{t+1} - own).  The upstream gradients of all blocks are
 // fetched first (independent loads in flight together), then the lane-private row updates run.
-template <class G>
+template <class G, int MODE>
 struct VnBwdLoad {
-    BwdLane<G> &c;
+    BwdLane<G, MODE> &c;
     float *g;                 // [N] per-thread (only the blocks of degree >= 2 are touched)
     template <int J, int XROW, int... R>
     __device__ __forceinline__ void col() {
         g[J] = c.g_at(J * G::Z + c.z);
     }
 };
-template <class G>
+template <class G, int MODE>
 struct VnBwd {
-    BwdLane<G> &c;
+    BwdLane<G, MODE> &c;
     const float *g;
     template <int J, int XROW, int... R>
     __device__ __forceinline__ void col() {
@@ -77,9 +78,9 @@ struct VnBwd {
 };
 
 // sum of the block's dv2c_t (after the CN phase) -> d xa_input contribution of the blocks of degree >= 2
-template <class G>
+template <class G, int MODE>
 struct VnChainSum {
-    BwdLane<G> &c;
+    BwdLane<G, MODE> &c;
     float *dx;                // [N] per-thread, indexed by block
     template <int J, int XROW, int... R>
     __device__ __forceinline__ void col() {
@@ -91,8 +92,8 @@ struct VnChainSum {
 
 // operands of one check: the forward's CN inputs (dumped v2c, or the channel-input state for degree-1 blocks) and, for
 // degree-1 blocks, the upstream gradient of the block (their dc2v)
-template <class G, class... Es>
-__device__ __forceinline__ void cn_check_bwd_load(const BwdLane<G> &c, float *pv, float *pg) {
+template <class G, int MODE, class... Es>
+__device__ __forceinline__ void cn_check_bwd_load(const BwdLane<G, MODE> &c, float *pv, float *pg) {
     constexpr int D = sizeof...(Es);
     constexpr int rows[D] = {Es::row...};
     constexpr int shf[D] = {Es::shift...};
@@ -112,83 +113,101 @@ __device__ __forceinline__ void cn_check_bwd_load(const BwdLane<G> &c, float *pv
     }
 }
 
+// One check, backwards.  Forward recap (per edge k): mag_k = min(min_{j != k} |u_j|, 10000) (zeros masked to 10000),
+// sign_k negative iff an even number of the OTHER inputs is positive, out_k = sign_k * relu(mag_k * w + b) (Neural) or
+// the conditioned Boosted form.  mag_k takes only two values per check (m1 for k != i1, m2 for k == i1), so everything
+// that depends on it alone is computed once per variant; signs are carried as XOR masks on the raw words.
 template <class G, int MODE, bool kVn, int kThreads, class... Es>
-__device__ __forceinline__ void cn_check_bwd_core(BwdLane<G> &c, const float *pv, const float *pg) {
+__device__ __forceinline__ void cn_check_bwd_core(BwdLane<G, MODE> &c, const float *pv, const float *pg) {
     constexpr int D = sizeof...(Es);
     constexpr int rows[D] = {Es::row...};
     constexpr int shf[D] = {Es::shift...};
     constexpr int eix[D] = {Es::e...};
     constexpr int col1[D] = {Es::col1...};
     constexpr int Z = G::Z;
-    float u[D], dc[D], smask[D];
-    unsigned par = 0;
+    constexpr uint32_t kSign = 0x80000000u;
+    float u[D], av[D], dc[D];
+    uint32_t sb[D];           // sign word of u_k ("not positive" <=> bit 31 set; a Neural zero counts as not positive)
+    bool pass[D];             // the input conditioning (clamp / quantiser window) lets the gradient through
+    uint32_t xall = ((D - 1) & 1) ? 0u : kSign;
+    float m1 = 3.0e38f, m2 = 3.0e38f;
 #pragma unroll
     for (int k = 0; k < D; k++) {
         float v = pv[k];
         if (col1[k] < 0) dc[k] = c.rot[shf[k]][rows[k] * Z];
         else dc[k] = pg[k];
-        float mkk = 1.0f;
         if constexpr (MODE == 2) {
-            mkk = (fabsf(v) <= 7.5f) ? 1.0f : 0.0f;
+            pass[k] = fabsf(v) <= 7.5f;
             v = quant5(v);
         } else if constexpr (MODE == 1) {
-            mkk = (v >= c.lo && v <= c.hi) ? 1.0f : 0.0f;
+            pass[k] = (v >= c.lo && v <= c.hi);
             v = clamp_rng(v, c.lo, c.hi);
+        } else {
+            pass[k] = true;
         }
         if constexpr (MODE != 0) v = (v == 0.0f) ? 0.0001f : v;
         u[k] = v;
-        smask[k] = mkk;
-        par ^= (v > 0.0f) ? 1u : 0u;
+        float a = fabsf(v);
+        if constexpr (MODE == 0) {
+            sb[k] = (v == 0.0f) ? kSign : __float_as_uint(v);
+            a = (a > 0.0f) ? a : 10000.0f;
+        } else {
+            sb[k] = __float_as_uint(v);
+        }
+        av[k] = a;
+        xall ^= sb[k];
+        m2 = fminf(m2, fmaxf(m1, a));       // two smallest magnitudes (m2 == m1 when the minimum occurs twice)
+        m1 = fminf(m1, a);
     }
-    // two smallest magnitudes, FIRST-index tie rule (torch.min on CPU)
-    float m1 = 3.0e38f, m2 = 3.0e38f;
-    int i1 = -1, i2 = -1;
+    // FIRST-index tie rule of torch.min on CPU: i1 = first k attaining m1, i2 = first k != i1 attaining m2
+    int i1 = 0, i2 = 0;
 #pragma unroll
-    for (int k = 0; k < D; k++) {
-        float av = fabsf(u[k]);
-        av = (av > 0.0f) ? av : 10000.0f;
-        if (av < m1) { m2 = m1; i2 = i1; m1 = av; i1 = k; }
-        else if (av < m2) { m2 = av; i2 = k; }
+    for (int k = D - 1; k >= 0; k--) i1 = (av[k] == m1) ? k : i1;
+#pragma unroll
+    for (int k = D - 1; k >= 0; k--) i2 = (av[k] == m2 && k != i1) ? k : i2;
+    // the two variants of everything that depends on the others' minimum alone
+    const bool capA = !(m1 < 10000.0f), capB = !(m2 < 10000.0f);
+    float madjA = fminf(m1, 10000.0f), madjB = fminf(m2, 10000.0f);
+    if constexpr (MODE != 0) {
+        madjA = (madjA > 0.0001f) ? madjA : addf(madjA, -0.0001f);
+        madjB = (madjB > 0.0001f) ? madjB : addf(madjB, -0.0001f);
     }
     float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
     for (int k = 0; k < D; k++) {
-        const float others_min = (k == i1) ? m2 : m1;
-        const bool from_cap = !(others_min < 10000.0f);
-        const float mag = fminf(others_min, 10000.0f);
-        const float sgn = (par ^ ((u[k] > 0.0f) ? 1u : 0u)) ? 1.0f : -1.0f;
+        const bool first = (k == i1);
+        const float msel = first ? madjB : madjA;
+        const uint32_t smask = (xall ^ sb[k]) & kSign;                  // bit 31 set <=> sign_k negative
         const float2 wb = c_wb[c.wb_base + eix[k]];
-        float coef, dmag, gwv;
+        float dm;
         if constexpr (MODE == 0) {
-            const float pre = addf(mulf(mag, wb.x), wb.y);
-            coef = (pre > 0.0f) ? dc[k] * sgn : 0.0f;
-            gwv = coef * mag;
-            dmag = coef * wb.x;
+            const float pre = addf(mulf(msel, wb.x), wb.y);
+            const float base = (pre > 0.0f) ? dc[k] : 0.0f;
+            const float coef = __uint_as_float(__float_as_uint(base) ^ smask);      // dc * sign_k
+            __stcg(c.scr + eix[k] * kThreads, coef * msel);
             __stcg(c.scr + (G::E + eix[k]) * kThreads, coef);
+            dm = coef * wb.x;
         } else {
-            const float madj = (mag > 0.0001f) ? mag : addf(mag, -0.0001f);
-            const float o = mulf(madj, sgn);
-            const float ao = fabsf(o);
-            const float so = (o > 0.0f) ? 1.0f : ((o < 0.0f) ? -1.0f : 0.0f);
-            const float pre = mulf(ao, wb.x);
-            const float m0 = fmaxf(pre, 0.0f);
-            float pm;
-            if constexpr (MODE == 2) pm = (m0 <= 7.5f) ? 1.0f : 0.0f;
-            else pm = (m0 >= c.lo && m0 <= c.hi) ? 1.0f : 0.0f;
-            coef = (pre > 0.0f) ? dc[k] * so * pm : 0.0f;
-            gwv = coef * ao;
-            dmag = coef * wb.x * so * sgn;
+            const float o = __uint_as_float(__float_as_uint(msel) ^ smask);         // madj * sign_k
+            const float pre = mulf(fabsf(o), wb.x);
+            bool live = pre > 0.0f;
+            if constexpr (MODE == 2) live = live && (pre <= 7.5f);
+            else live = live && (pre >= c.lo && pre <= c.hi);
+            const float base = live ? dc[k] : 0.0f;
+            __stcg(c.scr + eix[k] * kThreads, base * o);                            // dc * sign(o) * |o|
+            dm = __uint_as_float(__float_as_uint(base * wb.x) ^ smask);             // d out / d madj = w * sign_k
         }
-        __stcg(c.scr + eix[k] * kThreads, gwv);
-        if (!from_cap) {
-            if (k == i1) s2 += dmag; else s1 += dmag;
-        }
+        if (first) s2 += dm;
+        else s1 += dm;
     }
+    s1 = capA ? 0.0f : s1;      // a capped / all-masked minimum is a constant
+    s2 = capB ? 0.0f : s2;
 #pragma unroll
     for (int k = 0; k < D; k++) {
         float du = (k == i1) ? s1 : ((k == i2) ? s2 : 0.0f);
-        const float su = (u[k] > 0.0f) ? 1.0f : ((u[k] < 0.0f) ? -1.0f : 0.0f);
-        du = du * su * smask[k];
+        du = __uint_as_float(__float_as_uint(du) ^ (__float_as_uint(u[k]) & kSign));    // * sign(u_k)
+        if constexpr (MODE == 0) du = (u[k] == 0.0f) ? 0.0f : du;
+        du = pass[k] ? du : 0.0f;
         if (col1[k] < 0) c.rot[shf[k]][rows[k] * Z] = du;           // dv2c_t, variable-lane domain
         else if constexpr (kVn) c.dxr[rows[k] < 0 ? -rows[k] - 1 : 0] = du;   // (register-resident: G::kDeg1Smem == 0)
     }
@@ -196,11 +215,11 @@ __device__ __forceinline__ void cn_check_bwd_core(BwdLane<G> &c, const float *pv
 
 template <class G, int MODE, bool kVn, int kThreads>
 struct CnBwd {
-    BwdLane<G> &c;
+    BwdLane<G, MODE> &c;
     float pv[2][G::kMaxRowDeg], pg[2][G::kMaxRowDeg];     // operand slots (G::checks_pipelined)
     template <int SLOT, class... Es>
     __device__ __forceinline__ void ld() {
-        cn_check_bwd_load<G, Es...>(c, pv[SLOT], pg[SLOT]);
+        cn_check_bwd_load<G, MODE, Es...>(c, pv[SLOT], pg[SLOT]);
     }
     template <int SLOT, class... Es>
     __device__ __forceinline__ void chk() {
@@ -212,9 +231,9 @@ struct CnBwd {
 // grad_wVN[t][j] += dz * xin_{t-1};  chain_t = dz * w   (BoostedNeuralLDPCDecoder.py:325-337)
 // Runs in batches of kChainBatch blocks: a batch's channel-input loads are issued together, then consumed.
 constexpr int kChainBatch = 13;
-template <class G, int BATCH>
+template <class G, int MODE, int BATCH>
 struct VnChainLoad {
-    BwdLane<G> &c;
+    BwdLane<G, MODE> &c;
     const float *xprev;       // &hist_xin[t][b][0]
     float *xp;                // [kChainBatch]
     template <int J, int DEST>
@@ -224,7 +243,7 @@ struct VnChainLoad {
 };
 template <class G, int MODE, int kThreads, int BATCH>
 struct VnChainStep {
-    BwdLane<G> &c;
+    BwdLane<G, MODE> &c;
     float *chain;             // [N] per-thread
     const float *dx_blocks;   // [N] per-thread: sums for blocks of degree >= 2
     const float *xpb;         // [kChainBatch]
@@ -244,10 +263,10 @@ struct VnChainStep {
     }
 };
 template <class G, int MODE, int kThreads, int BATCH>
-__device__ __forceinline__ void vn_chain_batches(BwdLane<G> &c, float *chain, const float *dxb, const float *xprev, const float *vw) {
+__device__ __forceinline__ void vn_chain_batches(BwdLane<G, MODE> &c, float *chain, const float *dxb, const float *xprev, const float *vw) {
     if constexpr (BATCH * kChainBatch < G::N) {
         float xp[kChainBatch];
-        VnChainLoad<G, BATCH> l{c, xprev, xp};
+        VnChainLoad<G, MODE, BATCH> l{c, xprev, xp};
         G::blocks(l);
         VnChainStep<G, MODE, kThreads, BATCH> st{c, chain, dxb, xp, vw};
         G::blocks(st);
@@ -287,7 +306,7 @@ __global__ void __launch_bounds__(SpecBwdCfg<G>::kThreads, 1) nldpc_spec_backwar
     float *slab = slabs + (size_t)cw_in_cta * G::kSlab;
     float *scr_cta = a.scratch + (size_t)blockIdx.x * kRows * kThreads;
 
-    BwdLane<G> c;
+    BwdLane<G, MODE> c;
     c.lane = slab + z;
     c.z = z;
     c.lo = a.lo;
@@ -318,9 +337,9 @@ __global__ void __launch_bounds__(SpecBwdCfg<G>::kThreads, 1) nldpc_spec_backwar
             c.wb_base = wb_off + t * E;
             {
                 float g[N];
-                VnBwdLoad<G> l{c, g};
+                VnBwdLoad<G, MODE> l{c, g};
                 G::vcols(l);
-                VnBwd<G> f{c, g};
+                VnBwd<G, MODE> f{c, g};
                 G::vcols(f);
             }
             __syncthreads();     // (also: the previous iteration's scratch rows have been folded by every warp)
@@ -330,7 +349,7 @@ __global__ void __launch_bounds__(SpecBwdCfg<G>::kThreads, 1) nldpc_spec_backwar
             }
             __syncthreads();
             if constexpr (kVn) {
-                VnChainSum<G> s{c, dxb};
+                VnChainSum<G, MODE> s{c, dxb};
                 G::vcols(s);
                 vn_chain_batches<G, MODE, kThreads, 0>(c, chain, dxb, a.hist_xin + ((size_t)t * a.B + bb) * NZ, a.vn_w + (size_t)t * N);
                 __syncthreads();
