@@ -86,3 +86,67 @@ def test_fused_multi_iter_bce_matches_torch():
     crit.fused = True
     loose = [base[t].clone() for t in range(T)]
     assert abs(crit(loose, y, coeff_param=list(range(T))).item() - plain.item()) < 2e-6 * abs(plain.item())
+
+
+def _grads(model_fn, x, y, T, generic):
+    """gradients of one multi-iteration BCE step; `generic` forces the table-driven kernels (NLDPC_FORCE_GENERIC)"""
+    import os
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.LDPCDecoderLoss import LDPCDecoderLoss
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.LossType import LossType
+    os.environ["NLDPC_FORCE_GENERIC"] = "1" if generic else "0"
+    try:
+        m = model_fn()
+        outs = m(x) if not hasattr(m, "fold_weights") else m(x, target_iter=list(range(T)))
+        loss = LDPCDecoderLoss(LossType.BCE, etha=1.0)(outs, y, coeff_param=list(range(T)))
+        loss.backward()
+        torch.cuda.synchronize()
+        return {n: p.grad.detach().cpu().numpy().copy() for n, p in m.named_parameters() if p.grad is not None}
+    finally:
+        os.environ["NLDPC_FORCE_GENERIC"] = "0"
+
+
+@pytest.mark.parametrize("code,B", [("nr_bg2_set0", 148 * 16 * 2 + 5), ("wimax_n576_r34", 37), ("nr_bg2_set0", 1)])
+@pytest.mark.parametrize("kind", ["neural", "ms_cn", "qms_cn_vn", "qms_cn2_vn2"])
+def test_specialised_backward_equals_table_driven(code, B, kind):
+    """the graph-as-immediates backward sweep (nldpc_spec_backward.cuh) against the table-driven kernel on ragged batches:
+    last tile partly empty, several tiles per CTA, a single codeword"""
+    from neural_ldpc_decoder_torch_b200 import TannerGraph, load_basegraph
+    from neural_ldpc_decoder_torch_b200.training import DeviceBatchGenerator
+    bg, Z = load_basegraph(code)
+    graph = TannerGraph(bg, Z)
+    dev = torch.device("cuda")
+    T = 4
+    qbit = 5 if kind.startswith("qms") else None
+    x, y = DeviceBatchGenerator(graph, [1.0, 2.0, 3.0], dev, seed=7, qms_qbit=qbit)(B)
+    gen = torch.Generator().manual_seed(3)
+
+    if kind == "neural":
+        from test_neural_gpu import make_model
+        w = (0.3 + torch.rand((T, graph.E), generator=gen)).numpy()
+        b = (0.2 * torch.randn((T, graph.E), generator=gen)).numpy()
+        model_fn = lambda: make_model(bg, Z, T, B, w, b)   # noqa: E731
+    else:
+        from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder import ConnectingMatrix, ConnectingMatrixTorch
+        from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.BoostedNeuralLDPCDecoder import BoostedNeuralLDPCDecoder
+        from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.DecoderType import DecoderType
+        from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.NodeWeightSharingConfig import NodeWeightSharingConfig
+        sharing = {"ms_cn": (1, 0, 0), "qms_cn_vn": (3, 0, 3), "qms_cn2_vn2": (2, 0, 2)}[kind]
+        dec = DecoderType.MS if kind == "ms_cn" else DecoderType.QMS
+        vals = {}
+
+        def model_fn():
+            cm = ConnectingMatrixTorch(ConnectingMatrix(Z=Z, basegraph=bg), device=dev)
+            m = BoostedNeuralLDPCDecoder(T, B, cm, node_weight_sharing_config=NodeWeightSharingConfig(*sharing), decoding_type=dec).to(dev)
+            with torch.no_grad():
+                for n, p in m.named_parameters():
+                    if n not in vals:
+                        vals[n] = 0.6 + 0.6 * torch.rand(p.shape, generator=gen)
+                    p.copy_(vals[n].to(dev))
+            return m
+
+    spec = _grads(model_fn, x, y, T, generic=False)
+    tabl = _grads(model_fn, x, y, T, generic=True)
+    assert spec.keys() == tabl.keys() and len(spec) > 0
+    for n in spec:
+        scale = max(float(np.abs(tabl[n]).max()), 1e-12)
+        assert float(np.abs(spec[n] - tabl[n]).max()) <= 3e-5 * scale, (n, spec[n].reshape(-1)[:4], tabl[n].reshape(-1)[:4])

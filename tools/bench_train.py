@@ -74,7 +74,7 @@ def main():
         print(json.dumps({"metric": "train_step_codewords_per_s", "value": B * world * args.steps / (ms * 1e-3), "unit": "codewords/s",
                           "n_gpus": world, "steps": args.steps, "ms_per_step": ms / args.steps, "batch_per_gpu": B, "iterations": T,
                           "config": "BoostedNeuralLDPCDecoder BG2 z16 QMS5 cn3/vn3, BCE etha=1, clip 1.0, Adam 1e-3, clamp [0,2]",
-                          "first_loss": float(losses[0]), "last_loss": float(losses[-1])}))
+                          "first_loss": float(losses[0].detach()), "last_loss": float(losses[-1].detach())}))
     if world > 1:
         dist.destroy_process_group()
 
