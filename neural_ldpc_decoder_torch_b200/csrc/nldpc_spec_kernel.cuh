@@ -64,6 +64,14 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
 // (other q-bit grids, SP and the UCN indicator run on the table-driven kernel)
 __device__ __forceinline__ float clamp_rng(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 __device__ __forceinline__ float quant5(float x) { return clamp_rng(mulf(rintf(mulf(x, 2.0f)), 0.5f), -7.5f, 7.5f); }   // (:190-191)
+// The same value on the full-rate FADD pipe: clamp first (identical result: rint(2x)/2 is monotone and fixes +-7.5), then
+// round to the 0.5 grid by adding and subtracting 1.5 * 2^22, whose ulp is 0.5 and whose mantissa is even in that unit, so
+// the sum rounds half-to-even exactly like rint(2x).  Differs from quant5 only in the SIGN of a zero result (always +0.0
+// here, -0.0 from rint for -0.25 <= x < 0): used where the value is next compared, min-ed or added to a +0-started sum.
+__device__ __forceinline__ float quant5_grid(float x) {
+    constexpr float kMagic = 6291456.0f;
+    return addf(addf(clamp_rng(x, -7.5f, 7.5f), kMagic), -kMagic);
+}
 template <int MODE>
 __device__ __forceinline__ float condition(float x, float lo, float hi) {        // QMS: quantise, MS: clamp (:386-389, :507-510)
     if constexpr (MODE == 2) return quant5(x);
@@ -372,8 +380,15 @@ __device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c) {
 #pragma unroll
     for (int k = 0; k < D; k++) {
         raw[k] = rows[k] >= 0 ? c.rot[shf[k]][rows[k] * G::Z] : c.xreg[rows[k] < 0 ? -rows[k] - 1 : 0];   // gather (:380-384)
-        const float v = condition<MODE>(raw[k], c.lo, c.hi);
-        u[k] = (v == 0.0f) ? 0.0001f : v;                                // x + 1e-4 * [x == 0] (:391-393)
+        if constexpr (MODE == 2) {
+            // QMS q=5: every non-zero input is a multiple of 0.5, so the reference's zero handling — 0 -> +1e-4 (:391-393),
+            // then mag - 1e-4 where mag <= 1e-4 (:416), i.e. 1e-4 - 1e-4 = 0 — is "a zero counts as positive and as
+            // magnitude 0": quant5_grid yields +0.0 for every zero, so neither step needs an instruction.
+            u[k] = quant5_grid(raw[k]);
+        } else {
+            const float v = condition<MODE>(raw[k], c.lo, c.hi);
+            u[k] = (v == 0.0f) ? 0.0001f : v;                            // x + 1e-4 * [x == 0] (:391-393)
+        }
     }
     constexpr int H = (D + 1) / 2;
     float se[H + 1];
@@ -399,14 +414,27 @@ __device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c) {
             pe = fmin3(pe, fabsf(u[k - 1]), fabsf(u[k]));
         }
         if (col1[k] >= 0 && !kEmit) continue;
-        const float madj = (mag > 0.0001f) ? mag : addf(mag, -0.0001f);   // (:416)
         const float wk = c_wb[c.wb_base + eix[k]].x;
-        float m = fmaxf(mulf(fabsf(madj), wk), 0.0f);                     // |o| * W, ReLU (:431-505)
-        m = condition<MODE>(m, c.lo, c.hi);                               // (:507-510)
-        // sign(o) = sign(madj) * sgn;  sgn is negative iff the number of positive OTHER inputs is even (:417-423)
-        const unsigned sb = (x ^ __float_as_uint(u[k]) ^ __float_as_uint(madj)) & 0x80000000u;
-        float c2v = __uint_as_float(__float_as_uint(m) | sb);
-        c2v = (madj == 0.0f) ? 0.0f : c2v;                                // m * sign(0) (:512)
+        float c2v;
+        if constexpr (MODE == 2) {
+            // madj == mag >= 0 (see above); m >= 0 so only the upper clamp of the quantiser can bind
+            float m = fmaxf(mulf(mag, wk), 0.0f);                             // |o| * W, ReLU (:431-505)
+            constexpr float kMagic = 6291456.0f;
+            m = addf(addf(fminf(m, 7.5f), kMagic), -kMagic);                  // quantise (:507-510)
+            const unsigned sb = (x ^ __float_as_uint(u[k])) & 0x80000000u;    // negative iff #positive others is even (:417-423)
+            c2v = __uint_as_float(__float_as_uint(m) | sb);
+            // m * sign(o) with sign(0) = 0 (:512): mag == 0 gives +0.0, not -0.0.  A -0.0 message is absorbed by the
+            // +0-started sums that consume it, so only iterations whose messages are exported (self.llr) pay for it.
+            if constexpr (kEmit) c2v = (mag == 0.0f) ? 0.0f : c2v;
+        } else {
+            const float madj = (mag > 0.0001f) ? mag : addf(mag, -0.0001f);   // (:416)
+            float m = fmaxf(mulf(fabsf(madj), wk), 0.0f);                     // |o| * W, ReLU (:431-505)
+            m = condition<MODE>(m, c.lo, c.hi);                               // (:507-510)
+            // sign(o) = sign(madj) * sgn;  sgn is negative iff the number of positive OTHER inputs is even (:417-423)
+            const unsigned sb = (x ^ __float_as_uint(u[k]) ^ __float_as_uint(madj)) & 0x80000000u;
+            c2v = __uint_as_float(__float_as_uint(m) | sb);
+            c2v = (madj == 0.0f) ? 0.0f : c2v;                                // m * sign(0) (:512)
+        }
         if constexpr (kEmit) {
             if (c.llr_last) c.llr_last[(size_t)(c.rot[shf[k]] - (c.lane - c.z)) * G::E + eix[k]] = c2v;   // self.llr[T][b][z][e]
         }
