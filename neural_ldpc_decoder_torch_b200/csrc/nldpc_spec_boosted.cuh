@@ -2,6 +2,7 @@
 // Included by one translation unit per code so the 8 variants of each compile in parallel.
 #pragma once
 #include <algorithm>
+#include <type_traits>
 
 #include "nldpc_spec_host.cuh"
 
@@ -12,7 +13,7 @@ template <class G, int MODE, bool kXo>
 int boosted_prepare_one() {
     cudaError_t e;
     if ((e = set_smem(nldpc_spec_neural_kernel<G, true, true, MODE, kXo>, SpecCfg<G, kXo>::kSmemBytes)) != cudaSuccess) return (int)e;
-    if ((e = set_smem(nldpc_spec_neural_kernel<G, false, true, MODE, kXo>, SpecCfg<G, kXo>::kSmemBytes)) != cudaSuccess) return (int)e;
+    if ((e = set_smem(nldpc_spec_neural_kernel<G, false, true, MODE, kXo>, SpecCfg<G, false>::kSmemBytes)) != cudaSuccess) return (int)e;
     return 0;
 }
 
@@ -28,13 +29,17 @@ int boosted_prepare() {
 
 template <class G, int MODE, bool kXo>
 int boosted_launch_one(const DecodeArgs &args, int sm_count, cudaStream_t st) {
-    using Cfg = SpecCfg<G, kXo>;
-    const int n_units = (args.B + Cfg::Shape::kCw - 1) / Cfg::Shape::kCw;
-    const int ctas = (n_units + Cfg::kGroups - 1) / Cfg::kGroups;
-    const int grid = std::min(ctas, sm_count * Cfg::kCtasPerSm);
     const bool every = args.soft_mode == 1 || args.hard_mode == 1;
-    if (every) nldpc_spec_neural_kernel<G, true, true, MODE, kXo><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(args);
-    else nldpc_spec_neural_kernel<G, false, true, MODE, kXo><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(args);
+    auto launch = [&](auto every_tag) {
+        constexpr bool kEvery = decltype(every_tag)::value;
+        using Cfg = SpecCfg<G, kXo && kEvery>;       // list mode keeps xa_origin rows on chip, throughput mode re-reads it (xo_global)
+        const int n_units = (args.B + Cfg::Shape::kCw - 1) / Cfg::Shape::kCw;
+        const int ctas = (n_units + Cfg::kGroups - 1) / Cfg::kGroups;
+        const int grid = std::min(ctas, sm_count * Cfg::kCtasPerSm);
+        nldpc_spec_neural_kernel<G, kEvery, true, MODE, kXo><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(args);
+    };
+    if (every) launch(std::true_type{});
+    else launch(std::false_type{});
     return (int)cudaGetLastError();
 }
 

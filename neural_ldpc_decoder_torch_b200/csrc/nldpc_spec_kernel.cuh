@@ -86,6 +86,19 @@ __device__ __forceinline__ float boosted_out(L &c, int q, float xo, float tot) {
     return clamp_rng(sum, c.lo, c.hi);
 }
 
+// Where xa_origin lives when VN weights make the on-chip channel value (xa_input) drift away from it — the `kXo` parameter:
+//   0  no VN weights: xa_origin == xa_input, nothing extra;
+//   1  its own N shared rows per codeword (list mode: every iteration produces marginals, the rows are read T times);
+//   2  not kept at all (throughput mode: marginals only after the last iteration): the raw value is read again from global
+//      memory — an L2 hit, the codeword was bulk-loaded moments ago — and quantised if QMS (:517-518); the slab stays at
+//      its plain size, so the CTA keeps all its codewords (BG2: 8 groups instead of 7).
+template <int MODE, class L>
+__device__ __forceinline__ float xo_global(const L &c, int q) {
+    const float v = __ldg(c.xa_cw + q);
+    if constexpr (MODE == 2) return quant5(v);
+    else return v;
+}
+
 template <int Z>
 struct GroupShape {
     static constexpr int kLanes = (Z == 16 || Z == 32) ? 32 : (Z == 24 ? 96 : 0);
@@ -120,6 +133,7 @@ struct NeuralLane {
     float zmin;              // min |v2c| written by this lane in the current VN phase (0 => the zero-safe CN phase is needed)
     // Boosted decoder (MODE != 0)
     int xo_off;              // float offset from the xin rows to the xo rows (0: xa_origin and xa_input are the same rows)
+    const float *xa_cw;      // &xa[b][0] in global memory (kXo == 2)
     float lo, hi;            // allowed_llr_range
     float *llr_last;         // &llr_last[b][0][0] ([Z][E]) while the last iteration's CN phase runs, else nullptr
     uint8_t *mask;           // training dump: &hist_mask[t_emit][b][0] of the iteration being emitted, or nullptr
@@ -178,7 +192,7 @@ struct VnFirst {
 };
 
 // iterations >= 1: v2c[k] = x + (((0 + c[0]) + c[1]) + ... skipping k); kEmit: marginal of the previous iteration
-template <class G, bool kEmit, int MODE = 0, bool kXo = false>
+template <class G, bool kEmit, int MODE = 0, int kXo = 0>
 struct VnStep {
     NeuralLane<G> &c;
     template <int J, int XROW, int... R>
@@ -214,13 +228,13 @@ struct VnStep {
         }
         if constexpr (kEmit) {
             if constexpr (MODE == 0) c.template emit<J>(addf(x, p));       // out = xa + llr @ W_output (:94-96)
-            else c.template emit<J>(boosted_out(c, J * G::Z + c.z, kXo ? c.lane[c.xo_off + J * G::Z] : x, p));   // Boosted :520-521
+            else c.template emit<J>(boosted_out(c, J * G::Z + c.z, kXo == 2 ? xo_global<MODE>(c, J * G::Z + c.z) : (kXo == 1 ? c.lane[c.xo_off + J * G::Z] : x), p));   // Boosted :520-521
         }
     }
 };
 
 // marginal only (after the last CN phase)
-template <class G, int MODE = 0, bool kXo = false>
+template <class G, int MODE = 0, int kXo = 0>
 struct Marginal {
     NeuralLane<G> &c;
     template <int J, int XROW, int... R>
@@ -228,7 +242,7 @@ struct Marginal {
         float p = 0.0f;
         ((p = addf(p, c.lane[R * G::Z])), ...);
         if constexpr (MODE == 0) c.template emit<J>(addf(c.lane[XROW * G::Z], p));
-        else c.template emit<J>(boosted_out(c, J * G::Z + c.z, c.lane[(kXo ? c.xo_off + J * G::Z : XROW * G::Z)], p));
+        else c.template emit<J>(boosted_out(c, J * G::Z + c.z, kXo == 2 ? xo_global<MODE>(c, J * G::Z + c.z) : c.lane[(kXo == 1 ? c.xo_off + J * G::Z : XROW * G::Z)], p));
     }
 };
 
@@ -242,7 +256,7 @@ __device__ __forceinline__ float &xa_ref(NeuralLane<G> &c) {
 // after the bulk-TMA load: move this lane's raw channel LLRs from the staging area (message rows) to their places.
 // MODE 0 also screens for exact zeros; Boosted quantises xa_origin once if QMS (:517-518) and, with VN weights (kXo),
 // keeps it in its own rows while xa_input starts as the raw value.
-template <class G, int MODE, bool kXo>
+template <class G, int MODE, int kXo>
 struct PlaceXa {
     NeuralLane<G> &c;
     const float *stage;      // &staging[z]
@@ -255,8 +269,8 @@ struct PlaceXa {
             xa_ref<G, DEST>(c) = v;
         } else {
             const float xq = (MODE == 2) ? quant5(v) : v;
-            if constexpr (kXo) {
-                c.lane[c.xo_off + J * G::Z] = xq;
+            if constexpr (kXo != 0) {
+                if constexpr (kXo == 1) c.lane[c.xo_off + J * G::Z] = xq;
                 xa_ref<G, DEST>(c) = v;
             } else {
                 xa_ref<G, DEST>(c) = xq;
@@ -369,7 +383,7 @@ __device__ __forceinline__ void cn_check_core(NeuralLane<G> &c) {
 // Boosted MS / QMS check update, BoostedNeuralLDPCDecoder.py:380-526 (no UCN mixing): condition the inputs (quantise or
 // clamp), nudge exact zeros to +1e-4, min over the others, mag - 1e-4 [mag <= 1e-4], o = mag * sgn, |o| * W_cn, ReLU,
 // condition again, * sign(o) (sign(0) = 0).  kXo: xa_origin lives in its own rows (VN weights make xa_input drift).
-template <class G, bool kEmit, int MODE, bool kXo, class... Es>
+template <class G, bool kEmit, int MODE, int kXo, class... Es>
 __device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c) {
     constexpr int D = sizeof...(Es);
     constexpr int rows[D] = {Es::row...};
@@ -441,13 +455,14 @@ __device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c) {
         if (col1[k] < 0) {
             c.rot[shf[k]][rows[k] * G::Z] = c2v;
         } else if constexpr (kEmit) {
-            const float xo = kXo ? c.rot[shf[k]][c.xo_off + col1[k] * G::Z] : raw[k];
-            c.emit_rot(col1[k], shf[k], boosted_out(c, col1[k] * G::Z + (int)(c.rot[shf[k]] - (c.lane - c.z)), xo, addf(0.0f, c2v)));   // (:513-526)
+            const int q = col1[k] * G::Z + (int)(c.rot[shf[k]] - (c.lane - c.z));
+            const float xo = kXo == 2 ? xo_global<MODE>(c, q) : (kXo == 1 ? c.rot[shf[k]][c.xo_off + col1[k] * G::Z] : raw[k]);
+            c.emit_rot(col1[k], shf[k], boosted_out(c, q, xo, addf(0.0f, c2v)));   // (:513-526)
         }
     }
 }
 
-template <class G, bool kEmit, int MODE, bool kXo>
+template <class G, bool kEmit, int MODE, int kXo>
 struct CnBoosted {
     NeuralLane<G> &c;
     template <class... Es>
@@ -501,11 +516,11 @@ constexpr int slab_with_xo(int slab, int nz, int z) {
     return s;
 }
 
-template <class G, bool kXo = false>
+template <class G, bool kXoRows = false>
 struct SpecCfg {
     using Shape = GroupShape<G::Z>;
-    static constexpr int kSlabF = kXo ? slab_with_xo(G::kSlab, G::N * G::Z, G::Z) : G::kSlab;   // floats per codeword slab
-    static constexpr int kXoOff = kXo ? (G::kXRows + G::S) * G::Z : 0;   // N xo rows follow the message rows
+    static constexpr int kSlabF = kXoRows ? slab_with_xo(G::kSlab, G::N * G::Z, G::Z) : G::kSlab;   // floats per codeword slab
+    static constexpr int kXoOff = kXoRows ? (G::kXRows + G::S) * G::Z : 0;   // N xo rows follow the message rows
     static constexpr int kHardBytes = (G::N * G::Z + 7) / 8;
     static constexpr int kHardStride = (kHardBytes + 15) & ~15;           // per-codeword staging, 16 B multiple
     static constexpr int kPerCw = kSlabF * 4 + kHardStride;              // shared bytes per codeword
@@ -543,8 +558,9 @@ struct SpecCfg {
 // kEvery: outputs are produced after every iteration (drop-in list mode / per-iteration hard decisions);
 // otherwise only after the last one (throughput mode) and the loop body carries no output code at all.
 template <class G, bool kEvery, bool kConstW, int MODE = 0, bool kXo = false>
-__global__ void __launch_bounds__(SpecCfg<G, kXo>::kThreads, SpecCfg<G, kXo>::kCtasPerSm) nldpc_spec_neural_kernel(const DecodeArgs a) {
-    using Cfg = SpecCfg<G, kXo>;
+__global__ void __launch_bounds__(SpecCfg<G, kXo && kEvery>::kThreads, SpecCfg<G, kXo && kEvery>::kCtasPerSm) nldpc_spec_neural_kernel(const DecodeArgs a) {
+    using Cfg = SpecCfg<G, kXo && kEvery>;            // xa_origin rows only in list mode (see xo_global)
+    constexpr int kXoMode = !kXo ? 0 : (kEvery ? 1 : 2);
     static_assert(MODE == 0 || kConstW, "the Boosted variants read their weights from the constant arena");
     static_assert(MODE != 0 || !kXo, "xo rows only exist for the Boosted decoder with VN weights");
     using Shape = typename Cfg::Shape;
@@ -597,6 +613,7 @@ __global__ void __launch_bounds__(SpecCfg<G, kXo>::kThreads, SpecCfg<G, kXo>::kC
         const int b0 = unit * Shape::kCw;
         const int b = b0 + cwl;
         c.valid = b < a.B;
+        c.xa_cw = a.xa + (size_t)min(b, a.B - 1) * NZ;      // (padding lanes re-read the last codeword; their outputs are dropped)
         const int ncw = max(0, min(Shape::kCw, a.B - b0));
         // ---- bulk-TMA the group's channel LLRs (one 1-D copy per codeword) ----
         if (gl == 0 && ncw > 0) {
@@ -619,7 +636,7 @@ __global__ void __launch_bounds__(SpecCfg<G, kXo>::kThreads, SpecCfg<G, kXo>::kC
         // before iteration 0 overwrites the staging area.
         bool xa_zero = false;
         {
-            PlaceXa<G, MODE, kXo> pl{c, c.lane + G::kXRows * Z, 1.0f};
+            PlaceXa<G, MODE, kXoMode> pl{c, c.lane + G::kXRows * Z, 1.0f};
             G::blocks(pl);
             xa_zero = (pl.zm == 0.0f);
         }
@@ -636,7 +653,7 @@ __global__ void __launch_bounds__(SpecCfg<G, kXo>::kThreads, SpecCfg<G, kXo>::kC
             if constexpr (MODE == 0) {
                 cn_phase<G, kEmitNow, kConstW>(c, xa_zero, a.xa + (size_t)min(b, a.B - 1) * NZ + z);
             } else {
-                CnBoosted<G, kEmitNow, MODE, kXo> f{c};
+                CnBoosted<G, kEmitNow, MODE, kXoMode> f{c};
                 G::checks(f);
             }
         };
@@ -690,7 +707,7 @@ __global__ void __launch_bounds__(SpecCfg<G, kXo>::kThreads, SpecCfg<G, kXo>::kC
                     c.soft = (soft_all && soft_cw) ? soft_cw + (size_t)(t - 1) * soft_iter : nullptr;
                     c.hb = hard_all ? hb_cw : nullptr;
                     c.mask = (MODE != 0 && dump) ? a.hist_mask + ((size_t)(t - 1) * a.B + b) * NZ : nullptr;
-                    VnStep<G, true, MODE, kXo> f{c};
+                    VnStep<G, true, MODE, kXoMode> f{c};
                     G::vcols(f);
                     if (hard_all) flush_hard(t - 1);
                 }
@@ -717,7 +734,7 @@ __global__ void __launch_bounds__(SpecCfg<G, kXo>::kThreads, SpecCfg<G, kXo>::kC
                     VnFirst<G> f{c};
                     G::vcols(f);
                 } else {
-                    VnStep<G, false, MODE, kXo> f{c};
+                    VnStep<G, false, MODE, kXoMode> f{c};
                     G::vcols(f);
                 }
                 phase_sync();
@@ -737,7 +754,7 @@ __global__ void __launch_bounds__(SpecCfg<G, kXo>::kThreads, SpecCfg<G, kXo>::kC
             c.soft = soft_cw ? soft_cw + (soft_all ? (size_t)(a.T - 1) * soft_iter : 0) : nullptr;
             c.hb = hb_cw;
             c.mask = (MODE != 0 && kEvery && a.hist_mask && c.valid) ? a.hist_mask + ((size_t)(a.T - 1) * a.B + b) * NZ : nullptr;
-            Marginal<G, MODE, kXo> f{c};
+            Marginal<G, MODE, kXoMode> f{c};
             G::vcols(f);
             if (hard_any) flush_hard(a.T - 1);
         }
