@@ -143,6 +143,54 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def other_configs(dev, B, steps=20):
+    """the other BASELINE.json configs on one GPU, same batch, packed hard decisions after the last iteration (informational:
+    the headline stays configs[1]); inputs resident in HBM, CUDA-event timing"""
+    import torch
+    from neural_ldpc_decoder_torch_b200 import TannerGraph, load_basegraph
+    from neural_ldpc_decoder_torch_b200 import boosted_neural_ldpc_decoder as bn
+    from neural_ldpc_decoder_torch_b200 import neural_ldpc_decoder as nn_
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.BoostedNeuralLDPCDecoder import BoostedNeuralLDPCDecoder
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.DecoderType import DecoderType
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.NodeWeightSharingConfig import NodeWeightSharingConfig
+    from neural_ldpc_decoder_torch_b200.training import DeviceBatchGenerator
+    out = []
+
+    def measure(name, fn):
+        with torch.no_grad():
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out.append({"workload": name, "value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms})
+
+    try:
+        bg, Z = load_basegraph("wimax_n576_r34")
+        graph = TannerGraph(bg, Z)
+        x, _ = DeviceBatchGenerator(graph, [3.0], dev, all_zero=True)(B)
+        m = nn_.NeuralLDPCDecoder(10, B, nn_.ConnectingMatrixTorch(nn_.ConnectingMatrix(Z=Z, basegraph=bg), device=dev)).to(dev)
+        measure("NeuralLDPCDecoder WiMAX N=576 R=3/4 z=24, 10 iterations, batch %d (configs[0] shape at bench batch)" % B, lambda: m.decode_hard(x))
+        xq, _ = DeviceBatchGenerator(graph, [3.0], dev, all_zero=True, qms_qbit=5)(B)
+        cmb = bn.ConnectingMatrixTorch(bn.ConnectingMatrix(Z=Z, basegraph=bg), device=dev)
+        mb = BoostedNeuralLDPCDecoder(20, B, cmb, node_weight_sharing_config=NodeWeightSharingConfig(3, 0, 0), decoding_type=DecoderType.QMS).to(dev)
+        measure("BoostedNeuralLDPCDecoder WiMAX z=24, QMS q=5, cn=3, 20 iterations, batch %d (configs[2])" % B, lambda: mb.decode_hard(xq))
+        bg2, Z2 = load_basegraph(CODE)
+        g2 = TannerGraph(bg2, Z2)
+        x2, _ = DeviceBatchGenerator(g2, [3.0], dev, all_zero=True, qms_qbit=5)(B)
+        cm2 = bn.ConnectingMatrixTorch(bn.ConnectingMatrix(Z=Z2, basegraph=bg2), device=dev)
+        m2 = BoostedNeuralLDPCDecoder(20, B, cm2, node_weight_sharing_config=NodeWeightSharingConfig(3, 0, 3), decoding_type=DecoderType.QMS).to(dev)
+        measure("BoostedNeuralLDPCDecoder BG2 z=16, QMS q=5, cn=3 / vn=3, 20 iterations, batch %d (train config, decode only)" % B, lambda: m2.decode_hard(x2))
+    except Exception as exc:   # informational block: never take the headline line down with it
+        out.append({"error": repr(exc)})
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -296,6 +344,8 @@ def main():
                     "d2h_bytes_per_step": int(B * ((NZ + 7) // 8)), "steps": e2e_steps,
                     "api": "nldpc_neural_decode_host (NeuralLDPCDecoder.decode_host)"},
         }
+        if world == 1:
+            line["other_configs"] = other_configs(dev, B)
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample = cpu_port_throughput(bg, Z, T, w_np, b_np)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
