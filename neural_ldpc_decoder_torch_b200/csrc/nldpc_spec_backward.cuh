@@ -137,15 +137,18 @@ __device__ __forceinline__ void cn_check_bwd_core(BwdLane<G, MODE> &c, const flo
         if (col1[k] < 0) dc[k] = c.rot[shf[k]][rows[k] * Z];
         else dc[k] = pg[k];
         if constexpr (MODE == 2) {
+            // QMS q=5 as in the forward fast path (cn_check_boosted_core): grid rounding on the FADD pipe gives +0.0 for a
+            // zero, which stands for the reference's "+1e-4, then mag - 1e-4 = 0"; no gradient flows through it either
+            // way (relu'(0) = 0).
             pass[k] = fabsf(v) <= 7.5f;
-            v = quant5(v);
+            v = quant5_grid(v);
         } else if constexpr (MODE == 1) {
             pass[k] = (v >= c.lo && v <= c.hi);
             v = clamp_rng(v, c.lo, c.hi);
+            v = (v == 0.0f) ? 0.0001f : v;
         } else {
             pass[k] = true;
         }
-        if constexpr (MODE != 0) v = (v == 0.0f) ? 0.0001f : v;
         u[k] = v;
         float a = fabsf(v);
         if constexpr (MODE == 0) {
@@ -168,7 +171,7 @@ __device__ __forceinline__ void cn_check_bwd_core(BwdLane<G, MODE> &c, const flo
     // the two variants of everything that depends on the others' minimum alone
     const bool capA = !(m1 < 10000.0f), capB = !(m2 < 10000.0f);
     float madjA = fminf(m1, 10000.0f), madjB = fminf(m2, 10000.0f);
-    if constexpr (MODE != 0) {
+    if constexpr (MODE == 1) {
         madjA = (madjA > 0.0001f) ? madjA : addf(madjA, -0.0001f);
         madjB = (madjB > 0.0001f) ? madjB : addf(madjB, -0.0001f);
     }

@@ -49,6 +49,9 @@ int main() {
     cudaMalloc(&cyc, 148 * 8);
     for (int warps : {4, 8, 16}) {
         run<2048>(warps, out, cyc);
+        run<3072>(warps, out, cyc);
+        run<4096>(warps, out, cyc);
+        run<5120>(warps, out, cyc);
         run<6144>(warps, out, cyc);
         run<10240>(warps, out, cyc);
         run<16384>(warps, out, cyc);
