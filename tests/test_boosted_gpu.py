@@ -128,3 +128,32 @@ def test_boosted_stateless_decode_methods(graphs):
         assert np.array_equal(hall[t], np.packbits(d["out"][t] < 0, axis=1, bitorder="little"))
     assert np.array_equal(m.decode_soft_last(xa).cpu().numpy(), d["out"][-1])
     assert np.array_equal(m.decode_soft_last(xa, n_iters=5).cpu().numpy(), d["out"][4])
+
+
+@pytest.mark.parametrize("code,sharing,dec,B,T", [("bg2", (3, 0, 3), "QMS", 37, 20), ("wimax", (1, 0, 2), "QMS", 101, 12),
+                                                  ("bg2", (1, 0, 3), "MS", 33, 6), ("bg2", (3, 0, 0), "QMS", 2385, 5)])
+def test_boosted_throughput_mode_matches_oracle(code, sharing, dec, B, T, graphs):
+    """throughput mode (outputs only after the last iteration; with VN weights xa_origin is re-read from global memory,
+    exact zeros take the folded QMS zero handling) on ragged batches: packed decisions and last-iteration LLRs vs oracle"""
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder import ConnectingMatrix, ConnectingMatrixTorch, Functions
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.BoostedNeuralLDPCDecoder import BoostedNeuralLDPCDecoder
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.DecoderType import DecoderType
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.NodeWeightSharingConfig import NodeWeightSharingConfig
+    bg, Z = graphs[code]
+    rs = np.random.RandomState(B * 7 + T)
+    xa = awgn_llr(code, B, seed=B + 1, sigma=1.0)
+    xa[0, :2] = 0.0
+    xa[B - 1, 3] = 0.0
+    if dec == "QMS":
+        xa = Functions.Cal_MSA_Q(xa, 5).astype(np.float32)
+    cm = ConnectingMatrixTorch(ConnectingMatrix(Z=Z, basegraph=bg), device=torch.device("cuda"))
+    m = BoostedNeuralLDPCDecoder(T, 1, cm, node_weight_sharing_config=NodeWeightSharingConfig(*sharing), decoding_type=DecoderType[dec]).cuda()
+    with torch.no_grad():
+        for p in m.parameters():
+            p.copy_(torch.from_numpy(rs.uniform(0.4, 1.3, size=tuple(p.shape)).astype(np.float32)))
+    x = torch.from_numpy(xa).cuda()
+    hard = m.decode_hard(x).cpu().numpy()
+    soft = m.decode_soft_last(x).cpu().numpy()
+    ref = oracle_forward(m.cpu(), xa)
+    assert np.array_equal(soft, ref[-1]), np.abs(soft - ref[-1]).max()
+    assert np.array_equal(hard, np.packbits(ref[-1] < 0, axis=1, bitorder="little"))
