@@ -281,7 +281,11 @@ template <class G>
 struct SpecBwdCfg {
     using Fwd = SpecCfg<G, false>;
     using Shape = typename Fwd::Shape;
+#ifdef NLDPC_FORCE_GROUPS
+    static constexpr int kGroups = Shape::kLanes == 32 ? 8 : Fwd::kGroups;
+#else
     static constexpr int kGroups = Fwd::kGroups;            // same CTA shape as the forward
+#endif
     static constexpr int kThreads = kGroups * Shape::kLanes;
     static constexpr int kWarps = kThreads / 32;
     static constexpr int kCwPerCta = kGroups * Shape::kCw;
