@@ -8,25 +8,48 @@
 
 namespace nldpc {
 
+__device__ __forceinline__ float bce_term(float x, float yi, float c, float inv_n, float *g) {
+    const float e = __expf(-fabsf(x));
+    // binary_cross_entropy_with_logits: max(x,0) - x*y + log(1 + exp(-|x|))
+    const float l = fmaxf(x, 0.0f) - x * yi + log1pf(e);
+    const float r = __fdividef(1.0f, 1.0f + e);
+    const float s = (x >= 0.0f) ? r : e * r;                              // sigmoid(x)
+    *g = c * (s - yi) * inv_n;
+    return c * l;
+}
+
+// VEC = 4: 16-byte loads / stores (n % 4 == 0 and 16 B aligned bases), else scalar.  The per-thread partial sum is fp32 over
+// one element group (<= 4 T terms), then fp64 across groups.
+template <int VEC>
 __global__ void __launch_bounds__(256) multi_iter_bce_kernel(const float *__restrict__ soft, const float *__restrict__ y,
                                                              const float *__restrict__ coef, int T, size_t n, float inv_n,
                                                              float *__restrict__ loss, float *__restrict__ gout) {
     __shared__ double red[8];
     double acc = 0.0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float yi = __ldg(y + i);
-        for (int t = 0; t < T; t++) {
-            const float x = __ldcs(soft + (size_t)t * n + i);
-            const float c = __ldg(coef + t);
-            const float e = expf(-fabsf(x));
-            // binary_cross_entropy_with_logits: max(x,0) - x*y + log(1 + exp(-|x|))
-            const float l = fmaxf(x, 0.0f) - x * yi + log1pf(e);
-            acc += (double)(c * l);
-            if (gout) {
-                const float s = (x >= 0.0f) ? 1.0f / (1.0f + e) : e / (1.0f + e);      // sigmoid(x)
-                __stcs(gout + (size_t)t * n + i, c * (s - yi) * inv_n);
+    const size_t n_grp = n / VEC;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_grp; i += (size_t)gridDim.x * blockDim.x) {
+        float part = 0.0f;
+        if constexpr (VEC == 4) {
+            const float4 yi = __ldg(reinterpret_cast<const float4 *>(y) + i);
+            for (int t = 0; t < T; t++) {
+                const float4 x = __ldcs(reinterpret_cast<const float4 *>(soft + (size_t)t * n) + i);
+                const float c = __ldg(coef + t);
+                float4 g;
+                part += bce_term(x.x, yi.x, c, inv_n, &g.x);
+                part += bce_term(x.y, yi.y, c, inv_n, &g.y);
+                part += bce_term(x.z, yi.z, c, inv_n, &g.z);
+                part += bce_term(x.w, yi.w, c, inv_n, &g.w);
+                if (gout) __stcs(reinterpret_cast<float4 *>(gout + (size_t)t * n) + i, g);
+            }
+        } else {
+            const float yi = __ldg(y + i);
+            for (int t = 0; t < T; t++) {
+                float g;
+                part += bce_term(__ldcs(soft + (size_t)t * n + i), yi, __ldg(coef + t), inv_n, &g);
+                if (gout) __stcs(gout + (size_t)t * n + i, g);
             }
         }
+        acc += (double)part;
     }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -43,9 +66,11 @@ int launch_multi_iter_bce(const float *soft, const float *y, const float *coef, 
     cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), st);
     if (e != cudaSuccess) return (int)e;
     if (n == 0) return 0;
-    const size_t want = (n + 255) / 256;
+    const bool vec = (n % 4 == 0) && (((uintptr_t)soft | (uintptr_t)y | (uintptr_t)gout) % 16 == 0);
+    const size_t want = ((vec ? n / 4 : n) + 255) / 256;
     const int grid = (int)(want < (size_t)sm_count * 16 ? want : (size_t)sm_count * 16);
-    multi_iter_bce_kernel<<<grid, 256, 0, st>>>(soft, y, coef, T, n, (float)(1.0 / (double)n), loss, gout);
+    if (vec) multi_iter_bce_kernel<4><<<grid, 256, 0, st>>>(soft, y, coef, T, n, (float)(1.0 / (double)n), loss, gout);
+    else multi_iter_bce_kernel<1><<<grid, 256, 0, st>>>(soft, y, coef, T, n, (float)(1.0 / (double)n), loss, gout);
     return (int)cudaGetLastError();
 }
 
