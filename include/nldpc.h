@@ -154,6 +154,13 @@ int nldpc_boosted_backward(const nldpc_graph_t *g, const nldpc_boosted_cfg_t *cf
 int nldpc_multi_iter_bce(const float *soft_dev, const float *y_dev, const float *coef_dev, int T, size_t n_per_iter,
                          float *loss_dev, float *gout_dev, void *stream);
 
+/* Gradient of the same loss alone, with the upstream gradient folded in (what autograd's backward of
+ * LDPCDecoderLoss.forward produces, LDPCDecoderLoss.py:73-108):
+ *   gout_dev [T][n] = gscale * coef_t * (sigmoid(soft[t][i]) - y[i]) / n,  gscale_dev: 1 float on the device (dL/dloss) or NULL = 1.
+ * Lets the forward call above run without gout (reads only) and keeps no [T][n] tensor alive between forward and backward. */
+int nldpc_multi_iter_bce_grad(const float *soft_dev, const float *y_dev, const float *coef_dev, const float *gscale_dev, int T,
+                              size_t n_per_iter, float *gout_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

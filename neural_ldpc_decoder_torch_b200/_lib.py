@@ -75,6 +75,8 @@ def lib():
             L.nldpc_boosted_forward.argtypes = [vp, ctypes.POINTER(BoostedCfg), vp, vp, vp, vp, ci, ci, ci, vp, ci, vp, vp, vp]
             L.nldpc_multi_iter_bce.restype = ci
             L.nldpc_multi_iter_bce.argtypes = [vp, vp, vp, ci, ctypes.c_size_t, vp, vp, vp]
+            L.nldpc_multi_iter_bce_grad.restype = ci
+            L.nldpc_multi_iter_bce_grad.argtypes = [vp, vp, vp, vp, ci, ctypes.c_size_t, vp, vp]
             _lib = L
     return _lib
 

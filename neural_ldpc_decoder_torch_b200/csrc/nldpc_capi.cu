@@ -477,8 +477,8 @@ static int boosted_dispatch(const nldpc_graph *g, const DecodeArgs &a, cudaStrea
 }
 
 namespace nldpc {
-int launch_multi_iter_bce(const float *soft, const float *y, const float *coef, int T, size_t n, float *loss, float *gout, int sm_count,
-                          cudaStream_t st);
+int launch_multi_iter_bce(const float *soft, const float *y, const float *coef, const float *gscale, int T, size_t n, float *loss,
+                          float *gout, int sm_count, cudaStream_t st);
 }
 
 extern "C" int nldpc_multi_iter_bce(const float *soft_dev, const float *y_dev, const float *coef_dev, int T, size_t n_per_iter,
@@ -487,7 +487,18 @@ extern "C" int nldpc_multi_iter_bce(const float *soft_dev, const float *y_dev, c
     int dev = 0, sms = 148;
     CUDA_TRY(cudaGetDevice(&dev));
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int rc = launch_multi_iter_bce(soft_dev, y_dev, coef_dev, T, n_per_iter, loss_dev, gout_dev, sms, (cudaStream_t)stream);
+    const int rc = launch_multi_iter_bce(soft_dev, y_dev, coef_dev, nullptr, T, n_per_iter, loss_dev, gout_dev, sms, (cudaStream_t)stream);
     if (rc != 0) return fail(rc, std::string("nldpc_multi_iter_bce: ") + cudaGetErrorString((cudaError_t)rc));
+    return NLDPC_OK;
+}
+
+extern "C" int nldpc_multi_iter_bce_grad(const float *soft_dev, const float *y_dev, const float *coef_dev, const float *gscale_dev, int T,
+                                         size_t n_per_iter, float *gout_dev, void *stream) {
+    if (!soft_dev || !y_dev || !coef_dev || !gout_dev || T <= 0) return fail(NLDPC_E_INVALID, "nldpc_multi_iter_bce_grad: bad argument");
+    int dev = 0, sms = 148;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int rc = launch_multi_iter_bce(soft_dev, y_dev, coef_dev, gscale_dev, T, n_per_iter, nullptr, gout_dev, sms, (cudaStream_t)stream);
+    if (rc != 0) return fail(rc, std::string("nldpc_multi_iter_bce_grad: ") + cudaGetErrorString((cudaError_t)rc));
     return NLDPC_OK;
 }

@@ -22,10 +22,12 @@ __device__ __forceinline__ float bce_term(float x, float yi, float c, float inv_
 // one element group (<= 4 T terms), then fp64 across groups.
 template <int VEC>
 __global__ void __launch_bounds__(256) multi_iter_bce_kernel(const float *__restrict__ soft, const float *__restrict__ y,
-                                                             const float *__restrict__ coef, int T, size_t n, float inv_n,
-                                                             float *__restrict__ loss, float *__restrict__ gout) {
+                                                             const float *__restrict__ coef, const float *__restrict__ gscale, int T,
+                                                             size_t n, float inv_n_host, float *__restrict__ loss,
+                                                             float *__restrict__ gout) {
     __shared__ double red[8];
     double acc = 0.0;
+    const float inv_n = gscale ? inv_n_host * __ldg(gscale) : inv_n_host;      // upstream dL (a device scalar) folded into the gradient
     const size_t n_grp = n / VEC;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_grp; i += (size_t)gridDim.x * blockDim.x) {
         float part = 0.0f;
@@ -57,20 +59,22 @@ __global__ void __launch_bounds__(256) multi_iter_bce_kernel(const float *__rest
     if (threadIdx.x < 32) {
         double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
         for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (threadIdx.x == 0) atomicAdd(loss, (float)(v * (double)inv_n));
+        if (threadIdx.x == 0 && loss) atomicAdd(loss, (float)(v * (double)inv_n_host));
     }
 }
 
-int launch_multi_iter_bce(const float *soft, const float *y, const float *coef, int T, size_t n, float *loss, float *gout, int sm_count,
-                          cudaStream_t st) {
-    cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), st);
-    if (e != cudaSuccess) return (int)e;
+int launch_multi_iter_bce(const float *soft, const float *y, const float *coef, const float *gscale, int T, size_t n, float *loss,
+                          float *gout, int sm_count, cudaStream_t st) {
+    if (loss) {
+        cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), st);
+        if (e != cudaSuccess) return (int)e;
+    }
     if (n == 0) return 0;
     const bool vec = (n % 4 == 0) && (((uintptr_t)soft | (uintptr_t)y | (uintptr_t)gout) % 16 == 0);
     const size_t want = ((vec ? n / 4 : n) + 255) / 256;
     const int grid = (int)(want < (size_t)sm_count * 16 ? want : (size_t)sm_count * 16);
-    if (vec) multi_iter_bce_kernel<4><<<grid, 256, 0, st>>>(soft, y, coef, T, n, (float)(1.0 / (double)n), loss, gout);
-    else multi_iter_bce_kernel<1><<<grid, 256, 0, st>>>(soft, y, coef, T, n, (float)(1.0 / (double)n), loss, gout);
+    if (vec) multi_iter_bce_kernel<4><<<grid, 256, 0, st>>>(soft, y, coef, gscale, T, n, (float)(1.0 / (double)n), loss, gout);
+    else multi_iter_bce_kernel<1><<<grid, 256, 0, st>>>(soft, y, coef, gscale, T, n, (float)(1.0 / (double)n), loss, gout);
     return (int)cudaGetLastError();
 }
 

@@ -135,9 +135,12 @@ def _neural_train_setup_ctx(ctx, inputs, output):
     xa, w, b, graph_id = inputs
     ctx.save_for_backward(xa, w, b, output[1])
     ctx.graph_id = graph_id
+    ctx.set_materialize_grads(False)     # no zero tensor the size of the training dump for its (unused) gradient
 
 
 def _neural_train_bwd(ctx, gout, gws):
+    if gout is None:
+        return None, None, None, None
     xa, w, b, ws = ctx.saved_tensors
     gw, gb = torch.ops.nldpc.neural_backward(xa, w, b, gout.contiguous(), ctx.graph_id, ws)
     return None, gw, gb, None
@@ -299,9 +302,14 @@ def _boosted_setup_ctx(ctx, inputs, output):
     ctx.cfg = (graph_id, T, dec, qbit, lo, hi, compute_ucn, ucn_mix)
     ctx.stateful = llr_init is not None or xin_init is not None or app_init is not None
     ctx.soft_all = soft_mode == _lib.NLDPC_OUT_ALL
+    # autograd would otherwise hand the backward a ZERO tensor for every output without a gradient — including one the size
+    # of the training dump (20 GB at B = 65536, T = 20: 5 ms of fill per step)
+    ctx.set_materialize_grads(False)
 
 
 def _boosted_bwd(ctx, gsoft, gllr, gxin, ghard, gdump):
+    if gsoft is None:
+        return (None,) * 20
     xa, vn_w, cn_w, ucn_w, dump = ctx.saved_tensors
     graph_id, T, dec, qbit, lo, hi, compute_ucn, ucn_mix = ctx.cfg
     if not ctx.soft_all:
@@ -345,13 +353,41 @@ def _(soft, y, coef, want_grad):
     return soft.new_empty(()), (torch.empty_like(soft) if want_grad else soft.new_empty((0,)))
 
 
+@torch.library.custom_op("nldpc::multi_iter_bce_grad", mutates_args=())
+def multi_iter_bce_grad(soft: torch.Tensor, y: torch.Tensor, coef: torch.Tensor, gscale: torch.Tensor) -> torch.Tensor:
+    """dL/dsoft of multi_iter_bce with the upstream scalar gradient `gscale` (a device tensor) folded in: one pass, no
+    [T, ...] tensor kept between forward and backward"""
+    _check_cuda_f32("soft", soft)
+    _check_cuda_f32("y", y)
+    _check_cuda_f32("coef", coef)
+    _check_cuda_f32("gscale", gscale)
+    T, n = soft.shape[0], y.numel()
+    if soft.numel() != T * n or coef.numel() != T or gscale.numel() != 1:
+        raise ValueError("soft must be [T, *y.shape], coef [T], gscale a scalar")
+    soft, y, coef, gscale = soft.contiguous(), y.contiguous(), coef.contiguous(), gscale.contiguous()
+    gout = torch.empty_like(soft)
+    with torch.cuda.device(soft.device):
+        rc = _lib.lib().nldpc_multi_iter_bce_grad(_ptr(soft), _ptr(y), _ptr(coef), _ptr(gscale), T, n, _ptr(gout), _stream(soft))
+    _lib.check(rc, "nldpc_multi_iter_bce_grad")
+    return gout
+
+
+@multi_iter_bce_grad.register_fake
+def _(soft, y, coef, gscale):
+    return torch.empty_like(soft)
+
+
 def _bce_setup_ctx(ctx, inputs, output):
-    ctx.save_for_backward(output[1])
+    soft, y, coef, want_grad = inputs
+    ctx.save_for_backward(soft, y, coef)
+    ctx.set_materialize_grads(False)
 
 
 def _bce_bwd(ctx, gloss, ggout):
-    (gout,) = ctx.saved_tensors
-    return gout * gloss, None, None, None
+    if gloss is None:
+        return None, None, None, None
+    soft, y, coef = ctx.saved_tensors
+    return torch.ops.nldpc.multi_iter_bce_grad(soft, y, coef, gloss.to(torch.float32)), None, None, None
 
 
 multi_iter_bce.register_autograd(_bce_bwd, setup_context=_bce_setup_ctx)
@@ -378,5 +414,5 @@ def fused_multi_iter_bce(outputs, y, etha=1.0, coeff_param=None):
     w = [float(pow(etha, c)) for c in coeffs]
     tot = sum(w)
     coef = torch.tensor([v / tot if tot > 0 else v for v in w], dtype=torch.float32, device=base.device)
-    loss, _ = torch.ops.nldpc.multi_iter_bce(base, y.to(torch.float32), coef, base.requires_grad)
+    loss, _ = torch.ops.nldpc.multi_iter_bce(base, y.to(torch.float32), coef, False)    # the gradient is produced in backward
     return 1.0 * loss

@@ -82,6 +82,12 @@ def test_fused_multi_iter_bce_matches_torch():
     plain.backward()
     assert abs(fused.item() - plain.item()) < 2e-6 * abs(plain.item())
     assert float((gf - base.grad).abs().max()) < 1e-6 * float(base.grad.abs().max()) + 1e-12
+    # the upstream gradient (a device scalar) is folded into the gradient kernel: scaled loss
+    base.grad = None
+    crit.fused = True
+    (0.37 * crit(list(base.unbind(0)), y, coeff_param=list(range(T)))).backward()
+    assert float((base.grad - 0.37 * gf).abs().max()) < 1e-6 * float(gf.abs().max()) + 1e-12
+    base.grad = None
     # a list that is NOT a set of views of one tensor silently takes the per-iteration path
     crit.fused = True
     loose = [base[t].clone() for t in range(T)]
