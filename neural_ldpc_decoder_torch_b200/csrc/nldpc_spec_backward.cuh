@@ -90,26 +90,70 @@ struct VnChainSum {
     }
 };
 
+// ---- operand staging with cp.async ------------------------------------------------------------------------------------
+// ptxas, at 255 registers, sinks register-destination loads issued a check ahead back to 10-45 instructions before their
+// first use (measured in SASS), which leaves every check exposed to the full L2 / HBM latency.  An asynchronous
+// global -> shared copy has no register destination and cannot be sunk past its wait: each lane copies ITS OWN operands of
+// check i+1 into a private staging slot [stage][entry][thread] (conflict-free, no cross-lane synchronisation needed) while
+// check i computes, then waits for the group and reads them back with LDS.
+__device__ __forceinline__ void cp_async4(const float *dst_smem, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <class G>
+struct BwdStage {
+    static constexpr int kEnt = G::kMaxRowDeg + 2;     // per check: D operand values, then (gradient, mask word) of its degree-1 edge
+};
+
 // operands of one check: the forward's CN inputs (dumped v2c, or the channel-input state for degree-1 blocks) and, for
-// degree-1 blocks, the upstream gradient of the block (their dc2v)
-template <class G, int MODE, class... Es>
-__device__ __forceinline__ void cn_check_bwd_load(const BwdLane<G, MODE> &c, float *pv, float *pg) {
+// degree-1 blocks, the upstream gradient of the block (their dc2v) with its clamp-mask byte
+template <class G, int MODE, int kThreads, class... Es>
+__device__ __forceinline__ void cn_check_bwd_issue(const BwdLane<G, MODE> &c, const float *stg) {
     constexpr int D = sizeof...(Es);
     constexpr int rows[D] = {Es::row...};
     constexpr int shf[D] = {Es::shift...};
     constexpr int col1[D] = {Es::col1...};
     constexpr int Z = G::Z;
+    constexpr int n_deg1 = ((Es::col1 >= 0 ? 1 : 0) + ...);
+    static_assert(n_deg1 <= 1 && D <= G::kMaxRowDeg, "staging holds one degree-1 edge per check");
 #pragma unroll
     for (int k = 0; k < D; k++) {
         const int zz = (int)(c.rot[shf[k]] - (c.lane - c.z));
-        float v = 0.0f;
         if (col1[k] < 0) {                                       // stored edge: message row
-            v = __ldg(c.hv + (rows[k] - G::kXRows) * Z + zz);
-        } else {                                                 // degree-1 block: channel input, upstream gradient
-            v = __ldg(c.xin + col1[k] * Z + zz);
-            pg[k] = c.g_at(col1[k] * Z + zz);
+            cp_async4(stg + k * kThreads, c.hv + (rows[k] - G::kXRows) * Z + zz);
+        } else {                                                 // degree-1 block: channel input, upstream gradient (+ mask)
+            const int q = col1[k] * Z + zz;
+            cp_async4(stg + k * kThreads, c.xin + q);
+            cp_async4(stg + G::kMaxRowDeg * kThreads, c.gt + q);
+            if constexpr (MODE != 0) cp_async4(stg + (G::kMaxRowDeg + 1) * kThreads, c.mk + (q & ~3));
         }
-        pv[k] = v;     // (padding lanes carry codeword 0's values: harmless, every gradient they meet is zero)
+    }
+    cp_async_commit();
+}
+
+template <class G, int MODE, int kThreads, class... Es>
+__device__ __forceinline__ void cn_check_bwd_fetch(const BwdLane<G, MODE> &c, const float *stg, float *pv, float *pg) {
+    constexpr int D = sizeof...(Es);
+    constexpr int shf[D] = {Es::shift...};
+    constexpr int col1[D] = {Es::col1...};
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        pv[k] = stg[k * kThreads];     // (padding lanes carry codeword 0's values: harmless, every gradient they meet is zero)
+        if (col1[k] >= 0) {
+            const float gv = stg[G::kMaxRowDeg * kThreads];
+            bool keep = c.valid;
+            if constexpr (MODE != 0) {
+                const int zz = (int)(c.rot[shf[k]] - (c.lane - c.z));
+                const uint32_t w = __float_as_uint(stg[(G::kMaxRowDeg + 1) * kThreads]);
+                keep = keep && (((w >> (8 * ((col1[k] * G::Z + zz) & 3))) & 0xffu) != 0);
+            }
+            pg[k] = keep ? gv : 0.0f;
+        }
     }
 }
 
@@ -219,14 +263,21 @@ __device__ __forceinline__ void cn_check_bwd_core(BwdLane<G, MODE> &c, const flo
 template <class G, int MODE, bool kVn, int kThreads>
 struct CnBwd {
     BwdLane<G, MODE> &c;
-    float pv[2][G::kMaxRowDeg], pg[2][G::kMaxRowDeg];     // operand slots (G::checks_pipelined)
+    const float *stg;         // &stage[0][0][tid]
+    int n_ld = 0, n_chk = 0;  // (compile-time after inlining: the sequence is straight-line)
     template <int SLOT, class... Es>
     __device__ __forceinline__ void ld() {
-        cn_check_bwd_load<G, MODE, Es...>(c, pv[SLOT], pg[SLOT]);
+        cn_check_bwd_issue<G, MODE, kThreads, Es...>(c, stg + SLOT * BwdStage<G>::kEnt * kThreads);
+        n_ld++;
     }
     template <int SLOT, class... Es>
     __device__ __forceinline__ void chk() {
-        cn_check_bwd_core<G, MODE, kVn, kThreads, Es...>(c, pv[SLOT], pg[SLOT]);
+        if (n_ld - n_chk >= 2) cp_async_wait<1>();       // the next check's group may stay in flight
+        else cp_async_wait<0>();
+        n_chk++;
+        float pv[G::kMaxRowDeg], pg[G::kMaxRowDeg];
+        cn_check_bwd_fetch<G, MODE, kThreads, Es...>(c, stg + SLOT * BwdStage<G>::kEnt * kThreads, pv, pg);
+        cn_check_bwd_core<G, MODE, kVn, kThreads, Es...>(c, pv, pg);
     }
 };
 
@@ -292,8 +343,9 @@ struct SpecBwdCfg {
     static_assert(kThreads % 128 == 0 && kThreads <= kSpecBwdScratchLanes, "scratch rows are read back as float4 per lane");
     static constexpr size_t slab_bytes() { return (size_t)kCwPerCta * G::kSlab * 4; }
     __host__ __device__ static constexpr int rows(int mode, bool vn) { return mode == 0 ? 2 * G::E : G::E + (vn ? G::N : 0); }
-    // message slabs + per-CTA totals [T][rows]
-    static constexpr size_t smem_bytes(int T, int mode, bool vn) { return slab_bytes() + (size_t)T * rows(mode, vn) * 4 + 64; }
+    static constexpr size_t stage_bytes() { return (size_t)2 * BwdStage<G>::kEnt * kThreads * 4; }
+    // message slabs + operand staging (2 stages) + per-CTA totals [T][rows]
+    static constexpr size_t smem_bytes(int T, int mode, bool vn) { return slab_bytes() + stage_bytes() + (size_t)T * rows(mode, vn) * 4 + 64; }
 };
 
 template <class G, int MODE, bool kVn>
@@ -304,7 +356,8 @@ __global__ void __launch_bounds__(SpecBwdCfg<G>::kThreads, 1) nldpc_spec_backwar
     constexpr int kThreads = Cfg::kThreads, kRows = Cfg::rows(MODE, kVn), kPer = kThreads / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *slabs = reinterpret_cast<float *>(smem_raw);
-    float *tot = slabs + (size_t)Cfg::kCwPerCta * G::kSlab;        // [T][kRows]
+    float *stage = slabs + (size_t)Cfg::kCwPerCta * G::kSlab;      // [2][kEnt][kThreads]
+    float *tot = stage + 2 * BwdStage<G>::kEnt * kThreads;         // [T][kRows]
 
     const int tid = threadIdx.x, warp = tid >> 5, ln = tid & 31;
     const int grp = tid / Shape::kLanes, gl = tid - grp * Shape::kLanes;
@@ -351,7 +404,7 @@ __global__ void __launch_bounds__(SpecBwdCfg<G>::kThreads, 1) nldpc_spec_backwar
             }
             __syncthreads();     // (also: the previous iteration's scratch rows have been folded by every warp)
             {
-                CnBwd<G, MODE, kVn, kThreads> f{c};
+                CnBwd<G, MODE, kVn, kThreads> f{c, stage + tid};
                 G::checks_pipelined(f);
             }
             __syncthreads();
