@@ -110,8 +110,8 @@ int spec_backward_scratch_rows(int id) {
 int spec_launch_backward(int id, const BwdArgs &a, int sm_count, cudaStream_t st) {
     if (a.mode == 0) {
         switch (id) {
-            case 0: return spec_bwd_launch<gen::Bg2Z16, false>(a, sm_count, st);
-            case 1: return spec_bwd_launch<gen::WimaxZ24, false>(a, sm_count, st);
+            case 0: return spec_bwd_launch<gen::Bg2Z16, false>(a, 0, sm_count, st);
+            case 1: return spec_bwd_launch<gen::WimaxZ24, false>(a, 1, sm_count, st);
             default: return -1;
         }
     }

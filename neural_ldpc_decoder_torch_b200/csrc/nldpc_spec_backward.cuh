@@ -20,6 +20,10 @@
 
 namespace nldpc {
 
+// runtime descriptors of the looped checks (G::loop_desc()), per translation unit like c_wb; graph id * kDescStride is the base
+constexpr int kDescStride = 512;
+__constant__ uint32_t c_desc[2 * kDescStride];
+
 __device__ __forceinline__ float bwd_warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -38,6 +42,10 @@ struct BwdLane {
     const float *xin;         // CN inputs of the degree-1 blocks: &xa[b][0] (Neural) or &hist_xin[t+1][b][0]
     int wb_base;              // constant-arena offset of {w,b}[t][0]
     float *scr;               // &scratch[cta][0][tid]: this thread's slot of every scratch row
+    float *chn;               // &scratch[cta][E + N][tid]: VN-weight chain state of the looped degree-1 blocks (kVn), by register index
+    const float *xprev;       // &hist_xin[t][b][0] (kVn)
+    const float *vw;          // w_VN[t] (kVn)
+    bool last_iter;           // t == T - 1: the chain starts from zero
     float lo, hi;
     int z;
     bool valid;
@@ -157,20 +165,18 @@ __device__ __forceinline__ void cn_check_bwd_fetch(const BwdLane<G, MODE> &c, co
     }
 }
 
-// One check, backwards.  Forward recap (per edge k): mag_k = min(min_{j != k} |u_j|, 10000) (zeros masked to 10000),
-// sign_k negative iff an even number of the OTHER inputs is positive, out_k = sign_k * relu(mag_k * w + b) (Neural) or
-// the conditioned Boosted form.  mag_k takes only two values per check (m1 for k != i1, m2 for k == i1), so everything
-// that depends on it alone is computed once per variant; signs are carried as XOR masks on the raw words.
-template <class G, int MODE, bool kVn, int kThreads, class... Es>
-__device__ __forceinline__ void cn_check_bwd_core(BwdLane<G, MODE> &c, const float *pv, const float *pg) {
-    constexpr int D = sizeof...(Es);
-    constexpr int rows[D] = {Es::row...};
-    constexpr int shf[D] = {Es::shift...};
-    constexpr int eix[D] = {Es::e...};
-    constexpr int col1[D] = {Es::col1...};
-    constexpr int Z = G::Z;
+// One check, backwards — the arithmetic, independent of where operands come from.  Forward recap (per edge k):
+// mag_k = min(min_{j != k} |u_j|, 10000) (zeros masked to 10000), sign_k negative iff an even number of the OTHER inputs is
+// positive, out_k = sign_k * relu(mag_k * w + b) (Neural) or the conditioned Boosted form.  mag_k takes only two values per
+// check (m1 for k != i1, m2 for k == i1), so everything that depends on it alone is computed once per variant; signs are
+// carried as XOR masks on the raw words.
+//   in : pv[k] forward CN input (raw), dc[k] upstream gradient of the edge's c2v, wb[k] = {w, b}
+//   out: gw[k] (and gb[k], Neural) per-lane weight-gradient terms, du[k] gradient w.r.t. the raw CN input
+template <int MODE, int D>
+__device__ __forceinline__ void cn_bwd_math(const float *pv, const float *dc, const float2 *wb, float lo, float hi, float *gw, float *gb,
+                                            float *du) {
     constexpr uint32_t kSign = 0x80000000u;
-    float u[D], av[D], dc[D];
+    float u[D], av[D];
     uint32_t sb[D];           // sign word of u_k ("not positive" <=> bit 31 set; a Neural zero counts as not positive)
     bool pass[D];             // the input conditioning (clamp / quantiser window) lets the gradient through
     uint32_t xall = ((D - 1) & 1) ? 0u : kSign;
@@ -178,8 +184,6 @@ __device__ __forceinline__ void cn_check_bwd_core(BwdLane<G, MODE> &c, const flo
 #pragma unroll
     for (int k = 0; k < D; k++) {
         float v = pv[k];
-        if (col1[k] < 0) dc[k] = c.rot[shf[k]][rows[k] * Z];
-        else dc[k] = pg[k];
         if constexpr (MODE == 2) {
             // QMS q=5 as in the forward fast path (cn_check_boosted_core): grid rounding on the FADD pipe gives +0.0 for a
             // zero, which stands for the reference's "+1e-4, then mag - 1e-4 = 0"; no gradient flows through it either
@@ -187,8 +191,8 @@ __device__ __forceinline__ void cn_check_bwd_core(BwdLane<G, MODE> &c, const flo
             pass[k] = fabsf(v) <= 7.5f;
             v = quant5_grid(v);
         } else if constexpr (MODE == 1) {
-            pass[k] = (v >= c.lo && v <= c.hi);
-            v = clamp_rng(v, c.lo, c.hi);
+            pass[k] = (v >= lo && v <= hi);
+            v = clamp_rng(v, lo, hi);
             v = (v == 0.0f) ? 0.0001f : v;
         } else {
             pass[k] = true;
@@ -225,24 +229,23 @@ __device__ __forceinline__ void cn_check_bwd_core(BwdLane<G, MODE> &c, const flo
         const bool first = (k == i1);
         const float msel = first ? madjB : madjA;
         const uint32_t smask = (xall ^ sb[k]) & kSign;                  // bit 31 set <=> sign_k negative
-        const float2 wb = c_wb[c.wb_base + eix[k]];
         float dm;
         if constexpr (MODE == 0) {
-            const float pre = addf(mulf(msel, wb.x), wb.y);
+            const float pre = addf(mulf(msel, wb[k].x), wb[k].y);
             const float base = (pre > 0.0f) ? dc[k] : 0.0f;
             const float coef = __uint_as_float(__float_as_uint(base) ^ smask);      // dc * sign_k
-            __stcg(c.scr + eix[k] * kThreads, coef * msel);
-            __stcg(c.scr + (G::E + eix[k]) * kThreads, coef);
-            dm = coef * wb.x;
+            gw[k] = coef * msel;
+            gb[k] = coef;
+            dm = coef * wb[k].x;
         } else {
             const float o = __uint_as_float(__float_as_uint(msel) ^ smask);         // madj * sign_k
-            const float pre = mulf(fabsf(o), wb.x);
+            const float pre = mulf(fabsf(o), wb[k].x);
             bool live = pre > 0.0f;
             if constexpr (MODE == 2) live = live && (pre <= 7.5f);
-            else live = live && (pre >= c.lo && pre <= c.hi);
+            else live = live && (pre >= lo && pre <= hi);
             const float base = live ? dc[k] : 0.0f;
-            __stcg(c.scr + eix[k] * kThreads, base * o);                            // dc * sign(o) * |o|
-            dm = __uint_as_float(__float_as_uint(base * wb.x) ^ smask);             // d out / d madj = w * sign_k
+            gw[k] = base * o;                                                       // dc * sign(o) * |o|
+            dm = __uint_as_float(__float_as_uint(base * wb[k].x) ^ smask);          // d out / d madj = w * sign_k
         }
         if (first) s2 += dm;
         else s1 += dm;
@@ -251,14 +254,144 @@ __device__ __forceinline__ void cn_check_bwd_core(BwdLane<G, MODE> &c, const flo
     s2 = capB ? 0.0f : s2;
 #pragma unroll
     for (int k = 0; k < D; k++) {
-        float du = (k == i1) ? s1 : ((k == i2) ? s2 : 0.0f);
-        du = __uint_as_float(__float_as_uint(du) ^ (__float_as_uint(u[k]) & kSign));    // * sign(u_k)
-        if constexpr (MODE == 0) du = (u[k] == 0.0f) ? 0.0f : du;
-        du = pass[k] ? du : 0.0f;
-        if (col1[k] < 0) c.rot[shf[k]][rows[k] * Z] = du;           // dv2c_t, variable-lane domain
-        else if constexpr (kVn) c.dxr[rows[k] < 0 ? -rows[k] - 1 : 0] = du;   // (register-resident: G::kDeg1Smem == 0)
+        float d = (k == i1) ? s1 : ((k == i2) ? s2 : 0.0f);
+        d = __uint_as_float(__float_as_uint(d) ^ (__float_as_uint(u[k]) & kSign));      // * sign(u_k)
+        if constexpr (MODE == 0) d = (u[k] == 0.0f) ? 0.0f : d;
+        du[k] = pass[k] ? d : 0.0f;
     }
 }
+
+// unrolled form: every table entry of the check is an immediate
+template <class G, int MODE, bool kVn, int kThreads, class... Es>
+__device__ __forceinline__ void cn_check_bwd_core(BwdLane<G, MODE> &c, const float *pv, const float *pg) {
+    constexpr int D = sizeof...(Es);
+    constexpr int rows[D] = {Es::row...};
+    constexpr int shf[D] = {Es::shift...};
+    constexpr int eix[D] = {Es::e...};
+    constexpr int col1[D] = {Es::col1...};
+    constexpr int Z = G::Z;
+    float dc[D], gw[D], gb[D], du[D];
+    float2 wb[D];
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        if (col1[k] < 0) dc[k] = c.rot[shf[k]][rows[k] * Z];
+        else dc[k] = pg[k];
+        wb[k] = c_wb[c.wb_base + eix[k]];
+    }
+    cn_bwd_math<MODE, D>(pv, dc, wb, c.lo, c.hi, gw, gb, du);
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        __stcg(c.scr + eix[k] * kThreads, gw[k]);
+        if constexpr (MODE == 0) __stcg(c.scr + (G::E + eix[k]) * kThreads, gb[k]);
+        if (col1[k] < 0) c.rot[shf[k]][rows[k] * Z] = du[k];          // dv2c_t, variable-lane domain
+        else if constexpr (kVn) c.dxr[rows[k] < 0 ? -rows[k] - 1 : 0] = du[k];   // (register-resident: G::kDeg1Smem == 0)
+    }
+}
+
+// ---- looped form: checks with D stored edges + ONE trailing degree-1 register block, table entries at run time ----------
+// The unrolled iteration body of BG2 is 12 K instructions = 190 KB and the sweep is instruction-delivery bound;
+// truncation experiments put the cliff between 80 KB and 160 KB.  The 38 "extension" checks of BG2 differ only in their
+// table entries, so they run as four short loops (one per stored-edge count) over one-word descriptors in constant memory:
+// ~4 more address instructions per edge, but a body of ~5 K instructions.
+template <class G>
+__device__ __forceinline__ int rot_lane(int z, int s) {
+    int zz = z + s;
+    if constexpr ((G::Z & (G::Z - 1)) == 0) return zz & (G::Z - 1);
+    else return zz >= G::Z ? zz - G::Z : zz;
+}
+
+template <class G, int MODE, bool kVn, int kThreads, int D>
+__device__ __forceinline__ void cn_loop_issue(const BwdLane<G, MODE> &c, const float *stg, int w0) {
+    constexpr int Z = G::Z;
+    static_assert(D + 4 <= BwdStage<G>::kEnt, "staging entries");
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        const uint32_t w = c_desc[w0 + k];
+        const int row = w & 0xff, zz = rot_lane<G>(c.z, (w >> 8) & 0xff);
+        cp_async4(stg + k * kThreads, c.hv + (row - G::kXRows) * Z + zz);
+    }
+    const int q = (int)(c_desc[w0 + D] & 0xff) * Z + c.z;          // degree-1 block J, identity circulant
+    cp_async4(stg + D * kThreads, c.xin + q);
+    cp_async4(stg + (D + 1) * kThreads, c.gt + q);
+    if constexpr (MODE != 0) cp_async4(stg + (D + 2) * kThreads, c.mk + (q & ~3));
+    if constexpr (kVn) cp_async4(stg + (D + 3) * kThreads, c.xprev + q);
+    cp_async_commit();
+}
+
+template <class G, int MODE, bool kVn, int kThreads, int D>
+__device__ __forceinline__ void cn_loop_compute(BwdLane<G, MODE> &c, const float *stg, int w0) {
+    constexpr int Z = G::Z, NE = D + 1;
+    float *slab0 = c.lane - c.z;
+    float pv[NE], dc[NE], gw[NE], gb[NE], du[NE];
+    float2 wb[NE];
+    float *msg[D];
+    int eix[NE];
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        const uint32_t w = c_desc[w0 + k];
+        msg[k] = slab0 + (w & 0xff) * Z + rot_lane<G>(c.z, (w >> 8) & 0xff);
+        eix[k] = w >> 16;
+        pv[k] = stg[k * kThreads];
+        dc[k] = *msg[k];
+        wb[k] = c_wb[c.wb_base + eix[k]];
+    }
+    const uint32_t w1 = c_desc[w0 + D];
+    const int J = w1 & 0xff, ridx = (w1 >> 8) & 0xff;
+    eix[D] = w1 >> 16;
+    const int q = J * Z + c.z;
+    pv[D] = stg[D * kThreads];
+    {
+        const float gv = stg[(D + 1) * kThreads];
+        bool keep = c.valid;
+        if constexpr (MODE != 0) keep = keep && (((__float_as_uint(stg[(D + 2) * kThreads]) >> (8 * (q & 3))) & 0xffu) != 0);
+        dc[D] = keep ? gv : 0.0f;
+    }
+    wb[D] = c_wb[c.wb_base + eix[D]];
+    float chain_prev = 0.0f;
+    if constexpr (kVn) {
+        if (!c.last_iter) chain_prev = __ldcg(c.chn + ridx * kThreads);      // (own slot, written by this thread one iteration ago)
+    }
+    cn_bwd_math<MODE, NE>(pv, dc, wb, c.lo, c.hi, gw, gb, du);
+#pragma unroll
+    for (int k = 0; k < NE; k++) {
+        __stcg(c.scr + eix[k] * kThreads, gw[k]);
+        if constexpr (MODE == 0) __stcg(c.scr + (G::E + eix[k]) * kThreads, gb[k]);
+        if (k < D) *msg[k] = du[k];
+    }
+    if constexpr (kVn) {     // VN-weight chain step of block J (VnChainStep), inline: the block belongs to this check alone
+        float dx = chain_prev + du[D];
+        const float xp = stg[(D + 3) * kThreads];
+        const float w = __ldg(c.vw + J);
+        if constexpr (MODE == 2) {
+            if (!(fabsf(mulf(xp, w)) <= 7.5f)) dx = 0.0f;
+        }
+        __stcg(c.scr + (G::E + J) * kThreads, dx * xp);
+        __stcg(c.chn + ridx * kThreads, dx * w);
+    }
+}
+
+template <class G, int MODE, bool kVn, int kThreads>
+struct CnBwdLoops {
+    BwdLane<G, MODE> &c;
+    const float *stg;         // &stage[0][0][tid]
+    int base;                 // first descriptor word of this graph in c_desc
+    template <int D, int FIRST, int COUNT>
+    __device__ __forceinline__ void cls() {
+        constexpr int kStage = BwdStage<G>::kEnt * kThreads;
+        cn_loop_issue<G, MODE, kVn, kThreads, D>(c, stg, base + FIRST);
+#pragma unroll 1
+        for (int i = 0; i < COUNT; i++) {
+            const int w0 = base + FIRST + i * (D + 1);
+            if (i + 1 < COUNT) {
+                cn_loop_issue<G, MODE, kVn, kThreads, D>(c, stg + ((i + 1) & 1) * kStage, w0 + (D + 1));
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            cn_loop_compute<G, MODE, kVn, kThreads, D>(c, stg + (i & 1) * kStage, w0);
+        }
+    }
+};
 
 template <class G, int MODE, bool kVn, int kThreads>
 struct CnBwd {
@@ -321,9 +454,9 @@ __device__ __forceinline__ void vn_chain_batches(BwdLane<G, MODE> &c, float *cha
     if constexpr (BATCH * kChainBatch < G::N) {
         float xp[kChainBatch];
         VnChainLoad<G, MODE, BATCH> l{c, xprev, xp};
-        G::blocks(l);
+        G::blocks_rest(l);      // (the degree-1 blocks of looped checks are stepped inside cn_loop_compute)
         VnChainStep<G, MODE, kThreads, BATCH> st{c, chain, dxb, xp, vw};
-        G::blocks(st);
+        G::blocks_rest(st);
         vn_chain_batches<G, MODE, kThreads, BATCH + 1>(c, chain, dxb, xprev, vw);
     }
 }
@@ -349,7 +482,7 @@ struct SpecBwdCfg {
 };
 
 template <class G, int MODE, bool kVn>
-__global__ void __launch_bounds__(SpecBwdCfg<G>::kThreads, 1) nldpc_spec_backward_kernel(const BwdArgs a, const int wb_off) {
+__global__ void __launch_bounds__(SpecBwdCfg<G>::kThreads, 1) nldpc_spec_backward_kernel(const BwdArgs a, const int wb_off, const int desc_base) {
     using Cfg = SpecBwdCfg<G>;
     using Shape = typename Cfg::Shape;
     constexpr int Z = G::Z, NZ = G::N * G::Z, E = G::E, N = G::N;
@@ -364,7 +497,10 @@ __global__ void __launch_bounds__(SpecBwdCfg<G>::kThreads, 1) nldpc_spec_backwar
     const int cwl = gl / Z, z = gl - cwl * Z;
     const int cw_in_cta = grp * Shape::kCw + cwl;
     float *slab = slabs + (size_t)cw_in_cta * G::kSlab;
-    float *scr_cta = a.scratch + (size_t)blockIdx.x * kRows * kThreads;
+    // per CTA: kRows partial-sum rows, then (kVn) the chain state of the looped degree-1 blocks
+    constexpr int kScrRows = kRows + ((kVn && G::kLoopChecks > 0) ? G::kXRegs : 0);
+    static_assert(kScrRows <= 2 * G::E + G::N, "workspace scratch is sized for 2E + N rows per CTA");
+    float *scr_cta = a.scratch + (size_t)blockIdx.x * kScrRows * kThreads;
 
     BwdLane<G, MODE> c;
     c.lane = slab + z;
@@ -372,6 +508,7 @@ __global__ void __launch_bounds__(SpecBwdCfg<G>::kThreads, 1) nldpc_spec_backwar
     c.lo = a.lo;
     c.hi = a.hi;
     c.scr = scr_cta + tid;
+    c.chn = scr_cta + (size_t)kRows * kThreads + tid;
 #pragma unroll
     for (int s = 0; s < Z; s++) c.rot[s] = slab + ((z + s) % Z);
 
@@ -395,6 +532,11 @@ __global__ void __launch_bounds__(SpecBwdCfg<G>::kThreads, 1) nldpc_spec_backwar
             c.mk = (MODE != 0) ? a.hist_mask + ((size_t)t * a.B + bb) * NZ : nullptr;
             c.xin = (MODE == 0) ? a.xa + bb * NZ : a.hist_xin + ((size_t)(t + 1) * a.B + bb) * NZ;
             c.wb_base = wb_off + t * E;
+            c.last_iter = (t == a.T - 1);
+            if constexpr (kVn) {
+                c.xprev = a.hist_xin + ((size_t)t * a.B + bb) * NZ;
+                c.vw = a.vn_w + (size_t)t * N;
+            }
             {
                 float g[N];
                 VnBwdLoad<G, MODE> l{c, g};
@@ -405,7 +547,11 @@ __global__ void __launch_bounds__(SpecBwdCfg<G>::kThreads, 1) nldpc_spec_backwar
             __syncthreads();     // (also: the previous iteration's scratch rows have been folded by every warp)
             {
                 CnBwd<G, MODE, kVn, kThreads> f{c, stage + tid};
-                G::checks_pipelined(f);
+                G::checks_pipelined_rest(f);
+                if constexpr (G::kLoopChecks > 0) {
+                    CnBwdLoops<G, MODE, kVn, kThreads> l{c, stage + tid, desc_base};
+                    G::loop_classes(l);
+                }
             }
             __syncthreads();
             if constexpr (kVn) {
@@ -443,8 +589,23 @@ __global__ void __launch_bounds__(SpecBwdCfg<G>::kThreads, 1) nldpc_spec_backwar
 
 namespace {
 
+// descriptors of the looped checks -> this translation unit's c_desc, once per device
+template <class G>
+cudaError_t ensure_loop_desc(int graph_slot, cudaStream_t st) {
+    static_assert(G::kLoopDescWords <= kDescStride, "descriptor slot too small");
+    static bool done[64] = {};
+    if (G::kLoopChecks == 0) return cudaSuccess;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (done[dev & 63]) return cudaSuccess;
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_desc, G::loop_desc(), sizeof(uint32_t) * G::kLoopDescWords,
+                                            sizeof(uint32_t) * (size_t)graph_slot * kDescStride, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) done[dev & 63] = true;
+    return e;
+}
+
 template <class G, int MODE, bool kVn>
-int spec_bwd_launch_one(const BwdArgs &a, int wb_off, int sm_count, cudaStream_t st) {
+int spec_bwd_launch_one(const BwdArgs &a, int wb_off, int graph_slot, int sm_count, cudaStream_t st) {
     using Cfg = SpecBwdCfg<G>;
     const size_t smem = Cfg::smem_bytes(a.T, MODE, kVn);
     static bool prepared = false;    // per translation unit and variant; the attribute is idempotent
@@ -453,9 +614,11 @@ int spec_bwd_launch_one(const BwdArgs &a, int wb_off, int sm_count, cudaStream_t
         if (e != cudaSuccess) return (int)e;
         prepared = true;
     }
+    cudaError_t e = ensure_loop_desc<G>(graph_slot, st);
+    if (e != cudaSuccess) return (int)e;
     const int n_tiles = (a.B + Cfg::kCwPerCta - 1) / Cfg::kCwPerCta;
     const int grid = std::min(n_tiles, sm_count);
-    nldpc_spec_backward_kernel<G, MODE, kVn><<<grid, Cfg::kThreads, smem, st>>>(a, wb_off);
+    nldpc_spec_backward_kernel<G, MODE, kVn><<<grid, Cfg::kThreads, smem, st>>>(a, wb_off, graph_slot * kDescStride);
     return (int)cudaGetLastError();
 }
 
@@ -464,7 +627,7 @@ int spec_bwd_launch_one(const BwdArgs &a, int wb_off, int sm_count, cudaStream_t
 // it reads that unit's constant arena (a second instantiation elsewhere would be folded with this one by the linker and
 // read the other unit's, never written, arena).
 template <class G, bool kBoosted>
-int spec_bwd_launch(const BwdArgs &a, int sm_count, cudaStream_t st) {
+int spec_bwd_launch(const BwdArgs &a, int graph_slot, int sm_count, cudaStream_t st) {
     if (G::kDeg1Smem != 0) return -1;                         // the lane-private chain assumes identity circulants on degree-1 blocks
     if (!a.scratch || kBoosted != (a.mode != 0)) return -1;
     if (a.mode != 0 && (a.ucn_mix || a.hist_ucn)) return -1;
@@ -481,10 +644,10 @@ int spec_bwd_launch(const BwdArgs &a, int sm_count, cudaStream_t st) {
     pack_wb_kernel<<<(len + 255) / 256, 256, 0, st>>>(a.w, a.mode == 0 ? a.b : nullptr, arena.base + off, len);
     int rc;
     if constexpr (!kBoosted) {
-        rc = spec_bwd_launch_one<G, 0, false>(a, off, sm_count, st);
+        rc = spec_bwd_launch_one<G, 0, false>(a, off, graph_slot, sm_count, st);
     } else {
-        if (a.mode == 1) rc = a.gvn ? spec_bwd_launch_one<G, 1, true>(a, off, sm_count, st) : spec_bwd_launch_one<G, 1, false>(a, off, sm_count, st);
-        else rc = a.gvn ? spec_bwd_launch_one<G, 2, true>(a, off, sm_count, st) : spec_bwd_launch_one<G, 2, false>(a, off, sm_count, st);
+        if (a.mode == 1) rc = a.gvn ? spec_bwd_launch_one<G, 1, true>(a, off, graph_slot, sm_count, st) : spec_bwd_launch_one<G, 1, false>(a, off, graph_slot, sm_count, st);
+        else rc = a.gvn ? spec_bwd_launch_one<G, 2, true>(a, off, graph_slot, sm_count, st) : spec_bwd_launch_one<G, 2, false>(a, off, graph_slot, sm_count, st);
     }
     const cudaError_t rel = arena.release_after(off, len, st);
     if (rc != 0) return rc;
