@@ -319,7 +319,7 @@ __device__ __forceinline__ void cn_loop_issue(const BwdLane<G, MODE> &c, const f
 }
 
 template <class G, int MODE, bool kVn, int kThreads, int D>
-__device__ __forceinline__ void cn_loop_compute(BwdLane<G, MODE> &c, const float *stg, int w0) {
+__device__ __forceinline__ void cn_loop_compute(BwdLane<G, MODE> &c, const float *stg, int w0, float chain_prev) {
     constexpr int Z = G::Z, NE = D + 1;
     float *slab0 = c.lane - c.z;
     float pv[NE], dc[NE], gw[NE], gb[NE], du[NE];
@@ -347,10 +347,6 @@ __device__ __forceinline__ void cn_loop_compute(BwdLane<G, MODE> &c, const float
         dc[D] = keep ? gv : 0.0f;
     }
     wb[D] = c_wb[c.wb_base + eix[D]];
-    float chain_prev = 0.0f;
-    if constexpr (kVn) {
-        if (!c.last_iter) chain_prev = __ldcg(c.chn + ridx * kThreads);      // (own slot, written by this thread one iteration ago)
-    }
     cn_bwd_math<MODE, NE>(pv, dc, wb, c.lo, c.hi, gw, gb, du);
 #pragma unroll
     for (int k = 0; k < NE; k++) {
@@ -375,20 +371,35 @@ struct CnBwdLoops {
     BwdLane<G, MODE> &c;
     const float *stg;         // &stage[0][0][tid]
     int base;                 // first descriptor word of this graph in c_desc
+    // VN-weight chain state of the check's degree-1 block (own slot, written by this thread one iteration ago; L2, not the
+    // non-coherent L1).  Loaded one check ahead into a loop-carried register: ptxas cannot sink it across the back edge.
+    template <int D>
+    __device__ __forceinline__ float chain_state(int w0) const {
+        if constexpr (!kVn) return 0.0f;
+        if (c.last_iter) return 0.0f;
+        return __ldcg(c.chn + ((c_desc[w0 + D] >> 8) & 0xff) * kThreads);
+    }
     template <int D, int FIRST, int COUNT>
     __device__ __forceinline__ void cls() {
         constexpr int kStage = BwdStage<G>::kEnt * kThreads;
         cn_loop_issue<G, MODE, kVn, kThreads, D>(c, stg, base + FIRST);
+        // chain state two checks ahead (the scratch rows compete with the streamed dump in L2 and often come from HBM)
+        float chain_cur = chain_state<D>(base + FIRST);
+        float chain_next = COUNT > 1 ? chain_state<D>(base + FIRST + (D + 1)) : 0.0f;
 #pragma unroll 1
         for (int i = 0; i < COUNT; i++) {
             const int w0 = base + FIRST + i * (D + 1);
+            float chain_next2 = 0.0f;
+            if (i + 2 < COUNT) chain_next2 = chain_state<D>(w0 + 2 * (D + 1));
             if (i + 1 < COUNT) {
                 cn_loop_issue<G, MODE, kVn, kThreads, D>(c, stg + ((i + 1) & 1) * kStage, w0 + (D + 1));
                 cp_async_wait<1>();
             } else {
                 cp_async_wait<0>();
             }
-            cn_loop_compute<G, MODE, kVn, kThreads, D>(c, stg + (i & 1) * kStage, w0);
+            cn_loop_compute<G, MODE, kVn, kThreads, D>(c, stg + (i & 1) * kStage, w0, chain_cur);
+            chain_cur = chain_next;
+            chain_next = chain_next2;
         }
     }
 };
@@ -562,16 +573,25 @@ __global__ void __launch_bounds__(SpecBwdCfg<G>::kThreads, 1) nldpc_spec_backwar
             }
             // fold this iteration's scratch rows (written by this CTA only, read back through L2) into the per-CTA totals;
             // row r always belongs to warp r % kWarps, lane 0 -> plain read-modify-write
-            for (int r = warp; r < kRows; r += Cfg::kWarps) {
-                const float4 *p = reinterpret_cast<const float4 *>(scr_cta + (size_t)r * kThreads + ln * kPer);
-                float s = 0.0f;
+            constexpr int kFoldBatch = 4;       // rows in flight per warp (the read-back is an L2 round trip)
+            for (int r0 = warp; r0 < kRows; r0 += Cfg::kWarps * kFoldBatch) {
+                float4 v[kFoldBatch][kPer / 4];
 #pragma unroll
-                for (int q = 0; q < kPer / 4; q++) {
-                    const float4 v = __ldcg(p + q);
-                    s += (v.x + v.y) + (v.z + v.w);
+                for (int j = 0; j < kFoldBatch; j++) {
+                    const int r = r0 + j * Cfg::kWarps;
+                    const float4 *p = reinterpret_cast<const float4 *>(scr_cta + (size_t)(r < kRows ? r : r0) * kThreads + ln * kPer);
+#pragma unroll
+                    for (int q = 0; q < kPer / 4; q++) v[j][q] = __ldcg(p + q);
                 }
-                s = bwd_warp_sum(s);
-                if (ln == 0) tot[(size_t)t * kRows + r] += s;
+#pragma unroll
+                for (int j = 0; j < kFoldBatch; j++) {
+                    const int r = r0 + j * Cfg::kWarps;
+                    float sum = 0.0f;
+#pragma unroll
+                    for (int q = 0; q < kPer / 4; q++) sum += (v[j][q].x + v[j][q].y) + (v[j][q].z + v[j][q].w);
+                    sum = bwd_warp_sum(sum);
+                    if (ln == 0 && r < kRows) tot[(size_t)t * kRows + r] += sum;
+                }
             }
         }
     }
