@@ -53,7 +53,9 @@ def test_boosted_oracle_parity_random(code, sharing, dec, q, B, T, graphs):
     out = to_np(m(torch.from_numpy(xa).cuda()))
     ref, llr = oracle_forward(m.cpu(), xa, return_llr=True)
     assert np.array_equal(out, ref), np.abs(out - ref).max()
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32)), "bit patterns (sign of zero) differ"
     assert np.array_equal(m.llr[T].cpu().numpy(), llr[-1].transpose(0, 2, 1))
+    assert np.array_equal(m.llr[T].cpu().numpy().view(np.uint32), np.ascontiguousarray(llr[-1].transpose(0, 2, 1)).view(np.uint32))
 
 
 def test_boosted_stateful_staged_runs_match_one_shot(graphs):
@@ -156,4 +158,5 @@ def test_boosted_throughput_mode_matches_oracle(code, sharing, dec, B, T, graphs
     soft = m.decode_soft_last(x).cpu().numpy()
     ref = oracle_forward(m.cpu(), xa)
     assert np.array_equal(soft, ref[-1]), np.abs(soft - ref[-1]).max()
+    assert np.array_equal(soft.view(np.uint32), ref[-1].view(np.uint32)), "bit patterns (sign of zero) differ"
     assert np.array_equal(hard, np.packbits(ref[-1] < 0, axis=1, bitorder="little"))

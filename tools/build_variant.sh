@@ -8,7 +8,7 @@ ROOT=$(cd "$(dirname "$0")/.." && pwd)
 NAME=$1; DEFS=$2; shift 2
 OUT=$ROOT/build/exp/$NAME
 mkdir -p "$OUT"
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC -Xptxas -v"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC -Xptxas -v $NLDPC_EXTRA_NVFLAGS"
 OBJS=""
 for f in "$ROOT"/build/csrc/*.o; do
   b=$(basename "$f" .o); skip=0
