@@ -609,17 +609,20 @@ __global__ void __launch_bounds__(SpecBwdCfg<G>::kThreads, 1) nldpc_spec_backwar
 
 namespace {
 
-// descriptors of the looped checks -> this translation unit's c_desc, once per device
+// descriptors of the looped checks -> this translation unit's c_desc, once per device.  Synchronous on purpose: when the call
+// returns the table is in place for launches on ANY stream (the flag is shared by all of them).
 template <class G>
-cudaError_t ensure_loop_desc(int graph_slot, cudaStream_t st) {
+cudaError_t ensure_loop_desc(int graph_slot) {
     static_assert(G::kLoopDescWords <= kDescStride, "descriptor slot too small");
+    static std::mutex mu;
     static bool done[64] = {};
     if (G::kLoopChecks == 0) return cudaSuccess;
     int dev = 0;
     cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
     if (done[dev & 63]) return cudaSuccess;
-    cudaError_t e = cudaMemcpyToSymbolAsync(c_desc, G::loop_desc(), sizeof(uint32_t) * G::kLoopDescWords,
-                                            sizeof(uint32_t) * (size_t)graph_slot * kDescStride, cudaMemcpyHostToDevice, st);
+    cudaError_t e = cudaMemcpyToSymbol(c_desc, G::loop_desc(), sizeof(uint32_t) * G::kLoopDescWords,
+                                       sizeof(uint32_t) * (size_t)graph_slot * kDescStride, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) done[dev & 63] = true;
     return e;
 }
@@ -634,7 +637,7 @@ int spec_bwd_launch_one(const BwdArgs &a, int wb_off, int graph_slot, int sm_cou
         if (e != cudaSuccess) return (int)e;
         prepared = true;
     }
-    cudaError_t e = ensure_loop_desc<G>(graph_slot, st);
+    cudaError_t e = ensure_loop_desc<G>(graph_slot);
     if (e != cudaSuccess) return (int)e;
     const int n_tiles = (a.B + Cfg::kCwPerCta - 1) / Cfg::kCwPerCta;
     const int grid = std::min(n_tiles, sm_count);
