@@ -631,11 +631,13 @@ template <class G, int MODE, bool kVn>
 int spec_bwd_launch_one(const BwdArgs &a, int wb_off, int graph_slot, int sm_count, cudaStream_t st) {
     using Cfg = SpecBwdCfg<G>;
     const size_t smem = Cfg::smem_bytes(a.T, MODE, kVn);
-    static bool prepared = false;    // per translation unit and variant; the attribute is idempotent
-    if (!prepared) {
+    static bool prepared[64] = {};   // per translation unit, variant and device; the attribute is idempotent
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!prepared[dev & 63]) {
         cudaError_t e = set_smem(nldpc_spec_backward_kernel<G, MODE, kVn>, kSmemBudget);
         if (e != cudaSuccess) return (int)e;
-        prepared = true;
+        prepared[dev & 63] = true;
     }
     cudaError_t e = ensure_loop_desc<G>(graph_slot);
     if (e != cudaSuccess) return (int)e;
