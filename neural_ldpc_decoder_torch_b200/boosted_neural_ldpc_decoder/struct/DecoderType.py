@@ -1,8 +1,2 @@
-from enum import Enum
-
-
-class DecoderType(Enum):
-    """check-node arithmetic: sum-product, min-sum, quantised min-sum (reference: struct/DecoderType.py)"""
-    SP = 0
-    MS = 1
-    QMS = 2
+"""re-export: the definition lives in struct/_defs.py"""
+from ._defs import DecoderType  # noqa: F401

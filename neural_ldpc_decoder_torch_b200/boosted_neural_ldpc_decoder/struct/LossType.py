@@ -1,7 +1,2 @@
-from enum import Enum
-
-
-class LossType(Enum):
-    BCE = "BCE"
-    SoftBEROnAllZero = "SoftBEROnAllZero"
-    FEROnAllZero = "FEROnAllZero"
+"""re-export: the definition lives in struct/_defs.py"""
+from ._defs import LossType  # noqa: F401

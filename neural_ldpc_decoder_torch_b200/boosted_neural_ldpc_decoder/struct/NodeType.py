@@ -1,7 +1,2 @@
-from enum import Enum
-
-
-class NodeType(Enum):
-    CN = "CN"
-    UCN = "UCN"
-    VN = "VN"
+"""re-export: the definition lives in struct/_defs.py"""
+from ._defs import NodeType  # noqa: F401

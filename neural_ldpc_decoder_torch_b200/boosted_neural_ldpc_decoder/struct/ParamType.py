@@ -1,6 +1,2 @@
-from enum import Enum
-
-
-class ParamType(Enum):
-    Weight = "weight"
-    Bias = "bias"
+"""re-export: the definition lives in struct/_defs.py"""
+from ._defs import ParamType  # noqa: F401

@@ -15,64 +15,65 @@ import numpy as np
 import torch
 
 
+def _txt_name(param_name: str) -> str:
+    return param_name.translate(str.maketrans("./", "__")) + ".txt"
+
+
+def _write_matrix(path: str, t: torch.Tensor) -> None:
+    """np.savetxt of one tensor; tensors of rank > 2 are flattened to [shape[0], -1] with the original shape in the header"""
+    arr = t.detach().cpu().numpy()
+    if arr.ndim <= 2:
+        np.savetxt(path, arr)
+    else:
+        np.savetxt(path, arr.reshape(arr.shape[0], -1), header=f"Original shape: {arr.shape}\nReshaped to 2D for savetxt")
+
+
 class CheckPointUtil:
     def __init__(self, checkpoint_dir: str = "checkpoints", dump_lifting_matrices: bool = False):
-        self.checkpoint_dir = checkpoint_dir
-        self.dump_lifting_matrices = dump_lifting_matrices
-        os.makedirs(checkpoint_dir, exist_ok=True)
+        self.checkpoint_dir, self.dump_lifting_matrices = checkpoint_dir, dump_lifting_matrices
+        os.makedirs(self.checkpoint_dir, exist_ok=True)
+
+    def _in_dir(self, name: str) -> str:
+        return os.path.join(self.checkpoint_dir, name)
 
     def save(self, filepath: str, model: torch.nn.Module, optimizer: Optional[torch.optim.Optimizer] = None,
              epoch: Optional[int] = None, metrics: Optional[Dict[str, float]] = None,
              config: Optional[Dict[str, Any]] = None) -> str:
-        path = os.path.join(self.checkpoint_dir, filepath)
-        data = {'model_state_dict': model.state_dict()}
-        if optimizer is not None:
-            data['optimizer_state_dict'] = optimizer.state_dict()
-        if epoch is not None:
-            data['epoch'] = epoch
-        if metrics is not None:
-            data.update(metrics)
+        # key order as the reference writes it: model, optimizer, epoch, the metrics flattened into the top level, config
+        optional = (("optimizer_state_dict", None if optimizer is None else optimizer.state_dict()), ("epoch", epoch))
+        data = {"model_state_dict": model.state_dict(), **{k: v for k, v in optional if v is not None}}
+        data.update(metrics or {})
         if config is not None:
-            data['config'] = config
-        torch.save(data, path)
-        return path
+            data["config"] = config
+        torch.save(data, self._in_dir(filepath))
+        return self._in_dir(filepath)
 
     def save_weights(self, filepath: str, model: torch.nn.Module, as_txt: bool = False) -> str:
-        pth = filepath if filepath.endswith('.pth') else filepath + '.pth'
-        weights_path = os.path.join(self.checkpoint_dir, pth)
+        weights_path = self._in_dir(filepath if filepath.endswith(".pth") else filepath + ".pth")
         state = model.state_dict()
         torch.save(state, weights_path)
-        if as_txt:
-            base = filepath.replace('.pth', '')
-            txt_dir = os.path.join(self.checkpoint_dir, f"{base}_weights_txt")
-            os.makedirs(txt_dir, exist_ok=True)
-            index = os.path.join(txt_dir, "index.txt")
-            with open(index, 'w') as f:
-                f.write(f"# Model weights saved at: {datetime.now().strftime('%Y-%m-%d %H:%M:%S')}\n")
-                f.write(f"# Total parameters: {sum(p.numel() for p in model.parameters())}\n")
-                f.write("# Format: Each parameter saved in separate .txt file\n")
-                f.write("-" * 80 + "\n")
-                f.write("Parameter_Name, Shape, Filename\n")
-                for name, t in state.items():
-                    if name.split('.')[-1].startswith("Lift_Matrix") and not self.dump_lifting_matrices:
-                        f.write(f"{name}, {list(t.shape)}, <skipped: derived from the base graph>\n")
-                        continue
-                    fname = name.replace('.', '_').replace('/', '_') + ".txt"
-                    arr = t.cpu().numpy()
-                    if arr.ndim > 2:
-                        shape = arr.shape
-                        np.savetxt(os.path.join(txt_dir, fname), arr.reshape(shape[0], -1),
-                                   header=f"Original shape: {shape}\nReshaped to 2D for savetxt")
-                    else:
-                        np.savetxt(os.path.join(txt_dir, fname), arr)
-                    f.write(f"{name}, {list(t.shape)}, {fname}\n")
+        if not as_txt:
+            return weights_path
+        txt_dir = self._in_dir(filepath.replace(".pth", "") + "_weights_txt")
+        os.makedirs(txt_dir, exist_ok=True)
+        lines = [f"# Model weights saved at: {datetime.now():%Y-%m-%d %H:%M:%S}",
+                 f"# Total parameters: {sum(p.numel() for p in model.parameters())}",
+                 "# Format: Each parameter saved in separate .txt file", "-" * 80, "Parameter_Name, Shape, Filename"]
+        for name, t in state.items():
+            derived = name.rsplit(".", 1)[-1].startswith("Lift_Matrix") and not self.dump_lifting_matrices
+            target = "<skipped: derived from the base graph>" if derived else _txt_name(name)
+            if not derived:
+                _write_matrix(os.path.join(txt_dir, target), t)
+            lines.append(f"{name}, {list(t.shape)}, {target}")
+        with open(os.path.join(txt_dir, "index.txt"), "w") as f:
+            f.write("\n".join(lines) + "\n")
         return weights_path
 
     def load(self, filepath: str, model: torch.nn.Module, optimizer: Optional[torch.optim.Optimizer] = None,
              device: Optional[torch.device] = None) -> Dict[str, Any]:
-        path = filepath if os.path.isabs(filepath) else os.path.join(self.checkpoint_dir, filepath)
-        checkpoint = torch.load(path, map_location=device) if device is not None else torch.load(path)
-        model.load_state_dict(checkpoint['model_state_dict'])
-        if optimizer is not None and 'optimizer_state_dict' in checkpoint:
-            optimizer.load_state_dict(checkpoint['optimizer_state_dict'])
-        return checkpoint
+        path = filepath if os.path.isabs(filepath) else self._in_dir(filepath)
+        ckpt = torch.load(path, **({} if device is None else {"map_location": device}))
+        model.load_state_dict(ckpt["model_state_dict"])        # strict, like the reference
+        if optimizer is not None and "optimizer_state_dict" in ckpt:
+            optimizer.load_state_dict(ckpt["optimizer_state_dict"])
+        return ckpt

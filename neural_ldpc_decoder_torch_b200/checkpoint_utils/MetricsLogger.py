@@ -8,25 +8,29 @@ from typing import Any, Dict, Optional
 
 class MetricsLogger:
     def __init__(self, log_dir: str = "checkpoints", filename: str = "training_metrics.txt"):
-        self.log_dir = log_dir
-        self.log_file = os.path.join(log_dir, filename)
         os.makedirs(log_dir, exist_ok=True)
-        self.best_ber = float('inf')
+        self.log_dir, self.log_file = log_dir, os.path.join(log_dir, filename)
+        self.best_ber = float("inf")
+
+    @staticmethod
+    def _cell(key: str, value: float) -> str:
+        return format(value, ".6e" if "ber" in key.lower() else ".6f")
 
     def log(self, epoch: int, metrics: Dict[str, float], checkpoint_filename: str, config: Optional[Dict[str, Any]] = None):
-        now = datetime.now().strftime('%Y-%m-%d %H:%M:%S')
-        if epoch == 0 and config is not None:
-            with open(self.log_file, 'w') as f:
-                f.write(f"# Training started: {now}\n")
-                f.write(f"# Config: {', '.join(f'{k}={v}' for k, v in config.items())}\n")
-                f.write(f"# Columns: Epoch, Timestamp, {', '.join(metrics.keys())}, Checkpoint_File\n")
-                f.write("-" * 120 + "\n")
-        cells = [f"{v:.6e}" if 'ber' in k.lower() else f"{v:.6f}" for k, v in metrics.items()]
-        with open(self.log_file, 'a') as f:
-            f.write(f"{epoch:4d}, {now}, " + ", ".join(cells) + f", {checkpoint_filename}\n")
+        stamp = f"{datetime.now():%Y-%m-%d %H:%M:%S}"
+        out = []
+        starts_file = epoch == 0 and config is not None          # a fresh run rewrites the file and puts a header block first
+        if starts_file:
+            out += [f"# Training started: {stamp}",
+                    "# Config: " + ", ".join(f"{k}={v}" for k, v in config.items()),
+                    "# Columns: Epoch, Timestamp, " + ", ".join(metrics) + ", Checkpoint_File",
+                    "-" * 120]
+        out.append(", ".join([f"{epoch:4d}", stamp, *(self._cell(k, v) for k, v in metrics.items()), checkpoint_filename]))
+        with open(self.log_file, "w" if starts_file else "a") as f:
+            f.write("\n".join(out) + "\n")
 
     def is_best(self, ber: float) -> bool:
-        if ber < self.best_ber:
+        better = ber < self.best_ber
+        if better:
             self.best_ber = ber
-            return True
-        return False
+        return better
