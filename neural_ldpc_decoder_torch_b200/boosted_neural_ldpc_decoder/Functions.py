@@ -33,36 +33,32 @@ class Functions:
 
     @staticmethod
     def qms_clipping_torch(x: torch.Tensor, q_bit: int) -> torch.Tensor:
-        if q_bit in _QGRID:
-            lim = float(_QGRID[q_bit][1])
-            return torch.clamp(x, -lim, lim)
-        return x
+        lim = _QGRID.get(q_bit, (None, None))[1]
+        return x if lim is None else torch.clamp(x, -float(lim), float(lim))
+
+    @staticmethod
+    def _to_grid(x, q_bit, rnd):
+        """x rounded to the grid of `q_bit` (before clipping): steps of 1 / scale; `rnd` is the array library's round"""
+        scale = _QGRID[q_bit][0]
+        if scale == 1.0:
+            return rnd(x)
+        return rnd(x * 2.0) / 2.0 if scale == 2.0 else rnd(x / 2) * 2
 
     @staticmethod
     def cal_msa_q_torch(x: torch.Tensor, q_bit: int) -> torch.Tensor:
         """forward: quantised value; backward: gradient of the clip (straight-through)."""
         if q_bit not in _QGRID:
             return x
-        scale, lim = _QGRID[q_bit]
-        if q_bit == 5:
-            q = torch.clamp(torch.round(x * 2.0) / 2.0, -lim, lim)
-        elif q_bit == 3:
-            q = torch.clamp(torch.round(x / 2) * 2, -lim, lim)
-        else:
-            q = torch.clamp(torch.round(x), -lim, lim)
+        lim = _QGRID[q_bit][1]
         clip = torch.clamp(x, -lim, lim)
-        return clip + (q - clip).detach()
+        return clip + (torch.clamp(Functions._to_grid(x, q_bit, torch.round), -lim, lim) - clip).detach()
 
     @staticmethod
     def Cal_MSA_Q(x, q_bit):
-        if q_bit == 5:
-            return np.clip(np.round(x * 2) / 2, -7.5, 7.5)
-        if q_bit == 3:
-            return np.clip(np.round(x / 2) * 2, -6, 6)
-        if q_bit in _QGRID:
-            lim = _QGRID[q_bit][1]
-            return np.clip(np.round(x), -lim, lim)
-        return x
+        if q_bit not in _QGRID:
+            return x
+        lim = _QGRID[q_bit][1]
+        return np.clip(Functions._to_grid(x, q_bit, np.round), -lim, lim)
 
     @staticmethod
     def evaluate_ber_fer(expected: torch.Tensor, actual: list):

@@ -16,34 +16,20 @@ _DENSE_DTYPE = {
 class ConnectingMatrixTorch:
     _DENSE_DTYPE = _DENSE_DTYPE
 
-    def __init__(
-            self,
-            connecting_matrix: ConnectingMatrix,
-            device: torch.device = torch.device('cpu'),
-            dtype_w_odd2even: torch.dtype = torch.float32,
-            dtype_w_skipconn2even: torch.dtype = torch.float32,
-            dtype_w_even2odd: torch.dtype = torch.float32,
-            dtype_w_output: torch.dtype = torch.float32,
-            dtype_lifting_matrix: torch.dtype = torch.float32,
-    ):
-        self.device = torch.device(device)
-        self._cm = connecting_matrix
-        self.graph = connecting_matrix.graph
-        self.N = connecting_matrix.N
-        self.M = connecting_matrix.M
-        self.Z = connecting_matrix.Z
-        self.basegraph = connecting_matrix.basegraph.copy()
-        self.sum_edge_c = connecting_matrix.sum_edge_c.copy()
-        self.sum_edge_v = connecting_matrix.sum_edge_v.copy()
-        self.sum_edge = connecting_matrix.sum_edge.copy()
-        self.dtype_w_odd2even = dtype_w_odd2even
-        self.dtype_w_skipconn2even = dtype_w_skipconn2even
-        self.dtype_w_even2odd = dtype_w_even2odd
-        self.dtype_w_output = dtype_w_output
+    def __init__(self, connecting_matrix: ConnectingMatrix, device: torch.device = torch.device("cpu"),
+                 dtype_w_odd2even: torch.dtype = torch.float32, dtype_w_skipconn2even: torch.dtype = torch.float32,
+                 dtype_w_even2odd: torch.dtype = torch.float32, dtype_w_output: torch.dtype = torch.float32,
+                 dtype_lifting_matrix: torch.dtype = torch.float32):
+        cm = self._cm = connecting_matrix
+        self.device, self.graph = torch.device(device), cm.graph
+        self.N, self.M, self.Z = cm.N, cm.M, cm.Z
+        for name in ("basegraph", "sum_edge_c", "sum_edge_v", "sum_edge"):          # own copies, as the reference keeps
+            setattr(self, name, getattr(cm, name).copy())
+        self.neurons_per_even_layer, self.neurons_per_odd_layer = np.copy(self.sum_edge), np.copy(self.sum_edge)
+        self.dtype_w_odd2even, self.dtype_w_skipconn2even = dtype_w_odd2even, dtype_w_skipconn2even
+        self.dtype_w_even2odd, self.dtype_w_output = dtype_w_even2odd, dtype_w_output
         self.dtype_lifting_matrix = dtype_lifting_matrix
-        self.neurons_per_even_layer = np.copy(self.sum_edge)
-        self.neurons_per_odd_layer = np.copy(self.sum_edge)
-        self._dense_t = {}
+        self._dense_t = {}      # dense matrix name -> tensor on self.device, filled on first access
 
     def __getattr__(self, name):
         table = type(self)._DENSE_DTYPE
