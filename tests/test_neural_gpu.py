@@ -126,7 +126,7 @@ def test_small_random_graph_generic_kernel():
 def test_host_buffer_api_matches_device_api(graphs):
     bg, Z = graphs["bg2"]
     E = int((bg != -1).sum())
-    B, T = 40000, 4          # > one chunk of the host API (16384) -> exercises the 3-stream pipeline
+    B, T = 40000, 4          # several chunks of the host API (4096 codewords each) -> exercises the 3-stream pipeline
     xa = awgn_llr("bg2", B, seed=11)
     rs = np.random.RandomState(2)
     w = rs.uniform(0.3, 1.3, (T, E)).astype(np.float32)

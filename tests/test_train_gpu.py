@@ -156,3 +156,41 @@ def test_specialised_backward_equals_table_driven(code, B, kind):
     for n in spec:
         scale = max(float(np.abs(tabl[n]).max()), 1e-12)
         assert float(np.abs(spec[n] - tabl[n]).max()) <= 3e-5 * scale, (n, spec[n].reshape(-1)[:4], tabl[n].reshape(-1)[:4])
+
+
+def test_two_streams_do_not_share_constant_arena_ranges():
+    """decode + gradient launches issued back to back on two CUDA streams with DIFFERENT weights: each launch packs its weights
+    into its own range of the constant arena (ring allocator with per-range events), so results must equal the serial runs"""
+    from neural_ldpc_decoder_torch_b200 import TannerGraph, load_basegraph
+    from neural_ldpc_decoder_torch_b200.training import DeviceBatchGenerator
+    from test_neural_gpu import make_model
+    bg, Z = load_basegraph("nr_bg2_set0")
+    graph = TannerGraph(bg, Z)
+    dev = torch.device("cuda")
+    T, B = 6, 3000
+    x, y = DeviceBatchGenerator(graph, [1.5, 3.0], dev, seed=11)(B)
+    gen = torch.Generator().manual_seed(5)
+    ws = [((0.3 + torch.rand((T, graph.E), generator=gen)).numpy(), (0.2 * torch.randn((T, graph.E), generator=gen)).numpy()) for _ in range(2)]
+    models = [make_model(bg, Z, T, B, w, b) for w, b in ws]
+
+    def run(m):
+        for p in m.parameters():
+            p.grad = None
+        outs = m(x)
+        torch.nn.functional.binary_cross_entropy_with_logits(-outs[-1], y).backward()
+        return outs[-1].detach().clone(), torch.stack([p.grad for p in m.weights_var]).clone()
+
+    serial = [run(m) for m in models]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    conc = [None, None]
+    for rep in range(5):
+        for i in (0, 1):
+            streams[i].wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(streams[i]):
+                conc[i] = run(models[i])
+        torch.cuda.synchronize()
+        for i in (0, 1):
+            assert torch.equal(conc[i][0], serial[i][0])
+            scale = float(serial[i][1].abs().max())
+            assert float((conc[i][1] - serial[i][1]).abs().max()) <= 3e-5 * scale
