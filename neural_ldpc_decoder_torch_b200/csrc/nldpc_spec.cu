@@ -40,8 +40,7 @@ template <class G>
 int launch_neural(const DecodeArgs &a, int sm_count, cudaStream_t st) {
     using Cfg = SpecCfg<G>;
     const int n_units = (a.B + Cfg::Shape::kCw - 1) / Cfg::Shape::kCw;
-    const int ctas = (n_units + Cfg::kGroups - 1) / Cfg::kGroups;
-    const int grid = std::min(ctas, sm_count * Cfg::kCtasPerSm);
+        const int grid = std::min(n_units, sm_count * Cfg::kCtasPerSm);
     const bool every = a.soft_mode == 1 || a.hard_mode == 1 || a.hist_v2c != nullptr;
     DecodeArgs args = a;
     // weights -> constant arena (uniform-datapath reads in the kernel); LDG variant if they do not fit

@@ -34,8 +34,7 @@ int boosted_launch_one(const DecodeArgs &args, int sm_count, cudaStream_t st) {
         constexpr bool kEvery = decltype(every_tag)::value;
         using Cfg = SpecCfg<G, kXo && kEvery>;       // list mode keeps xa_origin rows on chip, throughput mode re-reads it (xo_global)
         const int n_units = (args.B + Cfg::Shape::kCw - 1) / Cfg::Shape::kCw;
-        const int ctas = (n_units + Cfg::kGroups - 1) / Cfg::kGroups;
-        const int grid = std::min(ctas, sm_count * Cfg::kCtasPerSm);
+                const int grid = std::min(n_units, sm_count * Cfg::kCtasPerSm);
         nldpc_spec_neural_kernel<G, kEvery, true, MODE, kXo><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(args);
     };
     if (every) launch(std::true_type{});

@@ -28,9 +28,6 @@ namespace nldpc {
 constexpr int kConstFloat2 = 7680;                 // 60 KB of the 64 KB constant bank
 __constant__ float2 c_wb[kConstFloat2];   // this header is included by exactly one translation unit (nldpc_spec.cu)
 
-#ifndef NLDPC_DYNAMIC_UNITS
-#define NLDPC_DYNAMIC_UNITS 0    // 1: groups of a CTA pull work units from a shared counter (experiment)
-#endif
 #ifndef NLDPC_CTA_LOCKSTEP
 #define NLDPC_CTA_LOCKSTEP 0   // 1: CTA-wide barrier between phases (warps share the instruction stream)
 #endif
@@ -615,26 +612,14 @@ __global__ void __launch_bounds__(SpecCfg<G, kXo && kEvery>::kThreads, SpecCfg<G
         if constexpr (NLDPC_CTA_LOCKSTEP) __syncthreads();
         else group_sync<Shape::kLanes>(grp);
     };
-#if NLDPC_DYNAMIC_UNITS
-    // experiment (one-warp groups only): the CTA owns a contiguous range of units and its groups pull from it, so that
-    // unevenly loaded sub-partitions do not set the finish time
-    __shared__ int unit_ctr;
-    constexpr bool kDyn = Shape::kLanes == 32;
-    const int per_cta = (n_units + gridDim.x - 1) / gridDim.x;
-    const int u_lo = kDyn ? blockIdx.x * per_cta : blockIdx.x * Cfg::kGroups, u_hi = kDyn ? min(n_units, u_lo + per_cta) : n_units;
-    if (threadIdx.x == 0) unit_ctr = u_lo;
-    __syncthreads();
-    for (int unit0 = u_lo;; unit0 += unit_stride) {
-        int unit = unit0 + grp;
-        if constexpr (kDyn) {
-            if (gl == 0) unit = atomicAdd(&unit_ctr, 1);
-            unit = __shfl_sync(0xffffffffu, unit, 0);
-        }
-        if (unit >= u_hi) break;
-#else
+#if NLDPC_CTA_LOCKSTEP
     for (int unit0 = blockIdx.x * Cfg::kGroups; unit0 < n_units; unit0 += unit_stride) {
         const int unit = unit0 + grp;
-        if (!NLDPC_CTA_LOCKSTEP && unit >= n_units) break;
+#else
+    // units are dealt out CTA-major: group g of CTA b takes units b + gridDim.x * (g + kGroups * k).  A batch too small to fill
+    // the machine then spreads over all SMs with fewer busy warps each (the host launches min(n_units, resident CTAs) CTAs),
+    // which is what a latency-bound small decode wants; for large batches the order of units is irrelevant.
+    for (int unit = blockIdx.x + grp * (int)gridDim.x; unit < n_units; unit += unit_stride) {
 #endif
         const int b0 = unit * Shape::kCw;
         const int b = b0 + cwl;
