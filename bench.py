@@ -179,6 +179,16 @@ def other_configs(dev, B, steps=20):
         x1k = x[:1024].contiguous()
         measure("NeuralLDPCDecoder WiMAX N=576 R=3/4 z=24, 10 iterations, batch 1024 (configs[0] as the reference runs it: one launch, latency bound)",
                 lambda: m.decode_hard(x1k), batch=1024)
+        with torch.no_grad():       # the same launch captured once into a CUDA graph and replayed (host launch cost removed)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                m.decode_hard(x1k)
+            torch.cuda.current_stream().wait_stream(side)
+            cuda_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cuda_graph):
+                m.decode_hard(x1k)
+        measure("the same, batch 1024, replayed from a CUDA graph", cuda_graph.replay, batch=1024)
         xq, _ = DeviceBatchGenerator(graph, [3.0], dev, all_zero=True, qms_qbit=5)(B)
         cmb = bn.ConnectingMatrixTorch(bn.ConnectingMatrix(Z=Z, basegraph=bg), device=dev)
         mb = BoostedNeuralLDPCDecoder(20, B, cmb, node_weight_sharing_config=NodeWeightSharingConfig(3, 0, 0), decoding_type=DecoderType.QMS).to(dev)

@@ -40,15 +40,15 @@ template <class G>
 int launch_neural(const DecodeArgs &a, int sm_count, cudaStream_t st) {
     using Cfg = SpecCfg<G>;
     const int n_units = (a.B + Cfg::Shape::kCw - 1) / Cfg::Shape::kCw;
-        const int grid = std::min(n_units, sm_count * Cfg::kCtasPerSm);
+    const int grid = std::min(n_units, sm_count * Cfg::kCtasPerSm);
     const bool every = a.soft_mode == 1 || a.hard_mode == 1 || a.hist_v2c != nullptr;
     DecodeArgs args = a;
     // weights -> constant arena (uniform-datapath reads in the kernel); LDG variant if they do not fit
     ConstArena &arena = arena_for_current_device();
     const int len = a.T * G::E;
-    cudaError_t err;
-    const int off = arena.acquire(len, st, &err);
-    if (err != cudaSuccess) return (int)err;
+    cudaError_t err = cudaSuccess;
+    const int off = stream_is_capturing(st) ? -1 : arena.acquire(len, st, &err);
+    if (off >= 0 && err != cudaSuccess) return (int)err;
     args.wb_off = off;
     if (off >= 0) {
         pack_wb_kernel<<<(len + 255) / 256, 256, 0, st>>>(a.w, a.b, arena.base + off, len);

@@ -655,6 +655,7 @@ template <class G, bool kBoosted>
 int spec_bwd_launch(const BwdArgs &a, int graph_slot, int sm_count, cudaStream_t st) {
     if (G::kDeg1Smem != 0) return -1;                         // the lane-private chain assumes identity circulants on degree-1 blocks
     if (!a.scratch || kBoosted != (a.mode != 0)) return -1;
+    if (stream_is_capturing(st)) return -1;                   // CUDA graph capture: see stream_is_capturing
     if (a.mode != 0 && (a.ucn_mix || a.hist_ucn)) return -1;
     if (a.mode == 2 && a.qbit != 5) return -1;
     if (a.mode != 0 && !a.w) return -1;                       // no CN weights: nothing but VN rows to learn; keep it simple

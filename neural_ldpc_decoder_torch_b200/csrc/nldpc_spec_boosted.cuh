@@ -48,6 +48,7 @@ int boosted_launch(const DecodeArgs &a, int sm_count, cudaStream_t st) {
     const bool qms5 = a.decoder_type == 2 && a.qbit == 5, ms = a.decoder_type == 1;
     if (!(qms5 || ms) || a.compute_ucn || a.llr_init || a.xin_init || a.xin_out || a.app_init) return -1;
     if (a.hist_v2c && a.soft_mode != 1) return -1;      // the training dump rides on the every-iteration variant
+    if (stream_is_capturing(st)) return -1;             // CUDA graph capture: no launch-time arena bookkeeping (table-driven kernel)
     ConstArena &arena = arena_for_current_device();
     const int len = a.T * G::E;
     cudaError_t err;

@@ -11,6 +11,18 @@ namespace nldpc {
 
 namespace {
 
+// True while `st` is being captured into a CUDA graph.  The constant arena hands out ranges at LAUNCH time (event queries,
+// host-side bookkeeping), which a replayed graph would not repeat — captured launches therefore read their weights from
+// global memory (Neural: the LDG variant of the same kernel; Boosted / backward: the table-driven kernels).
+inline bool stream_is_capturing(cudaStream_t st) {
+    cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &status) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return status != cudaStreamCaptureStatusNone;
+}
+
 // {w[i], b[i]} -> constant arena (written through its global address; visible to the launches that follow
 // on the same stream: the constant cache is invalidated at kernel boundaries)
 __global__ void pack_wb_kernel(const float *__restrict__ w, const float *__restrict__ b, float2 *__restrict__ dst, int n) {

@@ -178,3 +178,37 @@ def test_cpu_tensor_fails_loudly(graphs):
     m = make_model(bg, Z, 2, 4)
     with pytest.raises(NldpcError):
         m(torch.zeros((4, bg.shape[1], Z)))
+
+
+def test_decode_is_cuda_graph_capturable(graphs):
+    """the decode ops can be captured into a CUDA graph (small-batch, launch-bound use): captured launches avoid the
+    launch-time constant-arena bookkeeping and read their weights from global memory; replay must reproduce the eager result
+    and follow in-place updates of inputs and weights"""
+    bg, Z = graphs["wimax"]
+    T, B = 10, 1024
+    rs = np.random.RandomState(3)
+    w = rs.uniform(0.3, 1.3, size=(T, int((bg != -1).sum()))).astype(np.float32)
+    b = (0.2 * rs.randn(*w.shape)).astype(np.float32)
+    m = make_model(bg, Z, T, B, w, b)
+    x = torch.from_numpy(awgn_llr("wimax", B, seed=5, sigma=0.9)).cuda()
+    with torch.no_grad():
+        eager = m.decode_hard(x).clone()
+        static_x = x.clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            m.decode_hard(static_x)                      # warm-up on the side stream
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = m.decode_hard(static_x)
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, eager)
+        # new inputs and new weights, same graph
+        x2 = torch.from_numpy(awgn_llr("wimax", B, seed=6, sigma=1.1)).cuda()
+        static_x.copy_(x2)
+        m.weights_var[3].mul_(0.9)
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, m.decode_hard(x2))
