@@ -161,6 +161,22 @@ int nldpc_multi_iter_bce(const float *soft_dev, const float *y_dev, const float 
 int nldpc_multi_iter_bce_grad(const float *soft_dev, const float *y_dev, const float *coef_dev, const float *gscale_dev, int T,
                               size_t n_per_iter, float *gout_dev, void *stream);
 
+/* Per-iteration bit / frame error counts: replaces Functions.evaluate_ber_fer (Functions.py:86-102) — the reference's
+ * 4 elementwise passes + 2 reductions per iteration become one read of the T soft outputs.
+ *   soft_dev    : iteration t at soft_dev + t * iter_stride (in floats), each [B][NZ] (NZ = N*Z), e.g. the [T][B][NZ]
+ *                 tensor of nldpc_neural_forward / nldpc_boosted_forward with iter_stride = B*NZ
+ *   y_dev       : [B][NZ] fp32 labels (the reference compares ((out < 0) ? 1.0 : 0.0) != y as floats, :90-93 — note the
+ *                 predicate is inverted w.r.t. the true decision; kept as is)
+ *   counts_dev  : [2][T] uint64, OVERWRITTEN: counts[0][t] = differing positions, counts[1][t] = codewords with >= 1
+ * Current device, asynchronous on `stream`. */
+int nldpc_count_errors(const float *soft_dev, size_t iter_stride, const float *y_dev, int T, int B, int NZ,
+                       uint64_t *counts_dev, void *stream);
+/* The same on the packed hard decisions the decode entry points write (bit i%8 of byte i/8 = out[i] < 0;
+ * [T][B][ceil(NZ/8)] with iteration t at hard_dev + t * iter_stride_bytes).  y_packed_dev: labels packed the same way,
+ * or NULL = the all-zero codeword.  Bits past NZ in a row's last byte are ignored. */
+int nldpc_count_errors_packed(const uint8_t *hard_dev, size_t iter_stride_bytes, const uint8_t *y_packed_dev, int T, int B,
+                              int NZ, uint64_t *counts_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

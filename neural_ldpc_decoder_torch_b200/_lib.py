@@ -77,6 +77,10 @@ def lib():
             L.nldpc_multi_iter_bce.argtypes = [vp, vp, vp, ci, ctypes.c_size_t, vp, vp, vp]
             L.nldpc_multi_iter_bce_grad.restype = ci
             L.nldpc_multi_iter_bce_grad.argtypes = [vp, vp, vp, vp, ci, ctypes.c_size_t, vp, vp]
+            L.nldpc_count_errors.restype = ci
+            L.nldpc_count_errors.argtypes = [vp, ctypes.c_size_t, vp, ci, ci, ci, vp, vp]
+            L.nldpc_count_errors_packed.restype = ci
+            L.nldpc_count_errors_packed.argtypes = [vp, ctypes.c_size_t, vp, ci, ci, ci, vp, vp]
             _lib = L
     return _lib
 

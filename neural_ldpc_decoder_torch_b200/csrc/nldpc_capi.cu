@@ -507,3 +507,35 @@ extern "C" int nldpc_multi_iter_bce_grad(const float *soft_dev, const float *y_d
     if (rc != 0) return fail(rc, std::string("nldpc_multi_iter_bce_grad: ") + cudaGetErrorString((cudaError_t)rc));
     return NLDPC_OK;
 }
+
+namespace nldpc {
+int launch_count_errors(const float *soft, size_t iter_stride, const float *y, int T, int B, int NZ, unsigned long long *counts,
+                        int sm_count, cudaStream_t st);
+int launch_count_errors_packed(const uint8_t *hard, size_t iter_stride, const uint8_t *yp, int T, int B, int NZ,
+                               unsigned long long *counts, int sm_count, cudaStream_t st);
+}
+
+extern "C" int nldpc_count_errors(const float *soft_dev, size_t iter_stride, const float *y_dev, int T, int B, int NZ,
+                                  uint64_t *counts_dev, void *stream) {
+    if (!counts_dev || T <= 0 || B < 0 || NZ < 0 || ((!soft_dev || !y_dev) && B > 0 && NZ > 0))
+        return fail(NLDPC_E_INVALID, "nldpc_count_errors: bad argument");
+    int dev = 0, sms = 148;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int rc = launch_count_errors(soft_dev, iter_stride, y_dev, T, B, NZ, (unsigned long long *)counts_dev, sms, (cudaStream_t)stream);
+    if (rc != 0) return fail(rc, std::string("nldpc_count_errors: ") + cudaGetErrorString((cudaError_t)rc));
+    return NLDPC_OK;
+}
+
+extern "C" int nldpc_count_errors_packed(const uint8_t *hard_dev, size_t iter_stride_bytes, const uint8_t *y_packed_dev, int T, int B,
+                                         int NZ, uint64_t *counts_dev, void *stream) {
+    if (!counts_dev || T <= 0 || B < 0 || NZ < 0 || (!hard_dev && B > 0 && NZ > 0))
+        return fail(NLDPC_E_INVALID, "nldpc_count_errors_packed: bad argument");
+    int dev = 0, sms = 148;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int rc = launch_count_errors_packed(hard_dev, iter_stride_bytes, y_packed_dev, T, B, NZ, (unsigned long long *)counts_dev, sms,
+                                              (cudaStream_t)stream);
+    if (rc != 0) return fail(rc, std::string("nldpc_count_errors_packed: ") + cudaGetErrorString((cudaError_t)rc));
+    return NLDPC_OK;
+}

@@ -416,3 +416,82 @@ def fused_multi_iter_bce(outputs, y, etha=1.0, coeff_param=None):
     coef = torch.tensor([v / tot if tot > 0 else v for v in w], dtype=torch.float32, device=base.device)
     loss, _ = torch.ops.nldpc.multi_iter_bce(base, y.to(torch.float32), coef, False)    # the gradient is produced in backward
     return 1.0 * loss
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# bit / frame error counts per iteration (Functions.evaluate_ber_fer, Functions.py:86-102)
+@torch.library.custom_op("nldpc::count_errors", mutates_args=())
+def count_errors(soft: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """soft [T, B, NZ] iteration outputs, y [B, NZ] fp32 labels -> int64 [2, T]: row 0 = positions where
+    ((out < 0) ? 1 : 0) != y, row 1 = codewords with at least one (one fused pass; exact integer counts)."""
+    _check_cuda_f32("soft", soft)
+    _check_cuda_f32("y", y)
+    if soft.dim() != 3 or y.dim() != 2 or tuple(soft.shape[1:]) != tuple(y.shape):
+        raise ValueError("soft must be [T, B, NZ] and y [B, NZ]")
+    T, B, NZ = soft.shape
+    if T == 0:
+        return torch.zeros((2, 0), dtype=torch.int64, device=soft.device)
+    if not (soft.stride(2) == 1 and soft.stride(1) == NZ) and B * NZ > 0:      # rows must be dense; the iteration stride is free
+        soft = soft.contiguous()
+    y = y.contiguous()
+    counts = torch.empty((2, T), dtype=torch.int64, device=soft.device)
+    with torch.cuda.device(soft.device):
+        rc = _lib.lib().nldpc_count_errors(_ptr(soft), soft.stride(0) if B * NZ > 0 else 0, _ptr(y), T, B, NZ, _ptr(counts), _stream(soft))
+    _lib.check(rc, "nldpc_count_errors")
+    return counts
+
+
+@count_errors.register_fake
+def _(soft, y):
+    return soft.new_empty((2, soft.shape[0]), dtype=torch.int64)
+
+
+@torch.library.custom_op("nldpc::count_errors_packed", mutates_args=())
+def count_errors_packed(hard: torch.Tensor, n_bits: int, y_packed: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """hard uint8 [T, B, ceil(n_bits/8)] (or [B, ...] = one iteration) packed decisions as the decode ops write them,
+    y_packed the labels packed the same way (None = all-zero codeword) -> int64 [2, T] as count_errors."""
+    if not hard.is_cuda:
+        raise _lib.NldpcError(f"hard is on {hard.device}: the B200 path has no CPU fallback — move it to a CUDA device")
+    if hard.dtype != torch.uint8 or (y_packed is not None and y_packed.dtype != torch.uint8):
+        raise TypeError("packed decisions / labels must be uint8")
+    if hard.dim() == 2:
+        hard = hard.unsqueeze(0)
+    hb = (n_bits + 7) // 8
+    if hard.dim() != 3 or hard.shape[2] != hb or (y_packed is not None and tuple(y_packed.shape) != tuple(hard.shape[1:])):
+        raise ValueError("hard must be [T, B, ceil(n_bits/8)] and y_packed [B, ceil(n_bits/8)]")
+    T, B, _ = hard.shape
+    if T == 0:
+        return torch.zeros((2, 0), dtype=torch.int64, device=hard.device)
+    hard = hard.contiguous()
+    yp = y_packed.contiguous() if y_packed is not None else None
+    counts = torch.empty((2, T), dtype=torch.int64, device=hard.device)
+    with torch.cuda.device(hard.device):
+        rc = _lib.lib().nldpc_count_errors_packed(_ptr(hard), B * hb, _ptr(yp), T, B, n_bits, _ptr(counts), _stream(hard))
+    _lib.check(rc, "nldpc_count_errors_packed")
+    return counts
+
+
+@count_errors_packed.register_fake
+def _(hard, n_bits, y_packed=None):
+    return hard.new_empty((2, hard.shape[0] if hard.dim() == 3 else 1), dtype=torch.int64)
+
+
+def fused_ber_fer_counts(expected, actual):
+    """Functions.evaluate_ber_fer on the device: `actual` is a list of T CUDA fp32 [B, NZ] tensors (views of one [T, B, NZ]
+    tensor are read in place; anything else is counted tensor by tensor, still one pass each).  Returns int64 [2, T] on the
+    device, or None when the inputs are not CUDA fp32 2-D tensors of one shape (caller uses the torch formulation)."""
+    if not isinstance(actual, (list, tuple)) or len(actual) == 0 or not isinstance(expected, torch.Tensor):
+        return None
+    if not (expected.is_cuda and expected.dtype == torch.float32 and expected.dim() == 2):
+        return None
+    for o in actual:
+        if not (isinstance(o, torch.Tensor) and o.is_cuda and o.dtype == torch.float32 and tuple(o.shape) == tuple(expected.shape)
+                and o.device == expected.device):
+            return None
+    base = actual[0]._base
+    if base is not None and base.dim() == 3 and base.shape[0] == len(actual) and tuple(base.shape[1:]) == tuple(expected.shape):
+        step = base.stride(0)
+        if all(o._base is base and o.storage_offset() == base.storage_offset() + t * step and o.stride() == base.stride()[1:]
+               for t, o in enumerate(actual)):
+            return torch.ops.nldpc.count_errors(base.detach(), expected)
+    return torch.cat([torch.ops.nldpc.count_errors(o.detach().unsqueeze(0), expected) for o in actual], dim=1)

@@ -143,3 +143,24 @@ def quantize(x, qbit):
     y = np.empty_like(x)
     lib().nldpc_oracle_quantize(x.reshape(-1), y.reshape(-1), x.size, int(qbit))
     return y
+
+
+def count_errors(soft, y):
+    """[T,B,NZ] f32 iteration outputs, [B,NZ] f32 labels -> int64 [2,T]: row 0 = positions where the decided bit
+    ((out < 0) as 0.0/1.0, Functions.py:90) differs from the label (:93-94), row 1 = codewords with at least one (:98-99)."""
+    soft = np.asarray(soft, dtype=np.float32)
+    y = np.asarray(y, dtype=np.float32)
+    with np.errstate(invalid="ignore"):
+        wrong = (soft < 0).astype(np.float32) != y[None]
+    per = wrong.sum(axis=2, dtype=np.int64)
+    return np.stack([per.sum(axis=1, dtype=np.int64), (per > 0).sum(axis=1, dtype=np.int64)]).astype(np.int64)
+
+
+def count_errors_packed(hard, n_bits, y_packed=None):
+    """the same on packed decisions [T,B,ceil(n_bits/8)] u8 (pack_hard layout); y_packed None = all-zero codeword"""
+    hard = np.asarray(hard, dtype=np.uint8)
+    bits = np.unpackbits(hard, axis=-1, bitorder="little")[..., :n_bits]
+    if y_packed is not None:
+        bits = bits ^ np.unpackbits(np.asarray(y_packed, dtype=np.uint8), axis=-1, bitorder="little")[None, ..., :n_bits]
+    per = bits.sum(axis=2, dtype=np.int64)
+    return np.stack([per.sum(axis=1, dtype=np.int64), (per > 0).sum(axis=1, dtype=np.int64)]).astype(np.int64)
