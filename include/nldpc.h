@@ -177,6 +177,17 @@ int nldpc_count_errors(const float *soft_dev, size_t iter_stride, const float *y
 int nldpc_count_errors_packed(const uint8_t *hard_dev, size_t iter_stride_bytes, const uint8_t *y_packed_dev, int T, int B,
                               int NZ, uint64_t *counts_dev, void *stream);
 
+/* Tail of one training step on the flat weight vector, one launch: replaces clip_grad_norm_ + Adam.step + the clamp of
+ * _apply_constraints (train/train_BoostedNeuralLDPCDecoder.py:291-294, BoostedNeuralLDPCDecoder.py:153-179).
+ *   param_dev, grad_dev, exp_avg_dev, exp_avg_sq_dev : [n] fp32, all UPDATED in place (grad receives the clipped gradient)
+ *   state_dev  : 2 floats: [0] step count so far (incremented by the kernel — the launch is CUDA-graph replayable),
+ *                [1] receives the total gradient norm before clipping
+ *   grad_scale : multiplies the gradient first (1 / world_size after a SUM all-reduce); max_norm <= 0 disables clipping
+ *   lr, beta1, beta2, eps : torch.optim.Adam defaults 1e-3, 0.9, 0.999, 1e-8 (no weight decay, no amsgrad) */
+int nldpc_clip_adam_clamp(float *param_dev, float *grad_dev, float *exp_avg_dev, float *exp_avg_sq_dev, float *state_dev, int n,
+                          float grad_scale, float max_norm, double lr, double beta1, double beta2, double eps, float clamp_lo,
+                          float clamp_hi, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

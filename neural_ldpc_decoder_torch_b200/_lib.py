@@ -77,6 +77,9 @@ def lib():
             L.nldpc_multi_iter_bce.argtypes = [vp, vp, vp, ci, ctypes.c_size_t, vp, vp, vp]
             L.nldpc_multi_iter_bce_grad.restype = ci
             L.nldpc_multi_iter_bce_grad.argtypes = [vp, vp, vp, vp, ci, ctypes.c_size_t, vp, vp]
+            L.nldpc_clip_adam_clamp.restype = ci
+            L.nldpc_clip_adam_clamp.argtypes = [vp, vp, vp, vp, vp, ci, ctypes.c_float, ctypes.c_float, ctypes.c_double, ctypes.c_double,
+                                                ctypes.c_double, ctypes.c_double, ctypes.c_float, ctypes.c_float, vp]
             L.nldpc_count_errors.restype = ci
             L.nldpc_count_errors.argtypes = [vp, ctypes.c_size_t, vp, ci, ci, ci, vp, vp]
             L.nldpc_count_errors_packed.restype = ci

@@ -539,3 +539,19 @@ extern "C" int nldpc_count_errors_packed(const uint8_t *hard_dev, size_t iter_st
     if (rc != 0) return fail(rc, std::string("nldpc_count_errors_packed: ") + cudaGetErrorString((cudaError_t)rc));
     return NLDPC_OK;
 }
+
+namespace nldpc {
+int launch_clip_adam_clamp(float *p, float *g, float *m, float *v, float *state, int n, float grad_scale, float max_norm, double lr,
+                           double beta1, double beta2, double eps, float lo, float hi, cudaStream_t st);
+}
+
+extern "C" int nldpc_clip_adam_clamp(float *param_dev, float *grad_dev, float *exp_avg_dev, float *exp_avg_sq_dev, float *state_dev, int n,
+                                     float grad_scale, float max_norm, double lr, double beta1, double beta2, double eps, float clamp_lo,
+                                     float clamp_hi, void *stream) {
+    if (n < 0 || (n > 0 && (!param_dev || !grad_dev || !exp_avg_dev || !exp_avg_sq_dev)) || !state_dev || !(clamp_lo <= clamp_hi))
+        return fail(NLDPC_E_INVALID, "nldpc_clip_adam_clamp: bad argument");
+    const int rc = launch_clip_adam_clamp(param_dev, grad_dev, exp_avg_dev, exp_avg_sq_dev, state_dev, n, grad_scale, max_norm, lr, beta1,
+                                          beta2, eps, clamp_lo, clamp_hi, (cudaStream_t)stream);
+    if (rc != 0) return fail(rc, std::string("nldpc_clip_adam_clamp: ") + cudaGetErrorString((cudaError_t)rc));
+    return NLDPC_OK;
+}

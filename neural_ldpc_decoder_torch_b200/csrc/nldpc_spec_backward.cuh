@@ -612,7 +612,7 @@ namespace {
 // descriptors of the looped checks -> this translation unit's c_desc, once per device.  Synchronous on purpose: when the call
 // returns the table is in place for launches on ANY stream (the flag is shared by all of them).
 template <class G>
-cudaError_t ensure_loop_desc(int graph_slot) {
+cudaError_t ensure_loop_desc(int graph_slot, bool capturing) {
     static_assert(G::kLoopDescWords <= kDescStride, "descriptor slot too small");
     static std::mutex mu;
     static bool done[64] = {};
@@ -621,6 +621,7 @@ cudaError_t ensure_loop_desc(int graph_slot) {
     cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lock(mu);
     if (done[dev & 63]) return cudaSuccess;
+    if (capturing) return cudaErrorStreamCaptureUnsupported;      // first use inside a capture: the caller falls back
     cudaError_t e = cudaMemcpyToSymbol(c_desc, G::loop_desc(), sizeof(uint32_t) * G::kLoopDescWords,
                                        sizeof(uint32_t) * (size_t)graph_slot * kDescStride, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) done[dev & 63] = true;
@@ -628,18 +629,20 @@ cudaError_t ensure_loop_desc(int graph_slot) {
 }
 
 template <class G, int MODE, bool kVn>
-int spec_bwd_launch_one(const BwdArgs &a, int wb_off, int graph_slot, int sm_count, cudaStream_t st) {
+int spec_bwd_launch_one(const BwdArgs &a, int wb_off, int graph_slot, int sm_count, cudaStream_t st, bool capturing) {
     using Cfg = SpecBwdCfg<G>;
     const size_t smem = Cfg::smem_bytes(a.T, MODE, kVn);
     static bool prepared[64] = {};   // per translation unit, variant and device; the attribute is idempotent
     int dev = 0;
     cudaGetDevice(&dev);
     if (!prepared[dev & 63]) {
+        if (capturing) return -1;            // one-off set-up belongs to an eager (warm-up) launch
         cudaError_t e = set_smem(nldpc_spec_backward_kernel<G, MODE, kVn>, kSmemBudget);
         if (e != cudaSuccess) return (int)e;
         prepared[dev & 63] = true;
     }
-    cudaError_t e = ensure_loop_desc<G>(graph_slot);
+    cudaError_t e = ensure_loop_desc<G>(graph_slot, capturing);
+    if (e == cudaErrorStreamCaptureUnsupported && capturing) return -1;
     if (e != cudaSuccess) return (int)e;
     const int n_tiles = (a.B + Cfg::kCwPerCta - 1) / Cfg::kCwPerCta;
     const int grid = std::min(n_tiles, sm_count);
@@ -655,7 +658,7 @@ template <class G, bool kBoosted>
 int spec_bwd_launch(const BwdArgs &a, int graph_slot, int sm_count, cudaStream_t st) {
     if (G::kDeg1Smem != 0) return -1;                         // the lane-private chain assumes identity circulants on degree-1 blocks
     if (!a.scratch || kBoosted != (a.mode != 0)) return -1;
-    if (stream_is_capturing(st)) return -1;                   // CUDA graph capture: see stream_is_capturing
+    const bool capturing = stream_is_capturing(st);           // CUDA graph capture: see ConstArena::acquire_captured
     if (a.mode != 0 && (a.ucn_mix || a.hist_ucn)) return -1;
     if (a.mode == 2 && a.qbit != 5) return -1;
     if (a.mode != 0 && !a.w) return -1;                       // no CN weights: nothing but VN rows to learn; keep it simple
@@ -663,18 +666,19 @@ int spec_bwd_launch(const BwdArgs &a, int graph_slot, int sm_count, cudaStream_t
     if (Cfg::smem_bytes(a.T, a.mode, a.gvn != nullptr) > (size_t)kSmemBudget) return -1;
     ConstArena &arena = arena_for_current_device();
     const int len = a.T * G::E;
-    cudaError_t err;
-    const int off = arena.acquire(len, st, &err);
+    cudaError_t err = cudaSuccess;
+    const int off = capturing ? arena.acquire_captured(len) : arena.acquire(len, st, &err);
     if (err != cudaSuccess) return (int)err;
     if (off < 0) return -1;
     pack_wb_kernel<<<(len + 255) / 256, 256, 0, st>>>(a.w, a.mode == 0 ? a.b : nullptr, arena.base + off, len);
     int rc;
     if constexpr (!kBoosted) {
-        rc = spec_bwd_launch_one<G, 0, false>(a, off, graph_slot, sm_count, st);
+        rc = spec_bwd_launch_one<G, 0, false>(a, off, graph_slot, sm_count, st, capturing);
     } else {
-        if (a.mode == 1) rc = a.gvn ? spec_bwd_launch_one<G, 1, true>(a, off, graph_slot, sm_count, st) : spec_bwd_launch_one<G, 1, false>(a, off, graph_slot, sm_count, st);
-        else rc = a.gvn ? spec_bwd_launch_one<G, 2, true>(a, off, graph_slot, sm_count, st) : spec_bwd_launch_one<G, 2, false>(a, off, graph_slot, sm_count, st);
+        if (a.mode == 1) rc = a.gvn ? spec_bwd_launch_one<G, 1, true>(a, off, graph_slot, sm_count, st, capturing) : spec_bwd_launch_one<G, 1, false>(a, off, graph_slot, sm_count, st, capturing);
+        else rc = a.gvn ? spec_bwd_launch_one<G, 2, true>(a, off, graph_slot, sm_count, st, capturing) : spec_bwd_launch_one<G, 2, false>(a, off, graph_slot, sm_count, st, capturing);
     }
+    if (capturing) return rc;
     const cudaError_t rel = arena.release_after(off, len, st);
     if (rc != 0) return rc;
     return (int)rel;

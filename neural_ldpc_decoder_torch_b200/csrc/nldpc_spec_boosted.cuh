@@ -48,11 +48,11 @@ int boosted_launch(const DecodeArgs &a, int sm_count, cudaStream_t st) {
     const bool qms5 = a.decoder_type == 2 && a.qbit == 5, ms = a.decoder_type == 1;
     if (!(qms5 || ms) || a.compute_ucn || a.llr_init || a.xin_init || a.xin_out || a.app_init) return -1;
     if (a.hist_v2c && a.soft_mode != 1) return -1;      // the training dump rides on the every-iteration variant
-    if (stream_is_capturing(st)) return -1;             // CUDA graph capture: no launch-time arena bookkeeping (table-driven kernel)
+    const bool capturing = stream_is_capturing(st);      // CUDA graph capture: fixed arena range, no launch-time bookkeeping
     ConstArena &arena = arena_for_current_device();
     const int len = a.T * G::E;
-    cudaError_t err;
-    const int off = arena.acquire(len, st, &err);
+    cudaError_t err = cudaSuccess;
+    const int off = capturing ? arena.acquire_captured(len) : arena.acquire(len, st, &err);
     if (err != cudaSuccess) return (int)err;
     if (off < 0) return -1;
     DecodeArgs args = a;
@@ -61,7 +61,7 @@ int boosted_launch(const DecodeArgs &a, int sm_count, cudaStream_t st) {
     int rc;
     if (ms) rc = a.vn_w ? boosted_launch_one<G, 1, true>(args, sm_count, st) : boosted_launch_one<G, 1, false>(args, sm_count, st);
     else rc = a.vn_w ? boosted_launch_one<G, 2, true>(args, sm_count, st) : boosted_launch_one<G, 2, false>(args, sm_count, st);
-    if (rc != 0) return rc;
+    if (rc != 0 || capturing) return rc;
     return (int)arena.release_after(off, len, st);
 }
 

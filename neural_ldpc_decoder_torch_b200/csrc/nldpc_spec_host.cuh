@@ -12,8 +12,9 @@ namespace nldpc {
 namespace {
 
 // True while `st` is being captured into a CUDA graph.  The constant arena hands out ranges at LAUNCH time (event queries,
-// host-side bookkeeping), which a replayed graph would not repeat — captured launches therefore read their weights from
-// global memory (Neural: the LDG variant of the same kernel; Boosted / backward: the table-driven kernels).
+// host-side bookkeeping), which a replayed graph would not repeat.  Captured launches therefore either read their weights
+// from global memory (Neural: the LDG variant of the same kernel) or use the fixed range ConstArena::acquire_captured hands
+// out (Boosted forward / backward sweeps: same specialised kernels as eager launches).
 inline bool stream_is_capturing(cudaStream_t st) {
     cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &status) != cudaSuccess) {
@@ -68,6 +69,16 @@ struct ConstArena {
             }
         }
         return off;
+    }
+    // Launch being captured into a CUDA graph: every captured launch uses the range at offset 0 — inside a graph the
+    // pack -> consumer pairs are ordered by the capture stream, and a replay is ordered against eager launches of the stream
+    // it is replayed on.  What nothing orders is a replay against launches of this library running CONCURRENTLY on another
+    // stream of the device (the ring's events cannot be re-recorded by a replay): callers must not do that.
+    // -1 when the arena has not been set up by an earlier eager launch (the caller then uses the table-driven kernel).
+    int acquire_captured(int len) {
+        if (len > kConstFloat2) return -1;
+        std::lock_guard<std::mutex> lk(mu);
+        return base ? 0 : -1;
     }
     // call after the consumer kernel has been enqueued on `st`
     cudaError_t release_after(int off, int len, cudaStream_t st) {

@@ -393,6 +393,9 @@ def _bce_bwd(ctx, gloss, ggout):
 multi_iter_bce.register_autograd(_bce_bwd, setup_context=_bce_setup_ctx)
 
 
+_coef_cache = {}
+
+
 def fused_multi_iter_bce(outputs, y, etha=1.0, coeff_param=None):
     """Drop-in for LDPCDecoderLoss(BCE)(outputs, y, coeff_param) when `outputs` is the list a decoder's forward returned
     (views of ONE [T, B, N*Z] tensor): a single fused kernel for the loss and its gradient.  Returns None when the list
@@ -413,7 +416,12 @@ def fused_multi_iter_bce(outputs, y, etha=1.0, coeff_param=None):
         coeffs = list(coeff_param) if isinstance(coeff_param, (list, tuple)) else [coeff_param] * T
     w = [float(pow(etha, c)) for c in coeffs]
     tot = sum(w)
-    coef = torch.tensor([v / tot if tot > 0 else v for v in w], dtype=torch.float32, device=base.device)
+    key = (base.device, tuple(v / tot if tot > 0 else v for v in w))
+    coef = _coef_cache.get(key)
+    if coef is None:                # one H2D copy per distinct coefficient vector, none per step (CUDA-graph capturable)
+        if len(_coef_cache) > 64:
+            _coef_cache.clear()
+        coef = _coef_cache[key] = torch.tensor(key[1], dtype=torch.float32, device=base.device)
     loss, _ = torch.ops.nldpc.multi_iter_bce(base, y.to(torch.float32), coef, False)    # the gradient is produced in backward
     return 1.0 * loss
 
@@ -495,3 +503,23 @@ def fused_ber_fer_counts(expected, actual):
                for t, o in enumerate(actual)):
             return torch.ops.nldpc.count_errors(base.detach(), expected)
     return torch.cat([torch.ops.nldpc.count_errors(o.detach().unsqueeze(0), expected) for o in actual], dim=1)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clip_grad_norm_ + Adam + clamp on the flat weight vector (train/train_BoostedNeuralLDPCDecoder.py:291-294)
+def clip_adam_clamp_(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, state: torch.Tensor,
+                     grad_scale: float = 1.0, max_norm: float = 1.0, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                     clamp=(0.0, 2.0)):
+    """In place, one launch, no host synchronisation (CUDA-graph replayable: the step counter is state[0] on the device)."""
+    n = param.numel()
+    for name, t in (("param", param), ("grad", grad), ("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq), ("state", state)):
+        _check_cuda_f32(name, t)
+        if not t.is_contiguous() or (name != "state" and t.numel() != n):
+            raise ValueError(f"{name} must be a contiguous fp32 vector of {n} elements")
+    if state.numel() != 2:
+        raise ValueError("state must hold 2 floats (step count, last gradient norm)")
+    with torch.cuda.device(param.device):
+        rc = _lib.lib().nldpc_clip_adam_clamp(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), _ptr(state), n, float(grad_scale),
+                                              float(max_norm), float(lr), float(betas[0]), float(betas[1]), float(eps), float(clamp[0]),
+                                              float(clamp[1]), _stream(param))
+    _lib.check(rc, "nldpc_clip_adam_clamp")

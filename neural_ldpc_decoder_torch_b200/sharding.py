@@ -4,6 +4,8 @@ gradient all-reduces below (torch.distributed: NCCL over NVLink on GPUs, gloo in
 import torch
 import torch.distributed as dist
 
+from . import ops  # noqa: F401  (registers torch.ops.nldpc.*)
+
 
 def shard_bounds(total: int, world: int, rank: int):
     """contiguous [begin, end) of `total` codewords owned by `rank` (sizes differ by at most one)"""
@@ -39,6 +41,9 @@ def allreduce_mean_grads_(params):
 def count_errors_packed(hard: torch.Tensor, expected_bits_packed: torch.Tensor):
     """bit / frame error counts from packed hard decisions [B, nbytes] (uint8) against packed expected bits.
     Returns int64 tensor [bit_errors, frame_errors, bits, frames] on hard's device (all-reduce it across ranks)."""
+    if hard.is_cuda:            # fused kernel (nldpc_count_errors_packed): one pass, no [B, nbytes] int64 temporaries
+        c = torch.ops.nldpc.count_errors_packed(hard, hard.shape[1] * 8, expected_bits_packed)
+        return torch.cat([c[:, 0], torch.tensor([hard.shape[0] * hard.shape[1] * 8, hard.shape[0]], dtype=torch.int64).to(hard.device)])
     x = torch.bitwise_xor(hard, expected_bits_packed)
     lut = torch.tensor([bin(i).count("1") for i in range(256)], dtype=torch.int64, device=hard.device)
     per_cw = lut[x.long()].sum(dim=1)

@@ -69,6 +69,130 @@ def train_step(model, criterion, optimizer, x, y, n_iters, max_grad_norm=1.0):
     return loss
 
 
+class FusedTrainer:
+    """The loop body of train/train_BoostedNeuralLDPCDecoder.py:274-294 with the optimiser tail in ONE launch and, optionally,
+    the whole step replayed from a CUDA graph.
+
+    * The trainable parameters (model.get_trainable_parameters() / model.parameters()) are re-pointed at slices of one flat
+      fp32 vector, their .grad at slices of a second one: the data-parallel exchange is ONE all-reduce (SUM) of that vector
+      with no gather / scatter copies, and clip_grad_norm_ + Adam + _apply_constraints is one nldpc_clip_adam_clamp launch
+      (1 / world_size folded in).  Parameter names, shapes and state_dict() are unchanged.
+    * graph=True captures zero-grad -> forward -> fused BCE -> backward -> [all-reduce] -> optimiser once and replays it per
+      step (inputs are copied into static buffers): for the reference's own batch size (20) the step is host-launch bound
+      (~3 ms eager), the replay removes that.  While capturing, the launches read their weights from global memory (the
+      table-driven kernels), so for large batches (>= a few thousand codewords) eager mode with the specialised kernels is
+      the faster choice."""
+
+    def __init__(self, model, criterion, n_iters, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, max_grad_norm=1.0, clamp=None,
+                 params=None, graph=False):
+        self.model, self.criterion, self.n_iters = model, criterion, int(n_iters)
+        self.lr, self.betas, self.eps, self.max_grad_norm = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(max_grad_norm)
+        if clamp is None:
+            rng = getattr(model, "allowed_weight_range", None)
+            clamp = (float(rng.start), float(rng.end)) if rng is not None else (-float("inf"), float("inf"))
+        self.clamp = clamp
+        if params is None:
+            params = model.get_trainable_parameters() if hasattr(model, "get_trainable_parameters") else model.parameters()
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        dev = self.params[0].device
+        if dev.type != "cuda" or any(p.device != dev or p.dtype != torch.float32 for p in self.params):
+            from ._lib import NldpcError
+            raise NldpcError("FusedTrainer needs fp32 parameters on one CUDA device (there is no CPU fallback)")
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.state = torch.zeros(2, dtype=torch.float32, device=dev)          # [step count, last gradient norm]
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                k = p.numel()
+                self.flat[off:off + k].copy_(p.detach().reshape(-1))
+                p.data = self.flat[off:off + k].view(p.shape)
+                p.grad = self.flat_grad[off:off + k].view(p.shape)
+                off += k
+        self.device = dev
+        self._graph = None
+        self._want_graph = bool(graph)
+        self._static = None
+
+    # -- pieces ---------------------------------------------------------------------------------------------------
+    def _world(self):
+        import torch.distributed as dist
+        return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+    def _step_body(self, x, y):
+        from . import ops
+        self.flat_grad.zero_()                                            # grads accumulate in place into the flat vector
+        outputs = self.model(x, target_iter=list(range(self.n_iters))) if self._takes_target_iter() else self.model(x)
+        loss = self.criterion(outputs, y, coeff_param=list(range(len(outputs))))
+        loss.backward()
+        world = self._world()
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)        # the one exchange of the step (NCCL over NVLink)
+        ops.clip_adam_clamp_(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.state, 1.0 / world, self.max_grad_norm,
+                             self.lr, self.betas, self.eps, self.clamp)
+        return loss.detach()
+
+    def _takes_target_iter(self):
+        return hasattr(self.model, "fetch_param")                        # the Boosted decoder; the Neural forward takes xa only
+
+    def _check_grad_views(self):
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * off or p.data_ptr() != self.flat.data_ptr() + 4 * off:
+                raise RuntimeError("a parameter or its .grad no longer aliases the trainer's flat vectors (zero_grad(set_to_none=True) "
+                                   "or .to() was called on the model): build a new FusedTrainer")
+            off += k
+
+    # -- public ---------------------------------------------------------------------------------------------------
+    def step(self, x, y):
+        """one optimisation step on (x [B,N,Z], y [B,N*Z]); returns the (detached) loss tensor, no host synchronisation"""
+        self.model.train()
+        if not self._want_graph:
+            self._check_grad_views()
+            return self._step_body(x, y)
+        if self._graph is None:
+            self._check_grad_views()
+            self._static = (torch.empty_like(x), torch.empty_like(y))
+            self._static[0].copy_(x)
+            self._static[1].copy_(y)
+            saved = [t.clone() for t in (self.flat, self.exp_avg, self.exp_avg_sq, self.state)]
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):                                 # warm-up on a side stream (allocator, caches, NCCL)
+                for _ in range(2):
+                    self._step_body(*self._static)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._static_loss = self._step_body(*self._static)
+            self._graph = graph
+            for t, s0 in zip((self.flat, self.exp_avg, self.exp_avg_sq, self.state), saved):
+                t.copy_(s0)                                               # the warm-up steps must not count: restore, then replay once
+            self._graph.replay()
+            return self._static_loss
+        if x.shape != self._static[0].shape or y.shape != self._static[1].shape:
+            raise ValueError("a graphed FusedTrainer is bound to the batch shape it was captured with")
+        self._static[0].copy_(x)
+        self._static[1].copy_(y)
+        self._graph.replay()
+        return self._static_loss
+
+    @property
+    def steps_done(self):
+        return int(self.state[0].item())
+
+    @property
+    def last_grad_norm(self):
+        return float(self.state[1].item())
+
+
 def wilson_interval(k, n, z=1.959963984540054):
     """95 % Wilson score interval of a binomial proportion (BER/FER curves are compared through it)"""
     if n == 0:

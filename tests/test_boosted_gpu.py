@@ -160,3 +160,40 @@ def test_boosted_throughput_mode_matches_oracle(code, sharing, dec, B, T, graphs
     assert np.array_equal(soft, ref[-1]), np.abs(soft - ref[-1]).max()
     assert np.array_equal(soft.view(np.uint32), ref[-1].view(np.uint32)), "bit patterns (sign of zero) differ"
     assert np.array_equal(hard, np.packbits(ref[-1] < 0, axis=1, bitorder="little"))
+
+
+def test_boosted_decode_is_cuda_graph_capturable(graphs):
+    """Captured Boosted launches run the same specialised kernels as eager ones (fixed constant-arena range,
+    ConstArena::acquire_captured): a replay reproduces the eager results bit for bit and follows in-place updates of the
+    inputs and of the weights; eager launches issued between replays on the same stream do not disturb it."""
+    d = load_golden(CASES[3])           # WiMAX QMS (3,0,3), T=20, B=8
+    m = build_module(d, device="cuda", batch=8)
+    xa = torch.from_numpy(d["xa"]).cuda()
+    with torch.no_grad():
+        eager_soft = m.decode_soft_last(xa).clone()
+        eager_hard = m.decode_hard(xa, all_iters=True).clone()
+        static_x = xa.clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            m.decode_soft_last(static_x)
+            m.decode_hard(static_x, all_iters=True)
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            soft = m.decode_soft_last(static_x)
+            hard = m.decode_hard(static_x, all_iters=True)
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(soft.view(torch.int32), eager_soft.view(torch.int32)) and torch.equal(hard, eager_hard)
+        assert np.array_equal(soft.cpu().numpy(), d["out"][-1])
+        x2 = (xa.flip(0) * 0.5).mul(2).round().div(2).contiguous()
+        static_x.copy_(x2)
+        for p in m.parameters():
+            p.mul_(0.875)
+        other = m.decode_soft_last(xa)                   # an eager launch in between (other weights range of the arena ring)
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(soft.view(torch.int32), m.decode_soft_last(x2).view(torch.int32))
+        assert torch.equal(hard, m.decode_hard(x2, all_iters=True))
+        assert other.shape == soft.shape

@@ -23,7 +23,7 @@ from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.LDPCDecoderLoss 
 from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.DecoderType import DecoderType  # noqa: E402
 from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.LossType import LossType  # noqa: E402
 from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.NodeWeightSharingConfig import NodeWeightSharingConfig  # noqa: E402
-from neural_ldpc_decoder_torch_b200.training import DeviceBatchGenerator, train_step  # noqa: E402
+from neural_ldpc_decoder_torch_b200.training import DeviceBatchGenerator, FusedTrainer, train_step  # noqa: E402
 
 
 def main():
@@ -32,6 +32,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--mode", default="torch", choices=["torch", "fused", "graph"],
+                    help="torch: clip_grad_norm_ / torch.optim.Adam / clamp as the reference calls them; fused: FusedTrainer (flat "
+                         "vector, one optimiser launch); graph: the same, whole step replayed from a CUDA graph")
+    ap.add_argument("--fixed-batch", action="store_true", help="reuse one batch (leaves the torch-op batch generator out of the step)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -49,8 +53,13 @@ def main():
     opt = torch.optim.Adam(model.get_trainable_parameters(), lr=1e-3)
     gen = DeviceBatchGenerator(graph, [2, 2.5, 3.0, 3.5, 4.0], dev, seed=2042 + rank, qms_qbit=5)
 
+    trainer = FusedTrainer(model, crit, T, lr=1e-3, graph=(args.mode == "graph")) if args.mode != "torch" else None
+    fixed = gen(B) if args.fixed_batch else None
+
     def step():
-        x, y = gen(B)
+        x, y = fixed if fixed is not None else gen(B)
+        if trainer is not None:
+            return trainer.step(x, y)
         return train_step(model, crit, opt, x, y, T)
 
     for _ in range(args.warmup):
@@ -72,7 +81,8 @@ def main():
         ms = float(t.item())
     if rank == 0:
         print(json.dumps({"metric": "train_step_codewords_per_s", "value": B * world * args.steps / (ms * 1e-3), "unit": "codewords/s",
-                          "n_gpus": world, "steps": args.steps, "ms_per_step": ms / args.steps, "batch_per_gpu": B, "iterations": T,
+                          "n_gpus": world, "steps": args.steps, "ms_per_step": ms / args.steps, "batch_per_gpu": B, "iterations": T, "mode": args.mode,
+                          "fixed_batch": bool(args.fixed_batch),
                           "config": "BoostedNeuralLDPCDecoder BG2 z16 QMS5 cn3/vn3, BCE etha=1, clip 1.0, Adam 1e-3, clamp [0,2]",
                           "first_loss": float(losses[0].detach()), "last_loss": float(losses[-1].detach())}))
     if world > 1:
