@@ -47,7 +47,8 @@ int launch_neural(const DecodeArgs &a, int sm_count, cudaStream_t st) {
     ConstArena &arena = arena_for_current_device();
     const int len = a.T * G::E;
     cudaError_t err = cudaSuccess;
-    const int off = stream_is_capturing(st) ? -1 : arena.acquire(len, st, &err);
+    const bool capturing = stream_is_capturing(st);      // CUDA graph capture: fixed arena range (ConstArena::acquire_captured)
+    const int off = capturing ? arena.acquire_captured(len) : arena.acquire(len, st, &err);
     if (off >= 0 && err != cudaSuccess) return (int)err;
     args.wb_off = off;
     if (off >= 0) {
@@ -55,7 +56,7 @@ int launch_neural(const DecodeArgs &a, int sm_count, cudaStream_t st) {
         if (every) nldpc_spec_neural_kernel<G, true, true><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(args);
         else nldpc_spec_neural_kernel<G, false, true><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(args);
         err = cudaGetLastError();
-        if (err != cudaSuccess) return (int)err;
+        if (err != cudaSuccess || capturing) return (int)err;
         return (int)arena.release_after(off, len, st);
     }
     if (every) nldpc_spec_neural_kernel<G, true, false><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(args);

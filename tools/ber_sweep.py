@@ -47,24 +47,28 @@ def main():
     rows = []
     for snr in args.snr:
         gen = DeviceBatchGenerator(graph, [snr], dev, seed=int(1000 * snr) + 7, all_zero=True, qms_qbit=5)
-        bit_err = frame_err = ok_frames = n = 0
-        checked = mism = 0
+        n = checked = mism = 0
+        counts = torch.zeros((2, 1), dtype=torch.int64, device=dev)       # accumulated on the device: no host sync per batch
+        ok = torch.zeros((), dtype=torch.int64, device=dev)
         t0 = time.perf_counter()
         while n < args.codewords:
             x, y = gen(B)
             out = model.decode_soft_last(x)
-            wrong = ((out < 0).float() != y)                      # reference predicate (inverted w.r.t. the true decision)
-            per = wrong.sum(dim=1)
-            bit_err += int(per.sum()); frame_err += int((per > 0).sum())
-            ok_frames += int((((out > 0).float() == y).all(dim=1)).sum())
+            # reference predicate (inverted w.r.t. the true decision, Functions.py:90): fused kernel, one pass over `out`
+            counts += torch.ops.nldpc.count_errors(out.unsqueeze(0), y)
+            ok += ((out > 0).float() == y).all(dim=1).sum()
             if checked < args.check:
                 import oracle
                 k = min(args.check - checked, B)
                 ref = oracle.boosted_forward(bg, Z, x[:k].cpu().numpy(), T, 2, 5, (-20.0, 20.0), None,
                                              np.full((T, graph.E), args.weights, np.float32))
                 mism += int((ref[-1] != out[:k].cpu().numpy()).sum())
+                want = oracle.count_errors(ref[-1:], y[:k].cpu().numpy())
+                got = torch.ops.nldpc.count_errors(out[:k].unsqueeze(0), y[:k]).cpu().numpy()
+                mism += int((want != got).sum())
                 checked += k
             n += B
+        bit_err, frame_err, ok_frames = int(counts[0, 0]), int(counts[1, 0]), int(ok)
         dt = time.perf_counter() - t0
         rows.append({"ebn0_db": snr, "codewords": n, "ber_refconv": bit_err / (n * graph.N * Z),
                      "ber_ci95": wilson_interval(bit_err, n * graph.N * Z), "fer_refconv": frame_err / n,
