@@ -79,9 +79,9 @@ class FusedTrainer:
       (1 / world_size folded in).  Parameter names, shapes and state_dict() are unchanged.
     * graph=True captures zero-grad -> forward -> fused BCE -> backward -> [all-reduce] -> optimiser once and replays it per
       step (inputs are copied into static buffers): for the reference's own batch size (20) the step is host-launch bound
-      (~3 ms eager), the replay removes that.  While capturing, the launches read their weights from global memory (the
-      table-driven kernels), so for large batches (>= a few thousand codewords) eager mode with the specialised kernels is
-      the faster choice."""
+      (~2.7 ms with torch ops, 1.9 ms eager here), the replay (1.1 ms) removes that.  While capturing, the
+      specialised kernels take their weights from a fixed constant-arena range, ConstArena::acquire_captured).  Single process
+      only: under torch.distributed use graph=False (the step then still has one all-reduce and one optimiser launch)."""
 
     def __init__(self, model, criterion, n_iters, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, max_grad_norm=1.0, clamp=None,
                  params=None, graph=False):
@@ -158,6 +158,10 @@ class FusedTrainer:
             self._check_grad_views()
             return self._step_body(x, y)
         if self._graph is None:
+            if self._world() > 1:
+                # measured: a 2-GPU run with the NCCL all-reduce inside the captured step did not complete (hung); the graphed
+                # step is a single-process tool (its use is the launch-bound small batch), data-parallel training runs eager
+                raise RuntimeError("FusedTrainer(graph=True) is single-process only; use graph=False under torch.distributed")
             self._check_grad_views()
             self._static = (torch.empty_like(x), torch.empty_like(y))
             self._static[0].copy_(x)

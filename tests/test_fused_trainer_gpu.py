@@ -107,3 +107,21 @@ def test_fused_trainer_neural_decoder():
         assert abs(float(loss) - float(l_new)) < 5e-6 * max(1.0, abs(float(loss)))
     for a, b in zip(m_ref.parameters(), m_new.parameters()):
         assert float((a.detach() - b.detach()).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("graph", [False])
+def test_fused_trainer_data_parallel_nccl(graph):
+    """2 ranks over NCCL on shards of one batch follow a single process on the whole batch (tools/check_fused_trainer_ddp.py)"""
+    import json
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533" if graph else "29532", os.path.join(root, "tools", "check_fused_trainer_ddp.py")] + (["--graph"] if graph else [])
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-1500:]
+    line = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["ok"] and line["ranks_identical"] and line["weights_moved_by"] > 1e-3
