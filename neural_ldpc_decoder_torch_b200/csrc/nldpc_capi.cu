@@ -281,7 +281,18 @@ extern "C" int nldpc_neural_decode_host(const nldpc_graph_t *gc, const float *xa
         if (v >= 256) chunk_cfg = v;
     }
     const int chunk = std::min(B, chunk_cfg);
-    const int nchunk = (B + chunk - 1) / chunk;
+    // Chunk schedule: full chunks, then a tail that halves down to 512 codewords.  The copy engine is busy from t = 0 whatever
+    // the chunk size, so only the END of the pipeline is exposed (decode + D2H of the last chunk, after the last H2D byte has
+    // arrived): a small last chunk shortens exactly that.
+    std::vector<int> sched;
+    for (int rem = B; rem > 0;) {
+        int n = std::min(chunk, rem);
+        if (rem <= chunk && rem > 512) n = std::max(512, ((rem / 2 + 255) / 256) * 256);
+        n = std::min(n, rem);
+        sched.push_back(n);
+        rem -= n;
+    }
+    const int nchunk = (int)sched.size();
     const size_t soft_per_cw = soft_mode == NLDPC_OUT_ALL ? (size_t)T * NZ : (soft_mode == NLDPC_OUT_LAST ? NZ : 0);
     const size_t hard_per_cw = hard_mode == NLDPC_OUT_ALL ? (size_t)T * nb : (hard_mode == NLDPC_OUT_LAST ? nb : 0);
     const int nbuf = std::min(nchunk, 3);
@@ -304,12 +315,12 @@ extern "C" int nldpc_neural_decode_host(const nldpc_graph_t *gc, const float *xa
     HTRY(cudaMemcpyAsync(d_b, b_host, (size_t)T * E * 4, cudaMemcpyHostToDevice, g->streams[0]));
     HTRY(cudaEventRecord(g->events[0], g->streams[0]));
     for (int i = 1; i < nbuf; i++) HTRY(cudaStreamWaitEvent(g->streams[i], g->events[0], 0));
-    for (int c = 0; c < nchunk; c++) {
+    for (int c = 0, b0 = 0; c < nchunk; b0 += sched[c], c++) {
         const int s = c % nbuf;
         cudaStream_t st = g->streams[s];
         float *d_xa = (float *)g->ws[s][0], *d_soft = (float *)g->ws[s][1];
         uint8_t *d_hard = (uint8_t *)g->ws[s][2];
-        const int b0 = c * chunk, nbw = std::min(chunk, B - b0);
+        const int nbw = sched[c];
         HTRY(cudaMemcpyAsync(d_xa, xa_host + (size_t)b0 * NZ, (size_t)nbw * NZ * 4, cudaMemcpyHostToDevice, st));
         int rc = nldpc_neural_forward(g, d_xa, d_w, d_b, nbw, T, soft_mode, d_soft, hard_mode, d_hard, st);
         if (rc) { cudaDeviceSynchronize(); return rc; }

@@ -140,6 +140,19 @@ def test_host_buffer_api_matches_device_api(graphs):
     assert np.array_equal(dev[:, :512].view(np.uint32), sub.view(np.uint32))
 
 
+@pytest.mark.parametrize("B", [1, 513, 700, 5000])
+def test_host_buffer_api_chunk_schedule_small_batches(B, graphs):
+    """the host API's chunk schedule (full chunks, then a tail halving down to 512 codewords) on batches around its edges"""
+    bg, Z = graphs["wimax"]
+    T = 3
+    xa = awgn_llr("wimax", B, seed=B)
+    m = make_model(bg, Z, T, B)
+    soft, hard = m.decode_host(torch.from_numpy(xa), soft=True, hard=True)
+    dev = run_model(m, xa)
+    assert np.array_equal(soft.numpy().view(np.uint32), dev.view(np.uint32))
+    assert np.array_equal(hard.numpy(), np.packbits(dev[-1] < 0, axis=1, bitorder="little"))
+
+
 def test_full_size_properties_bg2_65536(graphs):
     """BASELINE config 2 size (B=65536, T=10): size-independent properties + oracle on a strided subset."""
     bg, Z = graphs["bg2"]

@@ -54,7 +54,11 @@ def main():
     # (1) single process, whole batch — before the process group exists
     full = make(B)
     tr_full = FusedTrainer(full, crit, T, lr=1e-2)
-    loss_full = [float(tr_full.step(x, y)) for x, y in batches]
+    loss_full, g1_full = [], None
+    for x, y in batches:
+        loss_full.append(float(tr_full.step(x, y)))
+        if g1_full is None:
+            g1_full = tr_full.flat_grad.clone()          # clipped gradient of step 1 (both runs start from the same weights)
     # (2) N ranks, contiguous shards, one all-reduce of the flat gradient per step
     if args.graph and world > 1:
         raise SystemExit("FusedTrainer(graph=True) is single-process only (see its docstring)")
@@ -70,6 +74,8 @@ def main():
         l = tr.step(x[lo:hi].contiguous(), y[lo:hi].contiguous()).clone()
         dist.all_reduce(l, op=dist.ReduceOp.SUM)
         loss_part.append(float(l) / world)
+        if len(loss_part) == 1:
+            g1 = tr.flat_grad.clone()
     err = max(float((a.detach() - b.detach()).abs().max()) for a, b in zip(full.parameters(), part.parameters()))
     moved = max(float((a.detach() - 1.0).abs().max()) for a in full.parameters())
     errs = torch.tensor([err], device=dev)
@@ -80,16 +86,20 @@ def main():
     dist.broadcast(ref, src=0)
     same = torch.tensor([float(torch.equal(flat, ref))], device=dev)
     dist.all_reduce(same, op=dist.ReduceOp.MIN)
-    gdiff = float((tr.flat_grad - tr_full.flat_grad).abs().max())          # clipped gradients of the last step
+    gdiff = float((g1 - g1_full).abs().max())
+    gmax = float(g1_full.abs().max())
     if rank == 0:
-        # Adam divides every element's update by the root of its own squared-gradient history: for an element whose gradient
-        # is ~1e-6, the 1e-8 difference a different fp32 summation order makes moves the update visibly.  The weights must
-        # therefore agree to a small fraction of the distance they travelled, the losses and the rank-to-rank copies exactly
-        # as tightly as fp32 allows.
-        ok = float(errs) < 0.02 * moved and bool(same.item()) and all(abs(a - b) < 1e-5 * max(1.0, abs(a)) for a, b in zip(loss_full, loss_part))
+        # What must agree tightly is what the exchange computes: the all-reduced (mean) gradient of step 1, taken from identical
+        # weights, against the whole-batch gradient (fp32 summation order is the only difference), the step-1 loss, and the
+        # weights held by the ranks (bit-identical).  Later steps are compared loosely: Adam divides every element's update by
+        # the root of its own squared-gradient history, so for an element whose gradient is ~1e-7 a last-bit difference in the
+        # sum (the backward kernels accumulate with atomics) can flip the sign of its update (+-lr per step) — two runs of the
+        # SAME single process differ by as much (measured: max weight difference 1e-4 ... 1e-2 after 5 steps at lr = 1e-2).
+        ok = (gdiff < 1e-5 * gmax and bool(same.item()) and abs(loss_full[0] - loss_part[0]) < 2e-6 * max(1.0, abs(loss_full[0]))
+              and float(errs) < moved and all(abs(a - b) < 1e-3 * max(1.0, abs(a)) for a, b in zip(loss_full, loss_part)))
         print(json.dumps({"check": "fused_trainer_ddp", "world": world, "graph": args.graph, "steps": args.steps, "batch": B,
                           "max_weight_diff_vs_single_process": float(errs), "weights_moved_by": moved,
-                          "ranks_identical": bool(same.item()), "last_clipped_grad_diff": gdiff, "last_grad_absmin": float(tr_full.flat_grad.abs().min()), "loss_full": loss_full, "loss_sharded_mean": loss_part, "ok": ok}))
+                          "ranks_identical": bool(same.item()), "step1_grad_max_diff": gdiff, "step1_grad_absmax": gmax, "loss_full": loss_full, "loss_sharded_mean": loss_part, "ok": ok}))
     dist.destroy_process_group()
     if rank == 0 and not ok:
         sys.exit(1)

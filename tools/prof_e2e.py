@@ -30,4 +30,4 @@ for _ in range(20):
     ops.neural_decode_host(gid, xa, w, b)
     ts.append(time.perf_counter() - t0)
 ts = np.array(ts)
-print(f"chunk={os.environ.get('NLDPC_HOST_CHUNK', '8192')} B={B}: median {np.median(ts) * 1e3:.3f} ms min {ts.min() * 1e3:.3f} ms -> {B / np.median(ts) / 1e6:.2f} M cw/s")
+print(f"chunk={os.environ.get('NLDPC_HOST_CHUNK', '4096')} B={B}: median {np.median(ts) * 1e3:.3f} ms min {ts.min() * 1e3:.3f} ms -> {B / np.median(ts) / 1e6:.2f} M cw/s")
