@@ -199,6 +199,35 @@ def other_configs(dev, B, steps=20):
         cm2 = bn.ConnectingMatrixTorch(bn.ConnectingMatrix(Z=Z2, basegraph=bg2), device=dev)
         m2 = BoostedNeuralLDPCDecoder(20, B, cm2, node_weight_sharing_config=NodeWeightSharingConfig(3, 0, 3), decoding_type=DecoderType.QMS).to(dev)
         measure("BoostedNeuralLDPCDecoder BG2 z=16, QMS q=5, cn=3 / vn=3, 20 iterations, batch %d (train config, decode only)" % B, lambda: m2.decode_hard(x2))
+        # Functions.evaluate_ber_fer on the device (nldpc_count_errors): the one HBM-bound kernel of the path
+        soft = torch.randn((10, B, g2.N * Z2), device=dev) * 4.0 + 3.0
+        yz = torch.zeros((B, g2.N * Z2), device=dev)
+        measure("evaluate_ber_fer (nldpc_count_errors): T=10 fp32 outputs of %d BG2 codewords, exact bit / frame error counts per iteration" % B,
+                lambda: torch.ops.nldpc.count_errors(soft, yz))
+        out[-1]["hbm_gbs"] = 4 * g2.N * Z2 * 11 * B / (out[-1]["ms_per_step"] * 1e-3) / 1e9
+        del soft, yz
+        # training step (BASELINE configs[4]) at the reference's own batch size and at 4096 codewords: FusedTrainer
+        from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.LDPCDecoderLoss import LDPCDecoderLoss
+        from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.LossType import LossType
+        from neural_ldpc_decoder_torch_b200.training import FusedTrainer
+        for bt, graph_mode in ((20, True), (4096, False)):
+            mt = BoostedNeuralLDPCDecoder(20, bt, cm2, node_weight_sharing_config=NodeWeightSharingConfig(3, 0, 3), decoding_type=DecoderType.QMS).to(dev)
+            mt.store_llr = "none"
+            xt, yt = DeviceBatchGenerator(g2, [2, 2.5, 3.0, 3.5, 4.0], dev, seed=5, qms_qbit=5)(bt)
+            tr = FusedTrainer(mt, LDPCDecoderLoss(LossType.BCE, etha=1.0), 20, graph=graph_mode)
+            t_steps, ev0, ev1 = 50, torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for _ in range(3):
+                tr.step(xt, yt)
+            torch.cuda.synchronize()
+            ev0.record()
+            for _ in range(t_steps):
+                tr.step(xt, yt)
+            ev1.record()
+            torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1) / t_steps
+            out.append({"workload": "train step BoostedNeuralLDPCDecoder BG2 z=16 QMS q=5 cn=3/vn=3, 20 iterations, batch %d: forward + fused BCE + backward + "
+                                    "clip/Adam/clamp (FusedTrainer, %s; resident batch)" % (bt, "CUDA-graph replay" if graph_mode else "eager"),
+                        "value": bt / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms})
     except Exception as exc:   # informational block: never take the headline line down with it
         out.append({"error": repr(exc)})
     return out
