@@ -52,4 +52,8 @@ class ConnectingMatrixTorch:
         if device.type != "cuda":
             raise _lib.NldpcError(f"the B200 decode path needs a CUDA device, got {device}")
         idx = device.index if device.index is not None else torch.cuda.current_device()
-        return _lib.graph_id_for(self.basegraph, self.Z, idx)
+        cache = self.__dict__.setdefault("_graph_ids", {})      # per device: skips hashing the base graph on every call
+        gid = cache.get(idx)
+        if gid is None:
+            gid = cache[idx] = _lib.graph_id_for(self.basegraph, self.Z, idx)
+        return gid

@@ -64,6 +64,19 @@ class NeuralLDPCDecoder(nn.Module):
     def _stacked(self):
         return torch.stack(list(self.weights_var)), torch.stack(list(self.biases_var))
 
+    def _stacked_nograd(self, device):
+        """[T, E] weights / biases on `device` for decode-only calls, rebuilt only when a parameter changed (every in-place
+        update bumps Tensor._version; re-assigned storage changes data_ptr): saves two stack launches per decode."""
+        ps = list(self.weights_var) + list(self.biases_var)
+        key = (device, tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps))
+        hit = self.__dict__.get("_stack_cache")
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                w, b = self._stacked()
+                hit = (key, w.detach().to(device), b.detach().to(device))
+            self.__dict__["_stack_cache"] = hit
+        return hit[1], hit[2]
+
     def forward(self, xa):
         """xa [B, N, Z] float32 on a CUDA device -> list of T tensors [B, N*Z] (iteration outputs, :94-98)."""
         w, b = self._stacked()
@@ -81,9 +94,12 @@ class NeuralLDPCDecoder(nn.Module):
     def decode_hard(self, xa, all_iters=False):
         """Throughput mode: packed hard decisions `(out < 0)` (Functions.py:90 predicate), uint8
         [B, ceil(N*Z/8)] of the last iteration (or [T, B, ...]); soft outputs are never written to HBM."""
-        w, b = self._stacked()
         gid = self.conn_mat.graph_id(xa.device)
-        return torch.ops.nldpc.neural_hard(xa, w.to(xa.device), b.to(xa.device), gid, all_iters)
+        if xa.is_cuda and torch.cuda.is_current_stream_capturing():
+            w, b = self._stacked()                       # captured: a replay must re-read the live parameters
+            return torch.ops.nldpc.neural_hard(xa, w.to(xa.device), b.to(xa.device), gid, all_iters)
+        w, b = self._stacked_nograd(xa.device)
+        return ops.neural_hard_direct(xa, w, b, gid, all_iters)
 
     @torch.no_grad()
     def decode_host(self, xa_cpu, device=None, soft=False, hard=True):

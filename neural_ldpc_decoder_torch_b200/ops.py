@@ -63,9 +63,9 @@ def _(xa, w, b, graph_id):
     return xa.new_empty((w.shape[0], xa.shape[0], g.NZ))
 
 
-@torch.library.custom_op("nldpc::neural_hard", mutates_args=())
-def neural_hard(xa: torch.Tensor, w: torch.Tensor, b: torch.Tensor, graph_id: int, all_iters: bool) -> torch.Tensor:
-    """Packed hard decisions (out < 0), uint8 [B, ceil(N*Z/8)] (last iteration) or [T, B, ...] (all_iters)."""
+def neural_hard_direct(xa: torch.Tensor, w: torch.Tensor, b: torch.Tensor, graph_id: int, all_iters: bool) -> torch.Tensor:
+    """Body of nldpc::neural_hard, callable without the dispatcher (decode-only callers that hold no autograd state: the
+    custom-op dispatch costs more than the whole batch-1024 launch)."""
     g, xa, w, b = _prep(xa, w, b, graph_id)
     B, T = xa.shape[0], w.shape[0]
     shape = (T, B, g.hard_bytes) if all_iters else (B, g.hard_bytes)
@@ -75,6 +75,12 @@ def neural_hard(xa: torch.Tensor, w: torch.Tensor, b: torch.Tensor, graph_id: in
                                              _lib.NLDPC_OUT_ALL if all_iters else _lib.NLDPC_OUT_LAST, _ptr(hard), _stream(xa))
     _lib.check(rc, "nldpc_neural_forward")
     return hard
+
+
+@torch.library.custom_op("nldpc::neural_hard", mutates_args=())
+def neural_hard(xa: torch.Tensor, w: torch.Tensor, b: torch.Tensor, graph_id: int, all_iters: bool) -> torch.Tensor:
+    """Packed hard decisions (out < 0), uint8 [B, ceil(N*Z/8)] (last iteration) or [T, B, ...] (all_iters)."""
+    return neural_hard_direct(xa, w, b, graph_id, all_iters)
 
 
 @neural_hard.register_fake

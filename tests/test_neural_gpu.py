@@ -225,3 +225,39 @@ def test_decode_is_cuda_graph_capturable(graphs):
         g.replay()
         torch.cuda.synchronize()
         assert torch.equal(out, m.decode_hard(x2))
+
+
+def test_decode_hard_weight_cache_follows_parameter_updates(graphs):
+    """decode_hard keeps the stacked [T, E] weights between calls; every way a caller changes a parameter (in-place op,
+    optimiser step, .data re-assignment, load_state_dict) must be seen by the next decode"""
+    bg, Z = graphs["wimax"]
+    T, B = 4, 96
+    m = make_model(bg, Z, T, B)
+    x = torch.from_numpy(awgn_llr("wimax", B, seed=21, sigma=0.9)).cuda()
+
+    def fresh():
+        w, b = m._stacked()
+        return torch.ops.nldpc.neural_hard(x, w.detach(), b.detach(), m.conn_mat.graph_id(x.device), False)
+
+    assert torch.equal(m.decode_hard(x), fresh())
+    assert torch.equal(m.decode_hard(x), fresh())                      # cache hit
+    with torch.no_grad():
+        m.weights_var[1].mul_(0.5)
+    assert torch.equal(m.decode_hard(x), fresh())
+    opt = torch.optim.SGD(m.parameters(), lr=0.5)
+    torch.nn.functional.binary_cross_entropy_with_logits(m(x)[-1], torch.zeros(B, m.N * m.Z, device="cuda")).backward()
+    before = m.decode_hard(x).clone()
+    opt.step()
+    assert torch.equal(m.decode_hard(x), fresh())
+    m.biases_var[2].data = torch.full_like(m.biases_var[2].data, 0.3)
+    assert torch.equal(m.decode_hard(x), fresh())
+    sd = {k: v.clone() for k, v in m.state_dict().items() if k.startswith(("weights_var", "biases_var"))}
+    for k in sd:
+        sd[k] = sd[k] * 0.9
+    m.load_state_dict(sd, strict=False)
+    after = m.decode_hard(x)
+    assert torch.equal(after, fresh())
+    ref = oracle.neural_forward(bg, Z, x.cpu().numpy(), torch.stack(list(m.weights_var)).detach().cpu().numpy(),
+                                torch.stack(list(m.biases_var)).detach().cpu().numpy())
+    assert np.array_equal(after.cpu().numpy(), oracle.pack_hard(ref[-1]))
+    assert before.shape == after.shape
