@@ -345,16 +345,30 @@ class BoostedNeuralLDPCDecoder(nn.Module):
 
 
 def _decode(self, xa, n_iters, soft_mode, hard_mode):
-    from .. import _lib  # noqa: F401
+    from .. import ops
     T = self.iter_node_counts if n_iters is None else n_iters
     device = xa.device
     gid = self.conn_mat.graph_id(device)
-    vn_w, cn_w, ucn_w, compute_ucn, ucn_mix = self.fold_weights(list(range(T)), device)
     dec = {DecoderType.SP: 0, DecoderType.MS: 1, DecoderType.QMS: 2}[self.decoding_type]
-    soft, _, _, hard, _ = torch.ops.nldpc.boosted_forward(
-        xa, vn_w, cn_w, ucn_w, gid, T, dec, int(self.decoder_qms_qbit), float(self.allowed_llr_range.start),
-        float(self.allowed_llr_range.end), bool(compute_ucn), bool(ucn_mix), None, None, None, False, False, soft_mode, hard_mode,
-        False)
+    tail = (gid, T, dec, int(self.decoder_qms_qbit), float(self.allowed_llr_range.start), float(self.allowed_llr_range.end))
+    if torch.cuda.is_current_stream_capturing():
+        # captured into a CUDA graph: the folding ops belong to the graph, so a replay re-reads the live parameters
+        vn_w, cn_w, ucn_w, compute_ucn, ucn_mix = self.fold_weights(list(range(T)), device)
+        soft, _, _, hard, _ = torch.ops.nldpc.boosted_forward(xa, vn_w, cn_w, ucn_w, *tail, bool(compute_ucn), bool(ucn_mix), None, None,
+                                                              None, False, False, soft_mode, hard_mode, False)
+        return soft, hard
+    # decode-only: the folded [T, .] weight rows are kept between calls and rebuilt only when a parameter changed (in-place
+    # updates bump Tensor._version, re-assigned storage changes data_ptr); the op body is called without the dispatcher
+    ps = list(self.parameters())
+    key = (device, T, tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps))
+    hit = self.__dict__.get("_fold_cache")
+    if hit is None or hit[0] != key:
+        folded = self.fold_weights(list(range(T)), device)
+        hit = (key, tuple(t.detach() if isinstance(t, torch.Tensor) else t for t in folded))
+        self.__dict__["_fold_cache"] = hit
+    vn_w, cn_w, ucn_w, compute_ucn, ucn_mix = hit[1]
+    soft, _, _, hard, _ = ops.boosted_forward_direct(xa, vn_w, cn_w, ucn_w, *tail, bool(compute_ucn), bool(ucn_mix), None, None, None,
+                                                     False, False, soft_mode, hard_mode, False)
     return soft, hard
 
 

@@ -210,14 +210,11 @@ def _opt_f32(name, t, shape, device):
     return t.contiguous()
 
 
-@torch.library.custom_op("nldpc::boosted_forward", mutates_args=())
-def boosted_forward(xa: torch.Tensor, vn_w: Optional[torch.Tensor], cn_w: Optional[torch.Tensor], ucn_w: Optional[torch.Tensor],
-                    graph_id: int, T: int, decoder_type: int, qbit: int, llr_lo: float, llr_hi: float, compute_ucn: bool,
-                    ucn_mix: bool, llr_init: Optional[torch.Tensor], xin_init: Optional[torch.Tensor],
-                    app_init: Optional[torch.Tensor], want_llr: bool, want_xin: bool, soft_mode: int,
-                    hard_mode: int, want_dump: bool = False) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
-    """T consecutive iterations of the Boosted loop body.  Returns (soft [T,B,N*Z] | [B,N*Z] | empty per soft_mode,
-    llr_last [B,Z,E] | empty, xin_out [B,N,Z] | empty, packed hard decisions per hard_mode | empty).
+def boosted_forward_direct(xa, vn_w, cn_w, ucn_w, graph_id, T, decoder_type, qbit, llr_lo, llr_hi, compute_ucn, ucn_mix, llr_init,
+                           xin_init, app_init, want_llr, want_xin, soft_mode, hard_mode, want_dump=False):
+    """Body of nldpc::boosted_forward, callable without the dispatcher (decode-only callers that hold no autograd state).
+    T consecutive iterations of the Boosted loop body.  Returns (soft [T,B,N*Z] | [B,N*Z] | empty per soft_mode,
+    llr_last [B,Z,E] | empty, xin_out [B,N,Z] | empty, packed hard decisions per hard_mode | empty, training dump | 1 byte).
     Weight rows are indexed by executed iteration."""
     g = _lib.graph_by_id(graph_id)
     _check_cuda_f32("xa", xa)
@@ -252,6 +249,17 @@ def boosted_forward(xa: torch.Tensor, vn_w: Optional[torch.Tensor], cn_w: Option
                                               _ptr(llr_last) if want_llr else _vp(0), _stream(xa))
     _lib.check(rc, "nldpc_boosted_forward")
     return soft, llr_last, xin_out, hard, dump
+
+
+@torch.library.custom_op("nldpc::boosted_forward", mutates_args=())
+def boosted_forward(xa: torch.Tensor, vn_w: Optional[torch.Tensor], cn_w: Optional[torch.Tensor], ucn_w: Optional[torch.Tensor],
+                    graph_id: int, T: int, decoder_type: int, qbit: int, llr_lo: float, llr_hi: float, compute_ucn: bool,
+                    ucn_mix: bool, llr_init: Optional[torch.Tensor], xin_init: Optional[torch.Tensor],
+                    app_init: Optional[torch.Tensor], want_llr: bool, want_xin: bool, soft_mode: int,
+                    hard_mode: int, want_dump: bool = False) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """see boosted_forward_direct"""
+    return boosted_forward_direct(xa, vn_w, cn_w, ucn_w, graph_id, T, decoder_type, qbit, llr_lo, llr_hi, compute_ucn, ucn_mix, llr_init,
+                                  xin_init, app_init, want_llr, want_xin, soft_mode, hard_mode, want_dump)
 
 
 @boosted_forward.register_fake

@@ -197,3 +197,36 @@ def test_boosted_decode_is_cuda_graph_capturable(graphs):
         assert torch.equal(soft.view(torch.int32), m.decode_soft_last(x2).view(torch.int32))
         assert torch.equal(hard, m.decode_hard(x2, all_iters=True))
         assert other.shape == soft.shape
+
+
+def test_boosted_decode_weight_cache_follows_parameter_updates(graphs):
+    """the stateless decode methods keep the folded weight rows between calls; in-place updates, .data re-assignment and
+    load_state_dict must all be seen by the next decode (checked against the oracle with the module's current weights)"""
+    d = load_golden(CASES[3])           # WiMAX QMS (3,0,3), T=20, B=8
+    m = build_module(d, device="cuda", batch=8)
+    xa_np = d["xa"]
+    xa = torch.from_numpy(xa_np).cuda()
+
+    def check():
+        got = m.decode_soft_last(xa).cpu().numpy()
+        hard = m.decode_hard(xa).cpu().numpy()
+        ref = oracle_forward(copy_to_cpu(m), xa_np)
+        assert np.array_equal(got.view(np.uint32), ref[-1].view(np.uint32))
+        assert np.array_equal(hard, np.packbits(ref[-1] < 0, axis=1, bitorder="little"))
+
+    def copy_to_cpu(mod):
+        import copy
+        return copy.deepcopy(mod).cpu()
+
+    check()
+    check()                                           # cache hit
+    with torch.no_grad():
+        m.weight_CN_3.mul_(0.75)
+    check()
+    m.weight_VN_1.data = torch.full_like(m.weight_VN_1.data, 0.875)
+    check()
+    sd = {k: v * 0.5 + 0.25 for k, v in m.state_dict().items() if k.startswith("weight_")}
+    m.load_state_dict(sd, strict=False)
+    check()
+    assert m.decode_soft_last(xa, n_iters=5).shape == (8, m.N * m.Z)      # another T: its own cache entry
+    check()
