@@ -79,8 +79,11 @@ class NeuralLDPCDecoder(nn.Module):
 
     def forward(self, xa):
         """xa [B, N, Z] float32 on a CUDA device -> list of T tensors [B, N*Z] (iteration outputs, :94-98)."""
-        w, b = self._stacked()
         gid = self.conn_mat.graph_id(xa.device)
+        if not torch.is_grad_enabled() and not torch.cuda.is_current_stream_capturing():
+            # inference: cached stacked weights, no dispatcher (see _stacked_nograd)
+            return list(ops.neural_forward_direct(xa, *self._stacked_nograd(xa.device), gid).unbind(0))
+        w, b = self._stacked()
         if w.device != xa.device:
             w, b = w.to(xa.device), b.to(xa.device)
         if torch.is_grad_enabled() and (w.requires_grad or b.requires_grad):

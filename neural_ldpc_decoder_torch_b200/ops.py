@@ -45,8 +45,8 @@ def _prep(xa, w, b, graph_id):
     return g, xa.contiguous(), w.contiguous(), b.contiguous()
 
 
-@torch.library.custom_op("nldpc::neural_forward", mutates_args=())
-def neural_forward(xa: torch.Tensor, w: torch.Tensor, b: torch.Tensor, graph_id: int) -> torch.Tensor:
+def neural_forward_direct(xa: torch.Tensor, w: torch.Tensor, b: torch.Tensor, graph_id: int) -> torch.Tensor:
+    """Body of nldpc::neural_forward, callable without the dispatcher (inference under torch.no_grad())."""
     g, xa, w, b = _prep(xa, w, b, graph_id)
     B, T = xa.shape[0], w.shape[0]
     out = torch.empty((T, B, g.NZ), dtype=torch.float32, device=xa.device)
@@ -55,6 +55,11 @@ def neural_forward(xa: torch.Tensor, w: torch.Tensor, b: torch.Tensor, graph_id:
                                              _lib.NLDPC_OUT_NONE, _vp(0), _stream(xa))
     _lib.check(rc, "nldpc_neural_forward")
     return out
+
+
+@torch.library.custom_op("nldpc::neural_forward", mutates_args=())
+def neural_forward(xa: torch.Tensor, w: torch.Tensor, b: torch.Tensor, graph_id: int) -> torch.Tensor:
+    return neural_forward_direct(xa, w, b, graph_id)
 
 
 @neural_forward.register_fake
