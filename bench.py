@@ -193,6 +193,19 @@ def other_configs(dev, B, steps=20):
         cmb = bn.ConnectingMatrixTorch(bn.ConnectingMatrix(Z=Z, basegraph=bg), device=dev)
         mb = BoostedNeuralLDPCDecoder(20, B, cmb, node_weight_sharing_config=NodeWeightSharingConfig(3, 0, 0), decoding_type=DecoderType.QMS).to(dev)
         measure("BoostedNeuralLDPCDecoder WiMAX z=24, QMS q=5, cn=3, 20 iterations, batch %d (configs[2])" % B, lambda: mb.decode_hard(xq))
+        # the same decoder end to end through the host API with one-byte LLRs (nldpc_boosted_decode_host_q8): pinned int8 codes
+        # of the QMS-quantised inputs in, packed decisions back on the host, H2D / D2H inside the timed region
+        xq_host = torch.round(xq * 2.0).to(torch.int8).cpu().pin_memory()
+        for _ in range(3):
+            _, hh = mb.decode_host_q8(xq_host)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            _, hh = mb.decode_host_q8(xq_host)
+        dt = (time.perf_counter() - t0) / 10
+        out.append({"workload": "the same (configs[2]) end to end through the host API with int8 LLR codes (pinned host in, packed decisions on the "
+                                "host out; %d B H2D + %d B D2H per codeword)" % (graph.N * Z, (graph.N * Z + 7) // 8),
+                    "value": B / dt, "unit": UNIT, "ms_per_step": dt * 1e3})
         bg2, Z2 = load_basegraph(CODE)
         g2 = TannerGraph(bg2, Z2)
         x2, _ = DeviceBatchGenerator(g2, [3.0], dev, all_zero=True, qms_qbit=5)(B)

@@ -188,6 +188,17 @@ int nldpc_clip_adam_clamp(float *param_dev, float *grad_dev, float *exp_avg_dev,
                           float grad_scale, float max_norm, double lr, double beta1, double beta2, double eps, float clamp_lo,
                           float clamp_hi, void *stream);
 
+/* Host-buffer decode of the Boosted decoder with ONE-BYTE channel LLRs: x = scale * q.  The Boosted pipeline quantises its
+ * channel LLRs before the decoder sees them (boosted AWGNPassedDatagen.py:165-166 -> Functions.Cal_MSA_Q, Functions.py:70-83:
+ * multiples of 0.5 in +-7.5 for q_bit = 5, i.e. q = 2 x in [-15, 15], scale = 0.5), so the int8 code is lossless and the
+ * host -> device transfer (the bound of the end-to-end path) is 4x smaller than with fp32.  Stateless decode from the zero
+ * message state (cfg's state / dump pointers must be NULL), T iterations, results as nldpc_boosted_forward with HOST
+ * pointers; H2D, int8 -> fp32 expansion, decode and D2H of consecutive chunks overlap on internal streams.  Synchronous.
+ *   xq_host [B][N][Z] int8 (pinned or pageable); vn_w_host [T][N] / cn_w_host [T][E] / ucn_w_host [T][E] or NULL */
+int nldpc_boosted_decode_host_q8(const nldpc_graph_t *g, const nldpc_boosted_cfg_t *cfg, const int8_t *xq_host, float scale,
+                                 const float *vn_w_host, const float *cn_w_host, const float *ucn_w_host, int B, int T,
+                                 int soft_mode, float *soft_host, int hard_mode, uint8_t *hard_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,8 @@ def lib():
             L.nldpc_multi_iter_bce.argtypes = [vp, vp, vp, ci, ctypes.c_size_t, vp, vp, vp]
             L.nldpc_multi_iter_bce_grad.restype = ci
             L.nldpc_multi_iter_bce_grad.argtypes = [vp, vp, vp, vp, ci, ctypes.c_size_t, vp, vp]
+            L.nldpc_boosted_decode_host_q8.restype = ci
+            L.nldpc_boosted_decode_host_q8.argtypes = [vp, ctypes.POINTER(BoostedCfg), vp, ctypes.c_float, vp, vp, vp, ci, ci, ci, vp, ci, vp]
             L.nldpc_clip_adam_clamp.restype = ci
             L.nldpc_clip_adam_clamp.argtypes = [vp, vp, vp, vp, vp, ci, ctypes.c_float, ctypes.c_float, ctypes.c_double, ctypes.c_double,
                                                 ctypes.c_double, ctypes.c_double, ctypes.c_float, ctypes.c_float, vp]

@@ -344,6 +344,22 @@ class BoostedNeuralLDPCDecoder(nn.Module):
         return self.outputs
 
 
+def _folded_cached(self, T, device):
+    """fold_weights(range(T)) on `device` (a torch.device; CPU for the host API), detached, rebuilt only when a parameter changed"""
+    ps = list(self.parameters())
+    key = (device, T, tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps))
+    cache = self.__dict__.setdefault("_fold_cache", {})
+    hit = cache.get((device, T))
+    if hit is None or hit[0] != key:
+        with torch.no_grad():
+            folded = self.fold_weights(list(range(T)), self._param_device() if device.type == "cpu" else device)
+        hit = (key, tuple(t.detach().to(device).contiguous() if isinstance(t, torch.Tensor) else t for t in folded))
+        if len(cache) > 8:
+            cache.clear()
+        cache[(device, T)] = hit
+    return hit[1]
+
+
 def _decode(self, xa, n_iters, soft_mode, hard_mode):
     from .. import ops
     T = self.iter_node_counts if n_iters is None else n_iters
@@ -359,14 +375,7 @@ def _decode(self, xa, n_iters, soft_mode, hard_mode):
         return soft, hard
     # decode-only: the folded [T, .] weight rows are kept between calls and rebuilt only when a parameter changed (in-place
     # updates bump Tensor._version, re-assigned storage changes data_ptr); the op body is called without the dispatcher
-    ps = list(self.parameters())
-    key = (device, T, tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps))
-    hit = self.__dict__.get("_fold_cache")
-    if hit is None or hit[0] != key:
-        folded = self.fold_weights(list(range(T)), device)
-        hit = (key, tuple(t.detach() if isinstance(t, torch.Tensor) else t for t in folded))
-        self.__dict__["_fold_cache"] = hit
-    vn_w, cn_w, ucn_w, compute_ucn, ucn_mix = hit[1]
+    vn_w, cn_w, ucn_w, compute_ucn, ucn_mix = _folded_cached(self, T, device)
     soft, _, _, hard, _ = ops.boosted_forward_direct(xa, vn_w, cn_w, ucn_w, *tail, bool(compute_ucn), bool(ucn_mix), None, None, None,
                                                      False, False, soft_mode, hard_mode, False)
     return soft, hard
@@ -385,8 +394,29 @@ def decode_soft_last(self, xa, n_iters=None):
     return _decode(self, xa, n_iters, 2, 0)[0]
 
 
+@torch.no_grad()
+def decode_host_q8(self, xq_cpu, scale=0.5, device=None, n_iters=None, soft=False, hard=True):
+    """End-to-end host API with one-byte channel LLRs: `xq_cpu` int8 CPU tensor [B, N, Z], x = scale * q (the Boosted
+    pipeline's inputs are quantised by Functions.Cal_MSA_Q before they reach the decoder — q_bit 5: multiples of 0.5 in
+    +-7.5 — so q = round(x / scale) carries them without loss at a quarter of the PCIe bytes).  Stateless decode from the
+    zero state; returns (soft [B, N*Z] of the last iteration | None, packed hard decisions [B, ceil(N*Z/8)] | None) on the host."""
+    from .. import _lib, ops
+    device = torch.device(device if device is not None else self._param_device())
+    if device.type != "cuda":
+        device = torch.device("cuda")
+    T = self.iter_node_counts if n_iters is None else n_iters
+    gid = self.conn_mat.graph_id(device)
+    vn_w, cn_w, ucn_w, compute_ucn, ucn_mix = _folded_cached(self, T, torch.device("cpu"))
+    dec = {DecoderType.SP: 0, DecoderType.MS: 1, DecoderType.QMS: 2}[self.decoding_type]
+    return ops.boosted_decode_host_q8(gid, xq_cpu, scale, vn_w, cn_w, ucn_w, T, dec, int(self.decoder_qms_qbit),
+                                      float(self.allowed_llr_range.start), float(self.allowed_llr_range.end), bool(compute_ucn),
+                                      bool(ucn_mix), _lib.NLDPC_OUT_LAST if soft else _lib.NLDPC_OUT_NONE,
+                                      _lib.NLDPC_OUT_LAST if hard else _lib.NLDPC_OUT_NONE)
+
+
 BoostedNeuralLDPCDecoder.decode_hard = decode_hard
 BoostedNeuralLDPCDecoder.decode_soft_last = decode_soft_last
+BoostedNeuralLDPCDecoder.decode_host_q8 = decode_host_q8
 
 
 def _add_dense_buffers(module, state_dict, prefix, local_metadata):

@@ -42,8 +42,8 @@ struct nldpc_graph {
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t events[3] = {nullptr, nullptr, nullptr};
     // grow-only device workspace of the host-buffer API (per stream: xa chunk, soft chunk, hard chunk; + weights)
-    void *ws[3][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
-    size_t ws_bytes[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    void *ws[3][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+    size_t ws_bytes[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};      // [3] = int8 LLR chunk (nldpc_boosted_decode_host_q8)
     void *ws_wb = nullptr;
     size_t ws_wb_bytes = 0;
 };
@@ -186,7 +186,7 @@ extern "C" void nldpc_graph_destroy(nldpc_graph_t *g) {
         if (g->events[i]) cudaEventDestroy(g->events[i]);
     }
     for (int i = 0; i < 3; i++)
-        for (int k = 0; k < 3; k++)
+        for (int k = 0; k < 4; k++)
             if (g->ws[i][k]) cudaFree(g->ws[i][k]);
     if (g->ws_wb) cudaFree(g->ws_wb);
     if (g->tables) cudaFree(g->tables);
@@ -564,5 +564,92 @@ extern "C" int nldpc_clip_adam_clamp(float *param_dev, float *grad_dev, float *e
     const int rc = launch_clip_adam_clamp(param_dev, grad_dev, exp_avg_dev, exp_avg_sq_dev, state_dev, n, grad_scale, max_norm, lr, beta1,
                                           beta2, eps, clamp_lo, clamp_hi, (cudaStream_t)stream);
     if (rc != 0) return fail(rc, std::string("nldpc_clip_adam_clamp: ") + cudaGetErrorString((cudaError_t)rc));
+    return NLDPC_OK;
+}
+
+namespace nldpc {
+int launch_q8_to_f32(const int8_t *in, float *out, size_t n, float scale, int sm_count, cudaStream_t st);
+}
+
+extern "C" int nldpc_boosted_decode_host_q8(const nldpc_graph_t *gc, const nldpc_boosted_cfg_t *cfg, const int8_t *xq_host, float scale,
+                                            const float *vn_w_host, const float *cn_w_host, const float *ucn_w_host, int B, int T,
+                                            int soft_mode, float *soft_host, int hard_mode, uint8_t *hard_host) {
+    nldpc_graph *g = const_cast<nldpc_graph *>(gc);
+    if (!g || !cfg || B < 0 || T <= 0) return fail(NLDPC_E_INVALID, "nldpc_boosted_decode_host_q8: bad argument");
+    if (B == 0) return NLDPC_OK;
+    if (!xq_host) return fail(NLDPC_E_INVALID, "nldpc_boosted_decode_host_q8: NULL input pointer");
+    if (cfg->llr_init_dev || cfg->xin_init_dev || cfg->xin_out_dev || cfg->app_init_dev || cfg->train_dump_dev)
+        return fail(NLDPC_E_INVALID, "nldpc_boosted_decode_host_q8: stateless decode only (state / dump pointers must be NULL)");
+    if (int rc = check_modes(soft_mode, soft_host, hard_mode, hard_host)) return rc;
+    CUDA_TRY(cudaSetDevice(g->device));
+    if (int rc = ensure_streams(g)) return rc;
+    const size_t NZ = (size_t)g->N * g->Z, nb = (NZ + 7) / 8, E = (size_t)g->E, N = (size_t)g->N;
+    int chunk_cfg = 8192;      // the decode, not the copy, is the long stage here: larger chunks than the fp32 Neural path
+    if (const char *e = getenv("NLDPC_HOST_CHUNK")) {
+        const int v = atoi(e);
+        if (v >= 256) chunk_cfg = v;
+    }
+    const int chunk = std::min(B, chunk_cfg);
+    std::vector<int> sched;                   // full chunks, then a tail that halves down to 512 codewords (see nldpc_neural_decode_host)
+    for (int rem = B; rem > 0;) {
+        int n = std::min(chunk, rem);
+        if (rem <= chunk && rem > 512) n = std::max(512, ((rem / 2 + 255) / 256) * 256);
+        n = std::min(n, rem);
+        sched.push_back(n);
+        rem -= n;
+    }
+    const int nchunk = (int)sched.size();
+    const size_t soft_per_cw = soft_mode == NLDPC_OUT_ALL ? (size_t)T * NZ : (soft_mode == NLDPC_OUT_LAST ? NZ : 0);
+    const size_t hard_per_cw = hard_mode == NLDPC_OUT_ALL ? (size_t)T * nb : (hard_mode == NLDPC_OUT_LAST ? nb : 0);
+    const int nbuf = std::min(nchunk, 3);
+    const size_t wbytes = ((size_t)T * N + 2 * (size_t)T * E) * 4;
+    if (int rc = ws_reserve(&g->ws_wb, &g->ws_wb_bytes, wbytes)) return rc;
+    for (int i = 0; i < nbuf; i++) {
+        if (int rc = ws_reserve(&g->ws[i][0], &g->ws_bytes[i][0], (size_t)chunk * NZ * 4)) return rc;
+        if (soft_per_cw) if (int rc = ws_reserve(&g->ws[i][1], &g->ws_bytes[i][1], (size_t)chunk * soft_per_cw * 4)) return rc;
+        if (hard_per_cw) if (int rc = ws_reserve(&g->ws[i][2], &g->ws_bytes[i][2], (size_t)chunk * hard_per_cw)) return rc;
+        if (int rc = ws_reserve(&g->ws[i][3], &g->ws_bytes[i][3], (size_t)chunk * NZ)) return rc;
+    }
+    float *d_vn = (float *)g->ws_wb, *d_cn = d_vn + (size_t)T * N, *d_ucn = d_cn + (size_t)T * E;
+#define HTRY(expr)                                                                                 \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            cudaGetLastError(); cudaDeviceSynchronize();                                           \
+            return fail((int)_e, std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+        }                                                                                          \
+    } while (0)
+    if (vn_w_host) HTRY(cudaMemcpyAsync(d_vn, vn_w_host, (size_t)T * N * 4, cudaMemcpyHostToDevice, g->streams[0]));
+    if (cn_w_host) HTRY(cudaMemcpyAsync(d_cn, cn_w_host, (size_t)T * E * 4, cudaMemcpyHostToDevice, g->streams[0]));
+    if (ucn_w_host) HTRY(cudaMemcpyAsync(d_ucn, ucn_w_host, (size_t)T * E * 4, cudaMemcpyHostToDevice, g->streams[0]));
+    HTRY(cudaEventRecord(g->events[0], g->streams[0]));
+    for (int i = 1; i < nbuf; i++) HTRY(cudaStreamWaitEvent(g->streams[i], g->events[0], 0));
+    for (int c = 0, b0 = 0; c < nchunk; b0 += sched[c], c++) {
+        const int s = c % nbuf;
+        cudaStream_t st = g->streams[s];
+        float *d_xa = (float *)g->ws[s][0], *d_soft = (float *)g->ws[s][1];
+        uint8_t *d_hard = (uint8_t *)g->ws[s][2];
+        int8_t *d_q = (int8_t *)g->ws[s][3];
+        const int nbw = sched[c];
+        HTRY(cudaMemcpyAsync(d_q, xq_host + (size_t)b0 * NZ, (size_t)nbw * NZ, cudaMemcpyHostToDevice, st));
+        HTRY((cudaError_t)nldpc::launch_q8_to_f32(d_q, d_xa, (size_t)nbw * NZ, scale, g->sm_count, st));
+        int rc = nldpc_boosted_forward(g, cfg, d_xa, vn_w_host ? d_vn : nullptr, cn_w_host ? d_cn : nullptr, ucn_w_host ? d_ucn : nullptr,
+                                       nbw, T, soft_mode, d_soft, hard_mode, d_hard, nullptr, st);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+        if (soft_mode == NLDPC_OUT_ALL) {
+            HTRY(cudaMemcpy2DAsync(soft_host + (size_t)b0 * NZ, (size_t)B * NZ * 4, d_soft, (size_t)nbw * NZ * 4,
+                                   (size_t)nbw * NZ * 4, T, cudaMemcpyDeviceToHost, st));
+        } else if (soft_mode == NLDPC_OUT_LAST) {
+            HTRY(cudaMemcpyAsync(soft_host + (size_t)b0 * NZ, d_soft, (size_t)nbw * NZ * 4, cudaMemcpyDeviceToHost, st));
+        }
+        if (hard_mode == NLDPC_OUT_ALL) {
+            HTRY(cudaMemcpy2DAsync(hard_host + (size_t)b0 * nb, (size_t)B * nb, d_hard, (size_t)nbw * nb, (size_t)nbw * nb, T,
+                                   cudaMemcpyDeviceToHost, st));
+        } else if (hard_mode == NLDPC_OUT_LAST) {
+            HTRY(cudaMemcpyAsync(hard_host + (size_t)b0 * nb, d_hard, (size_t)nbw * nb, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    for (int i = 0; i < nbuf; i++) HTRY(cudaStreamSynchronize(g->streams[i]));
+#undef HTRY
     return NLDPC_OK;
 }

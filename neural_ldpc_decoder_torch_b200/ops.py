@@ -542,3 +542,38 @@ def clip_adam_clamp_(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Ten
                                               float(max_norm), float(lr), float(betas[0]), float(betas[1]), float(eps), float(clamp[0]),
                                               float(clamp[1]), _stream(param))
     _lib.check(rc, "nldpc_clip_adam_clamp")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# host-buffer Boosted decode with one-byte channel LLRs (nldpc_boosted_decode_host_q8)
+def boosted_decode_host_q8(graph_id: int, xq_host: torch.Tensor, scale: float, vn_w_host, cn_w_host, ucn_w_host, T: int,
+                           decoder_type: int, qbit: int, llr_lo: float, llr_hi: float, compute_ucn: bool, ucn_mix: bool,
+                           soft_mode: int = 0, hard_mode: int = 2):
+    """xq_host int8 CPU tensor [B, N, Z] (x = scale * q; pin it for full PCIe speed), folded weight rows as CPU fp32 tensors
+    or None -> (soft | None, hard | None) as pinned CPU tensors, shapes as the device op.  Synchronous."""
+    g = _lib.graph_by_id(graph_id)
+    if not isinstance(xq_host, torch.Tensor) or xq_host.is_cuda or xq_host.dtype != torch.int8:
+        raise TypeError("xq_host must be an int8 CPU tensor")
+    if xq_host.dim() != 3 or xq_host.shape[1] != g.N or xq_host.shape[2] != g.Z:
+        raise ValueError(f"xq_host must be [B, {g.N}, {g.Z}], got {tuple(xq_host.shape)}")
+    xq_host = xq_host.contiguous()
+    B = xq_host.shape[0]
+
+    def host_rows(name, t, cols):
+        if t is None:
+            return None
+        if t.is_cuda or t.dtype != torch.float32 or tuple(t.shape) != (T, cols):
+            raise ValueError(f"{name} must be a CPU fp32 tensor [{T}, {cols}]")
+        return t.contiguous()
+
+    vn_w_host, cn_w_host, ucn_w_host = host_rows("vn_w", vn_w_host, g.N), host_rows("cn_w", cn_w_host, g.E), host_rows("ucn_w", ucn_w_host, g.E)
+    soft = hard = None
+    if soft_mode != _lib.NLDPC_OUT_NONE:
+        soft = torch.empty(_out_shape(soft_mode, T, B, g.NZ), dtype=torch.float32, pin_memory=True)
+    if hard_mode != _lib.NLDPC_OUT_NONE:
+        hard = torch.empty(_out_shape(hard_mode, T, B, g.hard_bytes), dtype=torch.uint8, pin_memory=True)
+    cfg = _lib.BoostedCfg(decoder_type, qbit, llr_lo, llr_hi, int(compute_ucn), int(ucn_mix), None, None, None, None, None, 0)
+    rc = _lib.lib().nldpc_boosted_decode_host_q8(g.ptr, ctypes.byref(cfg), _ptr(xq_host), float(scale), _ptr(vn_w_host), _ptr(cn_w_host),
+                                                 _ptr(ucn_w_host), B, T, soft_mode, _ptr(soft), hard_mode, _ptr(hard))
+    _lib.check(rc, "nldpc_boosted_decode_host_q8")
+    return soft, hard

@@ -230,3 +230,32 @@ def test_boosted_decode_weight_cache_follows_parameter_updates(graphs):
     check()
     assert m.decode_soft_last(xa, n_iters=5).shape == (8, m.N * m.Z)      # another T: its own cache entry
     check()
+
+
+@pytest.mark.parametrize("code,sharing,B,T", [("wimax", (3, 0, 0), 20000, 20), ("bg2", (3, 0, 3), 9000, 6), ("wimax", (1, 0, 2), 700, 5)])
+def test_boosted_host_api_int8_llrs(code, sharing, B, T, graphs):
+    """nldpc_boosted_decode_host_q8: int8 codes of QMS-quantised LLRs through the chunked host pipeline == the device path on
+    the fp32 values they stand for (bit-exact), and == the oracle on a subset"""
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder import ConnectingMatrix, ConnectingMatrixTorch, Functions
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.BoostedNeuralLDPCDecoder import BoostedNeuralLDPCDecoder
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.DecoderType import DecoderType
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.NodeWeightSharingConfig import NodeWeightSharingConfig
+    bg, Z = graphs[code]
+    rs = np.random.RandomState(B + T)
+    xa = Functions.Cal_MSA_Q(awgn_llr(code, B, seed=B + 3, sigma=1.0), 5).astype(np.float32)
+    xa[0, :2] = 0.0
+    q = np.round(xa * 2.0).astype(np.int8)
+    assert np.array_equal(q.astype(np.float32) * 0.5, xa)                 # the int8 code is lossless on the QMS grid
+    cm = ConnectingMatrixTorch(ConnectingMatrix(Z=Z, basegraph=bg), device=torch.device("cuda"))
+    m = BoostedNeuralLDPCDecoder(T, 1, cm, node_weight_sharing_config=NodeWeightSharingConfig(*sharing), decoding_type=DecoderType.QMS).cuda()
+    with torch.no_grad():
+        for p in m.parameters():
+            p.copy_(torch.from_numpy(rs.uniform(0.4, 1.3, size=tuple(p.shape)).astype(np.float32)))
+    soft_h, hard_h = m.decode_host_q8(torch.from_numpy(q), soft=True, hard=True)
+    x = torch.from_numpy(xa).cuda()
+    assert np.array_equal(soft_h.numpy().view(np.uint32), m.decode_soft_last(x).cpu().numpy().view(np.uint32))
+    assert np.array_equal(hard_h.numpy(), m.decode_hard(x).cpu().numpy())
+    k = min(B, 64)
+    ref = oracle_forward(m.cpu(), xa[:k])
+    assert np.array_equal(soft_h.numpy()[:k].view(np.uint32), ref[-1].view(np.uint32))
+    assert np.array_equal(hard_h.numpy()[:k], np.packbits(ref[-1] < 0, axis=1, bitorder="little"))
