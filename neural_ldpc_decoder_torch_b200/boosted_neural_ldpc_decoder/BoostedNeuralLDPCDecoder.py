@@ -101,6 +101,7 @@ class BoostedNeuralLDPCDecoder(nn.Module):
 
         self._erow_cache = {}
         self._register_params()
+        self._flatten_params()
         self._register_state_dict_hook(_add_dense_buffers)
         self._register_load_state_dict_pre_hook(_drop_dense_buffers)
 
@@ -132,6 +133,15 @@ class BoostedNeuralLDPCDecoder(nn.Module):
             for iteration in self._iterations_with_params(sharing_type):
                 name = self._param_name(ParamType.Weight, node_type, iteration)
                 setattr(self, name, nn.Parameter(torch.full(shape, init[node_type], dtype=torch.float32)))
+
+    def _flatten_params(self):
+        from .._flatparams import flatten_
+        flatten_(list(self.parameters()))
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)          # .to() / .cuda() give every parameter its own storage again
+        self._flatten_params()
+        return out
 
     def _apply_constraints(self):
         """clamp weights into allowed_weight_range after an optimiser step (:153-179)"""
@@ -344,20 +354,52 @@ class BoostedNeuralLDPCDecoder(nn.Module):
         return self.outputs
 
 
-def _folded_cached(self, T, device):
-    """fold_weights(range(T)) on `device` (a torch.device; CPU for the host API), detached, rebuilt only when a parameter changed"""
+def _folded_live(self, T, device):
+    """fold_weights(range(T)) on `device` for the decode-only paths, read LIVE from the parameters: the parameters are slices
+    of one flat vector (_flatparams), so every folded row set is ONE gather through an index map (<= 3 launches instead of ~2 T
+    expand / stack launches).  Only the index maps are cached, keyed by the parameters' data pointers — never a value, so
+    `p.data.clamp_()` (the reference's `_apply_constraints`) or a kernel writing the weights cannot leave a stale copy behind.
+    Sharing types 4 / 5, parameters spread over several storages (`p.data = other`) or another device: plain fold_weights."""
+    from .._flatparams import element_offset, storage_base
+    cfg = self.node_weight_sharing_config
+    cn, ucn, vn = cfg.get(NodeType.CN), cfg.get(NodeType.UCN), cfg.get(NodeType.VN)
     ps = list(self.parameters())
-    key = (device, T, tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps))
-    cache = self.__dict__.setdefault("_fold_cache", {})
+    key = (device, T, tuple(p.data_ptr() for p in ps))
+    cache = self.__dict__.setdefault("_fold_index", {})
     hit = cache.get((device, T))
     if hit is None or hit[0] != key:
-        with torch.no_grad():
-            folded = self.fold_weights(list(range(T)), self._param_device() if device.type == "cpu" else device)
-        hit = (key, tuple(t.detach().to(device).contiguous() if isinstance(t, torch.Tensor) else t for t in folded))
+        maps = None
+        base = storage_base(ps, device) if (cn in (0, 1, 2, 3) and vn in (0, 1, 2, 3, 5) and ucn in (0, 1, 2, 3) and ps) else None
+        if base is not None:
+            E, N = int(self.sum_edge), self.N
+            erow = self._erow(device)
+            ar_e, ar_n = torch.arange(E, device=device), torch.arange(N, device=device)
+
+            def index_rows(node_type, sharing, cols):
+                rows = []
+                for t in range(T):
+                    off = element_offset(self.fetch_param(ParamType.Weight, node_type, t), base)
+                    if cols == N:
+                        rows.append(off + ar_n if sharing == 2 else torch.full((N,), off, dtype=torch.long, device=device))
+                    else:
+                        rows.append(off + ar_e if sharing == 1 else (off + erow if sharing == 2
+                                                                      else torch.full((E,), off, dtype=torch.long, device=device)))
+                return torch.stack(rows).contiguous()
+
+            maps = (index_rows(NodeType.VN, vn, N) if vn in (2, 3) else None,
+                    index_rows(NodeType.CN, cn, E) if cn in (1, 2, 3) else None,
+                    index_rows(NodeType.UCN, ucn, E) if (ucn == cn and cn in (1, 2, 3)) else None, base)
+        hit = (key, maps)
         if len(cache) > 8:
             cache.clear()
         cache[(device, T)] = hit
-    return hit[1]
+    if hit[1] is None:
+        with torch.no_grad():
+            folded = self.fold_weights(list(range(T)), device)
+        return tuple(t.detach() if isinstance(t, torch.Tensor) else t for t in folded)
+    i_vn, i_cn, i_ucn, base = hit[1]
+    take = lambda idx: None if idx is None else base[idx]       # noqa: E731
+    return take(i_vn), take(i_cn), take(i_ucn), ucn > 0, i_ucn is not None
 
 
 def _decode(self, xa, n_iters, soft_mode, hard_mode):
@@ -367,15 +409,9 @@ def _decode(self, xa, n_iters, soft_mode, hard_mode):
     gid = self.conn_mat.graph_id(device)
     dec = {DecoderType.SP: 0, DecoderType.MS: 1, DecoderType.QMS: 2}[self.decoding_type]
     tail = (gid, T, dec, int(self.decoder_qms_qbit), float(self.allowed_llr_range.start), float(self.allowed_llr_range.end))
-    if torch.cuda.is_current_stream_capturing():
-        # captured into a CUDA graph: the folding ops belong to the graph, so a replay re-reads the live parameters
-        vn_w, cn_w, ucn_w, compute_ucn, ucn_mix = self.fold_weights(list(range(T)), device)
-        soft, _, _, hard, _ = torch.ops.nldpc.boosted_forward(xa, vn_w, cn_w, ucn_w, *tail, bool(compute_ucn), bool(ucn_mix), None, None,
-                                                              None, False, False, soft_mode, hard_mode, False)
-        return soft, hard
-    # decode-only: the folded [T, .] weight rows are kept between calls and rebuilt only when a parameter changed (in-place
-    # updates bump Tensor._version, re-assigned storage changes data_ptr); the op body is called without the dispatcher
-    vn_w, cn_w, ucn_w, compute_ucn, ucn_mix = _folded_cached(self, T, device)
+    # decode-only: the folded [T, .] weight rows are gathered live from the flat parameter vector (_folded_live; captured into
+    # a CUDA graph the gathers belong to the graph, so a replay re-reads the parameters); no dispatcher
+    vn_w, cn_w, ucn_w, compute_ucn, ucn_mix = _folded_live(self, T, device)
     soft, _, _, hard, _ = ops.boosted_forward_direct(xa, vn_w, cn_w, ucn_w, *tail, bool(compute_ucn), bool(ucn_mix), None, None, None,
                                                      False, False, soft_mode, hard_mode, False)
     return soft, hard
@@ -406,9 +442,10 @@ def decode_host_q8(self, xq_cpu, scale=0.5, device=None, n_iters=None, soft=Fals
         device = torch.device("cuda")
     T = self.iter_node_counts if n_iters is None else n_iters
     gid = self.conn_mat.graph_id(device)
-    vn_w, cn_w, ucn_w, compute_ucn, ucn_mix = _folded_cached(self, T, torch.device("cpu"))
+    vn_w, cn_w, ucn_w, compute_ucn, ucn_mix = _folded_live(self, T, self._param_device())
+    host = lambda t: None if t is None else t.cpu().contiguous()       # noqa: E731
     dec = {DecoderType.SP: 0, DecoderType.MS: 1, DecoderType.QMS: 2}[self.decoding_type]
-    return ops.boosted_decode_host_q8(gid, xq_cpu, scale, vn_w, cn_w, ucn_w, T, dec, int(self.decoder_qms_qbit),
+    return ops.boosted_decode_host_q8(gid, xq_cpu, scale, host(vn_w), host(cn_w), host(ucn_w), T, dec, int(self.decoder_qms_qbit),
                                       float(self.allowed_llr_range.start), float(self.allowed_llr_range.end), bool(compute_ucn),
                                       bool(ucn_mix), _lib.NLDPC_OUT_LAST if soft else _lib.NLDPC_OUT_NONE,
                                       _lib.NLDPC_OUT_LAST if hard else _lib.NLDPC_OUT_NONE)

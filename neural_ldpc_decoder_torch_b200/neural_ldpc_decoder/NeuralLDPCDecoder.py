@@ -50,6 +50,7 @@ class NeuralLDPCDecoder(nn.Module):
         ])
         self._register_state_dict_hook(_add_dense_buffers)
         self._register_load_state_dict_pre_hook(_drop_dense_buffers)
+        self._flatten_params()
 
     # dense buffers of the reference (:27-32) as read-only attributes, for code that inspects them
     def __getattr__(self, name):
@@ -64,24 +65,49 @@ class NeuralLDPCDecoder(nn.Module):
     def _stacked(self):
         return torch.stack(list(self.weights_var)), torch.stack(list(self.biases_var))
 
+    def _flatten_params(self):
+        from .._flatparams import flatten_
+        flatten_(list(self.weights_var) + list(self.biases_var))       # weights [T, E] then biases [T, E], consecutive rows
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)                      # .to() / .cuda() give every parameter its own storage again
+        self._flatten_params()
+        return out
+
     def _stacked_nograd(self, device):
-        """[T, E] weights / biases on `device` for decode-only calls, rebuilt only when a parameter changed (every in-place
-        update bumps Tensor._version; re-assigned storage changes data_ptr): saves two stack launches per decode."""
-        ps = list(self.weights_var) + list(self.biases_var)
-        key = (device, tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps))
-        hit = self.__dict__.get("_stack_cache")
-        if hit is None or hit[0] != key:
-            with torch.no_grad():
-                w, b = self._stacked()
-                hit = (key, w.detach().to(device), b.detach().to(device))
-            self.__dict__["_stack_cache"] = hit
-        return hit[1], hit[2]
+        """[T, E] weights / biases on `device` for decode-only calls WITHOUT a stack launch: the parameters are consecutive rows
+        of one flat vector (see _flatparams), so the rows are a strided view — live, never a stale copy.  Only the layout check
+        is cached (keyed by the data pointers); a broken layout (`p.data = other`) or another device falls back to stacking."""
+        ws, bs = list(self.weights_var), list(self.biases_var)
+        ptrs = tuple(p.data_ptr() for p in ws) + tuple(p.data_ptr() for p in bs)
+        hit = self.__dict__.get("_rows_view")
+        if hit is None or hit[0] != ptrs or hit[1] != device:
+            views = None
+            T, E = len(ws), ws[0].numel()
+
+            def rows(ps):
+                p0 = ps[0]
+                sp = p0.untyped_storage().data_ptr()
+                ok = all(p.device == device and p.is_contiguous() and p.dtype == torch.float32 and p.untyped_storage().data_ptr() == sp
+                         and p.data_ptr() == p0.data_ptr() + 4 * E * t for t, p in enumerate(ps))
+                return torch.as_strided(p0.detach(), (T, E), (E, 1)) if ok else None
+
+            w, b = rows(ws), rows(bs)
+            if w is not None and b is not None:
+                views = (w, b)
+            hit = (ptrs, device, views)
+            self.__dict__["_rows_view"] = hit
+        if hit[2] is not None:
+            return hit[2]
+        with torch.no_grad():
+            w, b = self._stacked()
+        return w.detach().to(device), b.detach().to(device)
 
     def forward(self, xa):
         """xa [B, N, Z] float32 on a CUDA device -> list of T tensors [B, N*Z] (iteration outputs, :94-98)."""
         gid = self.conn_mat.graph_id(xa.device)
-        if not torch.is_grad_enabled() and not torch.cuda.is_current_stream_capturing():
-            # inference: cached stacked weights, no dispatcher (see _stacked_nograd)
+        if not torch.is_grad_enabled():
+            # inference: live [T, E] views of the flat parameter vector, no stack launches, no dispatcher (see _stacked_nograd)
             return list(ops.neural_forward_direct(xa, *self._stacked_nograd(xa.device), gid).unbind(0))
         w, b = self._stacked()
         if w.device != xa.device:
@@ -98,10 +124,7 @@ class NeuralLDPCDecoder(nn.Module):
         """Throughput mode: packed hard decisions `(out < 0)` (Functions.py:90 predicate), uint8
         [B, ceil(N*Z/8)] of the last iteration (or [T, B, ...]); soft outputs are never written to HBM."""
         gid = self.conn_mat.graph_id(xa.device)
-        if xa.is_cuda and torch.cuda.is_current_stream_capturing():
-            w, b = self._stacked()                       # captured: a replay must re-read the live parameters
-            return torch.ops.nldpc.neural_hard(xa, w.to(xa.device), b.to(xa.device), gid, all_iters)
-        w, b = self._stacked_nograd(xa.device)
+        w, b = self._stacked_nograd(xa.device)           # live views (or a fresh stack): a captured launch re-reads the parameters on replay
         return ops.neural_hard_direct(xa, w, b, gid, all_iters)
 
     @torch.no_grad()
@@ -110,8 +133,8 @@ class NeuralLDPCDecoder(nn.Module):
         from .. import _lib
         device = torch.device(device if device is not None else "cuda")
         gid = self.conn_mat.graph_id(device)
-        w, b = self._stacked()
-        return ops.neural_decode_host(gid, xa_cpu.contiguous(), w.detach().cpu().contiguous(), b.detach().cpu().contiguous(),
+        w, b = self._stacked_nograd(self._param_device())
+        return ops.neural_decode_host(gid, xa_cpu.contiguous(), w.cpu().contiguous(), b.cpu().contiguous(),
                                       _lib.NLDPC_OUT_ALL if soft else _lib.NLDPC_OUT_NONE,
                                       _lib.NLDPC_OUT_LAST if hard else _lib.NLDPC_OUT_NONE)
 

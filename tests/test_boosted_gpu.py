@@ -223,8 +223,12 @@ def test_boosted_decode_weight_cache_follows_parameter_updates(graphs):
     with torch.no_grad():
         m.weight_CN_3.mul_(0.75)
     check()
-    m.weight_VN_1.data = torch.full_like(m.weight_VN_1.data, 0.875)
+    m.weight_CN_2.data.fill_(0.625)                   # through .data (as the reference's _apply_constraints does): no version bump
     check()
+    assert m.__dict__["_fold_index"][(xa.device, 20)][1] is not None      # live gather through the cached index map
+    m.weight_VN_1.data = torch.full_like(m.weight_VN_1.data, 0.875)       # breaks the flat layout: plain fold_weights per call
+    check()
+    assert m.__dict__["_fold_index"][(xa.device, 20)][1] is None
     sd = {k: v * 0.5 + 0.25 for k, v in m.state_dict().items() if k.startswith("weight_")}
     m.load_state_dict(sd, strict=False)
     check()

@@ -73,6 +73,15 @@ def test_fused_trainer_follows_reference_training_loop(tag, graph):
         for (n, a), (_, b) in zip(m_ref.named_parameters(), m_new.named_parameters()):
             assert float((a.detach() - b.detach()).abs().max()) < 1e-5, (step, n)
     assert tr.steps_done == 6 and tr.last_grad_norm > 0.0
+    # the optimiser kernel writes the weights through raw pointers: the decode-only paths must see them (they read the
+    # parameters live, there is no cached copy to go stale)
+    with torch.no_grad():
+        vn_w, cn_w, ucn_w, compute_ucn, ucn_mix = m_new.fold_weights(list(range(T)), x.device)
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.DecoderType import DecoderType
+    dec = {DecoderType.SP: 0, DecoderType.MS: 1, DecoderType.QMS: 2}[m_new.decoding_type]
+    want = torch.ops.nldpc.boosted_forward(x, vn_w, cn_w, ucn_w, m_new.conn_mat.graph_id(x.device), T, dec, int(m_new.decoder_qms_qbit),
+                                           -20.0, 20.0, bool(compute_ucn), bool(ucn_mix), None, None, None, False, False, 2, 0, False)[0]
+    assert torch.equal(m_new.decode_soft_last(x).view(torch.int32), want.view(torch.int32))
     # names / shapes / state_dict keys are untouched by the flat-vector aliasing
     assert [n for n, _ in m_new.named_parameters()] == names
     assert set(m_new.state_dict().keys()) == set(m_ref.state_dict().keys())

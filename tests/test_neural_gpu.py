@@ -249,8 +249,15 @@ def test_decode_hard_weight_cache_follows_parameter_updates(graphs):
     before = m.decode_hard(x).clone()
     opt.step()
     assert torch.equal(m.decode_hard(x), fresh())
-    m.biases_var[2].data = torch.full_like(m.biases_var[2].data, 0.3)
+    m.weights_var[0].data.fill_(0.7)                  # through .data: no Tensor._version bump — the rows are read live, not cached
     assert torch.equal(m.decode_hard(x), fresh())
+    assert m.__dict__["_rows_view"][2] is not None    # still the zero-launch strided view of the flat parameter vector
+    m.biases_var[2].data = torch.full_like(m.biases_var[2].data, 0.3)      # breaks the flat layout: per-call stacking
+    assert torch.equal(m.decode_hard(x), fresh())
+    assert m.__dict__["_rows_view"][2] is None
+    with torch.no_grad():
+        outs = m(x)
+    assert torch.equal(torch.stack(outs), torch.ops.nldpc.neural_forward(x, *[t.detach() for t in m._stacked()], m.conn_mat.graph_id(x.device)))
     sd = {k: v.clone() for k, v in m.state_dict().items() if k.startswith(("weights_var", "biases_var"))}
     for k in sd:
         sd[k] = sd[k] * 0.9
