@@ -10,7 +10,7 @@
  * The reference expresses the Tanner-graph message passing as dense 0/1 matmuls and an
  * [B,Z,E,E] tile; this file restates the same arithmetic sparsely (O(E*Z) per iteration) with
  * the SAME fp32 operations in the SAME order, so results are bit-identical to the reference on
- * CPU (pinned by tests/golden/*.npz, generated from the live reference by tools/gen_golden.py).
+ * CPU (pinned by the .npz fixtures under tests/golden/, generated from the live reference by tools/gen_golden.py).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library.  The product path (neural_ldpc_decoder_torch_b200/csrc) never does.
