@@ -318,7 +318,12 @@ class BoostedNeuralLDPCDecoder(nn.Module):
             t0, t1 = run[0], run[-1]
             n_fixed = sum(1 for t in run if t in fixed_iteration)
             fw = None if fixed_iter_weight is None else list(fixed_iter_weight)[done_fixed:done_fixed + n_fixed]
-            vn_w, cn_w, ucn_w, compute_ucn, ucn_mix = self.fold_weights(run, device, fixed_iteration, fw)
+            inference = not torch.is_grad_enabled()
+            if inference and not fixed_iteration and t0 == 0:
+                # validation loops under no_grad: live gather from the flat parameter vector instead of ~2 T folding launches
+                vn_w, cn_w, ucn_w, compute_ucn, ucn_mix = _folded_live(self, len(run), device)
+            else:
+                vn_w, cn_w, ucn_w, compute_ucn, ucn_mix = self.fold_weights(run, device, fixed_iteration, fw)
             done_fixed += n_fixed
             x_run = xa[t0] if is_input_iterable else xa
             if is_input_iterable:
@@ -335,7 +340,8 @@ class BoostedNeuralLDPCDecoder(nn.Module):
             needs_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (vn_w, cn_w, ucn_w))
             want_dump = (needs_grad and llr_init is None and xin_state is None and app_init is None
                          and self.decoding_type != DecoderType.SP)
-            soft, llr_last, xin_out, _, _ = torch.ops.nldpc.boosted_forward(
+            run_op = ops.boosted_forward_direct if inference else torch.ops.nldpc.boosted_forward      # no autograd state: skip the dispatcher
+            soft, llr_last, xin_out, _, _ = run_op(
                 x_run, vn_w, cn_w, ucn_w, gid, len(run), dec, int(self.decoder_qms_qbit),
                 float(self.allowed_llr_range.start), float(self.allowed_llr_range.end), bool(compute_ucn), bool(ucn_mix),
                 llr_init, xin_state, app_init, want_llr, want_xin, 1, 0, want_dump)
