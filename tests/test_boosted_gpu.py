@@ -263,3 +263,24 @@ def test_boosted_host_api_int8_llrs(code, sharing, B, T, graphs):
     ref = oracle_forward(m.cpu(), xa[:k])
     assert np.array_equal(soft_h.numpy()[:k].view(np.uint32), ref[-1].view(np.uint32))
     assert np.array_equal(hard_h.numpy()[:k], np.packbits(ref[-1] < 0, axis=1, bitorder="little"))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_boosted_golden_under_no_grad(name):
+    """validation-loop use (forward under torch.no_grad(): live-gathered weights, dispatcher-free op) == the autograd path,
+    bit for bit, including the module state it leaves behind and a staged continuation"""
+    d = load_golden(name)
+    T = int(d["T"])
+    xa = torch.from_numpy(d["xa"]).cuda()
+    m_grad, m_inf = build_module(d, device="cuda"), build_module(d, device="cuda")
+    want = to_np(m_grad(xa))
+    with torch.no_grad():
+        got = to_np(m_inf(xa))
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert torch.equal(m_inf.llr[T].view(torch.int32), m_grad.llr[T].view(torch.int32))
+    if m_inf.decoding_type.name != "SP":
+        assert np.array_equal(got, d["out"])
+    k = max(1, T // 2)
+    with torch.no_grad():
+        first = to_np(m_inf(xa, target_iter=list(range(k))))
+    assert np.array_equal(first.view(np.uint32), want[:k].view(np.uint32))
