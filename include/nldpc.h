@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define NLDPC_ABI_VERSION 1
+#define NLDPC_ABI_VERSION 2
 
 /* error codes (negative); positive return values are cudaError_t */
 #define NLDPC_OK 0
@@ -125,6 +125,9 @@ typedef struct nldpc_boosted_cfg {
      * at least nldpc_backward_workspace_bytes(g, B, T, 1) bytes.  Pass the same buffer with have_dump = 1 to the backward. */
     void *train_dump_dev;
     size_t train_dump_bytes;
+    /* Optional [T][B][Z][E] fp32: receives self.llr[t + 1] of EVERY executed iteration (the reference stores each one,
+     * :512) from the same single launch; NULL = only llr_last_dev (if given) is written. */
+    float *llr_all_dev;
 } nldpc_boosted_cfg_t;
 
 /* Replaces the loop of BoostedNeuralLDPCDecoder.forward (:320-531) for iterations 0..T-1 from a

@@ -26,7 +26,8 @@ class BoostedCfg(ctypes.Structure):
     _fields_ = [("decoder_type", ctypes.c_int32), ("qbit", ctypes.c_int32), ("llr_lo", ctypes.c_float),
                 ("llr_hi", ctypes.c_float), ("compute_ucn", ctypes.c_int32), ("ucn_mix", ctypes.c_int32),
                 ("llr_init", ctypes.c_void_p), ("xin_init", ctypes.c_void_p), ("xin_out", ctypes.c_void_p),
-                ("app_init", ctypes.c_void_p), ("train_dump", ctypes.c_void_p), ("train_dump_bytes", ctypes.c_size_t)]
+                ("app_init", ctypes.c_void_p), ("train_dump", ctypes.c_void_p), ("train_dump_bytes", ctypes.c_size_t),
+                ("llr_all", ctypes.c_void_p)]
 
 
 def build(verbose=False):

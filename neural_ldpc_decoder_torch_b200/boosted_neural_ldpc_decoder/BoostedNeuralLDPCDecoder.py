@@ -10,10 +10,12 @@ What changes: the loop body (:320-531) runs as ONE CUDA launch per maximal run o
 (`torch.ops.nldpc.boosted_forward`); the weight-sharing types are folded into per-iteration rows by ordinary
 autograd-visible indexing/expansion, so gradients reach the actual parameters.
 
-Statefulness (:94-101): `self.outputs[t]` is written for every executed iteration.  `self.llr[t+1]`
-is written for the LAST iteration of every run (`store_llr = "last"`, default) — enough for staged training that continues
-from where the previous call stopped; set `store_llr = "all"` for the reference's every-iteration behaviour (one launch per
-iteration) or `"none"` to skip the state dump (12.6 KB per BG2 codeword).
+Statefulness (:94-101): `self.outputs[t]` and `self.llr[t+1]` are written for every executed
+iteration, as in the reference (:512, :523) — the kernel exports the c2v messages of all iterations of a run from the same
+launch (`store_llr = "all"`, default), so partial `target_iter` calls read exactly the state the reference would read
+(zeros where nothing was ever stored).  `store_llr = "last"` keeps only the state after the last iteration of a run and
+`"none"` skips the export (12.6 KB per BG2 codeword-iteration): throughput settings; with them a call that would continue
+from an iteration whose state was not stored raises instead of reading stale data.
 """
 from typing import Optional
 
@@ -96,14 +98,16 @@ class BoostedNeuralLDPCDecoder(nn.Module):
                         for _ in range(self.iter_node_counts)]
         self.llr = [torch.zeros((self.batch_size, self.Z, E), dtype=torch.float32, device=dev)
                     for _ in range(self.iter_node_counts + 1)]
-        self._llr_valid = [True] + [False] * self.iter_node_counts     # llr[0] is zeros forever (never written)
-        self.store_llr = "last"                                        # "last" | "all" | "none"
+        # the zero-initialised state IS the reference's state; entries only become invalid when a run executed an iteration
+        # without storing its messages (store_llr "last" / "none")
+        self._llr_valid = [True] * (self.iter_node_counts + 1)
+        self.store_llr = "all"                                         # "all" (reference state) | "last" | "none"
 
         self._erow_cache = {}
         self._register_params()
         self._flatten_params()
         self._register_state_dict_hook(_add_dense_buffers)
-        self._register_load_state_dict_pre_hook(_drop_dense_buffers)
+        self.register_load_state_dict_pre_hook(_drop_dense_buffers)
 
     # ---- parameters (same names and shapes as the reference, :105-151) -------------------------------------
     def _param_name(self, param_type: ParamType, node_type: NodeType, iterative_node_identifier: int):
@@ -300,10 +304,12 @@ class BoostedNeuralLDPCDecoder(nn.Module):
         device = first.device
         gid = self.conn_mat.graph_id(device)
 
-        # maximal runs of consecutive iterations -> one launch each (list-xa and store_llr="all": one iteration per launch)
+        # maximal runs of consecutive iterations -> one launch each (list-xa: one iteration per launch)
+        if self.store_llr not in ("all", "last", "none"):
+            raise ValueError(f"store_llr must be 'all', 'last' or 'none', got {self.store_llr!r}")
         runs, cur = [], []
         for t in iteration:
-            if cur and (t != cur[-1] + 1 or is_input_iterable or self.store_llr == "all"):
+            if cur and (t != cur[-1] + 1 or is_input_iterable):
                 runs.append(cur)
                 cur = []
             cur.append(t)
@@ -331,24 +337,38 @@ class BoostedNeuralLDPCDecoder(nn.Module):
             llr_init = None
             if t0 > 0:
                 if not self._llr_valid[t0]:
-                    raise RuntimeError(f"iteration {t0} continues from self.llr[{t0}], which no earlier call stored on this "
-                                       "module; run the preceding iterations first (or set model.store_llr = 'all')")
-                llr_init = self.llr[t0].to(device)
-            app_init = self.outputs[t0 - 1].to(device) if (compute_ucn and t0 > 0) else None
-            want_llr = self.store_llr != "none"
+                    raise RuntimeError(f"iteration {t0} continues from self.llr[{t0}], but the call that last executed iteration "
+                                       f"{t0 - 1} did not store it (model.store_llr = {self.store_llr!r}); use store_llr = 'all'")
+                llr_init = self.llr[t0].detach().to(device)            # a constant of this call, as a graph-less tensor is in the reference
+            app_init = self.outputs[t0 - 1].detach().to(device) if (compute_ucn and t0 > 0) else None
+            llr_mode = {"none": 0, "last": 1, "all": 2}[self.store_llr]
             want_xin = len(runs) > 1 and not is_input_iterable
             needs_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (vn_w, cn_w, ucn_w))
-            want_dump = (needs_grad and llr_init is None and xin_state is None and app_init is None
-                         and self.decoding_type != DecoderType.SP)
+            # Two configurations have no backward on this path: the SP decoder (the sweep kernels cover MS / QMS) and a
+            # target_iter list with gaps when VN weights are present (the compounding channel-input chain would have to carry
+            # gradients across launches).  Their forward works as in the reference; loss.backward() raises, and a warning
+            # says so now rather than only then.
+            no_bwd = self.decoding_type == DecoderType.SP or (xin_state is not None and vn_w is not None)
+            if needs_grad and no_bwd and not self.__dict__.get("_warned_no_bwd"):
+                import warnings
+                warnings.warn("BoostedNeuralLDPCDecoder (B200): this call is forward-only — "
+                              + ("the SP decoder has no backward kernel" if self.decoding_type == DecoderType.SP else
+                                 "a target_iter list with gaps cannot be trained when VN weights are present")
+                              + "; backward() through its outputs will raise.  Use torch.no_grad() for inference.")
+                self.__dict__["_warned_no_bwd"] = True
+            want_dump = needs_grad and not no_bwd
             run_op = ops.boosted_forward_direct if inference else torch.ops.nldpc.boosted_forward      # no autograd state: skip the dispatcher
-            soft, llr_last, xin_out, _, _ = run_op(
+            soft, llr_out, xin_out, _, _ = run_op(
                 x_run, vn_w, cn_w, ucn_w, gid, len(run), dec, int(self.decoder_qms_qbit),
                 float(self.allowed_llr_range.start), float(self.allowed_llr_range.end), bool(compute_ucn), bool(ucn_mix),
-                llr_init, xin_state, app_init, want_llr, want_xin, 1, 0, want_dump)
+                llr_init, xin_state, app_init, llr_mode, want_xin, 1, 0, want_dump)
             for k, t in enumerate(run):
                 self.outputs[t] = soft[k]
-            if want_llr:
-                self.llr[t1 + 1] = llr_last.detach()
+                if llr_mode == 2:
+                    self.llr[t + 1] = llr_out[k].detach()
+                self._llr_valid[t + 1] = llr_mode == 2
+            if llr_mode == 1:
+                self.llr[t1 + 1] = llr_out.detach()
                 self._llr_valid[t1 + 1] = True
             if want_xin:
                 xin_state = xin_out.detach()
@@ -470,6 +490,20 @@ def _add_dense_buffers(module, state_dict, prefix, local_metadata):
     return state_dict
 
 
-def _drop_dense_buffers(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
-    for key, _ in _BUFFERS:
-        state_dict.pop(prefix + key, None)
+def _drop_dense_buffers(module, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+    """load_state_dict pre-hook: the dense structure matrices are derived from the base graph, so they are not loaded — but a
+    checkpoint written for ANOTHER graph must fail like the reference's strict load does (size mismatch) instead of silently
+    attaching its weights to this graph: every buffer present in the checkpoint is compared with the synthesised one."""
+    for key, attr in _BUFFERS:
+        t = state_dict.pop(prefix + key, None)
+        if t is None:
+            if strict:
+                missing_keys.append(prefix + key)
+            continue
+        own = module.conn_mat.dense(attr, device=torch.device("cpu"))
+        if tuple(t.shape) != tuple(own.shape):
+            error_msgs.append(f"size mismatch for {prefix + key}: copying a param with shape {tuple(t.shape)} from checkpoint, "
+                              f"the shape in current model is {tuple(own.shape)}.")
+        elif not torch.equal(t.detach().to("cpu", own.dtype), own):
+            error_msgs.append(f"{prefix + key} in the checkpoint differs from the matrix this module derives from its base graph "
+                              "(the checkpoint was written for a different code)")

@@ -256,8 +256,9 @@ nldpc_generic_boosted_kernel(const GraphDev g, const DecodeArgs a, const Boosted
                 bc.app_row0 = (t == 0 && !a.app_init) ? 0 : lay.app_row0;
                 bc.xo_row0 = lay.xo_row0;
                 bc.app_store_row0 = track_app ? lay.app_row0 : -1;
-                bc.want_c2v1 = last && a.llr_last != nullptr;
-                bc.llr_last = (last && a.llr_last) ? a.llr_last + (size_t)b * Z * g.E : nullptr;
+                bc.want_c2v1 = (last && a.llr_last != nullptr) || a.llr_all != nullptr;
+                bc.llr_last = a.llr_all ? a.llr_all + ((size_t)t * a.B + b) * Z * g.E
+                                        : ((last && a.llr_last) ? a.llr_last + (size_t)b * Z * g.E : nullptr);
                 bc.E = g.E;
                 bc.mask_out = a.hist_mask ? a.hist_mask + ((size_t)t * a.B + b) * NZ : nullptr;
                 bc.ucn_out = (a.hist_ucn && track_app) ? a.hist_ucn + ((size_t)t * a.B + b) * g.M * Z : nullptr;

@@ -29,7 +29,7 @@ int boosted_prepare() {
 
 template <class G, int MODE, bool kXo>
 int boosted_launch_one(const DecodeArgs &args, int sm_count, cudaStream_t st) {
-    const bool every = args.soft_mode == 1 || args.hard_mode == 1;
+    const bool every = args.soft_mode == 1 || args.hard_mode == 1 || args.llr_all != nullptr;
     auto launch = [&](auto every_tag) {
         constexpr bool kEvery = decltype(every_tag)::value;
         using Cfg = SpecCfg<G, kXo && kEvery>;       // list mode keeps xa_origin rows on chip, throughput mode re-reads it (xo_global)

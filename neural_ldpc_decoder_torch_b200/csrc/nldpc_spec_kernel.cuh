@@ -731,7 +731,9 @@ __global__ void __launch_bounds__(SpecCfg<G, kXo && kEvery>::kThreads, SpecCfg<G
                 c.soft = (soft_cw && (soft_all || last)) ? soft_cw + (soft_all ? (size_t)t * soft_iter : 0) : nullptr;
                 c.hb = (hard_all || last) ? hb_cw : nullptr;
                 c.mask = (MODE != 0 && dump) ? a.hist_mask + ((size_t)t * a.B + b) * NZ : nullptr;
-                c.llr_last = (last && a.llr_last && c.valid) ? a.llr_last + (size_t)b * Z * G::E : nullptr;
+                c.llr_last = !c.valid ? nullptr
+                             : (a.llr_all ? a.llr_all + ((size_t)t * a.B + b) * Z * G::E
+                                          : ((last && a.llr_last) ? a.llr_last + (size_t)b * Z * G::E : nullptr));
                 cn_run(std::true_type{});
                 phase_sync();
             }

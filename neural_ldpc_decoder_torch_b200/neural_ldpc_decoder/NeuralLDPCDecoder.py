@@ -49,7 +49,7 @@ class NeuralLDPCDecoder(nn.Module):
             for _ in range(iter_node_counts)
         ])
         self._register_state_dict_hook(_add_dense_buffers)
-        self._register_load_state_dict_pre_hook(_drop_dense_buffers)
+        self.register_load_state_dict_pre_hook(_drop_dense_buffers)
         self._flatten_params()
 
     # dense buffers of the reference (:27-32) as read-only attributes, for code that inspects them
@@ -153,7 +153,20 @@ def _add_dense_buffers(module, state_dict, prefix, local_metadata):
     return state_dict
 
 
-def _drop_dense_buffers(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
-    """load_state_dict pre-hook: the dense structure matrices are derived from the base graph; accept and drop them."""
-    for key, _ in _BUFFERS:
-        state_dict.pop(prefix + key, None)
+def _drop_dense_buffers(module, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+    """load_state_dict pre-hook: the dense structure matrices are derived from the base graph, so they are not loaded — but a
+    checkpoint written for ANOTHER graph must fail like the reference's strict load does (size mismatch) instead of silently
+    attaching its weights to this graph: every buffer present in the checkpoint is compared with the synthesised one."""
+    for key, attr in _BUFFERS:
+        t = state_dict.pop(prefix + key, None)
+        if t is None:
+            if strict:
+                missing_keys.append(prefix + key)
+            continue
+        own = module.conn_mat.dense(attr, device=torch.device("cpu"))
+        if tuple(t.shape) != tuple(own.shape):
+            error_msgs.append(f"size mismatch for {prefix + key}: copying a param with shape {tuple(t.shape)} from checkpoint, "
+                              f"the shape in current model is {tuple(own.shape)}.")
+        elif not torch.equal(t.detach().to("cpu", own.dtype), own):
+            error_msgs.append(f"{prefix + key} in the checkpoint differs from the matrix this module derives from its base graph "
+                              "(the checkpoint was written for a different code)")

@@ -204,6 +204,10 @@ def _out_shape(mode, T, B, last):
     return (T, B, last) if mode == _lib.NLDPC_OUT_ALL else ((B, last) if mode == _lib.NLDPC_OUT_LAST else (0,))
 
 
+def _llr_shape(llr_mode, T, B, g):
+    return (T, B, g.Z, g.E) if llr_mode == 2 else ((B, g.Z, g.E) if llr_mode == 1 else (0,))
+
+
 def _opt_f32(name, t, shape, device):
     if t is None:
         return None
@@ -216,10 +220,11 @@ def _opt_f32(name, t, shape, device):
 
 
 def boosted_forward_direct(xa, vn_w, cn_w, ucn_w, graph_id, T, decoder_type, qbit, llr_lo, llr_hi, compute_ucn, ucn_mix, llr_init,
-                           xin_init, app_init, want_llr, want_xin, soft_mode, hard_mode, want_dump=False):
+                           xin_init, app_init, llr_mode, want_xin, soft_mode, hard_mode, want_dump=False):
     """Body of nldpc::boosted_forward, callable without the dispatcher (decode-only callers that hold no autograd state).
     T consecutive iterations of the Boosted loop body.  Returns (soft [T,B,N*Z] | [B,N*Z] | empty per soft_mode,
-    llr_last [B,Z,E] | empty, xin_out [B,N,Z] | empty, packed hard decisions per hard_mode | empty, training dump | 1 byte).
+    llr [B,Z,E] (llr_mode 1: self.llr[t_last+1]) | [T,B,Z,E] (llr_mode 2: every executed iteration, :512) | empty (0),
+    xin_out [B,N,Z] | empty, packed hard decisions per hard_mode | empty, training dump | 1 byte).
     Weight rows are indexed by executed iteration."""
     g = _lib.graph_by_id(graph_id)
     _check_cuda_f32("xa", xa)
@@ -237,7 +242,8 @@ def boosted_forward_direct(xa, vn_w, cn_w, ucn_w, graph_id, T, decoder_type, qbi
     app_init = _opt_f32("app_init", app_init, (B, g.NZ), dev)
     soft = torch.empty(_out_shape(soft_mode, T, B, g.NZ), dtype=torch.float32, device=dev)
     hard = torch.empty(_out_shape(hard_mode, T, B, g.hard_bytes), dtype=torch.uint8, device=dev)
-    llr_last = torch.empty((B, g.Z, g.E) if want_llr else (0,), dtype=torch.float32, device=dev)
+    llr_mode = int(llr_mode)
+    llr_last = torch.empty(_llr_shape(llr_mode, T, B, g), dtype=torch.float32, device=dev)
     xin_out = torch.empty((B, g.N, g.Z) if want_xin else (0,), dtype=torch.float32, device=dev)
     nbytes = int(_lib.lib().nldpc_backward_workspace_bytes(g.ptr, B, T, 1)) if want_dump else 0
     dump = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=dev)
@@ -246,12 +252,13 @@ def boosted_forward_direct(xa, vn_w, cn_w, ucn_w, graph_id, T, decoder_type, qbi
                           xin_init.data_ptr() if xin_init is not None else None,
                           xin_out.data_ptr() if want_xin else None,
                           app_init.data_ptr() if app_init is not None else None,
-                          dump.data_ptr() if want_dump else None, nbytes)
+                          dump.data_ptr() if want_dump else None, nbytes,
+                          llr_last.data_ptr() if llr_mode == 2 else None)
     with torch.cuda.device(dev):
         rc = _lib.lib().nldpc_boosted_forward(g.ptr, ctypes.byref(cfg), _ptr(xa), _ptr(vn_w), _ptr(cn_w), _ptr(ucn_w), B, T,
                                               soft_mode, _ptr(soft) if soft_mode else _vp(0), hard_mode,
                                               _ptr(hard) if hard_mode else _vp(0),
-                                              _ptr(llr_last) if want_llr else _vp(0), _stream(xa))
+                                              _ptr(llr_last) if llr_mode == 1 else _vp(0), _stream(xa))
     _lib.check(rc, "nldpc_boosted_forward")
     return soft, llr_last, xin_out, hard, dump
 
@@ -260,19 +267,19 @@ def boosted_forward_direct(xa, vn_w, cn_w, ucn_w, graph_id, T, decoder_type, qbi
 def boosted_forward(xa: torch.Tensor, vn_w: Optional[torch.Tensor], cn_w: Optional[torch.Tensor], ucn_w: Optional[torch.Tensor],
                     graph_id: int, T: int, decoder_type: int, qbit: int, llr_lo: float, llr_hi: float, compute_ucn: bool,
                     ucn_mix: bool, llr_init: Optional[torch.Tensor], xin_init: Optional[torch.Tensor],
-                    app_init: Optional[torch.Tensor], want_llr: bool, want_xin: bool, soft_mode: int,
+                    app_init: Optional[torch.Tensor], llr_mode: int, want_xin: bool, soft_mode: int,
                     hard_mode: int, want_dump: bool = False) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """see boosted_forward_direct"""
     return boosted_forward_direct(xa, vn_w, cn_w, ucn_w, graph_id, T, decoder_type, qbit, llr_lo, llr_hi, compute_ucn, ucn_mix, llr_init,
-                                  xin_init, app_init, want_llr, want_xin, soft_mode, hard_mode, want_dump)
+                                  xin_init, app_init, llr_mode, want_xin, soft_mode, hard_mode, want_dump)
 
 
 @boosted_forward.register_fake
 def _(xa, vn_w, cn_w, ucn_w, graph_id, T, decoder_type, qbit, llr_lo, llr_hi, compute_ucn, ucn_mix, llr_init, xin_init, app_init,
-      want_llr, want_xin, soft_mode, hard_mode, want_dump=False):
+      llr_mode, want_xin, soft_mode, hard_mode, want_dump=False):
     g = _lib.graph_by_id(graph_id)
     B = xa.shape[0]
-    return (xa.new_empty(_out_shape(soft_mode, T, B, g.NZ)), xa.new_empty((B, g.Z, g.E) if want_llr else (0,)),
+    return (xa.new_empty(_out_shape(soft_mode, T, B, g.NZ)), xa.new_empty(_llr_shape(llr_mode, T, B, g)),
             xa.new_empty((B, g.N, g.Z) if want_xin else (0,)),
             xa.new_empty(_out_shape(hard_mode, T, B, g.hard_bytes), dtype=torch.uint8), xa.new_empty((1,), dtype=torch.uint8))
 
@@ -298,7 +305,7 @@ def boosted_backward(xa: torch.Tensor, vn_w: Optional[torch.Tensor], cn_w: Optio
     nbytes = int(_lib.lib().nldpc_backward_workspace_bytes(g.ptr, B, T, 1))
     have_dump = dump is not None and dump.numel() >= nbytes
     ws = dump if have_dump else torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=dev)
-    cfg = _lib.BoostedCfg(decoder_type, qbit, llr_lo, llr_hi, int(compute_ucn), int(ucn_mix), None, None, None, None, None, 0)
+    cfg = _lib.BoostedCfg(decoder_type, qbit, llr_lo, llr_hi, int(compute_ucn), int(ucn_mix), None, None, None, None, None, 0, None)
     with torch.cuda.device(dev):
         rc = _lib.lib().nldpc_boosted_backward(g.ptr, ctypes.byref(cfg), _ptr(xa), _ptr(vn_w), _ptr(cn_w), _ptr(ucn_w), _ptr(gout), B, T,
                                                _ptr(gvn) if gvn.numel() else _vp(0), _ptr(gcn) if gcn.numel() else _vp(0),
@@ -315,11 +322,12 @@ def _(xa, vn_w, cn_w, ucn_w, gout, graph_id, T, decoder_type, qbit, llr_lo, llr_
 
 
 def _boosted_setup_ctx(ctx, inputs, output):
-    (xa, vn_w, cn_w, ucn_w, graph_id, T, dec, qbit, lo, hi, compute_ucn, ucn_mix, llr_init, xin_init, app_init, want_llr,
+    (xa, vn_w, cn_w, ucn_w, graph_id, T, dec, qbit, lo, hi, compute_ucn, ucn_mix, llr_init, xin_init, app_init, llr_mode,
      want_xin, soft_mode, hard_mode, want_dump) = inputs
     ctx.save_for_backward(xa, vn_w, cn_w, ucn_w, output[4] if want_dump else None)
     ctx.cfg = (graph_id, T, dec, qbit, lo, hi, compute_ucn, ucn_mix)
     ctx.stateful = llr_init is not None or xin_init is not None or app_init is not None
+    ctx.have_dump = bool(want_dump)
     ctx.soft_all = soft_mode == _lib.NLDPC_OUT_ALL
     # autograd would otherwise hand the backward a ZERO tensor for every output without a gradient — including one the size
     # of the training dump (20 GB at B = 65536, T = 20: 5 ms of fill per step)
@@ -333,9 +341,11 @@ def _boosted_bwd(ctx, gsoft, gllr, gxin, ghard, gdump):
     graph_id, T, dec, qbit, lo, hi, compute_ucn, ucn_mix = ctx.cfg
     if not ctx.soft_all:
         raise _lib.NldpcError("backward needs the per-iteration soft outputs (soft_mode = ALL)")
-    if ctx.stateful:
-        raise _lib.NldpcError("backward through a run that continues from stored state (partial target_iter after an earlier "
-                              "call) is not supported: run the trained iterations in one forward call starting at iteration 0")
+    if ctx.stateful and not ctx.have_dump:
+        # the stored state (llr_init / xin_init / app_init) is a constant of the call, exactly as the graph-less tensors the
+        # reference reads from self.llr / self.outputs are; the sweep only needs the dump the forward wrote WITH that state
+        raise _lib.NldpcError("backward through a run that continues from stored state needs the training dump of that run "
+                              "(call the forward op with want_dump=True)")
     gvn, gcn, gucn = torch.ops.nldpc.boosted_backward(xa, vn_w, cn_w, ucn_w, gsoft.contiguous(), graph_id, T, dec, qbit, lo, hi,
                                                       compute_ucn, ucn_mix, dump)
     return (None, gvn if vn_w is not None else None, gcn if cn_w is not None else None,
@@ -572,7 +582,7 @@ def boosted_decode_host_q8(graph_id: int, xq_host: torch.Tensor, scale: float, v
         soft = torch.empty(_out_shape(soft_mode, T, B, g.NZ), dtype=torch.float32, pin_memory=True)
     if hard_mode != _lib.NLDPC_OUT_NONE:
         hard = torch.empty(_out_shape(hard_mode, T, B, g.hard_bytes), dtype=torch.uint8, pin_memory=True)
-    cfg = _lib.BoostedCfg(decoder_type, qbit, llr_lo, llr_hi, int(compute_ucn), int(ucn_mix), None, None, None, None, None, 0)
+    cfg = _lib.BoostedCfg(decoder_type, qbit, llr_lo, llr_hi, int(compute_ucn), int(ucn_mix), None, None, None, None, None, 0, None)
     rc = _lib.lib().nldpc_boosted_decode_host_q8(g.ptr, ctypes.byref(cfg), _ptr(xq_host), float(scale), _ptr(vn_w_host), _ptr(cn_w_host),
                                                  _ptr(ucn_w_host), B, T, soft_mode, _ptr(soft), hard_mode, _ptr(hard))
     _lib.check(rc, "nldpc_boosted_decode_host_q8")

@@ -134,6 +134,7 @@ static void col_total(const graph_t *g, const float *c2v, float *tot /*[N][Z]*/)
 /* NeuralLDPCDecoder.forward (NeuralLDPCDecoder.py:44-100).  out: [T][B][N*Z].                 */
 typedef struct {
     const graph_t *g; const float *xa, *w, *b; int B, T; float *out; int rc;
+    int last_only; /* out is [B][N*Z]: only the last iteration is kept (full-size parity runs) */
 } neural_ctx_t;
 
 static void neural_range(void *p, int begin, int end) {
@@ -179,7 +180,8 @@ static void neural_range(void *p, int begin, int end) {
                     c2v[e * Z + z] = m * signf_(op);
                 }
             col_total(&g, c2v, tot);                                                 /* :94-98 */
-            float *ot = c->out + ((size_t)t * B + cw) * NZ;
+            if (c->last_only && t != c->T - 1) continue;
+            float *ot = c->out + (c->last_only ? (size_t)cw : (size_t)t * B + cw) * NZ;
             for (int q = 0; q < NZ; q++) ot[q] = x[q] + tot[q];
         }
     }
@@ -192,7 +194,18 @@ int nldpc_oracle_neural_forward(const int32_t *bg, int M, int N, int Z,
                                 int B, int T, float *out) {
     graph_t g;
     if (graph_build(&g, bg, M, N, Z)) return -1;
-    neural_ctx_t c = { &g, xa, w, b, B, T, out, 0 };
+    neural_ctx_t c = { &g, xa, w, b, B, T, out, 0, 0 };
+    parallel_for(B, neural_range, &c);
+    graph_free(&g);
+    return c.rc;
+}
+
+/* the same, keeping only the last iteration's output: out_last [B][N*Z] */
+int nldpc_oracle_neural_forward_last(const int32_t *bg, int M, int N, int Z,
+                                     const float *xa, const float *w, const float *b, int B, int T, float *out_last) {
+    graph_t g;
+    if (graph_build(&g, bg, M, N, Z)) return -1;
+    neural_ctx_t c = { &g, xa, w, b, B, T, out_last, 0, 1 };
     parallel_for(B, neural_range, &c);
     graph_free(&g);
     return c.rc;

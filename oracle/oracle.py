@@ -38,6 +38,8 @@ def lib():
         L.nldpc_oracle_neural_forward.restype = ctypes.c_int
         L.nldpc_oracle_neural_forward.argtypes = [_i32p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                   _f32p, _f32p, _f32p, ctypes.c_int, ctypes.c_int, _f32p]
+        L.nldpc_oracle_neural_forward_last.restype = ctypes.c_int
+        L.nldpc_oracle_neural_forward_last.argtypes = L.nldpc_oracle_neural_forward.argtypes
         L.nldpc_oracle_boosted_step.restype = ctypes.c_int
         L.nldpc_oracle_boosted_step.argtypes = [_i32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                 ctypes.c_float, ctypes.c_float,
@@ -71,6 +73,22 @@ def neural_forward(basegraph, Z, xa, w, b):
     rc = lib().nldpc_oracle_neural_forward(bg, M, N, Z, xa, w, b, B, T, out)
     if rc:
         raise RuntimeError(f"oracle neural_forward failed rc={rc}")
+    return out
+
+
+def neural_forward_last(basegraph, Z, xa, w, b):
+    """neural_forward keeping only the last iteration: -> out [B,N*Z] f32 (full-size parity runs: T times less memory)."""
+    bg = _bg(basegraph)
+    M, N = bg.shape
+    xa = np.ascontiguousarray(xa, dtype=np.float32)
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    B, T = xa.shape[0], w.shape[0]
+    assert xa.shape == (B, N, Z) and w.shape == b.shape and w.shape[1] == int((bg != -1).sum())
+    out = np.empty((B, N * Z), dtype=np.float32)
+    rc = lib().nldpc_oracle_neural_forward_last(bg, M, N, Z, xa, w, b, B, T, out)
+    if rc:
+        raise RuntimeError(f"oracle neural_forward_last failed rc={rc}")
     return out
 
 

@@ -100,9 +100,11 @@ def test_boosted_non_contiguous_and_llr_guard(graphs):
     d = load_golden(CASES[2])           # WiMAX QMS (3,0,0)
     xa = torch.from_numpy(d["xa"]).cuda()
     m = build_module(d, device="cuda")
+    m.store_llr = "last"
+    m(xa, target_iter=[0, 1, 2, 3])
     with pytest.raises(RuntimeError):
-        m(xa, target_iter=[5])          # self.llr[5] was never produced on this module
-    m.store_llr = "all"
+        m(xa, target_iter=[2])          # self.llr[2] was skipped by the run above (store_llr = "last"): no stale read
+    m.store_llr = "all"                 # default: every iteration's messages are stored, as in the reference (:512)
     m(xa, target_iter=[0, 1, 2, 3])
     out = m(xa, target_iter=[1, 3])     # re-runs 1 from llr[1], 3 from llr[3]: same values as before
     ref = oracle_forward(build_module(d), d["xa"])

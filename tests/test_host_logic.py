@@ -102,7 +102,7 @@ def test_c_abi_exports_every_declared_symbol():
     assert len(names) >= 8
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/nldpc.h but not exported"
-    assert lib.nldpc_abi_version() == 1
+    assert lib.nldpc_abi_version() == 2
 
 
 def test_product_package_never_imports_oracle():
@@ -151,3 +151,81 @@ def test_checkpoint_utils_roundtrip_and_reference_layout(tmp_path, graphs):
     assert lines[0].startswith("# Training started") and lines[2].startswith("# Columns: Epoch, Timestamp, loss, ber_last_iter")
     assert lines[-1].endswith("0.200000, 1.000000e-03, c2.pth")
     assert log.is_best(1e-3) and not log.is_best(2e-3) and log.is_best(5e-4)
+
+
+def _sha_t(t):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(t.detach().cpu().numpy().astype(np.float32)).tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("code", ["bg2", "wimax"])
+@pytest.mark.parametrize("family", ["neural", "boosted"])
+def test_dense_structure_matrices_equal_the_reference(code, family, graphs):
+    """every dense matrix synthesised for state_dict() is byte-identical to the one the reference builds
+    (neural ConnectingMatrix.py:68-140, boosted :82-163); SHA-256 fixtures from tools/gen_golden_checkpoint.py"""
+    from conftest import golden_json
+    want = golden_json("dense_matrix_sha.json")[f"{code}_{family}"]
+    bg, Z = graphs[code]
+    if family == "neural":
+        from neural_ldpc_decoder_torch_b200.neural_ldpc_decoder import ConnectingMatrix, ConnectingMatrixTorch, NeuralLDPCDecoder
+        m = NeuralLDPCDecoder(1, 2, ConnectingMatrixTorch(ConnectingMatrix(Z=Z, basegraph=bg)))
+    else:
+        from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder import ConnectingMatrix, ConnectingMatrixTorch
+        from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.BoostedNeuralLDPCDecoder import BoostedNeuralLDPCDecoder
+        m = BoostedNeuralLDPCDecoder(1, 2, ConnectingMatrixTorch(ConnectingMatrix(Z=Z, basegraph=bg)))
+    sd = m.state_dict()
+    dense = [k for k in sd if k.startswith(("W_", "Lift_"))]
+    assert dense == list(want.keys())                                   # same keys, same order
+    for k in dense:
+        assert list(sd[k].shape) == want[k]["shape"] and sd[k].dtype == torch.float32, k
+        assert _sha_t(sd[k]) == want[k]["sha256"], k
+        assert _sha_t(getattr(m, k)) == want[k]["sha256"], k           # ... and as the attribute the reference exposes
+
+
+def test_reference_written_checkpoints_load_strictly(tmp_path):
+    """checkpoints written by the REFERENCE's CheckPointUtil.save (fixtures: tools/gen_golden_checkpoint.py, toy code M=3 N=6
+    Z=4) load through the mirror's strict load (CheckPointUtil.py:125-159), and the mirror's own state_dict() reproduces the
+    reference's file key for key, value for value"""
+    import shutil
+    from conftest import GOLDEN
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder import ConnectingMatrix as BCM, ConnectingMatrixTorch as BCMT
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.BoostedNeuralLDPCDecoder import BoostedNeuralLDPCDecoder
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.DecoderType import DecoderType
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.NodeWeightSharingConfig import NodeWeightSharingConfig
+    from neural_ldpc_decoder_torch_b200.checkpoint_utils import CheckPointUtil
+    from neural_ldpc_decoder_torch_b200.neural_ldpc_decoder import ConnectingMatrix, ConnectingMatrixTorch, NeuralLDPCDecoder
+    toy = np.load(os.path.join(GOLDEN, "ref_ckpt_toy_graph.npz"))
+    bg, Z = toy["basegraph"], int(toy["Z"])
+    for f in ("ref_ckpt_neural_toy.pth", "ref_ckpt_boosted_toy.pth"):
+        shutil.copy(os.path.join(GOLDEN, f), tmp_path / f)
+    ck = CheckPointUtil(checkpoint_dir=str(tmp_path))
+
+    m = NeuralLDPCDecoder(3, 2, ConnectingMatrixTorch(ConnectingMatrix(Z=Z, basegraph=bg)))
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    got = ck.load("ref_ckpt_neural_toy.pth", m, optimizer=opt)
+    assert got["epoch"] == 7 and got["loss"] == 0.125 and got["config"] == {"T": 3, "code": "toy"}
+    ref_sd = got["model_state_dict"]
+    own_sd = m.state_dict()
+    assert list(own_sd.keys()) == list(ref_sd.keys())
+    for k in ref_sd:
+        assert own_sd[k].dtype == ref_sd[k].dtype and torch.equal(own_sd[k], ref_sd[k]), k
+    assert len(opt.state_dict()["state"]) == 6 and opt.state_dict()["state"][0]["step"] == 1      # Adam moments came along
+
+    mb = BoostedNeuralLDPCDecoder(4, 2, BCMT(BCM(Z=Z, basegraph=bg)), node_weight_sharing_config=NodeWeightSharingConfig(2, 2, 3),
+                                  decoding_type=DecoderType.QMS)
+    gotb = ck.load("ref_ckpt_boosted_toy.pth", mb, optimizer=torch.optim.Adam(mb.get_trainable_parameters()))
+    ref_sd, own_sd = gotb["model_state_dict"], mb.state_dict()
+    assert list(own_sd.keys()) == list(ref_sd.keys())
+    for k in ref_sd:
+        assert torch.equal(own_sd[k], ref_sd[k]), k
+    assert gotb["epoch"] == 2
+
+    # a checkpoint written for another graph must not load (the reference fails with a size mismatch)
+    bg2 = bg.copy()
+    bg2[0, 0] = 2                                                                                   # same shape, different shift
+    other = NeuralLDPCDecoder(3, 2, ConnectingMatrixTorch(ConnectingMatrix(Z=Z, basegraph=bg2)))
+    with pytest.raises(RuntimeError):
+        ck.load("ref_ckpt_neural_toy.pth", other)
+    wider = NeuralLDPCDecoder(3, 2, ConnectingMatrixTorch(ConnectingMatrix(Z=Z + 1, basegraph=bg)))
+    with pytest.raises(RuntimeError):
+        ck.load("ref_ckpt_neural_toy.pth", wider)

@@ -173,7 +173,21 @@ def test_full_size_properties_bg2_65536(graphs):
     with torch.no_grad():
         outs_p = m(xa[perm])
     assert torch.equal(outs_p[-1], outs[-1][perm])
-    # (3) oracle on a strided subset of codewords (every 128th), all iterations
+    # (3) oracle on EVERY codeword, every iteration: fp32 bit patterns of all 10 x 65536 x 832 outputs (trained-like weights)
+    rs = np.random.RandomState(0)
+    w = rs.uniform(0.3, 1.3, (T, E)).astype(np.float32)
+    b = (0.2 * rs.normal(size=(T, E))).astype(np.float32)
+    mt = make_model(bg, Z, T, B, w, b)
+    with torch.no_grad():
+        outs_t = mt(xa)
+    hard_t = mt.decode_hard(xa).cpu().numpy()
+    chunk = 8192
+    for b0 in range(0, B, chunk):
+        ref = oracle.neural_forward(bg, Z, xa[b0:b0 + chunk].cpu().numpy(), w, b)
+        got = np.stack([o[b0:b0 + chunk].cpu().numpy() for o in outs_t])
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), b0
+        assert np.array_equal(hard_t[b0:b0 + chunk], oracle.pack_hard(ref[-1])), b0
+    # ... and with the init weights on a strided subset (every 128th codeword)
     idx = np.arange(0, B, 128)
     ref = oracle.neural_forward(bg, Z, xa[idx].cpu().numpy(), np.full((T, E), 0.5, np.float32), np.zeros((T, E), np.float32))
     got = np.stack([o[idx].detach().cpu().numpy() for o in outs])
@@ -183,6 +197,55 @@ def test_full_size_properties_bg2_65536(graphs):
     assert bits.mean() > 0.99, bits.mean()
     first = (outs[0] < 0).float().mean().item()
     assert bits.mean() > first, (first, bits.mean())
+
+
+def test_config4_2pow20_codewords_sharded_every_decision_vs_oracle(graphs):
+    """BASELINE configs[3]: 2^20 BG2 codewords (3.49 GB of LLRs), packed-decision mode, split into the contiguous shards the
+    1/2/4/8-GPU runs use (sharding.shard_bounds): EVERY packed decision and every last-iteration LLR bit pattern of every
+    shard against the oracle."""
+    from neural_ldpc_decoder_torch_b200.sharding import shard_bounds
+    bg, Z = graphs["bg2"]
+    E = int((bg != -1).sum())
+    B, T, world = 1 << 20, 10, 8
+    g = torch.Generator(device="cuda").manual_seed(4242)
+    sigma = 1.2559
+    xa = torch.empty((B, 52, 16), device="cuda")
+    for b0 in range(0, B, 1 << 17):          # generate in pieces: bounded temporaries
+        xa[b0:b0 + (1 << 17)] = 2.0 * (sigma * torch.randn((1 << 17, 52, 16), generator=g, device="cuda") - 1.0) / sigma ** 2
+    rs = np.random.RandomState(1)
+    w = rs.uniform(0.3, 1.3, (T, E)).astype(np.float32)
+    b = (0.2 * rs.normal(size=(T, E))).astype(np.float32)
+    m = make_model(bg, Z, T, B, w, b)
+    whole = m.decode_hard(xa)                                           # one launch over all 2^20
+    n_bad_bits = 0
+    for rank in range(world):
+        lo, hi = shard_bounds(B, world, rank)
+        x_shard = xa[lo:hi]
+        hard = m.decode_hard(x_shard)                                   # what rank `rank` of an 8-GPU run computes
+        assert torch.equal(hard, whole[lo:hi])
+        soft = ops_last_soft(m, x_shard)
+        ref = oracle.neural_forward_last(bg, Z, x_shard.cpu().numpy(), w, b)
+        assert np.array_equal(soft.cpu().numpy().view(np.uint32), ref.view(np.uint32)), rank
+        assert np.array_equal(hard.cpu().numpy(), oracle.pack_hard(ref)), rank
+        n_bad_bits += int((ref >= 0).sum())
+    assert n_bad_bits < 0.02 * B * 832                                  # it decodes (all-zero word, bit 0 <-> LLR < 0)
+
+
+def ops_last_soft(m, xa):
+    """last-iteration soft output [B, N*Z] through the C ABI (soft_mode = LAST)"""
+    import ctypes
+    from neural_ldpc_decoder_torch_b200 import _lib
+    gid = m.conn_mat.graph_id(xa.device)
+    g = _lib.graph_by_id(gid)
+    w, b = m._stacked_nograd(xa.device)
+    w, b = w.contiguous(), b.contiguous()
+    out = torch.empty((xa.shape[0], g.NZ), dtype=torch.float32, device=xa.device)
+    vp = ctypes.c_void_p
+    rc = _lib.lib().nldpc_neural_forward(g.ptr, vp(xa.data_ptr()), vp(w.data_ptr()), vp(b.data_ptr()), xa.shape[0], w.shape[0],
+                                         _lib.NLDPC_OUT_LAST, vp(out.data_ptr()), _lib.NLDPC_OUT_NONE, vp(0),
+                                         vp(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc, "nldpc_neural_forward")
+    return out
 
 
 def test_cpu_tensor_fails_loudly(graphs):
