@@ -182,14 +182,17 @@ int nldpc_count_errors_packed(const uint8_t *hard_dev, size_t iter_stride_bytes,
 
 /* Tail of one training step on the flat weight vector, one launch: replaces clip_grad_norm_ + Adam.step + the clamp of
  * _apply_constraints (train/train_BoostedNeuralLDPCDecoder.py:291-294, BoostedNeuralLDPCDecoder.py:153-179).
- *   param_dev, grad_dev, exp_avg_dev, exp_avg_sq_dev : [n] fp32, all UPDATED in place (grad receives the clipped gradient)
+ *   param_dev, exp_avg_dev, exp_avg_sq_dev : [n] fp32, UPDATED in place
+ *   grad_dev   : [n_norm] fp32, n_norm >= n: the gradient norm of clip_grad_norm_(model.parameters()) runs over all n_norm
+ *                entries, the optimiser updates the first n (get_trainable_parameters()); all receive the clipped gradient
+ *   lr_dev     : optional device scalar read at run time instead of `lr` (a replayed CUDA graph then follows a schedule)
  *   state_dev  : 2 floats: [0] step count so far (incremented by the kernel — the launch is CUDA-graph replayable),
  *                [1] receives the total gradient norm before clipping
  *   grad_scale : multiplies the gradient first (1 / world_size after a SUM all-reduce); max_norm <= 0 disables clipping
  *   lr, beta1, beta2, eps : torch.optim.Adam defaults 1e-3, 0.9, 0.999, 1e-8 (no weight decay, no amsgrad) */
 int nldpc_clip_adam_clamp(float *param_dev, float *grad_dev, float *exp_avg_dev, float *exp_avg_sq_dev, float *state_dev, int n,
-                          float grad_scale, float max_norm, double lr, double beta1, double beta2, double eps, float clamp_lo,
-                          float clamp_hi, void *stream);
+                          int n_norm, float grad_scale, float max_norm, double lr, const float *lr_dev, double beta1, double beta2,
+                          double eps, float clamp_lo, float clamp_hi, void *stream);
 
 /* Host-buffer decode of the Boosted decoder with ONE-BYTE channel LLRs: x = scale * q.  The Boosted pipeline quantises its
  * channel LLRs before the decoder sees them (boosted AWGNPassedDatagen.py:165-166 -> Functions.Cal_MSA_Q, Functions.py:70-83:

@@ -81,8 +81,8 @@ def lib():
             L.nldpc_boosted_decode_host_q8.restype = ci
             L.nldpc_boosted_decode_host_q8.argtypes = [vp, ctypes.POINTER(BoostedCfg), vp, ctypes.c_float, vp, vp, vp, ci, ci, ci, vp, ci, vp]
             L.nldpc_clip_adam_clamp.restype = ci
-            L.nldpc_clip_adam_clamp.argtypes = [vp, vp, vp, vp, vp, ci, ctypes.c_float, ctypes.c_float, ctypes.c_double, ctypes.c_double,
-                                                ctypes.c_double, ctypes.c_double, ctypes.c_float, ctypes.c_float, vp]
+            L.nldpc_clip_adam_clamp.argtypes = [vp, vp, vp, vp, vp, ci, ci, ctypes.c_float, ctypes.c_float, ctypes.c_double, vp,
+                                                ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_float, ctypes.c_float, vp]
             L.nldpc_count_errors.restype = ci
             L.nldpc_count_errors.argtypes = [vp, ctypes.c_size_t, vp, ci, ci, ci, vp, vp]
             L.nldpc_count_errors_packed.restype = ci

@@ -439,7 +439,7 @@ def _decode(self, xa, n_iters, soft_mode, hard_mode):
     # a CUDA graph the gathers belong to the graph, so a replay re-reads the parameters); no dispatcher
     vn_w, cn_w, ucn_w, compute_ucn, ucn_mix = _folded_live(self, T, device)
     soft, _, _, hard, _ = ops.boosted_forward_direct(xa, vn_w, cn_w, ucn_w, *tail, bool(compute_ucn), bool(ucn_mix), None, None, None,
-                                                     False, False, soft_mode, hard_mode, False)
+                                                     0, False, soft_mode, hard_mode, False)
     return soft, hard
 
 

@@ -28,6 +28,27 @@ static int fail(int code, const std::string &msg) {
         }                                                                                                 \
     } while (0)
 
+// The entry points run on the graph's device and leave the calling thread's current device as they found it (a process
+// that drives several GPUs from one thread must not have its default device changed under it).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+        else if (err == cudaSuccess) prev = -1;      // already there: nothing to restore
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define ON_DEVICE(dev)                                                                                    \
+    DeviceGuard _dev_guard(dev);                                                                          \
+    if (_dev_guard.err != cudaSuccess) {                                                                  \
+        cudaGetLastError();                                                                               \
+        return fail((int)_dev_guard.err, std::string("cudaSetDevice: ") + cudaGetErrorString(_dev_guard.err)); \
+    }
+
 struct nldpc_graph {
     int device = 0;
     int M = 0, N = 0, Z = 0, E = 0, S = 0;
@@ -82,7 +103,7 @@ extern "C" int nldpc_graph_create(const int32_t *basegraph, int M, int N, int Z,
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail(NLDPC_E_NODEVICE, "nldpc_graph_create: device is not sm_100 (this library is built for sm_100a only)");
-    CUDA_TRY(cudaSetDevice(device));
+    ON_DEVICE(device);
 
     // ---- host tables (row-major edges; column lists in ascending check row) ----
     std::vector<int> erow, ecol, eshift, row_ptr(M + 1, 0);
@@ -102,8 +123,11 @@ extern "C" int nldpc_graph_create(const int32_t *basegraph, int M, int N, int Z,
     for (int e = 0; e < E; e++) col_deg[ecol[e]]++;
     for (int i = 0; i < M; i++)
         if (row_ptr[i + 1] - row_ptr[i] > kMaxDeg) return fail(NLDPC_E_UNSUPPORTED, "nldpc_graph_create: check degree > 32");
-    for (int j = 0; j < N; j++)
+    for (int j = 0; j < N; j++) {
         if (col_deg[j] > kMaxDeg) return fail(NLDPC_E_UNSUPPORTED, "nldpc_graph_create: variable degree > 32");
+        // a block no check touches has no edge that would produce its output (the kernels emit marginals edge-side)
+        if (col_deg[j] == 0) return fail(NLDPC_E_UNSUPPORTED, "nldpc_graph_create: variable block without any edge (all -1 column)");
+    }
     // stored slots: edges of variable blocks with degree >= 2, numbered column-major (block by block)
     std::vector<int> slot(E, -1), vcol_j, vcol_ptr(1, 0), vcol_row;
     int S = 0;
@@ -180,7 +204,7 @@ extern "C" int nldpc_graph_create(const int32_t *basegraph, int M, int N, int Z,
 
 extern "C" void nldpc_graph_destroy(nldpc_graph_t *g) {
     if (!g) return;
-    cudaSetDevice(g->device);
+    DeviceGuard guard(g->device);
     for (int i = 0; i < 3; i++) {
         if (g->streams[i]) cudaStreamDestroy(g->streams[i]);
         if (g->events[i]) cudaEventDestroy(g->events[i]);
@@ -224,7 +248,7 @@ extern "C" int nldpc_neural_forward(const nldpc_graph_t *g, const float *xa_dev,
     if (B == 0) return NLDPC_OK;   // empty batch: nothing to do (pointers may be NULL)
     if (!xa_dev || !w_dev || !b_dev) return fail(NLDPC_E_INVALID, "nldpc_neural_forward: NULL input pointer");
     if (int rc = check_modes(soft_mode, soft_dev, hard_mode, hard_dev)) return rc;
-    CUDA_TRY(cudaSetDevice(g->device));
+    ON_DEVICE(g->device);
     DecodeArgs a{};
     a.xa = xa_dev; a.w = w_dev; a.b = b_dev; a.B = B; a.T = T;
     a.soft_mode = soft_mode; a.soft = soft_dev; a.hard_mode = hard_mode; a.hard = hard_dev;
@@ -270,7 +294,7 @@ extern "C" int nldpc_neural_decode_host(const nldpc_graph_t *gc, const float *xa
     if (B == 0) return NLDPC_OK;
     if (!xa_host || !w_host || !b_host) return fail(NLDPC_E_INVALID, "nldpc_neural_decode_host: NULL input pointer");
     if (int rc = check_modes(soft_mode, soft_host, hard_mode, hard_host)) return rc;
-    CUDA_TRY(cudaSetDevice(g->device));
+    ON_DEVICE(g->device);
     if (int rc = ensure_streams(g)) return rc;
     const size_t NZ = (size_t)g->N * g->Z, nb = (NZ + 7) / 8, E = (size_t)g->E;
     // chunks: big enough to fill the GPU (~2 waves of resident codewords), small enough that the H2D copy of
@@ -353,7 +377,7 @@ extern "C" int nldpc_neural_backward(const nldpc_graph_t *g, const float *xa_dev
                                      const float *gout_dev, int B, int T, float *gw_dev, float *gb_dev, void *workspace_dev,
                                      size_t workspace_bytes, int have_dump, void *stream) {
     if (!g || B < 0 || T <= 0 || !gw_dev || !gb_dev) return fail(NLDPC_E_INVALID, "nldpc_neural_backward: bad argument");
-    CUDA_TRY(cudaSetDevice(g->device));
+    ON_DEVICE(g->device);
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaMemsetAsync(gw_dev, 0, (size_t)T * g->E * 4, st));
     CUDA_TRY(cudaMemsetAsync(gb_dev, 0, (size_t)T * g->E * 4, st));
@@ -392,7 +416,7 @@ extern "C" int nldpc_neural_forward_train(const nldpc_graph_t *g, const float *x
     const WsLayout l = ws_layout(g, B, T, 0);
     if (!workspace_dev || workspace_bytes < l.total)
         return fail(NLDPC_E_INVALID, "nldpc_neural_forward_train: workspace too small (see nldpc_backward_workspace_bytes)");
-    CUDA_TRY(cudaSetDevice(g->device));
+    ON_DEVICE(g->device);
     DecodeArgs a{};
     a.xa = xa_dev; a.w = w_dev; a.b = b_dev; a.B = B; a.T = T; a.soft_mode = NLDPC_OUT_ALL; a.soft = soft_dev;
     a.hist_v2c = reinterpret_cast<float *>((char *)workspace_dev + l.v2c);
@@ -410,7 +434,7 @@ extern "C" int nldpc_boosted_backward(const nldpc_graph_t *g, const nldpc_booste
         return fail(NLDPC_E_UNSUPPORTED, "nldpc_boosted_backward: runs that continue from stored state are forward-only");
     if ((vn_w_dev && !gvn_dev) || (cn_w_dev && !gcn_dev) || (cfg->ucn_mix && !gucn_dev))
         return fail(NLDPC_E_INVALID, "nldpc_boosted_backward: missing gradient output");
-    CUDA_TRY(cudaSetDevice(g->device));
+    ON_DEVICE(g->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (gvn_dev) CUDA_TRY(cudaMemsetAsync(gvn_dev, 0, (size_t)T * g->N * 4, st));
     if (gcn_dev) CUDA_TRY(cudaMemsetAsync(gcn_dev, 0, (size_t)T * g->E * 4, st));
@@ -460,7 +484,7 @@ extern "C" int nldpc_boosted_forward(const nldpc_graph_t *g, const nldpc_boosted
     if (cfg->ucn_mix && (!cn_w_dev || !ucn_w_dev || !cfg->compute_ucn))
         return fail(NLDPC_E_INVALID, "nldpc_boosted_forward: ucn_mix needs cn_w, ucn_w and compute_ucn");
     if (int rc = check_modes(soft_mode, soft_dev, hard_mode, hard_dev)) return rc;
-    CUDA_TRY(cudaSetDevice(g->device));
+    ON_DEVICE(g->device);
     DecodeArgs a{};
     a.xa = xa_dev; a.w = cn_w_dev; a.b = ucn_w_dev; a.vn_w = vn_w_dev; a.B = B; a.T = T;
     a.soft_mode = soft_mode; a.soft = soft_dev; a.hard_mode = hard_mode; a.hard = hard_dev; a.llr_last = llr_last_dev;
@@ -553,17 +577,18 @@ extern "C" int nldpc_count_errors_packed(const uint8_t *hard_dev, size_t iter_st
 }
 
 namespace nldpc {
-int launch_clip_adam_clamp(float *p, float *g, float *m, float *v, float *state, int n, float grad_scale, float max_norm, double lr,
-                           double beta1, double beta2, double eps, float lo, float hi, cudaStream_t st);
+int launch_clip_adam_clamp(float *p, float *g, float *m, float *v, float *state, int n, int n_norm, float grad_scale, float max_norm,
+                           double lr, const float *lr_dev, double beta1, double beta2, double eps, float lo, float hi, cudaStream_t st);
 }
 
 extern "C" int nldpc_clip_adam_clamp(float *param_dev, float *grad_dev, float *exp_avg_dev, float *exp_avg_sq_dev, float *state_dev, int n,
-                                     float grad_scale, float max_norm, double lr, double beta1, double beta2, double eps, float clamp_lo,
-                                     float clamp_hi, void *stream) {
-    if (n < 0 || (n > 0 && (!param_dev || !grad_dev || !exp_avg_dev || !exp_avg_sq_dev)) || !state_dev || !(clamp_lo <= clamp_hi))
+                                     int n_norm, float grad_scale, float max_norm, double lr, const float *lr_dev, double beta1,
+                                     double beta2, double eps, float clamp_lo, float clamp_hi, void *stream) {
+    if (n < 0 || n_norm < n || (n_norm > 0 && !grad_dev) || (n > 0 && (!param_dev || !exp_avg_dev || !exp_avg_sq_dev)) || !state_dev ||
+        !(clamp_lo <= clamp_hi))
         return fail(NLDPC_E_INVALID, "nldpc_clip_adam_clamp: bad argument");
-    const int rc = launch_clip_adam_clamp(param_dev, grad_dev, exp_avg_dev, exp_avg_sq_dev, state_dev, n, grad_scale, max_norm, lr, beta1,
-                                          beta2, eps, clamp_lo, clamp_hi, (cudaStream_t)stream);
+    const int rc = launch_clip_adam_clamp(param_dev, grad_dev, exp_avg_dev, exp_avg_sq_dev, state_dev, n, n_norm, grad_scale, max_norm, lr,
+                                          lr_dev, beta1, beta2, eps, clamp_lo, clamp_hi, (cudaStream_t)stream);
     if (rc != 0) return fail(rc, std::string("nldpc_clip_adam_clamp: ") + cudaGetErrorString((cudaError_t)rc));
     return NLDPC_OK;
 }
@@ -582,7 +607,7 @@ extern "C" int nldpc_boosted_decode_host_q8(const nldpc_graph_t *gc, const nldpc
     if (cfg->llr_init_dev || cfg->xin_init_dev || cfg->xin_out_dev || cfg->app_init_dev || cfg->train_dump_dev)
         return fail(NLDPC_E_INVALID, "nldpc_boosted_decode_host_q8: stateless decode only (state / dump pointers must be NULL)");
     if (int rc = check_modes(soft_mode, soft_host, hard_mode, hard_host)) return rc;
-    CUDA_TRY(cudaSetDevice(g->device));
+    ON_DEVICE(g->device);
     if (int rc = ensure_streams(g)) return rc;
     const size_t NZ = (size_t)g->N * g->Z, nb = (NZ + 7) / 8, E = (size_t)g->E, N = (size_t)g->N;
     int chunk_cfg = 8192;      // the decode, not the copy, is the long stage here: larger chunks than the fp32 Neural path

@@ -16,12 +16,15 @@ constexpr int kOptThreads = 256;
 // state[0] = step count (as float, exact up to 2^24 steps), state[1] = last total gradient norm (before clipping)
 __global__ void __launch_bounds__(kOptThreads) clip_adam_clamp_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m,
                                                                        float *__restrict__ v, float *__restrict__ state, int n,
-                                                                       float grad_scale, float max_norm, double lr, double beta1,
+                                                                       int n_norm, float grad_scale, float max_norm, double lr,
+                                                                       const float *__restrict__ lr_dev, double beta1,
                                                                        double beta2, double eps_d, float lo, float hi) {
     __shared__ double red[kOptThreads / 32];
     __shared__ float s_coef;
     double acc = 0.0;
-    for (int i = threadIdx.x; i < n; i += kOptThreads) {
+    // clip_grad_norm_(model.parameters()): the norm runs over ALL n_norm gradients, of which only the first n belong to
+    // parameters the optimiser updates (get_trainable_parameters(); the rest only receive the clipped gradient)
+    for (int i = threadIdx.x; i < n_norm; i += kOptThreads) {
         const float gi = g[i] * grad_scale;
         acc += (double)gi * (double)gi;
     }
@@ -46,6 +49,7 @@ __global__ void __launch_bounds__(kOptThreads) clip_adam_clamp_kernel(float *__r
     // torch.optim.Adam (single-tensor formulation): bias corrections from the step count
     // (computed in double like the Python scalars of torch's implementation, then used as fp32 scalars)
     const float bc2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
+    if (lr_dev) lr = (double)*lr_dev;          // learning rate read at run time: a replayed CUDA graph follows the schedule
     const float step_size = (float)(lr / (1.0 - pow(beta1, (double)step)));
     const float w1 = (float)(1.0 - beta1), b2 = (float)beta2, w2 = (float)(1.0 - beta2), eps = (float)eps_d;
     for (int i = threadIdx.x; i < n; i += kOptThreads) {
@@ -60,13 +64,15 @@ __global__ void __launch_bounds__(kOptThreads) clip_adam_clamp_kernel(float *__r
         v[i] = vi;
         p[i] = pi;
     }
+    for (int i = n + threadIdx.x; i < n_norm; i += kOptThreads) g[i] = g[i] * coef;
     __syncthreads();
     if (threadIdx.x == 0) state[0] = step;
 }
 
-int launch_clip_adam_clamp(float *p, float *g, float *m, float *v, float *state, int n, float grad_scale, float max_norm, double lr,
-                           double beta1, double beta2, double eps, float lo, float hi, cudaStream_t st) {
-    clip_adam_clamp_kernel<<<1, kOptThreads, 0, st>>>(p, g, m, v, state, n, grad_scale, max_norm, lr, beta1, beta2, eps, lo, hi);
+int launch_clip_adam_clamp(float *p, float *g, float *m, float *v, float *state, int n, int n_norm, float grad_scale, float max_norm,
+                           double lr, const float *lr_dev, double beta1, double beta2, double eps, float lo, float hi, cudaStream_t st) {
+    clip_adam_clamp_kernel<<<1, kOptThreads, 0, st>>>(p, g, m, v, state, n, n_norm, grad_scale, max_norm, lr, lr_dev, beta1, beta2, eps,
+                                                      lo, hi);
     return (int)cudaGetLastError();
 }
 

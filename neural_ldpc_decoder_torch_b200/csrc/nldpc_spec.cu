@@ -48,11 +48,12 @@ int launch_neural(const DecodeArgs &a, int sm_count, cudaStream_t st) {
     const int len = a.T * G::E;
     cudaError_t err = cudaSuccess;
     const bool capturing = stream_is_capturing(st);      // CUDA graph capture: fixed arena range (ConstArena::acquire_captured)
-    const int off = capturing ? arena.acquire_captured(len) : arena.acquire(len, st, &err);
-    if (off >= 0 && err != cudaSuccess) return (int)err;
+    // (a captured Neural decode reads its weights with LDG instead: no arena range is taken away from the eager ring for it)
+    const int off = capturing ? -1 : arena.acquire(len, st, &err);
+    if (err != cudaSuccess) return (int)err;
     args.wb_off = off;
     if (off >= 0) {
-        pack_wb_kernel<<<(len + 255) / 256, 256, 0, st>>>(a.w, a.b, arena.base + off, len);
+        if ((err = upload_wb(arena, a.w, a.b, off, len, st)) != cudaSuccess) return (int)err;
         if (every) nldpc_spec_neural_kernel<G, true, true><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(args);
         else nldpc_spec_neural_kernel<G, false, true><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(args);
         err = cudaGetLastError();

@@ -667,10 +667,10 @@ int spec_bwd_launch(const BwdArgs &a, int graph_slot, int sm_count, cudaStream_t
     ConstArena &arena = arena_for_current_device();
     const int len = a.T * G::E;
     cudaError_t err = cudaSuccess;
-    const int off = capturing ? arena.acquire_captured(len) : arena.acquire(len, st, &err);
+    const int off = capturing ? arena.acquire_captured(len, st, &err) : arena.acquire(len, st, &err);
     if (err != cudaSuccess) return (int)err;
     if (off < 0) return -1;
-    pack_wb_kernel<<<(len + 255) / 256, 256, 0, st>>>(a.w, a.mode == 0 ? a.b : nullptr, arena.base + off, len);
+    if ((err = upload_wb(arena, a.w, a.mode == 0 ? a.b : nullptr, off, len, st)) != cudaSuccess) return (int)err;
     int rc;
     if constexpr (!kBoosted) {
         rc = spec_bwd_launch_one<G, 0, false>(a, off, graph_slot, sm_count, st, capturing);

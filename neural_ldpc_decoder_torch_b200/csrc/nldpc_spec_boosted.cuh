@@ -52,12 +52,12 @@ int boosted_launch(const DecodeArgs &a, int sm_count, cudaStream_t st) {
     ConstArena &arena = arena_for_current_device();
     const int len = a.T * G::E;
     cudaError_t err = cudaSuccess;
-    const int off = capturing ? arena.acquire_captured(len) : arena.acquire(len, st, &err);
+    const int off = capturing ? arena.acquire_captured(len, st, &err) : arena.acquire(len, st, &err);
     if (err != cudaSuccess) return (int)err;
     if (off < 0) return -1;
     DecodeArgs args = a;
     args.wb_off = off;
-    pack_wb_kernel<<<(len + 255) / 256, 256, 0, st>>>(a.w, nullptr, arena.base + off, len);   // cn_w (or 1.0), no bias
+    if ((err = upload_wb(arena, a.w, nullptr, off, len, st)) != cudaSuccess) return (int)err;   // cn_w (or 1.0), no bias
     int rc;
     if (ms) rc = a.vn_w ? boosted_launch_one<G, 1, true>(args, sm_count, st) : boosted_launch_one<G, 1, false>(args, sm_count, st);
     else rc = a.vn_w ? boosted_launch_one<G, 2, true>(args, sm_count, st) : boosted_launch_one<G, 2, false>(args, sm_count, st);

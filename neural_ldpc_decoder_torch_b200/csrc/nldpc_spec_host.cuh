@@ -11,10 +11,10 @@ namespace nldpc {
 
 namespace {
 
-// True while `st` is being captured into a CUDA graph.  The constant arena hands out ranges at LAUNCH time (event queries,
-// host-side bookkeeping), which a replayed graph would not repeat.  Captured launches therefore either read their weights
-// from global memory (Neural: the LDG variant of the same kernel) or use the fixed range ConstArena::acquire_captured hands
-// out (Boosted forward / backward sweeps: same specialised kernels as eager launches).
+// True while `st` is being captured into a CUDA graph.  The constant arena hands out ring ranges at LAUNCH time (event
+// queries, host-side bookkeeping), which a replayed graph would not repeat.  Captured launches therefore either read their
+// weights from global memory (Neural: the LDG variant of the same kernel) or use the reserved range
+// ConstArena::acquire_captured hands out (Boosted forward / backward sweeps: same specialised kernels as eager launches).
 inline bool stream_is_capturing(cudaStream_t st) {
     cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &status) != cudaSuccess) {
@@ -24,33 +24,40 @@ inline bool stream_is_capturing(cudaStream_t st) {
     return status != cudaStreamCaptureStatusNone;
 }
 
-// {w[i], b[i]} -> constant arena (written through its global address; visible to the launches that follow
-// on the same stream: the constant cache is invalidated at kernel boundaries)
+// {w[i], b[i]} pairs -> a staging buffer in GLOBAL memory; upload_wb then copies the range into the __constant__ array with
+// cudaMemcpyToSymbolAsync (device to device, stream ordered, capturable as a memcpy node).  Device code never writes the
+// constant bank itself: CUDA leaves that undefined and gives no guarantee that the constant caches see it.
 __global__ void pack_wb_kernel(const float *__restrict__ w, const float *__restrict__ b, float2 *__restrict__ dst, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = make_float2(w ? w[i] : 1.0f, b ? b[i] : 0.0f);   // absent weights: x * 1 + 0 is exact
 }
 
-// Ring allocator over the constant arena, per device.  A range is reused only after the launch that read it
-// has finished: a launch on another stream that wants an overlapping range first waits on that launch's event.
+// Allocator over the constant arena (and the staging buffer, which mirrors it offset for offset), per device.
+//   [0, ring_end)            ring for eager launches.  A range is reused only after the launch that read it has finished: a
+//                            launch on another stream that wants an overlapping range first waits on that launch's event.
+//   [ring_end, kConstFloat2) ranges of launches captured into CUDA graphs: handed out top-down while capturing, never given
+//                            to an eager launch afterwards (a replay records no event the ring could wait on).
 struct ConstArena {
     struct Pending { int off, len; cudaEvent_t ev; cudaStream_t st; };
     std::mutex mu;
     int head = 0;
+    int ring_end = kConstFloat2;
     std::vector<Pending> pend;
     std::vector<cudaEvent_t> pool;
-    float2 *base = nullptr;
+    float2 *stage = nullptr;      // global-memory mirror of the arena (pack target, source of the symbol copy)
 
-    // returns offset (float2 units) or -1 when `len` does not fit at all
+    cudaError_t ensure_stage() {
+        if (stage) return cudaSuccess;
+        return cudaMalloc((void **)&stage, sizeof(float2) * kConstFloat2);
+    }
+
+    // eager launch: returns offset (float2 units) or -1 when `len` does not fit the ring at all
     int acquire(int len, cudaStream_t st, cudaError_t *err) {
         *err = cudaSuccess;
-        if (len > kConstFloat2) return -1;
         std::lock_guard<std::mutex> lk(mu);
-        if (!base) {
-            *err = cudaGetSymbolAddress((void **)&base, c_wb);
-            if (*err != cudaSuccess) return -1;
-        }
-        if (head + len > kConstFloat2) head = 0;
+        if (len > ring_end) return -1;
+        if ((*err = ensure_stage()) != cudaSuccess) return -1;
+        if (head + len > ring_end) head = 0;
         const int off = head;
         head += (len + 1) & ~1;   // keep 16-byte alignment
         for (size_t i = 0; i < pend.size();) {
@@ -70,15 +77,35 @@ struct ConstArena {
         }
         return off;
     }
-    // Launch being captured into a CUDA graph: every captured launch uses the range at offset 0 — inside a graph the
-    // pack -> consumer pairs are ordered by the capture stream, and a replay is ordered against eager launches of the stream
-    // it is replayed on.  What nothing orders is a replay against launches of this library running CONCURRENTLY on another
-    // stream of the device (the ring's events cannot be re-recorded by a replay): callers must not do that.
-    // -1 when the arena has not been set up by an earlier eager launch (the caller then uses the table-driven kernel).
-    int acquire_captured(int len) {
-        if (len > kConstFloat2) return -1;
+    // Launch being captured into a CUDA graph: a fixed range at the top of the arena, shared by all captured launches of the
+    // same length class (inside a graph the upload -> consumer pairs are ordered by the capture stream, and replays of
+    // graphs on one stream are ordered by that stream) and taken away from the eager ring for good, so no eager launch on any
+    // stream can overwrite weights a replay is reading.  The ring shrinks to what is left; eager launches that no longer fit
+    // it use the LDG / table-driven kernels.  -1 when `len` does not fit or a pending eager launch still occupies the range
+    // and cannot be waited for during capture (the caller then uses the kernel variant without the arena).
+    int acquire_captured(int len, cudaStream_t st, cudaError_t *err) {
+        *err = cudaSuccess;
         std::lock_guard<std::mutex> lk(mu);
-        return base ? 0 : -1;
+        if (len > kConstFloat2 || !stage) return -1;      // (no cudaMalloc while a capture is open: an eager launch comes first)
+        const int off = (kConstFloat2 - len) & ~1;
+        if (off < ring_end) {
+            // Eager launches enqueued earlier may still be reading the part of the ring being taken.  Nothing may be queried or
+            // synchronised while a capture is open, so the graph itself waits for them: an external event-wait node (a no-op
+            // on later replays, the event is never recorded again: it does not go back to the pool).
+            for (size_t i = 0; i < pend.size();) {
+                Pending &p = pend[i];
+                if (p.off + p.len > off) {
+                    if ((*err = cudaStreamWaitEvent(st, p.ev, cudaEventWaitExternal)) != cudaSuccess) return -1;
+                    pend[i] = pend.back();
+                    pend.pop_back();
+                } else {
+                    i++;
+                }
+            }
+            ring_end = off;
+            if (head > ring_end) head = 0;
+        }
+        return off;
     }
     // call after the consumer kernel has been enqueued on `st`
     cudaError_t release_after(int off, int len, cudaStream_t st) {
@@ -103,6 +130,16 @@ ConstArena &arena_for_current_device() {
     return arenas[dev & 63];
 }
 
+
+// {w, b} rows of one launch -> arena range [off, off + len): pack into the staging mirror, then a stream-ordered
+// device-to-device copy into the constant array (which also invalidates the constant caches for the consumer kernel)
+inline cudaError_t upload_wb(ConstArena &arena, const float *w, const float *b, int off, int len, cudaStream_t st) {
+    pack_wb_kernel<<<(len + 255) / 256, 256, 0, st>>>(w, b, arena.stage + off, len);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbolAsync(c_wb, arena.stage + off, sizeof(float2) * (size_t)len, sizeof(float2) * (size_t)off,
+                                   cudaMemcpyDeviceToDevice, st);
+}
 
 template <class K>
 cudaError_t set_smem(K kernel, size_t bytes) {

@@ -23,6 +23,13 @@ def _stream(t):
     return _vp(torch.cuda.current_stream(t.device).cuda_stream)
 
 
+def _aligned16(t):
+    """contiguous, 16-byte aligned storage: the kernels stage xa with bulk TMA copies (cp.async.bulk needs 16-byte aligned
+    sources); a contiguous view at an odd storage offset (flat[1:1+n].view(B, N, Z)) is copied once instead of faulting"""
+    t = t.contiguous()
+    return t.clone() if t.data_ptr() % 16 else t
+
+
 def _check_cuda_f32(name, t):
     if not isinstance(t, torch.Tensor):
         raise TypeError(f"{name} must be a torch.Tensor")
@@ -42,7 +49,7 @@ def _prep(xa, w, b, graph_id):
         raise ValueError(f"w and b must be [T, {g.E}]")
     if xa.device.index != g.device_index:
         raise ValueError("graph handle and tensors live on different devices")
-    return g, xa.contiguous(), w.contiguous(), b.contiguous()
+    return g, _aligned16(xa), w.contiguous(), b.contiguous()
 
 
 def neural_forward_direct(xa: torch.Tensor, w: torch.Tensor, b: torch.Tensor, graph_id: int) -> torch.Tensor:
@@ -233,7 +240,7 @@ def boosted_forward_direct(xa, vn_w, cn_w, ucn_w, graph_id, T, decoder_type, qbi
     if xa.device.index != g.device_index:
         raise ValueError("graph handle and tensors live on different devices")
     B, dev = xa.shape[0], xa.device
-    xa = xa.contiguous()
+    xa = _aligned16(xa)
     vn_w = _opt_f32("vn_w", vn_w, (T, g.N), dev)
     cn_w = _opt_f32("cn_w", cn_w, (T, g.E), dev)
     ucn_w = _opt_f32("ucn_w", ucn_w, (T, g.E), dev)
@@ -295,7 +302,7 @@ def boosted_backward(xa: torch.Tensor, vn_w: Optional[torch.Tensor], cn_w: Optio
     B, dev = xa.shape[0], xa.device
     if tuple(gout.shape) != (T, B, g.NZ):
         raise ValueError("gout must be [T, B, N*Z]")
-    xa, gout = xa.contiguous(), gout.contiguous()
+    xa, gout = _aligned16(xa), gout.contiguous()
     vn_w = _opt_f32("vn_w", vn_w, (T, g.N), dev)
     cn_w = _opt_f32("cn_w", cn_w, (T, g.E), dev)
     ucn_w = _opt_f32("ucn_w", ucn_w, (T, g.E), dev)
@@ -538,19 +545,26 @@ def fused_ber_fer_counts(expected, actual):
 # clip_grad_norm_ + Adam + clamp on the flat weight vector (train/train_BoostedNeuralLDPCDecoder.py:291-294)
 def clip_adam_clamp_(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, state: torch.Tensor,
                      grad_scale: float = 1.0, max_norm: float = 1.0, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                     clamp=(0.0, 2.0)):
-    """In place, one launch, no host synchronisation (CUDA-graph replayable: the step counter is state[0] on the device)."""
+                     clamp=(0.0, 2.0), lr_dev: Optional[torch.Tensor] = None):
+    """In place, one launch, no host synchronisation (CUDA-graph replayable: the step counter is state[0] on the device, the
+    learning rate is read from `lr_dev` when given).  `grad` may be longer than `param`: the extra entries (gradients of
+    parameters the optimiser does not update) enter the clipping norm and are scaled, as clip_grad_norm_(model.parameters())
+    does in the reference (train/train_BoostedNeuralLDPCDecoder.py:291)."""
     n = param.numel()
     for name, t in (("param", param), ("grad", grad), ("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq), ("state", state)):
         _check_cuda_f32(name, t)
-        if not t.is_contiguous() or (name != "state" and t.numel() != n):
+        if not t.is_contiguous() or (name not in ("state", "grad") and t.numel() != n):
             raise ValueError(f"{name} must be a contiguous fp32 vector of {n} elements")
-    if state.numel() != 2:
-        raise ValueError("state must hold 2 floats (step count, last gradient norm)")
+    if grad.numel() < n:
+        raise ValueError("grad must hold at least as many elements as param")
+    if state.numel() < 2:
+        raise ValueError("state must hold at least 2 floats (step count, last gradient norm)")
+    if lr_dev is not None:
+        _check_cuda_f32("lr_dev", lr_dev)
     with torch.cuda.device(param.device):
-        rc = _lib.lib().nldpc_clip_adam_clamp(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), _ptr(state), n, float(grad_scale),
-                                              float(max_norm), float(lr), float(betas[0]), float(betas[1]), float(eps), float(clamp[0]),
-                                              float(clamp[1]), _stream(param))
+        rc = _lib.lib().nldpc_clip_adam_clamp(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), _ptr(state), n, grad.numel(),
+                                              float(grad_scale), float(max_norm), float(lr), _ptr(lr_dev), float(betas[0]),
+                                              float(betas[1]), float(eps), float(clamp[0]), float(clamp[1]), _stream(param))
     _lib.check(rc, "nldpc_clip_adam_clamp")
 
 

@@ -96,16 +96,23 @@ class FusedTrainer:
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
+        # parameters the optimiser does not update (fixed_iterative_nodes_init_weight > 0) still receive gradients, and the
+        # reference clips over model.parameters() (train/...py:291): their gradients live behind the trainable ones in the flat
+        # gradient vector, enter the norm and are scaled, but no weight moves
+        own = {id(p) for p in self.params}
+        self.frozen = [p for p in model.parameters() if p.requires_grad and id(p) not in own]
         dev = self.params[0].device
-        if dev.type != "cuda" or any(p.device != dev or p.dtype != torch.float32 for p in self.params):
+        if dev.type != "cuda" or any(p.device != dev or p.dtype != torch.float32 for p in self.params + self.frozen):
             from ._lib import NldpcError
             raise NldpcError("FusedTrainer needs fp32 parameters on one CUDA device (there is no CPU fallback)")
         n = sum(p.numel() for p in self.params)
+        n_all = n + sum(p.numel() for p in self.frozen)
         self.flat = torch.empty(n, dtype=torch.float32, device=dev)
-        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(n_all, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         self.state = torch.zeros(2, dtype=torch.float32, device=dev)          # [step count, last gradient norm]
+        self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)   # read by the kernel at run time (set_lr)
         off = 0
         with torch.no_grad():
             for p in self.params:
@@ -114,10 +121,37 @@ class FusedTrainer:
                 p.data = self.flat[off:off + k].view(p.shape)
                 p.grad = self.flat_grad[off:off + k].view(p.shape)
                 off += k
+            for p in self.frozen:
+                k = p.numel()
+                p.grad = self.flat_grad[off:off + k].view(p.shape)
+                off += k
         self.device = dev
         self._graph = None
         self._want_graph = bool(graph)
         self._static = None
+
+    # -- schedule / checkpoint ------------------------------------------------------------------------------------
+    def set_lr(self, lr):
+        """learning-rate schedule (train/...py:262-266 sets param_group['lr'] per epoch): the kernel reads the rate from a device
+        scalar, so a captured step follows it too"""
+        self.lr = float(lr)
+        self.lr_dev.fill_(self.lr)
+
+    def state_dict(self):
+        """optimiser state for CheckPointUtil.save(optimizer=trainer): Adam moments per parameter, step count, lr"""
+        return {"step": int(self.state[0].item()), "lr": self.lr, "betas": self.betas, "eps": self.eps,
+                "exp_avg": self.exp_avg.detach().cpu().clone(), "exp_avg_sq": self.exp_avg_sq.detach().cpu().clone(),
+                "param_numels": [p.numel() for p in self.params]}
+
+    def load_state_dict(self, sd):
+        if list(sd["param_numels"]) != [p.numel() for p in self.params]:
+            raise ValueError("optimizer state belongs to a different parameter set")
+        with torch.no_grad():
+            self.exp_avg.copy_(sd["exp_avg"])
+            self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+            self.state[0] = float(sd["step"])
+        self.betas, self.eps = (float(sd["betas"][0]), float(sd["betas"][1])), float(sd["eps"])
+        self.set_lr(sd["lr"])
 
     # -- pieces ---------------------------------------------------------------------------------------------------
     def _world(self):
@@ -135,7 +169,7 @@ class FusedTrainer:
             import torch.distributed as dist
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)        # the one exchange of the step (NCCL over NVLink)
         ops.clip_adam_clamp_(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.state, 1.0 / world, self.max_grad_norm,
-                             self.lr, self.betas, self.eps, self.clamp)
+                             self.lr, self.betas, self.eps, self.clamp, lr_dev=self.lr_dev)
         return loss.detach()
 
     def _takes_target_iter(self):
@@ -143,9 +177,11 @@ class FusedTrainer:
 
     def _check_grad_views(self):
         off = 0
-        for p in self.params:
+        for p in self.params + self.frozen:
             k = p.numel()
-            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * off or p.data_ptr() != self.flat.data_ptr() + 4 * off:
+            is_param = off < self.flat.numel()
+            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * off or (
+                    is_param and p.data_ptr() != self.flat.data_ptr() + 4 * off):
                 raise RuntimeError("a parameter or its .grad no longer aliases the trainer's flat vectors (zero_grad(set_to_none=True) "
                                    "or .to() was called on the model): build a new FusedTrainer")
             off += k

@@ -80,7 +80,7 @@ def test_fused_trainer_follows_reference_training_loop(tag, graph):
     from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.DecoderType import DecoderType
     dec = {DecoderType.SP: 0, DecoderType.MS: 1, DecoderType.QMS: 2}[m_new.decoding_type]
     want = torch.ops.nldpc.boosted_forward(x, vn_w, cn_w, ucn_w, m_new.conn_mat.graph_id(x.device), T, dec, int(m_new.decoder_qms_qbit),
-                                           -20.0, 20.0, bool(compute_ucn), bool(ucn_mix), None, None, None, False, False, 2, 0, False)[0]
+                                           -20.0, 20.0, bool(compute_ucn), bool(ucn_mix), None, None, None, 0, False, 2, 0, False)[0]
     assert torch.equal(m_new.decode_soft_last(x).view(torch.int32), want.view(torch.int32))
     # names / shapes / state_dict keys are untouched by the flat-vector aliasing
     assert [n for n, _ in m_new.named_parameters()] == names
@@ -134,3 +134,68 @@ def test_fused_trainer_data_parallel_nccl(graph):
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-1500:]
     line = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
     assert line["ok"] and line["ranks_identical"] and line["weights_moved_by"] > 1e-3
+
+
+def test_fused_trainer_frozen_params_lr_schedule_and_state_dict():
+    """(1) fixed_iterative_nodes_init_weight > 0: the frozen parameters' gradients enter the clipping norm like in
+    clip_grad_norm_(model.parameters()) (train/...py:291) and no frozen weight moves; (2) set_lr reaches a CAPTURED step;
+    (3) state_dict / load_state_dict resume the Adam state."""
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder import ConnectingMatrix, ConnectingMatrixTorch
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.BoostedNeuralLDPCDecoder import BoostedNeuralLDPCDecoder
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.LDPCDecoderLoss import LDPCDecoderLoss
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.LossType import LossType
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.NodeWeightSharingConfig import NodeWeightSharingConfig
+    from neural_ldpc_decoder_torch_b200.training import FusedTrainer, train_step
+    d = load_golden("train_boosted_cn2vn3_qms")
+    T, B = int(d["T"]), d["xa"].shape[0]
+    x, y = torch.from_numpy(d["xa"]).cuda(), torch.from_numpy(d["y"]).cuda()
+    crit = LDPCDecoderLoss(LossType.BCE, etha=1.0)
+
+    def make():
+        cm = ConnectingMatrixTorch(ConnectingMatrix(Z=int(d["Z"]), basegraph=d["basegraph"]), device=torch.device("cuda"))
+        m = BoostedNeuralLDPCDecoder(T, B, cm, node_weight_sharing_config=NodeWeightSharingConfig(2, 0, 3),
+                                     fixed_iterative_nodes_init_weight=2).cuda()
+        m.store_llr = "none"
+        with torch.no_grad():
+            for n, p in m.named_parameters():
+                p.copy_(torch.from_numpy(d["param_" + n]))
+        return m
+
+    m_ref, m_new = make(), make()
+    assert len(m_ref.get_trainable_parameters()) < len(list(m_ref.parameters()))
+    opt = torch.optim.Adam(m_ref.get_trainable_parameters(), lr=1e-2)
+    tr = FusedTrainer(m_new, crit, T, lr=1e-2, max_grad_norm=0.01)          # a norm bound that clips: the coefficient matters
+    assert len(tr.frozen) == 4
+    for step in range(3):
+        train_step(m_ref, crit, opt, x, y, T, max_grad_norm=0.01)
+        tr.step(x, y)
+        for (n, a), (_, b) in zip(m_ref.named_parameters(), m_new.named_parameters()):
+            assert float((a.detach() - b.detach()).abs().max()) < 2e-6, (step, n)
+            assert float((a.grad - b.grad).abs().max()) <= 3e-5 * max(float(a.grad.abs().max()), 1e-12), (step, n)   # clipped grads
+    frozen0 = {n: torch.from_numpy(d["param_" + n]).cuda() for n, _ in m_new.named_parameters() if n.endswith(("_0", "_1"))}
+    assert all(torch.equal(dict(m_new.named_parameters())[n].detach(), v) for n, v in frozen0.items())
+
+    # (3) resume: a new trainer loaded with the state continues exactly like the old one
+    sd = tr.state_dict()
+    m_res = make()
+    m_res.load_state_dict(m_new.state_dict())
+    tr2 = FusedTrainer(m_res, crit, T, lr=123.0, max_grad_norm=0.01)
+    tr2.load_state_dict(sd)
+    tr.step(x, y)
+    tr2.step(x, y)
+    for a, b in zip(m_new.parameters(), m_res.parameters()):
+        assert torch.equal(a.detach(), b.detach())
+    assert tr2.steps_done == tr.steps_done == 4
+
+    # (2) a captured step follows set_lr
+    m_g = make()
+    trg = FusedTrainer(m_g, crit, T, lr=1e-2, graph=True)
+    trg.step(x, y)
+    before = torch.cat([p.detach().reshape(-1).clone() for p in m_g.get_trainable_parameters()])
+    trg.set_lr(0.0)
+    trg.step(x, y)
+    after = torch.cat([p.detach().reshape(-1) for p in m_g.get_trainable_parameters()])
+    assert torch.equal(before, after)                                       # lr = 0: the replayed step moves nothing
+    trg.set_lr(1e-2)
+    trg.step(x, y)
+    assert not torch.equal(before, torch.cat([p.detach().reshape(-1) for p in m_g.get_trainable_parameters()]))
