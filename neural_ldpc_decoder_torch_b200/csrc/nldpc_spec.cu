@@ -29,19 +29,22 @@ bool graph_matches(const int32_t *bg, int M, int N, int Z) {
 template <class G>
 int prepare() {
     cudaError_t e;
-    if ((e = set_smem(nldpc_spec_neural_kernel<G, true, true>, SpecCfg<G>::kSmemBytes)) != cudaSuccess) return (int)e;
-    if ((e = set_smem(nldpc_spec_neural_kernel<G, true, false>, SpecCfg<G>::kSmemBytes)) != cudaSuccess) return (int)e;
-    if ((e = set_smem(nldpc_spec_neural_kernel<G, false, true>, SpecCfg<G>::kSmemBytes)) != cudaSuccess) return (int)e;
-    if ((e = set_smem(nldpc_spec_neural_kernel<G, false, false>, SpecCfg<G>::kSmemBytes)) != cudaSuccess) return (int)e;
+    using Every = typename KernelCfg<G, true, false>::type;
+    using Last = typename KernelCfg<G, false, false>::type;
+    if ((e = set_smem(nldpc_spec_neural_kernel<G, true, true>, Every::kSmemBytes)) != cudaSuccess) return (int)e;
+    if ((e = set_smem(nldpc_spec_neural_kernel<G, true, false>, Every::kSmemBytes)) != cudaSuccess) return (int)e;
+    if ((e = set_smem(nldpc_spec_neural_kernel<G, false, true>, Last::kSmemBytes)) != cudaSuccess) return (int)e;
+    if ((e = set_smem(nldpc_spec_neural_kernel<G, false, false>, Last::kSmemBytes)) != cudaSuccess) return (int)e;
     return 0;
 }
 
 template <class G>
 int launch_neural(const DecodeArgs &a, int sm_count, cudaStream_t st) {
-    using Cfg = SpecCfg<G>;
-    const int n_units = (a.B + Cfg::Shape::kCw - 1) / Cfg::Shape::kCw;
-    const int grid = std::min(n_units, sm_count * Cfg::kCtasPerSm);
+    using Every = typename KernelCfg<G, true, false>::type;       // list mode may carry output staging rows
+    using Last = typename KernelCfg<G, false, false>::type;
+    const int n_units = (a.B + Last::Shape::kCw - 1) / Last::Shape::kCw;
     const bool every = a.soft_mode == 1 || a.hard_mode == 1 || a.hist_v2c != nullptr;
+    const int grid = std::min(n_units, sm_count * (every ? Every::kCtasPerSm : Last::kCtasPerSm));
     DecodeArgs args = a;
     // weights -> constant arena (uniform-datapath reads in the kernel); LDG variant if they do not fit
     ConstArena &arena = arena_for_current_device();
@@ -52,17 +55,27 @@ int launch_neural(const DecodeArgs &a, int sm_count, cudaStream_t st) {
     const int off = capturing ? -1 : arena.acquire(len, st, &err);
     if (err != cudaSuccess) return (int)err;
     args.wb_off = off;
+    // A group notes the units it has to decode a second time (exact zeros, see run_unit) in a 64-bit mask, so one launch gives
+    // a group at most 64 units: larger batches run as several launches over consecutive unit ranges (~150 k codewords each on
+    // BG2; the arguments stay the same, only [unit_begin, unit_end) moves).
+    const int groups = every ? Every::kGroups : Last::kGroups;
+    const long long per_launch = 64ll * grid * groups;
+    auto launch_all = [&](auto kernel_every, auto kernel_last) -> cudaError_t {
+        for (long long u0 = 0; u0 < n_units; u0 += per_launch) {
+            args.unit_begin = (int)u0;
+            args.unit_end = (int)std::min<long long>(n_units, u0 + per_launch);
+            if (every) kernel_every<<<grid, Every::kThreads, Every::kSmemBytes, st>>>(args);
+            else kernel_last<<<grid, Last::kThreads, Last::kSmemBytes, st>>>(args);
+        }
+        return cudaGetLastError();
+    };
     if (off >= 0) {
         if ((err = upload_wb(arena, a.w, a.b, off, len, st)) != cudaSuccess) return (int)err;
-        if (every) nldpc_spec_neural_kernel<G, true, true><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(args);
-        else nldpc_spec_neural_kernel<G, false, true><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(args);
-        err = cudaGetLastError();
+        err = launch_all(nldpc_spec_neural_kernel<G, true, true>, nldpc_spec_neural_kernel<G, false, true>);
         if (err != cudaSuccess || capturing) return (int)err;
         return (int)arena.release_after(off, len, st);
     }
-    if (every) nldpc_spec_neural_kernel<G, true, false><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(args);
-    else nldpc_spec_neural_kernel<G, false, false><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(args);
-    return (int)cudaGetLastError();
+    return (int)launch_all(nldpc_spec_neural_kernel<G, true, false>, nldpc_spec_neural_kernel<G, false, false>);
 }
 
 }  // namespace

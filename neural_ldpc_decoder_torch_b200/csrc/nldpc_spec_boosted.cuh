@@ -12,8 +12,8 @@ namespace {
 template <class G, int MODE, bool kXo>
 int boosted_prepare_one() {
     cudaError_t e;
-    if ((e = set_smem(nldpc_spec_neural_kernel<G, true, true, MODE, kXo>, SpecCfg<G, kXo>::kSmemBytes)) != cudaSuccess) return (int)e;
-    if ((e = set_smem(nldpc_spec_neural_kernel<G, false, true, MODE, kXo>, SpecCfg<G, false>::kSmemBytes)) != cudaSuccess) return (int)e;
+    if ((e = set_smem(nldpc_spec_neural_kernel<G, true, true, MODE, kXo>, KernelCfg<G, true, kXo>::type::kSmemBytes)) != cudaSuccess) return (int)e;
+    if ((e = set_smem(nldpc_spec_neural_kernel<G, false, true, MODE, kXo>, KernelCfg<G, false, kXo>::type::kSmemBytes)) != cudaSuccess) return (int)e;
     return 0;
 }
 
@@ -32,7 +32,7 @@ int boosted_launch_one(const DecodeArgs &args, int sm_count, cudaStream_t st) {
     const bool every = args.soft_mode == 1 || args.hard_mode == 1 || args.llr_all != nullptr;
     auto launch = [&](auto every_tag) {
         constexpr bool kEvery = decltype(every_tag)::value;
-        using Cfg = SpecCfg<G, kXo && kEvery>;       // list mode keeps xa_origin rows on chip, throughput mode re-reads it (xo_global)
+        using Cfg = typename KernelCfg<G, kEvery, kXo>::type;   // list mode keeps xa_origin rows on chip (throughput mode re-reads it, xo_global) and may stage its outputs
         const int n_units = (args.B + Cfg::Shape::kCw - 1) / Cfg::Shape::kCw;
                 const int grid = std::min(n_units, sm_count * Cfg::kCtasPerSm);
         nldpc_spec_neural_kernel<G, kEvery, true, MODE, kXo><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(args);

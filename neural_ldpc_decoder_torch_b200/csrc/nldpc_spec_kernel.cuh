@@ -28,8 +28,19 @@ namespace nldpc {
 constexpr int kConstFloat2 = 7680;                 // 60 KB of the 64 KB constant bank
 __constant__ float2 c_wb[kConstFloat2];   // this header is included by exactly one translation unit (nldpc_spec.cu)
 
-#ifndef NLDPC_CTA_LOCKSTEP
-#define NLDPC_CTA_LOCKSTEP 0   // 1: CTA-wide barrier between phases (warps share the instruction stream)
+#ifdef NLDPC_DEBUG_COUNT
+__device__ unsigned g_dbg_restarts;
+extern "C" unsigned nldpc_debug_restarts() { unsigned v = 0; cudaMemcpyFromSymbol(&v, g_dbg_restarts, 4); return v; }
+#endif
+// scheduling knobs (experiments: tools/build_variant.sh)
+#ifndef NLDPC_VN_QOUTER
+#define NLDPC_VN_QOUTER 1   // 1: VN chain pairs written operand-major
+#endif
+#ifndef NLDPC_PIPE_CN
+#define NLDPC_PIPE_CN 1     // 1: the next check's inputs are loaded before the current check computes
+#endif
+#ifndef NLDPC_PIPE_VN
+#define NLDPC_PIPE_VN 1     // 1: the next variable block's messages are loaded before the current block computes
 #endif
 
 // one edge of a check row: slab row accessed by the CN phase, circulant shift, row-major edge index
@@ -99,6 +110,26 @@ __device__ __forceinline__ float xo_global(const L &c, int q) {
     else return v;
 }
 
+// List mode (soft outputs after every iteration): a graph type wrapped in Staged<> makes the emit functions write each
+// marginal into a staging row that follows the codeword's slab (N rows of Z floats at float offset kStageOff, an
+// immediate), and the kernel ships the finished [N*Z] row of a codeword-iteration to global memory with ONE bulk TMA store
+// (cp.async.bulk.global.shared::cta) instead of N per-lane 4-byte STG instructions per iteration.
+template <class G0, int kOff>
+struct Staged : G0 {
+    static constexpr bool kStageOut = true;
+    static constexpr int kStageOff = kOff;
+};
+template <class G, class = void>
+struct stage_traits {
+    static constexpr bool on = false;
+    static constexpr int off = 0;
+};
+template <class G>
+struct stage_traits<G, std::void_t<decltype(G::kStageOut)>> {
+    static constexpr bool on = G::kStageOut;
+    static constexpr int off = G::kStageOff;
+};
+
 template <int Z>
 struct GroupShape {
     static constexpr int kLanes = (Z == 16 || Z == 32) ? 32 : (Z == 24 ? 96 : 0);
@@ -116,6 +147,26 @@ __device__ __forceinline__ void group_sync(int group_in_cta) {
     }
 }
 
+// OR of `pred` over the lanes of the group; for multi-warp groups this is a reducing named barrier (bar.red.or), i.e. it
+// also orders the group's shared-memory accesses like group_sync
+template <int kLanes>
+__device__ __forceinline__ bool group_any(int group_in_cta, bool pred) {
+    if constexpr (kLanes == 32) {
+        return __any_sync(0xffffffffu, pred);
+    } else {
+        int r;
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\t"
+            "setp.ne.s32 p, %1, 0;\n\t"
+            "bar.red.or.pred q, %2, %3, p;\n\t"
+            "selp.s32 %0, 1, 0, q;\n\t}"
+            : "=r"(r)
+            : "r"((int)pred), "r"(group_in_cta + 1), "n"(kLanes)
+            : "memory");
+        return r != 0;
+    }
+}
+
 // -----------------------------------------------------------------------------------------------------------
 // Per-thread state of the Neural decode (NeuralLDPCDecoder.py:44-100).
 template <class G>
@@ -129,6 +180,8 @@ struct NeuralLane {
     uint8_t *hb;             // this codeword's hard-decision staging bytes in shared memory (N*Z/8), or nullptr
     float xreg[G::kXRegs > 0 ? G::kXRegs : 1];   // channel LLRs of identity-circulant degree-1 blocks (lane-private)
     int z;
+    int grp;                 // group within the CTA (named barrier id for multi-warp groups)
+    bool gl0;                // lane 0 of the group: issues the bulk loads / stores
     bool valid;
     float zmin;              // min |v2c| written by this lane in the current VN phase (0 => the zero-safe CN phase is needed)
     // Boosted decoder (MODE != 0)
@@ -142,7 +195,11 @@ struct NeuralLane {
     // un-rotated: this lane holds bit (J, z)
     template <int J>
     __device__ __forceinline__ void emit(float v) {
-        if (soft) st_global_stream(soft + J * Z + z, v);
+        if constexpr (stage_traits<G>::on) {
+            if (soft) lane[stage_traits<G>::off + J * Z] = v;
+        } else {
+            if (soft) st_global_stream(soft + J * Z + z, v);
+        }
         if (hb) {
             if constexpr (Z == 16 || Z == 32) {
                 const unsigned bal = __ballot_sync(0xffffffffu, v < 0.0f);
@@ -160,7 +217,11 @@ struct NeuralLane {
     // (J and SHIFT are compile-time constants after unrolling/inlining)
     __device__ __forceinline__ void emit_rot(const int J, const int SHIFT, float v) {
         const int zz = (int)(rot[SHIFT] - (lane - z));      // (z + SHIFT) mod Z
-        if (soft) st_global_stream(soft + J * Z + zz, v);
+        if constexpr (stage_traits<G>::on) {
+            if (soft) rot[SHIFT][stage_traits<G>::off + J * Z] = v;
+        } else {
+            if (soft) st_global_stream(soft + J * Z + zz, v);
+        }
         if (hb) {
             if constexpr (Z == 16 || Z == 32) {
                 const unsigned bal = __ballot_sync(0xffffffffu, v < 0.0f);
@@ -177,6 +238,15 @@ struct NeuralLane {
         }
     }
 };
+
+// all lanes of the group: wait until the bulk stores issued from the staging rows have READ them (they may be overwritten)
+template <class G>
+__device__ __forceinline__ void stage_wait(const NeuralLane<G> &c) {
+    if constexpr (stage_traits<G>::on) {
+        if (c.gl0) tma_store_wait_read();
+        group_sync<GroupShape<G::Z>::kLanes>(c.grp);
+    }
+}
 
 // ---- VN phase functors (one `col<J, R...>()` call per variable block of degree >= 2) --------------------------
 // iteration 0: all c2v are zero -> v2c = xa + 0  (:49, :56-58)
@@ -195,14 +265,28 @@ struct VnFirst {
 template <class G, bool kEmit, int MODE = 0, int kXo = 0>
 struct VnStep {
     NeuralLane<G> &c;
-    template <int J, int XROW, int... R>
-    __device__ __forceinline__ void col() {
+    float mm[2][G::kMaxColDeg];     // messages of the block being computed / the block being fetched (registers)
+    float xx[2];
+    template <int SLOT, int J, int XROW, int... R>
+    __device__ __forceinline__ void pld() {
         constexpr int D = sizeof...(R);
         constexpr int rows[D] = {R...};
-        float m[D], pre[D];
 #pragma unroll
-        for (int k = 0; k < D; k++) m[k] = c.lane[rows[k] * G::Z];
-        const float x = c.lane[XROW * G::Z];
+        for (int k = 0; k < D; k++) mm[SLOT][k] = c.lane[rows[k] * G::Z];
+        xx[SLOT] = c.lane[XROW * G::Z];
+    }
+    template <int J, int XROW, int... R>
+    __device__ __forceinline__ void col() {
+        pld<0, J, XROW, R...>();
+        pcol<0, J, XROW, R...>();
+    }
+    template <int SLOT, int J, int XROW, int... R>
+    __device__ __forceinline__ void pcol() {
+        constexpr int D = sizeof...(R);
+        constexpr int rows[D] = {R...};
+        const float *m = mm[SLOT];
+        float pre[D];
+        const float x = xx[SLOT];
         float p = 0.0f;                       // running prefix ((0 + m0) + m1) + ...
 #pragma unroll
         for (int k = 0; k < D; k++) {
@@ -211,6 +295,28 @@ struct VnStep {
         }
         // chains k and k+1 advance together on the packed pipe: chain k is pre[k] + m[k+1] + m[k+2] + ...,
         // chain k+1 is pre[k+1] + m[k+2] + ...; from m[k+2] on both add the same operand (FADD2, broadcast).
+#if NLDPC_VN_QOUTER
+        // the same chains, written operand-major: all live chain pairs take m[q] before any takes m[q+1], so consecutive
+        // instructions are independent (each chain is a serial dependency of 4-cycle adds)
+        constexpr int P = D / 2;
+        f2 sp[P > 0 ? P : 1];
+#pragma unroll
+        for (int kk = 0; kk < P; kk++) sp[kk] = pack2(addf(pre[2 * kk], m[2 * kk + 1]), pre[2 * kk + 1]);
+#pragma unroll
+        for (int q = 2; q < D; q++) {
+            const f2 mq = pack2(m[q], m[q]);
+#pragma unroll
+            for (int kk = 0; kk < P; kk++)
+                if (2 * kk + 2 <= q) sp[kk] = add2(sp[kk], mq);
+        }
+#pragma unroll
+        for (int kk = 0; kk < P; kk++) {
+            const f2 s = add2(pack2(x, x), sp[kk]);
+            if constexpr (MODE == 0) c.zmin = fmin3(c.zmin, fabsf(lo(s)), fabsf(hi(s)));
+            c.lane[rows[2 * kk] * G::Z] = lo(s);
+            c.lane[rows[2 * kk + 1] * G::Z] = hi(s);
+        }
+#else
 #pragma unroll
         for (int k = 0; k + 1 < D; k += 2) {
             f2 s = pack2(addf(pre[k], m[k + 1]), pre[k + 1]);
@@ -221,6 +327,7 @@ struct VnStep {
             c.lane[rows[k] * G::Z] = lo(s);
             c.lane[rows[k + 1] * G::Z] = hi(s);
         }
+#endif
         if constexpr (D & 1) {
             const float v = addf(x, pre[D - 1]);
             if constexpr (MODE == 0) c.zmin = fminf(c.zmin, fabsf(v));
@@ -232,6 +339,15 @@ struct VnStep {
         }
     }
 };
+
+template <class G, class F>
+__device__ __forceinline__ void run_vcols(F &f) {
+#if NLDPC_PIPE_VN
+    G::vcols_pipelined(f);
+#else
+    G::vcols(f);
+#endif
+}
 
 // marginal only (after the last CN phase)
 template <class G, int MODE = 0, int kXo = 0>
@@ -321,19 +437,40 @@ struct ReloadXreg {
 // the warp runs the out-of-line kZeroSafe = true phase, which applies the reference's "exact zero -> magnitude 10000,
 // not positive" rule (:74, :78) at two extra instructions per edge.  Exact-zero v2c only occur for punctured /
 // quantised channel values, so the hot loop does not pay for them, and the whole CN phase stays one basic block.
-template <class G, bool kEmit, bool kConstW, bool kZeroSafe, class... Es>
-__device__ __forceinline__ void cn_check_core(NeuralLane<G> &c) {
+// gather of one check's inputs (:59-63): raw[k] = v2c of edge k at this lane's rotated position (or the lane register of a
+// degree-1 identity block).  Separate from the arithmetic so that the NEXT check's loads can be issued before this check's
+// stores (software pipelining, NLDPC_PIPE): ptxas cannot hoist them itself — every access goes through one of Z rotated base
+// pointers and a store through one may alias a load through another as far as it can tell.
+// The same stage also fetches the edges' {w, b} pairs: the constant load (LDC) has its own latency, and issued right before
+// the multiply that needs it the multiply stalled on it (ncu: short_scoreboard on FMUL, 13 % of all stall samples).
+template <class G, bool kEmit, bool kConstW, class... Es>
+__device__ __forceinline__ void cn_load(const NeuralLane<G> &c, float *raw, float2 *wb) {
     constexpr int D = sizeof...(Es);
     constexpr int rows[D] = {Es::row...};
     constexpr int shf[D] = {Es::shift...};
     constexpr int eix[D] = {Es::e...};
     constexpr int col1[D] = {Es::col1...};
-    float u[D], raw[D];
+#pragma unroll
+    for (int k = 0; k < D; k++)
+        raw[k] = rows[k] >= 0 ? c.rot[shf[k]][rows[k] * G::Z] : c.xreg[rows[k] < 0 ? -rows[k] - 1 : 0];
 #pragma unroll
     for (int k = 0; k < D; k++) {
-        raw[k] = rows[k] >= 0 ? c.rot[shf[k]][rows[k] * G::Z] : c.xreg[rows[k] < 0 ? -rows[k] - 1 : 0];   // gather (:59-63)
-        u[k] = (kZeroSafe && raw[k] == 0.0f) ? -10000.0f : raw[k];
+        if (col1[k] >= 0 && !kEmit) continue;                            // unstored edge, marginal not wanted now
+        if constexpr (kConstW) wb[k] = c_wb[c.wb_base + eix[k]];
+        else wb[k] = make_float2(__ldg(c.wt + eix[k]), __ldg(c.bt + eix[k]));
     }
+}
+
+template <class G, bool kEmit, bool kConstW, bool kZeroSafe, class... Es>
+__device__ __forceinline__ void cn_check_core(NeuralLane<G> &c, const float *raw, const float2 *wb) {
+    constexpr int D = sizeof...(Es);
+    constexpr int rows[D] = {Es::row...};
+    constexpr int shf[D] = {Es::shift...};
+    constexpr int eix[D] = {Es::e...};
+    constexpr int col1[D] = {Es::col1...};
+    float u[D];
+#pragma unroll
+    for (int k = 0; k < D; k++) u[k] = (kZeroSafe && raw[k] == 0.0f) ? -10000.0f : raw[k];
     // min over the other edges, capped at 10000 (:74-75): pairwise prefix/suffix minima with 3-input FMNMX
     constexpr int H = (D + 1) / 2;
     float se[H + 1];
@@ -360,14 +497,7 @@ __device__ __forceinline__ void cn_check_core(NeuralLane<G> &c) {
         }
         if (col1[k] >= 0 && !kEmit) continue;                            // unstored edge, marginal not wanted now
         // |o| * w + b, ReLU, sign: negative iff the number of positive OTHER inputs is even (:77-80, :89-91)
-        float wk, bk;
-        if constexpr (kConstW) {
-            const float2 wb = c_wb[c.wb_base + eix[k]];
-            wk = wb.x; bk = wb.y;
-        } else {
-            wk = __ldg(c.wt + eix[k]); bk = __ldg(c.bt + eix[k]);
-        }
-        float m = addf(mulf(mag, wk), bk);
+        float m = addf(mulf(mag, wb[k].x), wb[k].y);
         m = fmaxf(m, 0.0f);
         const unsigned sb = (x ^ __float_as_uint(u[k])) & 0x80000000u;
         const float c2v = __uint_as_float(__float_as_uint(m) | sb);
@@ -384,16 +514,15 @@ __device__ __forceinline__ void cn_check_core(NeuralLane<G> &c) {
 // clamp), nudge exact zeros to +1e-4, min over the others, mag - 1e-4 [mag <= 1e-4], o = mag * sgn, |o| * W_cn, ReLU,
 // condition again, * sign(o) (sign(0) = 0).  kXo: xa_origin lives in its own rows (VN weights make xa_input drift).
 template <class G, bool kEmit, int MODE, int kXo, class... Es>
-__device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c) {
+__device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c, const float *raw, const float2 *wb) {
     constexpr int D = sizeof...(Es);
     constexpr int rows[D] = {Es::row...};
     constexpr int shf[D] = {Es::shift...};
     constexpr int eix[D] = {Es::e...};
     constexpr int col1[D] = {Es::col1...};
-    float u[D], raw[D];
+    float u[D];
 #pragma unroll
     for (int k = 0; k < D; k++) {
-        raw[k] = rows[k] >= 0 ? c.rot[shf[k]][rows[k] * G::Z] : c.xreg[rows[k] < 0 ? -rows[k] - 1 : 0];   // gather (:380-384)
         if constexpr (MODE == 2) {
             // QMS q=5: every non-zero input is a multiple of 0.5, so the reference's zero handling — 0 -> +1e-4 (:391-393),
             // then mag - 1e-4 where mag <= 1e-4 (:416), i.e. 1e-4 - 1e-4 = 0 — is "a zero counts as positive and as
@@ -428,7 +557,7 @@ __device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c) {
             pe = fmin3(pe, fabsf(u[k - 1]), fabsf(u[k]));
         }
         if (col1[k] >= 0 && !kEmit) continue;
-        const float wk = c_wb[c.wb_base + eix[k]].x;
+        const float wk = wb[k].x;
         float c2v;
         if constexpr (MODE == 2) {
             // madj == mag >= 0 (see above); m >= 0 so only the upper clamp of the quantiser can bind
@@ -462,65 +591,80 @@ __device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c) {
     }
 }
 
+#ifndef NLDPC_PIPE_CN
+#define NLDPC_PIPE_CN 1     // 1: the next check's inputs are loaded before the current check computes
+#endif
 template <class G, bool kEmit, int MODE, int kXo>
 struct CnBoosted {
     NeuralLane<G> &c;
+    float raw[2][G::kMaxRowDeg];
+    __device__ __forceinline__ void first_deg1() { stage_wait(c); }      // (generated: before the first check that emits)
+    float2 wb[2][G::kMaxRowDeg];
     template <class... Es>
     __device__ __forceinline__ void chk() {
-        cn_check_boosted_core<G, kEmit, MODE, kXo, Es...>(c);
+        cn_load<G, kEmit, true, Es...>(c, raw[0], wb[0]);
+        cn_check_boosted_core<G, kEmit, MODE, kXo, Es...>(c, raw[0], wb[0]);
+    }
+    template <int SLOT, class... Es>
+    __device__ __forceinline__ void ld() {
+        cn_load<G, kEmit, true, Es...>(c, raw[SLOT], wb[SLOT]);
+    }
+    template <int SLOT, class... Es>
+    __device__ __forceinline__ void chk() {
+        cn_check_boosted_core<G, kEmit, MODE, kXo, Es...>(c, raw[SLOT], wb[SLOT]);
     }
 };
 
 template <class G, bool kEmit, bool kConstW, bool kZeroSafe>
 struct CnNeural {
     NeuralLane<G> &c;
+    float raw[2][G::kMaxRowDeg];
+    __device__ __forceinline__ void first_deg1() { stage_wait(c); }      // (generated: before the first check that emits)
+    float2 wb[2][G::kMaxRowDeg];
     template <class... Es>
     __device__ __forceinline__ void chk() {
-        cn_check_core<G, kEmit, kConstW, kZeroSafe, Es...>(c);
+        cn_load<G, kEmit, kConstW, Es...>(c, raw[0], wb[0]);
+        cn_check_core<G, kEmit, kConstW, kZeroSafe, Es...>(c, raw[0], wb[0]);
+    }
+    template <int SLOT, class... Es>
+    __device__ __forceinline__ void ld() {
+        cn_load<G, kEmit, kConstW, Es...>(c, raw[SLOT], wb[SLOT]);
+    }
+    template <int SLOT, class... Es>
+    __device__ __forceinline__ void chk() {
+        cn_check_core<G, kEmit, kConstW, kZeroSafe, Es...>(c, raw[SLOT], wb[SLOT]);
     }
 };
 
-// out-of-line zero-safe CN phase; takes the lane state by value (a pointer to it would force it into local memory)
-template <class G, bool kEmit, bool kConstW>
-__device__ __noinline__ void cn_phase_zero_safe(float *lane, int z, const float *wt, const float *bt, int wb_base, float *soft,
-                                                uint8_t *hb, const float *xa_lane) {
-    NeuralLane<G> c;
-    c.lane = lane; c.z = z; c.wt = wt; c.bt = bt; c.wb_base = wb_base; c.soft = soft; c.hb = hb; c.valid = true; c.zmin = 1.0f;
-#pragma unroll
-    for (int s = 0; s < G::Z; s++) c.rot[s] = (lane - z) + ((z + s) % G::Z);
-    if constexpr (G::kXRegs > 0) {
-        ReloadXreg<G> r{c, xa_lane};
-        G::blocks(r);
-    }
-    CnNeural<G, kEmit, kConstW, true> f{c};
+template <class G, class F>
+__device__ __forceinline__ void run_checks(F &f) {
+#if NLDPC_PIPE_CN
+    G::checks_pipelined(f);
+#else
     G::checks(f);
-}
-
-// CN phase dispatch: warp-uniform choice between the inlined fast phase and the out-of-line zero-safe phase
-template <class G, bool kEmit, bool kConstW>
-__device__ __forceinline__ void cn_phase(NeuralLane<G> &c, bool xa_zero, const float *xa_lane) {
-    const bool need_safe = __any_sync(0xffffffffu, xa_zero || c.zmin == 0.0f);
-    c.zmin = 10000.0f;
-    if (need_safe) {
-        cn_phase_zero_safe<G, kEmit, kConstW>(c.lane, c.z, c.wt, c.bt, c.wb_base, c.soft, c.hb, xa_lane);
-    } else {
-        CnNeural<G, kEmit, kConstW, false> f{c};
-        G::checks(f);
-    }
+#endif
 }
 
 // -----------------------------------------------------------------------------------------------------------
-constexpr int slab_with_xo(int slab, int nz, int z) {
-    int s = slab + nz;
+constexpr int slab_floats(int base, int extra, int z) {      // slab stride == Z (mod 32), multiple of 4 floats
+    int s = base + extra;
     while ((s % 32) != (z % 32) || (s % 4)) s++;
     return s;
 }
 
-template <class G, bool kXoRows = false>
+#ifndef NLDPC_STAGE_OUT
+#define NLDPC_STAGE_OUT 1   // 1: list-mode soft outputs leave through shared staging rows + bulk TMA stores (see Staged<>)
+#endif
+
+// kXoRows: N extra rows per codeword for xa_origin; kStage: N extra rows staging the soft output row (list mode)
+template <class G, bool kXoRows = false, bool kStage = false>
 struct SpecCfg {
     using Shape = GroupShape<G::Z>;
-    static constexpr int kSlabF = kXoRows ? slab_with_xo(G::kSlab, G::N * G::Z, G::Z) : G::kSlab;   // floats per codeword slab
+    static constexpr int kNZ = G::N * G::Z;
+    static constexpr int kSlabF = (kXoRows || kStage) ? slab_floats(G::kSlab, (kXoRows ? kNZ : 0) + (kStage ? kNZ : 0), G::Z) : G::kSlab;
     static constexpr int kXoOff = kXoRows ? (G::kXRows + G::S) * G::Z : 0;   // N xo rows follow the message rows
+    static constexpr int kStageOff = (G::kXRows + G::S) * G::Z + (kXoRows ? kNZ : 0);   // then the N staging rows
+    static_assert(!kStage || ((kStageOff * 4) % 16 == 0 && (kSlabF * 4) % 16 == 0 && (kNZ * 4) % 16 == 0), "bulk-store source alignment");
     static constexpr int kHardBytes = (G::N * G::Z + 7) / 8;
     static constexpr int kHardStride = (kHardBytes + 15) & ~15;           // per-codeword staging, 16 B multiple
     static constexpr int kPerCw = kSlabF * 4 + kHardStride;              // shared bytes per codeword
@@ -532,9 +676,12 @@ struct SpecCfg {
     // and take the best one that fits shared memory.  More than 2 warps per sub-partition do NOT pay off here: every warp
     // streams through ~60 KB of unrolled code and more resident warps mean more instruction-cache pressure (BG2: 1 CTA x
     // 10 warps 36.3 M cw/s vs 8 warps 43.2 M; WiMAX: 15 warps 57.2 M vs 12 warps 59.2 M vs 2 x 6 warps 55.4 M).
-    static constexpr int kMaxCwSm = (kSmemBudget - 2 * 1024 - 512) / kPerCw;
+    // what fits: every CTA needs its codewords, one mbarrier per group and 16 B; the SM has 228 KB, of which each resident
+    // CTA also takes 1 KB for the system, and one CTA may ask for at most 227 KB
+    static constexpr size_t cta_bytes(int g) { return (size_t)g * Shape::kCw * kPerCw + (size_t)g * 8 + 16; }
     static constexpr int score(int ctas, int g) {
-        if (g <= 0 || ctas * g * Shape::kCw > kMaxCwSm || g * Shape::kLanes > 512) return -1;
+        if (g <= 0 || g * Shape::kLanes > 512) return -1;
+        if (cta_bytes(g) > (size_t)kSmemBudget || ctas * (cta_bytes(g) + 1024) > (size_t)228 * 1024) return -1;
         const int w = g * Shape::kWarps;
         const int m = ctas * ((w + 3) / 4);
         const int u = m <= 1 ? 35 : (m == 2 ? 59 : (m == 3 ? 50 : 45));      // percent, from the measurements below
@@ -556,15 +703,29 @@ struct SpecCfg {
 #endif
     static constexpr int kThreads = kGroups * Shape::kLanes;
     static constexpr int kCwPerCta = kGroups * Shape::kCw;
-    static constexpr size_t kSmemBytes = (size_t)kCwPerCta * kPerCw + (size_t)kGroups * 8 + 16;
+    static constexpr size_t kSmemBytes = cta_bytes(kGroups);
     static_assert(G::S >= G::N, "the raw codeword is staged in the message rows");
 };
 
+// The configuration a kernel variant runs with (kernel and launchers must agree): xa_origin rows only in list mode with VN
+// weights (see xo_global); output staging in list mode whenever it does not cost resident codewords.
+template <class G, bool kEvery, bool kXo>
+struct KernelCfg {
+    static constexpr bool kXoRows = kXo && kEvery;
+    using Plain = SpecCfg<G, kXoRows, false>;
+    using Stage = SpecCfg<G, kXoRows, true>;
+    static constexpr bool kStage = NLDPC_STAGE_OUT && kEvery &&
+                                   (Stage::kCtasPerSm * Stage::kCwPerCta >= Plain::kCtasPerSm * Plain::kCwPerCta);
+    using type = std::conditional_t<kStage, Stage, Plain>;
+};
 // kEvery: outputs are produced after every iteration (drop-in list mode / per-iteration hard decisions);
 // otherwise only after the last one (throughput mode) and the loop body carries no output code at all.
-template <class G, bool kEvery, bool kConstW, int MODE = 0, bool kXo = false>
-__global__ void __launch_bounds__(SpecCfg<G, kXo && kEvery>::kThreads, SpecCfg<G, kXo && kEvery>::kCtasPerSm) nldpc_spec_neural_kernel(const DecodeArgs a) {
-    using Cfg = SpecCfg<G, kXo && kEvery>;            // xa_origin rows only in list mode (see xo_global)
+template <class G0, bool kEvery, bool kConstW, int MODE = 0, bool kXo = false>
+__global__ void __launch_bounds__(KernelCfg<G0, kEvery, kXo>::type::kThreads, KernelCfg<G0, kEvery, kXo>::type::kCtasPerSm)
+nldpc_spec_neural_kernel(const DecodeArgs a) {
+    using Cfg = typename KernelCfg<G0, kEvery, kXo>::type;
+    constexpr bool kStage = KernelCfg<G0, kEvery, kXo>::kStage;
+    using G = std::conditional_t<kStage, Staged<G0, Cfg::kStageOff>, G0>;      // (same graph program; emit() writes staging rows)
     constexpr int kXoMode = !kXo ? 0 : (kEvery ? 1 : 2);
     static_assert(MODE == 0 || kConstW, "the Boosted variants read their weights from the constant arena");
     static_assert(MODE != 0 || !kXo, "xo rows only exist for the Boosted decoder with VN weights");
@@ -575,7 +736,11 @@ __global__ void __launch_bounds__(SpecCfg<G, kXo && kEvery>::kThreads, SpecCfg<G
     uint8_t *hstage = smem_raw + (size_t)Cfg::kCwPerCta * Cfg::kSlabF * 4;
     uint64_t *bars = reinterpret_cast<uint64_t *>(hstage + (size_t)Cfg::kCwPerCta * Cfg::kHardStride);
 
-    const int grp = threadIdx.x / Shape::kLanes;            // group within the CTA
+    // group within the CTA, through a shuffle from lane 0: the value is the same, but the compiler now KNOWS it is warp-uniform,
+    // so everything derived from it (work-unit loop, iteration counter, weight offsets in the constant arena) lives on the
+    // uniform datapath: the per-edge {w, b} become LDCU loads into uniform registers consumed directly by FMUL / FADD instead
+    // of indexed LDC loads into vector registers whose latency the multiply waited for (ncu: short_scoreboard on FMUL).
+    const int grp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0) / Shape::kWarps;
     const int gl = threadIdx.x - grp * Shape::kLanes;       // lane within the group
     const int cwl = gl / Z;                                 // codeword within the group
     const int z = gl - cwl * Z;
@@ -592,6 +757,8 @@ __global__ void __launch_bounds__(SpecCfg<G, kXo && kEvery>::kThreads, SpecCfg<G
     NeuralLane<G> c;
     c.lane = slab + z;
     c.z = z;
+    c.grp = grp;
+    c.gl0 = gl == 0;
     c.xo_off = Cfg::kXoOff;
     c.lo = a.llr_lo;
     c.hi = a.llr_hi;
@@ -607,25 +774,24 @@ __global__ void __launch_bounds__(SpecCfg<G, kXo && kEvery>::kThreads, SpecCfg<G
     const bool soft_all = a.soft_mode == 1, hard_all = a.hard_mode == 1;
     const bool soft_any = a.soft_mode != 0, hard_any = a.hard_mode != 0;
 
-    // phase barrier: group-local by default; CTA-wide in lockstep mode (all warps then stream the same code)
-    auto phase_sync = [&]() {
-        if constexpr (NLDPC_CTA_LOCKSTEP) __syncthreads();
-        else group_sync<Shape::kLanes>(grp);
-    };
-#if NLDPC_CTA_LOCKSTEP
-    for (int unit0 = blockIdx.x * Cfg::kGroups; unit0 < n_units; unit0 += unit_stride) {
-        const int unit = unit0 + grp;
-#else
-    // units are dealt out CTA-major: group g of CTA b takes units b + gridDim.x * (g + kGroups * k).  A batch too small to fill
-    // the machine then spreads over all SMs with fewer busy warps each (the host launches min(n_units, resident CTAs) CTAs),
-    // which is what a latency-bound small decode wants; for large batches the order of units is irrelevant.
-    for (int unit = blockIdx.x + grp * (int)gridDim.x; unit < n_units; unit += unit_stride) {
-#endif
+    // phase barrier: group-local (a CTA-wide lockstep variant, so that all warps stream the same code, bought nothing:
+    // 42.4 vs 43.2 M cw/s in round 1)
+    auto phase_sync = [&]() { group_sync<Shape::kLanes>(grp); };
+    // The decode of one work unit.  kSafe = false is the fast path, which assumes that no CN input of the group is exactly
+    // zero: the channel LLRs are screened once, the VN phase tracks min |v2c| (half an instruction per edge), and when a zero
+    // shows up the unit is abandoned (return false) and decoded again from its channel LLRs with kSafe = true, whose CN phase
+    // applies the reference's "exact zero -> magnitude 10000, not positive" rule (:74, :78) at two more instructions per edge.
+    // Exact zeros need punctured / quantised inputs or an exact fp32 cancellation (a few dozen units per 65536 codewords at
+    // 2 dB), so the second attempt is noise; what matters is that the hot loop contains NO call and NO second code path: with
+    // the group index known to be warp-uniform (see above) its iteration counter and weight offsets then stay on the uniform
+    // datapath.  Outputs an abandoned attempt has already written are rewritten with identical values.
+    auto run_unit = [&](const int unit, auto safe_tag) __attribute__((always_inline)) -> bool {
         const int b0 = unit * Shape::kCw;
         const int b = b0 + cwl;
         c.valid = b < a.B;
         c.xa_cw = a.xa + (size_t)min(b, a.B - 1) * NZ;      // (padding lanes re-read the last codeword; their outputs are dropped)
         const int ncw = max(0, min(Shape::kCw, a.B - b0));
+        constexpr bool kSafe = decltype(safe_tag)::value;
         // ---- bulk-TMA the group's channel LLRs (one 1-D copy per codeword) ----
         if (gl == 0 && ncw > 0) {
             fence_proxy_async();
@@ -645,11 +811,12 @@ __global__ void __launch_bounds__(SpecCfg<G, kXo && kEvery>::kThreads, SpecCfg<G
         // the raw codeword sits in the message rows (staging); every lane moves its own elements to their places
         // (shared rows / registers).  Lane z only ever touches element z of a row in the VN phase, so no barrier is needed
         // before iteration 0 overwrites the staging area.
-        bool xa_zero = false;
         {
             PlaceXa<G, MODE, kXoMode> pl{c, c.lane + G::kXRows * Z, 1.0f};
             G::blocks(pl);
-            xa_zero = (pl.zm == 0.0f);
+            if constexpr (MODE == 0 && !kSafe) {
+                if (group_any<Shape::kLanes>(grp, pl.zm == 0.0f)) return false;
+            }
         }
         c.zmin = 10000.0f;
         // per-iteration pieces shared by both output modes
@@ -659,13 +826,25 @@ __global__ void __launch_bounds__(SpecCfg<G, kXo && kEvery>::kThreads, SpecCfg<G
                 G::blocks(sc);
             }
         };
+        // VN -> CN hand-over: the phase barrier and, on the Neural fast path, the group's zero screen in one step
+        auto vn_done = [&]() -> bool {
+            if constexpr (MODE == 0 && !kSafe) {
+                const bool zero_seen = group_any<Shape::kLanes>(grp, c.zmin == 0.0f);
+                if constexpr (Shape::kLanes == 32) __syncwarp();
+                return !zero_seen;
+            } else {
+                phase_sync();
+                return true;
+            }
+        };
         auto cn_run = [&](auto emit_tag) {
             constexpr bool kEmitNow = decltype(emit_tag)::value;
             if constexpr (MODE == 0) {
-                cn_phase<G, kEmitNow, kConstW>(c, xa_zero, a.xa + (size_t)min(b, a.B - 1) * NZ + z);
+                CnNeural<G, kEmitNow, kConstW, kSafe> f{c};
+                run_checks<G>(f);
             } else {
                 CnBoosted<G, kEmitNow, MODE, kXoMode> f{c};
-                G::checks(f);
+                run_checks<G>(f);
             }
         };
         float *soft_cw = (soft_any && c.valid) ? a.soft + (size_t)b * NZ : nullptr;     // + t*B*NZ in ALL mode
@@ -696,6 +875,24 @@ __global__ void __launch_bounds__(SpecCfg<G, kXo && kEvery>::kThreads, SpecCfg<G
             group_sync<Shape::kLanes>(grp);
         };
 
+        // list mode with output staging: the finished [N*Z] row of every codeword of the group -> soft[t_out][b], one bulk
+        // TMA store each (the rows sit behind the codewords' slabs, see Staged<>)
+        auto flush_soft = [&](int t_out) {
+            if constexpr (kStage) {
+                if (soft_any && (soft_all || t_out == a.T - 1)) {
+                    fence_proxy_async();                     // this lane's staging writes -> visible to the async proxy
+                    group_sync<Shape::kLanes>(grp);
+                    if (gl == 0) {
+                        float *dst = a.soft + ((soft_all ? (size_t)t_out * a.B : 0) + b0) * NZ;
+                        for (int q = 0; q < ncw; q++)
+                            tma_store_1d(dst + (size_t)q * NZ, slabs + (size_t)(grp * Shape::kCw + q) * Cfg::kSlabF + Cfg::kStageOff,
+                                         (uint32_t)(NZ * sizeof(float)));
+                        tma_store_commit();
+                    }
+                }
+            }
+        };
+
         if constexpr (kEvery) {
             for (int t = 0; t < a.T; t++) {
                 c.wt = a.w + (size_t)t * G::E;
@@ -718,15 +915,17 @@ __global__ void __launch_bounds__(SpecCfg<G, kXo && kEvery>::kThreads, SpecCfg<G
                     c.soft = (soft_all && soft_cw) ? soft_cw + (size_t)(t - 1) * soft_iter : nullptr;
                     c.hb = hard_all ? hb_cw : nullptr;
                     c.mask = (MODE != 0 && dump) ? a.hist_mask + ((size_t)(t - 1) * a.B + b) * NZ : nullptr;
+                    stage_wait(c);       // (graphs without degree-1 blocks emit only here; a no-op wait otherwise)
                     VnStep<G, true, MODE, kXoMode> f{c};
-                    G::vcols(f);
+                    run_vcols<G>(f);
+                    flush_soft(t - 1);
                     if (hard_all) flush_hard(t - 1);
                 }
                 if (dump) {   // the v2c every CN phase reads, slot-major (same slot order as the table-driven kernels)
                     float *hv = a.hist_v2c + (((size_t)t * a.B + b) * G::S) * Z + z;
                     for (int q = 0; q < G::S; q++) hv[(size_t)q * Z] = c.lane[(G::kXRows + q) * Z];
                 }
-                phase_sync();
+                if (!vn_done()) return false;
                 const bool last = t == a.T - 1;
                 c.soft = (soft_cw && (soft_all || last)) ? soft_cw + (soft_all ? (size_t)t * soft_iter : 0) : nullptr;
                 c.hb = (hard_all || last) ? hb_cw : nullptr;
@@ -748,9 +947,9 @@ __global__ void __launch_bounds__(SpecCfg<G, kXo && kEvery>::kThreads, SpecCfg<G
                     G::vcols(f);
                 } else {
                     VnStep<G, false, MODE, kXoMode> f{c};
-                    G::vcols(f);
+                    run_vcols<G>(f);
                 }
-                phase_sync();
+                if (!vn_done()) return false;
                 if (t < a.T - 1) {
                     cn_run(std::false_type{});
                 } else {
@@ -767,11 +966,45 @@ __global__ void __launch_bounds__(SpecCfg<G, kXo && kEvery>::kThreads, SpecCfg<G
             c.soft = soft_cw ? soft_cw + (soft_all ? (size_t)(a.T - 1) * soft_iter : 0) : nullptr;
             c.hb = hb_cw;
             c.mask = (MODE != 0 && kEvery && a.hist_mask && c.valid) ? a.hist_mask + ((size_t)(a.T - 1) * a.B + b) * NZ : nullptr;
+            if constexpr (kEvery) stage_wait(c);
             Marginal<G, MODE, kXoMode> f{c};
             G::vcols(f);
+            if constexpr (kEvery) flush_soft(a.T - 1);
             if (hard_any) flush_hard(a.T - 1);
         }
-        group_sync<Shape::kLanes>(grp);   // all lanes done with the slabs before the next TMA overwrites them
+        return true;
+    };      // run_unit
+
+    // Units are dealt out CTA-major: group g of CTA b takes units b + gridDim.x * (g + kGroups * k).  A batch too small to fill
+    // the machine then spreads over all SMs with fewer busy warps each (the host launches min(n_units, resident CTAs) CTAs),
+    // which is what a latency-bound small decode wants; for large batches the order of units is irrelevant.
+    // Pass 1 runs every unit on the fast path and notes the abandoned ones in a 64-bit mask (the host never gives a group more
+    // than 64 units per launch, see spec_units_per_launch); pass 2 — cold code BEHIND the hot loop, not inside it — decodes those.
+    const int unit_first = a.unit_begin + (int)blockIdx.x + grp * (int)gridDim.x;
+    const int unit_end = a.unit_end > 0 ? min(a.unit_end, n_units) : n_units;
+    unsigned long long failed = 0ull;
+    {
+        int k = 0;
+        for (int unit = unit_first; unit < unit_end; unit += unit_stride, k++) {
+            if (!run_unit(unit, std::false_type{})) failed |= 1ull << k;
+            group_sync<Shape::kLanes>(grp);   // all lanes done with the slabs before the next TMA overwrites them
+        }
+    }
+    if constexpr (MODE == 0) {
+        if (failed != 0ull) {
+            int k = 0;
+            for (int unit = unit_first; unit < unit_end; unit += unit_stride, k++) {
+                if (!((failed >> k) & 1ull)) continue;
+#ifdef NLDPC_DEBUG_COUNT
+                if (gl == 0) atomicAdd(&g_dbg_restarts, 1u);
+#endif
+                run_unit(unit, std::true_type{});
+                group_sync<Shape::kLanes>(grp);
+            }
+        }
+    }
+    if constexpr (kStage) {
+        if (gl == 0) tma_store_wait_all();      // the staging rows must outlive the bulk stores that read them
     }
 }
 
