@@ -6,6 +6,7 @@ Metric (BASELINE.json): decoded codewords/s (and Gbit/s) at 10 iterations, Neura
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --total 1048576 [--verify]      BASELINE configs[3]: 2^20 codewords sharded over the ranks (strong scaling)
 
 One "step" = one pass of the hot path (one kernel launch) over one batch of synthetic AWGN/BPSK LLRs.
   value : whole-job codewords/s with inputs resident in HBM (throughput mode: packed hard decisions out)
@@ -103,6 +104,111 @@ class ClockSampler(threading.Thread):
         self.join(timeout=1.0)
         med = float(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def stock_reference_timing(timeout_s=240):
+    """The UNMODIFIED reference (PyTorch, CPU) timed on this box's host cores in its own process (tools/time_stock_reference.py:
+    BASELINE configs[0] verbatim and BG2 at batch 256).  Needs baseline/_ref (tools/install_reference.sh) or /root/reference."""
+    import subprocess
+    try:
+        res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "time_stock_reference.py")], stdout=subprocess.PIPE,
+                             stderr=subprocess.PIPE, text=True, timeout=timeout_s)
+        if res.returncode != 0:
+            return {"unavailable": "time_stock_reference.py failed: " + res.stderr.strip().splitlines()[-1][:200]}
+        return json.loads(res.stdout.strip().splitlines()[-1])
+    except Exception as exc:
+        return {"unavailable": repr(exc)[:200]}
+
+
+def strong_sharded(total, dev, rank, world, gid, w, b, w_np, b_np, bg, Z, barrier, steps, verify):
+    """BASELINE configs[3]: `total` codewords (2^20 = 3.49 GB of LLRs) split into contiguous shards, one per rank
+    (sharding.shard_bounds), packed-decision output, no collective on the data path.  Returns (ms per pass over ALL codewords as
+    the max over ranks, mismatching codewords vs the port or None)."""
+    import torch
+    import torch.distributed as dist
+    from neural_ldpc_decoder_torch_b200.sharding import shard_bounds
+    N = bg.shape[1]
+    lo, hi = shard_bounds(total, world, rank)
+    n = hi - lo
+    gen = torch.Generator(device=dev).manual_seed(777 + 1000 * world + rank)
+    xs = torch.empty((n, N, Z), dtype=torch.float32, device=dev)
+    for c0 in range(0, n, 65536):      # generated in chunks: no 3.5 GB temporaries next to the shard itself
+        c1 = min(n, c0 + 65536)
+        xs[c0:c1] = 2.0 * (SIGMA * torch.randn((c1 - c0, N, Z), generator=gen, device=dev) - 1.0) / SIGMA ** 2
+    hard = None
+    for _ in range(3):
+        hard = torch.ops.nldpc.neural_hard(xs, w, b, gid, False)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        hard = torch.ops.nldpc.neural_hard(xs, w, b, gid, False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        tms = torch.tensor([ms], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    bad = None
+    if verify:      # every packed decision of this rank's shard against the CPU port (oracle: checker only)
+        import oracle
+        got = hard.cpu().numpy()
+        bad = 0
+        for c0 in range(0, n, 32768):
+            c1 = min(n, c0 + 32768)
+            ref = oracle.neural_forward_last(bg, Z, xs[c0:c1].cpu().numpy(), w_np, b_np)
+            bad += int((got[c0:c1] != oracle.pack_hard(ref)).any(axis=1).sum())
+        if world > 1:
+            tb = torch.tensor([bad], device=dev, dtype=torch.int64)
+            dist.all_reduce(tb)
+            bad = int(tb.item())
+    del xs, hard
+    torch.cuda.empty_cache()
+    barrier()
+    return ms, bad
+
+
+def train_leg(dev, rank, world, barrier, batch, steps=5):
+    """BASELINE configs[4]: the data-parallel training step (train/train_BoostedNeuralLDPCDecoder.py:270-294) at `batch` codewords
+    per GPU — forward + multi-iteration BCE + backward + ONE NCCL all-reduce of the flat weight gradient + clip / Adam / clamp
+    (training.FusedTrainer, eager).  Returns ms per step (max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    from neural_ldpc_decoder_torch_b200 import TannerGraph, load_basegraph
+    from neural_ldpc_decoder_torch_b200 import boosted_neural_ldpc_decoder as bn
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.BoostedNeuralLDPCDecoder import BoostedNeuralLDPCDecoder
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.LDPCDecoderLoss import LDPCDecoderLoss
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.DecoderType import DecoderType
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.LossType import LossType
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.NodeWeightSharingConfig import NodeWeightSharingConfig
+    from neural_ldpc_decoder_torch_b200.training import DeviceBatchGenerator, FusedTrainer
+    bg2, Z2 = load_basegraph(CODE)
+    g2 = TannerGraph(bg2, Z2)
+    cm2 = bn.ConnectingMatrixTorch(bn.ConnectingMatrix(Z=Z2, basegraph=bg2), device=dev)
+    mt = BoostedNeuralLDPCDecoder(20, batch, cm2, node_weight_sharing_config=NodeWeightSharingConfig(3, 0, 3), decoding_type=DecoderType.QMS).to(dev)
+    mt.store_llr = "none"
+    xt, yt = DeviceBatchGenerator(g2, [2, 2.5, 3.0, 3.5, 4.0], dev, seed=5 + rank, qms_qbit=5)(batch)
+    tr = FusedTrainer(mt, LDPCDecoderLoss(LossType.BCE, etha=1.0), 20, graph=False)
+    for _ in range(2):
+        tr.step(xt, yt)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = tr.step(xt, yt)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        tms = torch.tensor([ms], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    lossv = float(loss.item())
+    del tr, mt, xt, yt
+    torch.cuda.empty_cache()
+    barrier()
+    return ms, lossv
 
 
 def run_reference_arm(args, rank, world):
@@ -254,6 +360,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="codewords per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stock", action="store_true", help="skip timing the stock PyTorch reference on the host CPU")
+    ap.add_argument("--total", type=int, default=0, help="strong-scaling mode: this many codewords in total, sharded over the ranks (BASELINE configs[3]: 1048576)")
+    ap.add_argument("--verify", action="store_true", help="with --total: check EVERY packed decision against the CPU port")
+    ap.add_argument("--train-batch", type=int, default=65536, help="codewords per GPU of the training-step leg (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

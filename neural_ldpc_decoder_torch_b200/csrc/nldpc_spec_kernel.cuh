@@ -183,7 +183,7 @@ struct NeuralLane {
     int grp;                 // group within the CTA (named barrier id for multi-warp groups)
     bool gl0;                // lane 0 of the group: issues the bulk loads / stores
     bool valid;
-    float zmin;              // min |v2c| written by this lane in the current VN phase (0 => the zero-safe CN phase is needed)
+    float zmin;              // smallest |CN input| this lane has seen in the current unit (0 => the unit needs the zero-safe CN phase)
     // Boosted decoder (MODE != 0)
     int xo_off;              // float offset from the xin rows to the xo rows (0: xa_origin and xa_input are the same rows)
     const float *xa_cw;      // &xa[b][0] in global memory (kXo == 2)
@@ -256,7 +256,6 @@ struct VnFirst {
     template <int J, int XROW, int... R>
     __device__ __forceinline__ void col() {
         const float v = addf(c.lane[XROW * G::Z], 0.0f);
-        c.zmin = fminf(c.zmin, fabsf(v));       // (only read by the Neural CN dispatch)
         ((c.lane[R * G::Z] = v), ...);
     }
 };
@@ -312,7 +311,6 @@ struct VnStep {
 #pragma unroll
         for (int kk = 0; kk < P; kk++) {
             const f2 s = add2(pack2(x, x), sp[kk]);
-            if constexpr (MODE == 0) c.zmin = fmin3(c.zmin, fabsf(lo(s)), fabsf(hi(s)));
             c.lane[rows[2 * kk] * G::Z] = lo(s);
             c.lane[rows[2 * kk + 1] * G::Z] = hi(s);
         }
@@ -323,14 +321,12 @@ struct VnStep {
 #pragma unroll
             for (int q = k + 2; q < D; q++) s = add2(s, pack2(m[q], m[q]));
             s = add2(pack2(x, x), s);
-            if constexpr (MODE == 0) c.zmin = fmin3(c.zmin, fabsf(lo(s)), fabsf(hi(s)));
             c.lane[rows[k] * G::Z] = lo(s);
             c.lane[rows[k + 1] * G::Z] = hi(s);
         }
 #endif
         if constexpr (D & 1) {
             const float v = addf(x, pre[D - 1]);
-            if constexpr (MODE == 0) c.zmin = fminf(c.zmin, fabsf(v));
             c.lane[rows[D - 1] * G::Z] = v;
         }
         if constexpr (kEmit) {
@@ -480,6 +476,9 @@ __device__ __forceinline__ void cn_check_core(NeuralLane<G> &c, const float *raw
         if (2 * q + 1 < D) se[q] = fmin3(fabsf(u[2 * q]), fabsf(u[2 * q + 1]), se[q + 1]);
         else se[q] = fminf(fabsf(u[2 * q]), se[q + 1]);
     }
+    // zero screen of the fast path: se[0] is the smallest |input| of the whole check, so one FMNMX per check keeps the
+    // smallest CN input of the unit; the kernel looks at it once, after the last iteration (run_unit)
+    if constexpr (!kZeroSafe) c.zmin = fminf(c.zmin, se[0]);
     unsigned x = (D & 1) ? 0x80000000u : 0u;
 #pragma unroll
     for (int k = 0; k < D; k++) x ^= __float_as_uint(u[k]);
@@ -826,17 +825,6 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
                 G::blocks(sc);
             }
         };
-        // VN -> CN hand-over: the phase barrier and, on the Neural fast path, the group's zero screen in one step
-        auto vn_done = [&]() -> bool {
-            if constexpr (MODE == 0 && !kSafe) {
-                const bool zero_seen = group_any<Shape::kLanes>(grp, c.zmin == 0.0f);
-                if constexpr (Shape::kLanes == 32) __syncwarp();
-                return !zero_seen;
-            } else {
-                phase_sync();
-                return true;
-            }
-        };
         auto cn_run = [&](auto emit_tag) {
             constexpr bool kEmitNow = decltype(emit_tag)::value;
             if constexpr (MODE == 0) {
@@ -925,7 +913,7 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
                     float *hv = a.hist_v2c + (((size_t)t * a.B + b) * G::S) * Z + z;
                     for (int q = 0; q < G::S; q++) hv[(size_t)q * Z] = c.lane[(G::kXRows + q) * Z];
                 }
-                if (!vn_done()) return false;
+                phase_sync();
                 const bool last = t == a.T - 1;
                 c.soft = (soft_cw && (soft_all || last)) ? soft_cw + (soft_all ? (size_t)t * soft_iter : 0) : nullptr;
                 c.hb = (hard_all || last) ? hb_cw : nullptr;
@@ -949,7 +937,7 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
                     VnStep<G, false, MODE, kXoMode> f{c};
                     run_vcols<G>(f);
                 }
-                if (!vn_done()) return false;
+                phase_sync();
                 if (t < a.T - 1) {
                     cn_run(std::false_type{});
                 } else {
@@ -960,6 +948,11 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
                 }
                 phase_sync();
             }
+        }
+        // Neural fast path: did any CN phase of this unit see an exact zero?  (Then what it computed from there on is not the
+        // reference's result: abandon the unit; pass 2 decodes it again with the zero-safe CN phase and rewrites its outputs.)
+        if constexpr (MODE == 0 && !kSafe) {
+            if (group_any<Shape::kLanes>(grp, c.zmin == 0.0f)) return false;
         }
         // marginal of the last iteration for the blocks of degree >= 2
         {
@@ -995,6 +988,10 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
             int k = 0;
             for (int unit = unit_first; unit < unit_end; unit += unit_stride, k++) {
                 if (!((failed >> k) & 1ull)) continue;
+                if constexpr (kStage) {
+                    if (gl == 0) tma_store_wait_all();       // the abandoned attempt's bulk stores land before they are rewritten
+                    group_sync<Shape::kLanes>(grp);
+                }
 #ifdef NLDPC_DEBUG_COUNT
                 if (gl == 0) atomicAdd(&g_dbg_restarts, 1u);
 #endif
