@@ -446,6 +446,37 @@ def main():
         barrier()
         return ms, clocks
 
+    if args.total > 0:
+        # BASELINE configs[3]: strong scaling, `--total` codewords over all ranks; its own line
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        ms, bad = strong_sharded(args.total, dev, rank, world, gid, w, b, w_np, b_np, bg, Z, barrier, max(3, args.steps), args.verify)
+        clocks = sampler.result()
+        if rank == 0:
+            peaks = {}
+            try:
+                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                    peaks = json.load(f)
+            except Exception:
+                pass
+            peak = float(peaks.get("hbm_gbs", 6650.0))
+            v = args.total / (ms * 1e-3)
+            ach = (4 * NZ + NZ // 8) * (args.total / world) / (ms * 1e-3) / 1e9
+            line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": max(3, args.steps), "warmup": 3, "ms_per_step": ms,
+                    "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "gbit_per_s": v * NZ / 1e9,
+                    "config": {"workload": "NeuralLDPCDecoder 5G NR BG2 z=16, %d codewords in contiguous shards over %d GPU(s), 10 iterations, packed "
+                                           "decisions (BASELINE configs[3])" % (args.total, world), "total_codewords": args.total,
+                               "l2_policy": "every shard (%.2f GB) is larger than the 126 MB L2" % (4 * NZ * args.total / world / 1e9)},
+                    # per pass: pack_wb_kernel + one decode launch per 64 units per group (64 x 148 CTAs x codewords per CTA; nldpc_spec.cu)
+                    "gpu_launches": max(3, args.steps) * (1 + -(-(args.total // world) // (64 * 148 * gh.cw_per_cta))), "clocks": clocks,
+                    "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None},
+                    "verified_vs_port": None if bad is None else {"codewords_checked": args.total, "codewords_with_any_wrong_bit": bad}}
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     ms_packed, clocks = timed(step_packed, args.steps, args.warmup)
     ms_list, _ = timed(step_list, max(3, args.steps // 5), 3)
     n_list = max(3, args.steps // 5)
@@ -470,6 +501,16 @@ def main():
         dist.all_reduce(ts, op=dist.ReduceOp.MAX)
         e2e_s = float(ts.item())
     barrier()
+
+    # BASELINE configs[3] (2^20 codewords sharded, strong scaling) and configs[4] (data-parallel training step) ride along on every
+    # --gpus N run so that the driver's 1/2/4/8 sweep records them; inputs are released before each leg
+    del xa_host
+    strong_ms, _ = strong_sharded(1 << 20, dev, rank, world, gid, w, b, w_np, b_np, bg, Z, barrier, 5, False)
+    train_ms = train_loss = None
+    if args.train_batch > 0:
+        del xa
+        torch.cuda.empty_cache()
+        train_ms, train_loss = train_leg(dev, rank, world, barrier, args.train_batch)
 
     if rank == 0:
         total_cw = B * world
@@ -515,11 +556,22 @@ def main():
                     "ms_per_step_median": 1e3 * float(np.median(e2e_step_s)), "ms_per_step_max": 1e3 * float(np.max(e2e_step_s)),
                     "api": "nldpc_neural_decode_host (NeuralLDPCDecoder.decode_host)"},
         }
+        line["sharded_2p20"] = {"value": (1 << 20) / (strong_ms * 1e-3), "unit": UNIT, "ms_per_pass": strong_ms, "scaling": "strong",
+                                "workload": "BASELINE configs[3]: 2^20 BG2 codewords in contiguous shards over %d GPU(s), packed decisions, "
+                                            "max over ranks (python bench.py --total 1048576 --verify checks every decision vs the port)" % world}
+        if train_ms is not None:
+            line["train_step"] = {"value": args.train_batch * world / (train_ms * 1e-3), "unit": UNIT, "ms_per_step": train_ms, "scaling": "weak",
+                                  "loss": train_loss,
+                                  "workload": "BASELINE configs[4]: BoostedNeuralLDPCDecoder BG2 z=16 QMS q=5 cn=3/vn=3, 20 iterations, %d codewords per "
+                                              "GPU per step x %d GPU(s): forward + multi-iteration BCE + backward + NCCL all-reduce of the flat weight "
+                                              "gradient + clip/Adam/clamp (FusedTrainer, eager), max over ranks" % (args.train_batch, world)}
         if world == 1:
             line["other_configs"] = other_configs(dev, B)
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample = cpu_port_throughput(bg, Z, T, w_np, b_np)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        if world == 1 and not args.no_stock:
+            line["cpu_baseline_stock"] = stock_reference_timing()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
