@@ -5,12 +5,14 @@
 //   * one thread per (codeword, lane z), gradient messages in the forward's slab layout (rotation = pointer choice),
 //   * the forward's per-iteration v2c / channel-input state / clamp mask come from the HBM dump the training-mode forward
 //     wrote (coalesced 64 B rows per codeword),
-//   * the CTA runs in lockstep over iterations so that per-edge weight gradients can be accumulated hierarchically and
-//     WITHOUT atomics in the inner loop (fp32 atomicAdd on shared memory is an ATOMS.CAST.SPIN loop on sm_100):
-//     every lane stores its per-edge term to a private slot of an L2-resident scratch row [row][thread] (one STG per
-//     edge, immediate offsets) -> after the phase each warp owns a few rows, reads them back as float4 (L2 hits),
-//     warp-reduces and adds into a per-CTA [T][rows] table in shared memory -> one global atomicAdd per (t, row) per
-//     CTA at the end of the kernel,
+//   * per-edge weight gradients are accumulated hierarchically and WITHOUT atomics in the inner loop (fp32 atomicAdd on
+//     shared memory is an ATOMS.CAST.SPIN loop on sm_100), and without leaving the SM: every lane stores its per-edge
+//     term to its own column of a small WARP-PRIVATE shared-memory buffer [16 rows][32 lanes] (one conflict-free STS per
+//     edge); when 16 rows are full the warp sums each row (lane l: row l & 15, half l >> 4: four LDS.128, 15 adds, one
+//     shuffle) and adds the 16 sums into a per-CTA [T][rows] table in shared memory (one shared atomic per 16 rows per
+//     warp) -> one global atomicAdd per (t, row) per CTA at the end of the kernel.  (Round 1 kept the rows in an
+//     "L2-resident" global scratch [row][thread]; ncu showed 3 GB of them written back to DRAM per launch.)  With the
+//     fold private to the warp nothing is shared across groups any more, so the phases synchronise per group only,
 //   * the VN-weight chain (d xa_input) is lane-private and lives in registers.
 #pragma once
 #include <algorithm>
@@ -30,6 +32,42 @@ __device__ __forceinline__ float bwd_warp_sum(float v) {
     return v;
 }
 
+// Warp-private fold of per-lane weight-gradient terms (see the header comment).  Rows are identified by their POSITION in
+// the (fixed) order in which an iteration produces them; `RowOrder` below records the row each position stands for.
+constexpr int kFoldRows = 16, kFoldStride = 36;      // 36 floats per row: LDS.128 of a quarter warp hits 32 distinct banks
+struct Folder {
+    float *col;               // &buf[warp][0][lane]
+    const float *rd;          // &buf[warp][lane & 15][(lane >> 4) * 16]
+    float *tot_t;             // &tot[t][0], indexed by position
+    int nslot, pos0;          // rows buffered / position of the first of them (warp-uniform)
+    int ln;
+    __device__ __forceinline__ void begin(float *tot_row) {
+        tot_t = tot_row;
+        nslot = 0;
+        pos0 = 0;
+    }
+    __device__ __forceinline__ void flush() {
+        if (nslot == 0) return;
+        __syncwarp();
+        const float4 *p = reinterpret_cast<const float4 *>(rd);
+        const float4 a = p[0], b = p[1], c4 = p[2], d = p[3];
+        float sum = ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
+        sum += ((c4.x + c4.y) + (c4.z + c4.w)) + ((d.x + d.y) + (d.z + d.w));
+        sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+        if (ln < nslot && sum != 0.0f) atomicAdd(tot_t + pos0 + ln, sum);
+        __syncwarp();
+        pos0 += nslot;
+        nslot = 0;
+    }
+    __device__ __forceinline__ void reserve(int n) {
+        if (nslot + n > kFoldRows) flush();
+    }
+    __device__ __forceinline__ void put(float v) {
+        col[nslot * kFoldStride] = v;
+        nslot++;
+    }
+};
+
 template <class G, int MODE>
 struct BwdLane {
     static constexpr bool kMask = MODE != 0;     // Boosted: the output clamp mask gates the upstream gradient
@@ -41,8 +79,8 @@ struct BwdLane {
     const uint8_t *mk;        // &hist_mask[t][b][0] or nullptr
     const float *xin;         // CN inputs of the degree-1 blocks: &xa[b][0] (Neural) or &hist_xin[t+1][b][0]
     int wb_base;              // constant-arena offset of {w,b}[t][0]
-    float *scr;               // &scratch[cta][0][tid]: this thread's slot of every scratch row
-    float *chn;               // &scratch[cta][E + N][tid]: VN-weight chain state of the looped degree-1 blocks (kVn), by register index
+    Folder fold;              // weight-gradient terms of this iteration -> per-CTA totals
+    float *chn;               // &scratch[cta][0][tid]: VN-weight chain state of the looped degree-1 blocks (kVn), by register index
     const float *xprev;       // &hist_xin[t][b][0] (kVn)
     const float *vw;          // w_VN[t] (kVn)
     bool last_iter;           // t == T - 1: the chain starts from zero
@@ -279,10 +317,17 @@ __device__ __forceinline__ void cn_check_bwd_core(BwdLane<G, MODE> &c, const flo
         wb[k] = c_wb[c.wb_base + eix[k]];
     }
     cn_bwd_math<MODE, D>(pv, dc, wb, c.lo, c.hi, gw, gb, du);
+    // fold order (RowOrder::chk mirrors it): the check's weight rows, then (Neural) its bias rows
+    c.fold.reserve(D);
+#pragma unroll
+    for (int k = 0; k < D; k++) c.fold.put(gw[k]);
+    if constexpr (MODE == 0) {
+        c.fold.reserve(D);
+#pragma unroll
+        for (int k = 0; k < D; k++) c.fold.put(gb[k]);
+    }
 #pragma unroll
     for (int k = 0; k < D; k++) {
-        __stcg(c.scr + eix[k] * kThreads, gw[k]);
-        if constexpr (MODE == 0) __stcg(c.scr + (G::E + eix[k]) * kThreads, gb[k]);
         if (col1[k] < 0) c.rot[shf[k]][rows[k] * Z] = du[k];          // dv2c_t, variable-lane domain
         else if constexpr (kVn) c.dxr[rows[k] < 0 ? -rows[k] - 1 : 0] = du[k];   // (register-resident: G::kDeg1Smem == 0)
     }
@@ -348,12 +393,17 @@ __device__ __forceinline__ void cn_loop_compute(BwdLane<G, MODE> &c, const float
     }
     wb[D] = c_wb[c.wb_base + eix[D]];
     cn_bwd_math<MODE, NE>(pv, dc, wb, c.lo, c.hi, gw, gb, du);
+    // fold order (RowOrder::cls mirrors it): weight rows, (Neural) bias rows, (kVn) the VN row of block J
+    c.fold.reserve(NE);
 #pragma unroll
-    for (int k = 0; k < NE; k++) {
-        __stcg(c.scr + eix[k] * kThreads, gw[k]);
-        if constexpr (MODE == 0) __stcg(c.scr + (G::E + eix[k]) * kThreads, gb[k]);
-        if (k < D) *msg[k] = du[k];
+    for (int k = 0; k < NE; k++) c.fold.put(gw[k]);
+    if constexpr (MODE == 0) {
+        c.fold.reserve(NE);
+#pragma unroll
+        for (int k = 0; k < NE; k++) c.fold.put(gb[k]);
     }
+#pragma unroll
+    for (int k = 0; k < D; k++) *msg[k] = du[k];
     if constexpr (kVn) {     // VN-weight chain step of block J (VnChainStep), inline: the block belongs to this check alone
         float dx = chain_prev + du[D];
         const float xp = stg[(D + 3) * kThreads];
@@ -361,7 +411,8 @@ __device__ __forceinline__ void cn_loop_compute(BwdLane<G, MODE> &c, const float
         if constexpr (MODE == 2) {
             if (!(fabsf(mulf(xp, w)) <= 7.5f)) dx = 0.0f;
         }
-        __stcg(c.scr + (G::E + J) * kThreads, dx * xp);
+        c.fold.reserve(1);
+        c.fold.put(dx * xp);
         __stcg(c.chn + ridx * kThreads, dx * w);
     }
 }
@@ -455,7 +506,8 @@ struct VnChainStep {
             if constexpr (MODE == 2) {
                 if (!(fabsf(mulf(xp, w)) <= 7.5f)) dx = 0.0f;
             }
-            __stcg(c.scr + (G::E + J) * kThreads, dx * xp);     // Boosted rows: [E] CN weights, then [N] VN weights
+            c.fold.reserve(1);                                   // (RowOrder::put mirrors it)
+            c.fold.put(dx * xp);                                 // Boosted rows: [E] CN weights, then [N] VN weights
             chain[J] = dx * w;
         }
     }
@@ -472,6 +524,35 @@ __device__ __forceinline__ void vn_chain_batches(BwdLane<G, MODE> &c, float *cha
     }
 }
 
+// position -> row of the fold order, built once per CTA by one thread running the same traversal as the sweep
+template <class G, int MODE, bool kVn>
+struct RowOrder {
+    uint16_t *order;
+    int base;                 // first descriptor word of this graph in c_desc
+    int n = 0;
+    template <int SLOT, class... Es>
+    __device__ __forceinline__ void ld() {}
+    template <int SLOT, class... Es>
+    __device__ __forceinline__ void chk() {
+        ((order[n++] = (uint16_t)Es::e), ...);
+        if constexpr (MODE == 0) ((order[n++] = (uint16_t)(G::E + Es::e)), ...);
+    }
+    template <int D, int FIRST, int COUNT>
+    __device__ __forceinline__ void cls() {
+        for (int i = 0; i < COUNT; i++) {
+            const int w0 = base + FIRST + i * (D + 1);
+            for (int k = 0; k <= D; k++) order[n++] = (uint16_t)(c_desc[w0 + k] >> 16);
+            if constexpr (MODE == 0)
+                for (int k = 0; k <= D; k++) order[n++] = (uint16_t)(G::E + (c_desc[w0 + k] >> 16));
+            if constexpr (kVn) order[n++] = (uint16_t)(G::E + (c_desc[w0 + D] & 0xff));
+        }
+    }
+    template <int J, int DEST>
+    __device__ __forceinline__ void put() {
+        if constexpr (kVn) order[n++] = (uint16_t)(G::E + J);
+    }
+};
+
 template <class G>
 struct SpecBwdCfg {
     using Fwd = SpecCfg<G, false>;
@@ -484,12 +565,19 @@ struct SpecBwdCfg {
     static constexpr int kThreads = kGroups * Shape::kLanes;
     static constexpr int kWarps = kThreads / 32;
     static constexpr int kCwPerCta = kGroups * Shape::kCw;
-    static_assert(kThreads % 128 == 0 && kThreads <= kSpecBwdScratchLanes, "scratch rows are read back as float4 per lane");
-    static constexpr size_t slab_bytes() { return (size_t)kCwPerCta * G::kSlab * 4; }
+    static_assert(kThreads % 32 == 0 && kThreads <= kSpecBwdScratchLanes, "workspace scratch rows hold one float per thread");
+    // the sweep keeps only the MESSAGE rows of a codeword on chip (the channel rows of the forward's slab are not needed:
+    // channel inputs come from the dump), stride == Z (mod 32) as in the forward
+    static constexpr int kSlabF = slab_floats(G::S * G::Z, 0, G::Z);
+    static constexpr size_t slab_bytes() { return (size_t)kCwPerCta * kSlabF * 4; }
     __host__ __device__ static constexpr int rows(int mode, bool vn) { return mode == 0 ? 2 * G::E : G::E + (vn ? G::N : 0); }
     static constexpr size_t stage_bytes() { return (size_t)2 * BwdStage<G>::kEnt * kThreads * 4; }
-    // message slabs + operand staging (2 stages) + per-CTA totals [T][rows]
-    static constexpr size_t smem_bytes(int T, int mode, bool vn) { return slab_bytes() + stage_bytes() + (size_t)T * rows(mode, vn) * 4 + 64; }
+    static constexpr size_t fold_bytes() { return (size_t)kWarps * kFoldRows * kFoldStride * 4; }
+    static constexpr size_t order_bytes(int mode, bool vn) { return ((size_t)rows(mode, vn) * 2 + 15) & ~(size_t)15; }
+    // message slabs + operand staging (2 stages) + fold buffers + per-CTA totals [T][rows] + position -> row table
+    static constexpr size_t smem_bytes(int T, int mode, bool vn) {
+        return slab_bytes() + stage_bytes() + fold_bytes() + (size_t)T * rows(mode, vn) * 4 + order_bytes(mode, vn) + 64;
+    }
 };
 
 template <class G, int MODE, bool kVn>
@@ -497,33 +585,47 @@ __global__ void __launch_bounds__(SpecBwdCfg<G>::kThreads, 1) nldpc_spec_backwar
     using Cfg = SpecBwdCfg<G>;
     using Shape = typename Cfg::Shape;
     constexpr int Z = G::Z, NZ = G::N * G::Z, E = G::E, N = G::N;
-    constexpr int kThreads = Cfg::kThreads, kRows = Cfg::rows(MODE, kVn), kPer = kThreads / 32;
+    constexpr int kThreads = Cfg::kThreads, kRows = Cfg::rows(MODE, kVn);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *slabs = reinterpret_cast<float *>(smem_raw);
-    float *stage = slabs + (size_t)Cfg::kCwPerCta * G::kSlab;      // [2][kEnt][kThreads]
-    float *tot = stage + 2 * BwdStage<G>::kEnt * kThreads;         // [T][kRows]
+    float *stage = slabs + (size_t)Cfg::kCwPerCta * Cfg::kSlabF;   // [2][kEnt][kThreads]
+    float *foldb = stage + 2 * BwdStage<G>::kEnt * kThreads;       // [kWarps][kFoldRows][kFoldStride]
+    float *tot = foldb + Cfg::kWarps * kFoldRows * kFoldStride;     // [T][kRows], by fold position
+    uint16_t *order = reinterpret_cast<uint16_t *>(tot + (size_t)a.T * kRows);      // [kRows] position -> row
 
     const int tid = threadIdx.x, warp = tid >> 5, ln = tid & 31;
     const int grp = tid / Shape::kLanes, gl = tid - grp * Shape::kLanes;
     const int cwl = gl / Z, z = gl - cwl * Z;
     const int cw_in_cta = grp * Shape::kCw + cwl;
-    float *slab = slabs + (size_t)cw_in_cta * G::kSlab;
-    // per CTA: kRows partial-sum rows, then (kVn) the chain state of the looped degree-1 blocks
-    constexpr int kScrRows = kRows + ((kVn && G::kLoopChecks > 0) ? G::kXRegs : 0);
-    static_assert(kScrRows <= 2 * G::E + G::N, "workspace scratch is sized for 2E + N rows per CTA");
-    float *scr_cta = a.scratch + (size_t)blockIdx.x * kScrRows * kThreads;
+    // row indices of the graph program count the forward's channel rows too: point kXRows rows before this codeword's messages
+    float *slab = slabs + (size_t)cw_in_cta * Cfg::kSlabF - G::kXRows * Z;
+    // per CTA: the chain state of the looped degree-1 blocks (kVn), one row per register index
+    float *scr_cta = a.scratch + (size_t)blockIdx.x * (G::kXRegs > 0 ? G::kXRegs : 1) * kThreads;
 
     BwdLane<G, MODE> c;
     c.lane = slab + z;
     c.z = z;
     c.lo = a.lo;
     c.hi = a.hi;
-    c.scr = scr_cta + tid;
-    c.chn = scr_cta + (size_t)kRows * kThreads + tid;
+    c.chn = scr_cta + tid;
+    c.fold.col = foldb + (size_t)warp * kFoldRows * kFoldStride + ln;
+    c.fold.rd = foldb + (size_t)warp * kFoldRows * kFoldStride + (ln & 15) * kFoldStride + (ln >> 4) * 16;
+    c.fold.ln = ln;
 #pragma unroll
     for (int s = 0; s < Z; s++) c.rot[s] = slab + ((z + s) % Z);
 
     for (int i = tid; i < a.T * kRows; i += kThreads) tot[i] = 0.0f;
+    if (tid == 0) {
+        RowOrder<G, MODE, kVn> ro{order, desc_base};
+        G::checks_pipelined_rest(ro);
+        if constexpr (G::kLoopChecks > 0) G::loop_classes(ro);
+        if constexpr (kVn) G::blocks_rest(ro);
+    }
+    __syncthreads();
+
+    // phases synchronise per group (one codeword group = the lanes that share slabs); nothing else is shared between warps
+    // inside the sweep (fold buffers, staging slots and chain-state rows are private, the totals take atomics)
+    auto phase_sync = [&]() { group_sync<Shape::kLanes>(grp); };
 
     const int n_tiles = (a.B + Cfg::kCwPerCta - 1) / Cfg::kCwPerCta;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -536,7 +638,7 @@ __global__ void __launch_bounds__(SpecBwdCfg<G>::kThreads, 1) nldpc_spec_backwar
 #pragma unroll
             for (int j = 0; j < N; j++) chain[j] = 0.0f;
         }
-        __syncthreads();
+        phase_sync();
         for (int t = a.T - 1; t >= 0; t--) {
             c.hv = a.hist_v2c + (((size_t)t * a.B + bb) * G::S) * Z;
             c.gt = a.gout + ((size_t)t * a.B + bb) * NZ;
@@ -544,6 +646,7 @@ __global__ void __launch_bounds__(SpecBwdCfg<G>::kThreads, 1) nldpc_spec_backwar
             c.xin = (MODE == 0) ? a.xa + bb * NZ : a.hist_xin + ((size_t)(t + 1) * a.B + bb) * NZ;
             c.wb_base = wb_off + t * E;
             c.last_iter = (t == a.T - 1);
+            c.fold.begin(tot + (size_t)t * kRows);
             if constexpr (kVn) {
                 c.xprev = a.hist_xin + ((size_t)t * a.B + bb) * NZ;
                 c.vw = a.vn_w + (size_t)t * N;
@@ -555,50 +658,30 @@ __global__ void __launch_bounds__(SpecBwdCfg<G>::kThreads, 1) nldpc_spec_backwar
                 VnBwd<G, MODE> f{c, g};
                 G::vcols(f);
             }
-            __syncthreads();     // (also: the previous iteration's scratch rows have been folded by every warp)
+            phase_sync();
             {
                 CnBwd<G, MODE, kVn, kThreads> f{c, stage + tid};
                 G::checks_pipelined_rest(f);
                 if constexpr (G::kLoopChecks > 0) {
+                    c.fold.flush();      // the loops carry the fold counters in registers: enter them from a known state
                     CnBwdLoops<G, MODE, kVn, kThreads> l{c, stage + tid, desc_base};
                     G::loop_classes(l);
                 }
             }
-            __syncthreads();
+            phase_sync();
             if constexpr (kVn) {
                 VnChainSum<G, MODE> s{c, dxb};
                 G::vcols(s);
                 vn_chain_batches<G, MODE, kThreads, 0>(c, chain, dxb, a.hist_xin + ((size_t)t * a.B + bb) * NZ, a.vn_w + (size_t)t * N);
-                __syncthreads();
             }
-            // fold this iteration's scratch rows (written by this CTA only, read back through L2) into the per-CTA totals;
-            // row r always belongs to warp r % kWarps, lane 0 -> plain read-modify-write
-            constexpr int kFoldBatch = 4;       // rows in flight per warp (the read-back is an L2 round trip)
-            for (int r0 = warp; r0 < kRows; r0 += Cfg::kWarps * kFoldBatch) {
-                float4 v[kFoldBatch][kPer / 4];
-#pragma unroll
-                for (int j = 0; j < kFoldBatch; j++) {
-                    const int r = r0 + j * Cfg::kWarps;
-                    const float4 *p = reinterpret_cast<const float4 *>(scr_cta + (size_t)(r < kRows ? r : r0) * kThreads + ln * kPer);
-#pragma unroll
-                    for (int q = 0; q < kPer / 4; q++) v[j][q] = __ldcg(p + q);
-                }
-#pragma unroll
-                for (int j = 0; j < kFoldBatch; j++) {
-                    const int r = r0 + j * Cfg::kWarps;
-                    float sum = 0.0f;
-#pragma unroll
-                    for (int q = 0; q < kPer / 4; q++) sum += (v[j][q].x + v[j][q].y) + (v[j][q].z + v[j][q].w);
-                    sum = bwd_warp_sum(sum);
-                    if (ln == 0 && r < kRows) tot[(size_t)t * kRows + r] += sum;
-                }
-            }
+            c.fold.flush();
         }
+        phase_sync();
     }
     __syncthreads();
     // one global atomic per (t, row) per CTA
     for (int i = tid; i < a.T * kRows; i += kThreads) {
-        const int t = i / kRows, r = i - t * kRows;
+        const int t = i / kRows, r = order[i - t * kRows];
         const float v = tot[i];
         if (v == 0.0f) continue;
         if (r < E) atomicAdd(a.gw + (size_t)t * E + r, v);

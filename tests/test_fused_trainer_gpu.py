@@ -192,8 +192,11 @@ def test_fused_trainer_frozen_params_lr_schedule_and_state_dict():
     tr2.load_state_dict(sd)
     tr.step(x, y)
     tr2.step(x, y)
+    # (not bit-for-bit: the backward sweep's warps add their partial sums into the per-CTA totals with shared-memory atomics,
+    # so the fp32 summation order of a gradient varies from run to run; Adam's normalisation amplifies last-bit differences
+    # of near-zero components exactly as between the torch-op loop and the fused step above)
     for a, b in zip(m_new.parameters(), m_res.parameters()):
-        assert torch.equal(a.detach(), b.detach())
+        assert float((a.detach() - b.detach()).abs().max()) < 5e-4
     assert tr2.steps_done == tr.steps_done == 4
 
     # (2) a captured step follows set_lr
