@@ -149,6 +149,31 @@ int nldpc_boosted_backward(const nldpc_graph_t *g, const nldpc_boosted_cfg_t *cf
                            int B, int T, float *gvn_dev, float *gcn_dev, float *gucn_dev, void *workspace_dev,
                            size_t workspace_bytes, int have_dump, void *stream);
 
+/* Which training-dump format nldpc_boosted_forward writes for this configuration: 1 = check-packed records (specialised
+ * kernels), 0 = slot-major rows (table-driven kernels).  A caller that keeps the dump for nldpc_boosted_backward passes
+ * have_dump = 1 + this value (of the FORWARD call's cfg, state pointers included). */
+int nldpc_boosted_dump_format(const nldpc_graph_t *g, const nldpc_boosted_cfg_t *cfg, int T, int has_cn_w, int has_vn_w);
+
+/* ---- fused training step (replaces the loop body of train/train_BoostedNeuralLDPCDecoder.py:278-290: model(x) ->
+ * LDPCDecoderLoss(BCE)(outputs, y) -> loss.backward()) for the configurations the specialised kernels cover (built-in codes,
+ * MS / QMS q=5, CN weights [+ VN weights], no UCN, zero initial state).  Everything else: NLDPC_E_UNSUPPORTED, use the
+ * unfused entry points above.
+ *   forward : ONE launch runs the T iterations, evaluates L = sum_t coef[t] * mean_i bce_with_logits(out_t[i], y[i])
+ *             (LDPCDecoderLoss.py:73-108) and writes dL/dout (clamp mask folded in, scaled by gscale) plus the check-packed
+ *             dump into the workspace; *loss_sum_dev receives sum_t coef[t] * sum_i bce (divide by B*N*Z for L).
+ *   backward: the sweep over the workspace; gvn [T][N] (iff vn_w), gcn [T][E] are overwritten.
+ *   ybits   : labels as bits, [B][ceil(N*Z/8)], bit i of a codeword = (y[i] != 0), LSB first (nldpc_pack_labels). */
+size_t nldpc_boosted_train_workspace_bytes(const nldpc_graph_t *g, const nldpc_boosted_cfg_t *cfg, int B, int T, int has_cn_w,
+                                           int has_vn_w); /* 0 = configuration not covered */
+int nldpc_boosted_train_forward(const nldpc_graph_t *g, const nldpc_boosted_cfg_t *cfg, const float *xa_dev,
+                                const float *vn_w_dev, const float *cn_w_dev, int B, int T, const uint8_t *ybits_dev,
+                                const float *coef_dev, float gscale, double *loss_sum_dev, void *workspace_dev,
+                                size_t workspace_bytes, void *stream);
+int nldpc_boosted_train_backward(const nldpc_graph_t *g, const nldpc_boosted_cfg_t *cfg, const float *xa_dev,
+                                 const float *vn_w_dev, const float *cn_w_dev, int B, int T, float *gvn_dev, float *gcn_dev,
+                                 void *workspace_dev, size_t workspace_bytes, void *stream);
+int nldpc_pack_labels(const float *y_dev, size_t n_codewords, int NZ, uint8_t *bits_dev, void *stream);
+
 /* Fused multi-iteration BCE-with-logits loss and gradient: replaces the loop of LDPCDecoderLoss.forward
  * (LDPCDecoderLoss.py:73-108, BCE branch) over the T iteration outputs.
  *   soft_dev [T][n] logits (n = B*N*Z), y_dev [n] labels, coef_dev [T] = etha^{c_t} / sum_t etha^{c_t}

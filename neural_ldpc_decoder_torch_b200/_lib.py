@@ -74,6 +74,17 @@ def lib():
                                                  ctypes.c_size_t, ci, vp]
             L.nldpc_boosted_forward.restype = ci
             L.nldpc_boosted_forward.argtypes = [vp, ctypes.POINTER(BoostedCfg), vp, vp, vp, vp, ci, ci, ci, vp, ci, vp, vp, vp]
+            L.nldpc_boosted_dump_format.restype = ci
+            L.nldpc_boosted_dump_format.argtypes = [vp, ctypes.POINTER(BoostedCfg), ci, ci, ci]
+            L.nldpc_boosted_train_workspace_bytes.restype = ctypes.c_size_t
+            L.nldpc_boosted_train_workspace_bytes.argtypes = [vp, ctypes.POINTER(BoostedCfg), ci, ci, ci, ci]
+            L.nldpc_boosted_train_forward.restype = ci
+            L.nldpc_boosted_train_forward.argtypes = [vp, ctypes.POINTER(BoostedCfg), vp, vp, vp, ci, ci, vp, vp, ctypes.c_float, vp, vp,
+                                                      ctypes.c_size_t, vp]
+            L.nldpc_boosted_train_backward.restype = ci
+            L.nldpc_boosted_train_backward.argtypes = [vp, ctypes.POINTER(BoostedCfg), vp, vp, vp, ci, ci, vp, vp, vp, ctypes.c_size_t, vp]
+            L.nldpc_pack_labels.restype = ci
+            L.nldpc_pack_labels.argtypes = [vp, ctypes.c_size_t, ci, vp, vp]
             L.nldpc_multi_iter_bce.restype = ci
             L.nldpc_multi_iter_bce.argtypes = [vp, vp, vp, ci, ctypes.c_size_t, vp, vp, vp]
             L.nldpc_multi_iter_bce_grad.restype = ci

@@ -380,6 +380,33 @@ class BoostedNeuralLDPCDecoder(nn.Module):
         return self.outputs
 
 
+def _fused_bce_loss(self, xa, y, etha=1.0, coeff_param=None):
+    """`LDPCDecoderLoss(LossType.BCE, etha)(self(xa), y, coeff_param)` (train/train_BoostedNeuralLDPCDecoder.py:278-289) as ONE
+    forward launch — the T iterations, the loss and dL/dout without any [T, B, N*Z] tensor crossing HBM twice — whose backward
+    is the sweep kernel (ops.boosted_train_loss).  Differentiable w.r.t. the parameters like the two-call form.  Returns None
+    when the configuration is not covered (other codes, SP, UCN weights, no CN weights, sharing type 4 / 5, list inputs); the
+    caller then uses the two-call form.  Unlike forward() it does not refresh self.outputs / self.llr; labels must be 0 / 1."""
+    if not isinstance(xa, torch.Tensor) or not xa.is_cuda or tuple(xa.shape) != (self.batch_size, self.N, self.Z):
+        return None
+    cfg = self.node_weight_sharing_config
+    cn, ucn, vn = cfg.get(NodeType.CN), cfg.get(NodeType.UCN), cfg.get(NodeType.VN)
+    if self.decoding_type not in (DecoderType.MS, DecoderType.QMS) or ucn != 0 or cn not in (1, 2, 3) or vn not in (0, 1, 2, 3, 5):
+        return None
+    T, device = int(self.iter_node_counts), xa.device
+    dec = 1 if self.decoding_type == DecoderType.MS else 2
+    gid = self.conn_mat.graph_id(device)
+    lo, hi = float(self.allowed_llr_range.start), float(self.allowed_llr_range.end)
+    if not ops.boosted_train_covered(gid, dec, int(self.decoder_qms_qbit), lo, hi, T, True, vn in (2, 3)):
+        return None
+    vn_w, cn_w, _, _, _ = self.fold_weights(list(range(T)), device)
+    coef = ops.iteration_coefs(T, etha, coeff_param, device)
+    return 1.0 * ops.boosted_train_loss(xa, vn_w, cn_w, ops.pack_labels(y.to(torch.float32)), coef, gid, T, dec,
+                                        int(self.decoder_qms_qbit), lo, hi)
+
+
+BoostedNeuralLDPCDecoder.fused_bce_loss = _fused_bce_loss
+
+
 def _folded_live(self, T, device):
     """fold_weights(range(T)) on `device` for the decode-only paths, read LIVE from the parameters: the parameters are slices
     of one flat vector (_flatparams), so every folded row set is ONE gather through an index map (<= 3 launches instead of ~2 T

@@ -74,7 +74,11 @@ static WsLayout ws_layout(const nldpc_graph *g, int B, int T, int boosted) {
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     WsLayout l{};
     size_t off = 0;
-    l.v2c = off; off = up(off + (size_t)T * B * g->S * g->Z * 4);
+    // the CN inputs of every iteration: slot-major rows [S][Z] fp32 (table-driven kernels) or check-packed records (specialised
+    // kernels: E fp32 values per lane, degree-1 edges included, or padded fp16 records for QMS q=5) — sized for the larger one
+    size_t per_cw = (size_t)g->S * g->Z * 4;
+    if (g->spec_id >= 0) per_cw = std::max(per_cw, std::max(spec_dump_bytes_per_cw_iter(g->spec_id, 0), spec_dump_bytes_per_cw_iter(g->spec_id, 2)));
+    l.v2c = off; off = up(off + (size_t)T * B * per_cw);
     if (boosted) {
         l.xin = off; off = up(off + (size_t)(T + 1) * B * g->N * g->Z * 4);
         l.mask = off; off = up(off + (size_t)T * B * g->N * g->Z);
@@ -88,6 +92,27 @@ static WsLayout ws_layout(const nldpc_graph *g, int B, int T, int boosted) {
     return l;
 }
 static int boosted_dispatch(const nldpc_graph *g, const DecodeArgs &a, cudaStream_t st);
+static bool force_generic();
+
+// Which training-dump format a forward call with these arguments writes (and the backward sweep must be given):
+// 1 = check-packed records, written by the specialised forward for the specialised sweep; 0 = slot-major rows (table-driven
+// kernels).  Forward and backward decide with the same predicate; callers that keep a dump between the two calls pass the
+// format along (have_dump = 1 + format).
+static int neural_dump_fmt(const nldpc_graph *g, int T) {
+    return (g->spec_id >= 0 && !force_generic() && spec_backward_covers(g->spec_id, 0, T, true, false, false, 0)) ? 1 : 0;
+}
+static int boosted_dump_fmt(const nldpc_graph *g, const nldpc_boosted_cfg_t *cfg, int T, bool has_cn_w, bool has_vn_w) {
+    if (g->spec_id < 0 || force_generic()) return 0;
+    const bool qms5 = cfg->decoder_type == NLDPC_DEC_QMS && cfg->qbit == 5, ms = cfg->decoder_type == NLDPC_DEC_MS;
+    // what the specialised FORWARD takes (boosted_launch in nldpc_spec_boosted.cuh) ...
+    if (!(qms5 || ms) || cfg->compute_ucn || cfg->llr_init_dev || cfg->xin_init_dev || cfg->xin_out_dev || cfg->app_init_dev) return 0;
+    // ... and the specialised sweep
+    return spec_backward_covers(g->spec_id, qms5 ? 2 : 1, T, has_cn_w, has_vn_w, cfg->ucn_mix != 0, cfg->qbit) ? 1 : 0;
+}
+extern "C" int nldpc_boosted_dump_format(const nldpc_graph_t *g, const nldpc_boosted_cfg_t *cfg, int T, int has_cn_w, int has_vn_w) {
+    if (!g || !cfg || T <= 0) return 0;
+    return boosted_dump_fmt(g, cfg, T, has_cn_w != 0, has_vn_w != 0);
+}
 
 extern "C" const char *nldpc_last_error(void) { return g_err.c_str(); }
 extern "C" int nldpc_abi_version(void) { return NLDPC_ABI_VERSION; }
@@ -390,11 +415,12 @@ extern "C" int nldpc_neural_backward(const nldpc_graph_t *g, const float *xa_dev
     DecodeArgs a{};
     a.xa = xa_dev; a.w = w_dev; a.b = b_dev; a.B = B; a.T = T; a.wb_off = -1;
     a.hist_v2c = reinterpret_cast<float *>((char *)workspace_dev + l.v2c);
+    a.hist_fmt = neural_dump_fmt(g, T);
     if (!have_dump)
         if (int rc = neural_dispatch(g, a, st)) return rc;
     // (B) backward sweep
     BwdArgs ba{};
-    ba.xa = xa_dev; ba.w = w_dev; ba.b = b_dev; ba.gout = gout_dev; ba.hist_v2c = a.hist_v2c;
+    ba.xa = xa_dev; ba.w = w_dev; ba.b = b_dev; ba.gout = gout_dev; ba.hist_v2c = a.hist_v2c; ba.hist_fmt = a.hist_fmt;
     ba.gw = gw_dev; ba.gb = gb_dev; ba.B = B; ba.T = T; ba.mode = 0;
     if (g->spec_id >= 0 && !force_generic()) {
         ba.scratch = reinterpret_cast<float *>((char *)workspace_dev + l.scratch);
@@ -420,6 +446,7 @@ extern "C" int nldpc_neural_forward_train(const nldpc_graph_t *g, const float *x
     DecodeArgs a{};
     a.xa = xa_dev; a.w = w_dev; a.b = b_dev; a.B = B; a.T = T; a.soft_mode = NLDPC_OUT_ALL; a.soft = soft_dev;
     a.hist_v2c = reinterpret_cast<float *>((char *)workspace_dev + l.v2c);
+    a.hist_fmt = neural_dump_fmt(g, T);
     return neural_dispatch(g, a, (cudaStream_t)stream);
 }
 
@@ -451,10 +478,14 @@ extern "C" int nldpc_boosted_backward(const nldpc_graph_t *g, const nldpc_booste
     a.llr_lo = cfg->llr_lo; a.llr_hi = cfg->llr_hi;
     a.hist_v2c = reinterpret_cast<float *>(ws + l.v2c); a.hist_xin = reinterpret_cast<float *>(ws + l.xin);
     a.hist_mask = reinterpret_cast<uint8_t *>(ws + l.mask); a.hist_ucn = reinterpret_cast<uint8_t *>(ws + l.ucn);
+    // have_dump: 0 = none (the forward is re-run here), 1 = slot-major dump, 2 = check-packed dump (1 + nldpc_boosted_dump_format
+    // of the forward call that wrote it)
+    a.hist_fmt = have_dump ? (have_dump == 2 ? 1 : 0) : boosted_dump_fmt(g, cfg, T, cn_w_dev != nullptr, vn_w_dev != nullptr);
     int rc = 0;
     if (!have_dump)
         if ((rc = boosted_dispatch(g, a, st))) return rc;
     BwdArgs ba{};
+    ba.hist_fmt = a.hist_fmt;
     ba.xa = xa_dev; ba.w = cn_w_dev; ba.b = cfg->ucn_mix ? ucn_w_dev : nullptr; ba.vn_w = vn_w_dev; ba.gout = gout_dev;
     ba.hist_v2c = a.hist_v2c; ba.hist_xin = a.hist_xin; ba.hist_mask = a.hist_mask; ba.hist_ucn = cfg->ucn_mix ? a.hist_ucn : nullptr;
     ba.gw = gcn_dev; ba.gb = cfg->ucn_mix ? gucn_dev : nullptr; ba.gvn = vn_w_dev ? gvn_dev : nullptr;
@@ -500,8 +531,105 @@ extern "C" int nldpc_boosted_forward(const nldpc_graph_t *g, const nldpc_boosted
         char *ws = (char *)cfg->train_dump_dev;
         a.hist_v2c = reinterpret_cast<float *>(ws + l.v2c); a.hist_xin = reinterpret_cast<float *>(ws + l.xin);
         a.hist_mask = reinterpret_cast<uint8_t *>(ws + l.mask); a.hist_ucn = reinterpret_cast<uint8_t *>(ws + l.ucn);
+        a.hist_fmt = boosted_dump_fmt(g, cfg, T, cn_w_dev != nullptr, vn_w_dev != nullptr);
     }
     return boosted_dispatch(g, a, (cudaStream_t)stream);
+}
+
+// ---- fused training step pieces (training.FusedTrainer) ---------------------------------------------------------------
+// forward + multi-iteration BCE + dL/dout in ONE launch (no [T][B][N*Z] output, loss or mask tensor crosses HBM twice), the
+// sweep reads the workspace.  Covered: what the specialised kernels cover (built-in codes, MS / QMS q=5, CN weights, no UCN,
+// zero initial state); everything else returns NLDPC_E_UNSUPPORTED and the caller keeps the unfused path.
+struct TrainLayout { size_t dump, xin, gout, scratch, loss, total; };
+static TrainLayout train_layout(const nldpc_graph *g, int mode, int B, int T, bool has_vn_w) {
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    TrainLayout l{};
+    size_t off = 0;
+    l.dump = off; off = up(off + (size_t)T * B * spec_dump_bytes_per_cw_iter(g->spec_id, mode));
+    l.xin = off; if (has_vn_w) off = up(off + (size_t)T * B * g->N * g->Z * 4);       // rows 1..T-1 are used
+    l.gout = off; off = up(off + (size_t)T * B * g->N * g->Z * 4);
+    l.scratch = off; off = up(off + (size_t)g->sm_count * spec_backward_scratch_rows(g->spec_id) * kSpecBwdScratchLanes * 4);
+    l.loss = off; off = up(off + 8);
+    l.total = off;
+    return l;
+}
+static int train_mode(const nldpc_graph *g, const nldpc_boosted_cfg_t *cfg, int T, bool has_cn_w, bool has_vn_w) {
+    if (!boosted_dump_fmt(g, cfg, T, has_cn_w, has_vn_w)) return 0;
+    return cfg->decoder_type == NLDPC_DEC_QMS ? 2 : 1;
+}
+
+extern "C" size_t nldpc_boosted_train_workspace_bytes(const nldpc_graph_t *g, const nldpc_boosted_cfg_t *cfg, int B, int T,
+                                                      int has_cn_w, int has_vn_w) {
+    if (!g || !cfg || B <= 0 || T <= 0) return 0;
+    const int mode = train_mode(g, cfg, T, has_cn_w != 0, has_vn_w != 0);
+    return mode ? train_layout(g, mode, B, T, has_vn_w != 0).total : 0;
+}
+
+extern "C" int nldpc_boosted_train_forward(const nldpc_graph_t *g, const nldpc_boosted_cfg_t *cfg, const float *xa_dev,
+                                           const float *vn_w_dev, const float *cn_w_dev, int B, int T, const uint8_t *ybits_dev,
+                                           const float *coef_dev, float gscale, double *loss_sum_dev, void *workspace_dev,
+                                           size_t workspace_bytes, void *stream) {
+    if (!g || !cfg || B <= 0 || T <= 0 || !xa_dev || !ybits_dev || !coef_dev || !loss_sum_dev)
+        return fail(NLDPC_E_INVALID, "nldpc_boosted_train_forward: bad argument");
+    const int mode = train_mode(g, cfg, T, cn_w_dev != nullptr, vn_w_dev != nullptr);
+    if (!mode) return fail(NLDPC_E_UNSUPPORTED, "nldpc_boosted_train_forward: configuration not covered by the fused training kernels");
+    if (!(cfg->llr_lo <= cfg->llr_hi)) return fail(NLDPC_E_INVALID, "nldpc_boosted_train_forward: bad llr range");
+    const TrainLayout l = train_layout(g, mode, B, T, vn_w_dev != nullptr);
+    if (!workspace_dev || workspace_bytes < l.total)
+        return fail(NLDPC_E_INVALID, "nldpc_boosted_train_forward: workspace too small (see nldpc_boosted_train_workspace_bytes)");
+    ON_DEVICE(g->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)workspace_dev;
+    CUDA_TRY(cudaMemsetAsync(loss_sum_dev, 0, sizeof(double), st));
+    DecodeArgs a{};
+    a.xa = xa_dev; a.w = cn_w_dev; a.vn_w = vn_w_dev; a.B = B; a.T = T; a.wb_off = -1;
+    a.soft_mode = NLDPC_OUT_ALL; a.soft = reinterpret_cast<float *>(ws + l.gout);
+    a.decoder_type = cfg->decoder_type; a.qbit = cfg->qbit; a.llr_lo = cfg->llr_lo; a.llr_hi = cfg->llr_hi;
+    a.hist_v2c = reinterpret_cast<float *>(ws + l.dump); a.hist_xin = reinterpret_cast<float *>(ws + l.xin); a.hist_fmt = 1;
+    a.ybits = ybits_dev; a.coef = coef_dev; a.ginv = (float)((double)gscale / ((double)B * g->N * g->Z)); a.loss_acc = loss_sum_dev;
+    const int src = spec_launch_boosted(g->spec_id, a, g->sm_count, st);
+    if (src > 0) return fail(src, std::string("nldpc_boosted_train_forward: ") + cudaGetErrorString((cudaError_t)src));
+    if (src < 0) return fail(NLDPC_E_UNSUPPORTED, "nldpc_boosted_train_forward: the specialised forward declined the launch (constant arena full)");
+    return NLDPC_OK;
+}
+
+extern "C" int nldpc_boosted_train_backward(const nldpc_graph_t *g, const nldpc_boosted_cfg_t *cfg, const float *xa_dev,
+                                            const float *vn_w_dev, const float *cn_w_dev, int B, int T, float *gvn_dev,
+                                            float *gcn_dev, void *workspace_dev, size_t workspace_bytes, void *stream) {
+    if (!g || !cfg || B <= 0 || T <= 0 || !xa_dev || !gcn_dev || (vn_w_dev && !gvn_dev))
+        return fail(NLDPC_E_INVALID, "nldpc_boosted_train_backward: bad argument");
+    const int mode = train_mode(g, cfg, T, cn_w_dev != nullptr, vn_w_dev != nullptr);
+    if (!mode) return fail(NLDPC_E_UNSUPPORTED, "nldpc_boosted_train_backward: configuration not covered by the fused training kernels");
+    const TrainLayout l = train_layout(g, mode, B, T, vn_w_dev != nullptr);
+    if (!workspace_dev || workspace_bytes < l.total)
+        return fail(NLDPC_E_INVALID, "nldpc_boosted_train_backward: workspace too small (see nldpc_boosted_train_workspace_bytes)");
+    ON_DEVICE(g->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)workspace_dev;
+    if (gvn_dev) CUDA_TRY(cudaMemsetAsync(gvn_dev, 0, (size_t)T * g->N * 4, st));
+    CUDA_TRY(cudaMemsetAsync(gcn_dev, 0, (size_t)T * g->E * 4, st));
+    BwdArgs ba{};
+    ba.xa = xa_dev; ba.w = cn_w_dev; ba.vn_w = vn_w_dev; ba.gout = reinterpret_cast<const float *>(ws + l.gout);
+    ba.hist_fmt = 1; ba.hist_v2c = reinterpret_cast<const float *>(ws + l.dump); ba.hist_xin = reinterpret_cast<const float *>(ws + l.xin);
+    ba.hist_mask = nullptr;      // the forward folded the clamp mask into gout
+    ba.gw = gcn_dev; ba.gvn = vn_w_dev ? gvn_dev : nullptr;
+    ba.B = B; ba.T = T; ba.mode = mode; ba.qbit = cfg->qbit; ba.lo = cfg->llr_lo; ba.hi = cfg->llr_hi;
+    ba.scratch = reinterpret_cast<float *>(ws + l.scratch);
+    const int src = spec_launch_backward(g->spec_id, ba, g->sm_count, st);
+    if (src > 0) return fail(src, std::string("nldpc_boosted_train_backward: ") + cudaGetErrorString((cudaError_t)src));
+    if (src < 0) return fail(NLDPC_E_UNSUPPORTED, "nldpc_boosted_train_backward: the specialised sweep declined the launch");
+    return NLDPC_OK;
+}
+
+namespace nldpc {
+int launch_pack_labels(const float *y, size_t n_cw, int NZ, uint8_t *bits, cudaStream_t st);
+}
+extern "C" int nldpc_pack_labels(const float *y_dev, size_t n_codewords, int NZ, uint8_t *bits_dev, void *stream) {
+    if (NZ <= 0 || ((!y_dev || !bits_dev) && n_codewords > 0)) return fail(NLDPC_E_INVALID, "nldpc_pack_labels: bad argument");
+    if (n_codewords == 0) return NLDPC_OK;
+    const int rc = launch_pack_labels(y_dev, n_codewords, NZ, bits_dev, (cudaStream_t)stream);
+    if (rc != 0) return fail(rc, std::string("nldpc_pack_labels: ") + cudaGetErrorString((cudaError_t)rc));
+    return NLDPC_OK;
 }
 
 static int boosted_dispatch(const nldpc_graph *g, const DecodeArgs &a, cudaStream_t st) {
@@ -511,6 +639,8 @@ static int boosted_dispatch(const nldpc_graph *g, const DecodeArgs &a, cudaStrea
         if (src == 0) return NLDPC_OK;
         // src < 0: configuration not covered by the specialised kernels (SP, other q-bit grids, UCN, stateful runs)
     }
+    if (a.hist_v2c && a.hist_fmt == 1)      // (only when the constant arena cannot take the weights: T * E > 7680)
+        return fail(NLDPC_E_UNSUPPORTED, "nldpc_boosted_forward: the specialised forward declined a launch whose training dump the specialised sweep expects");
     const int rc = generic_launch_boosted(g->dev, a, g->sm_count, st);
     if (rc == -2) return fail(NLDPC_E_UNSUPPORTED, "nldpc_boosted_forward: one codeword's boosted state does not fit in shared memory");
     if (rc != 0) return fail(rc, std::string("nldpc_boosted_forward: ") + cudaGetErrorString((cudaError_t)rc));

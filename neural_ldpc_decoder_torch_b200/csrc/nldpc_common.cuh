@@ -55,6 +55,16 @@ struct DecodeArgs {
     float *hist_xin;         // [T+1][B][N][Z] (Boosted)
     uint8_t *hist_mask;      // [T][B][N*Z]   (Boosted)
     uint8_t *hist_ucn;       // [T][B][M][Z]  (Boosted, UCN)
+    // hist_fmt 1 (specialised kernels only; nldpc_spec_backward.cuh reads it): hist_v2c holds the CN inputs of every check
+    // as check-packed per-lane records [T][B][record][Z][P] (fp16 for QMS q=5, fp32 otherwise; degree-1 edges included),
+    // hist_xin only rows 1..T-1 and only with VN weights, hist_mask may be nullptr
+    int hist_fmt;
+    // fused multi-iteration BCE (training forward, Boosted): with `ybits` set the kernel writes dL/dout instead of out to `soft`
+    // (clamp mask folded in) and accumulates sum_t c_t * sum_i bce(out_t[i], y[i]) into *loss_acc
+    const uint8_t *ybits;    // [B][ceil(N*Z/8)] label bits, bit i of a codeword = y[i] != 0 (same packing as `hard`)
+    const float *coef;       // [T] c_t
+    float ginv;              // upstream dL / (B*N*Z)
+    double *loss_acc;
 };
 
 // host-side launch helpers of the table-driven kernel (nldpc_generic.cu)
@@ -67,13 +77,14 @@ struct BwdArgs {
     const float *w, *b;     // Neural: w/b [T][E];  Boosted: cn_w / ucn_w [T][E] or nullptr
     const float *vn_w;      // Boosted: [T][N] or nullptr
     const float *gout;      // [T][B][N*Z]
+    int hist_fmt;           // 0: slot-major fp32 dump (below), 1: check-packed dump (see DecodeArgs::hist_fmt)
     const float *hist_v2c;  // [T][B][S][Z]   v2c of the stored edges entering the CN phase of iteration t
     const float *hist_xin;  // [T+1][B][N][Z] channel-input state: [0] = before iteration 0, [t+1] = after iteration t's update (Boosted)
-    const uint8_t *hist_mask;   // [T][B][N*Z] 1 where the output clamp passed the gradient (Boosted)
+    const uint8_t *hist_mask;   // [T][B][N*Z] 1 where the output clamp passed the gradient (Boosted); nullptr: already folded into gout
     const uint8_t *hist_ucn;    // [T][B][M][Z] unsatisfied-check indicator (Boosted, ucn_mix) or nullptr
     float *gw, *gb;         // [T][E] (+=)   Neural: weights/biases;  Boosted: cn_w / ucn_w rows
     float *gvn;             // [T][N] (+=)   Boosted VN weights or nullptr
-    float *scratch;         // specialised kernel: [grid][rows][threads] per-iteration partial sums (L2-resident) or nullptr
+    float *scratch;         // specialised kernel: [grid][kXRegs][threads] VN-weight chain state of the looped blocks, or nullptr
     int B, T;
     int mode;               // 0 Neural, 1 Boosted MS, 2 Boosted QMS
     int qbit;

@@ -78,4 +78,28 @@ int launch_multi_iter_bce(const float *soft, const float *y, const float *coef, 
     return (int)cudaGetLastError();
 }
 
+// labels y [n_cw][NZ] fp32 -> bits [n_cw][ceil(NZ/8)], bit i of a codeword = (y[i] != 0), LSB first: the packing of the decode
+// kernels' hard decisions, which is also how the fused training forward (DecodeArgs::ybits) reads its labels
+__global__ void __launch_bounds__(256) pack_labels_kernel(const float *__restrict__ y, size_t n_cw, int NZ, int hb, uint8_t *__restrict__ bits) {
+    const size_t total = n_cw * (size_t)hb;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t cw = i / hb;
+        const int byte = (int)(i - cw * hb);
+        const float *src = y + cw * (size_t)NZ + (size_t)byte * 8;
+        unsigned v = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (byte * 8 + k < NZ && __ldcs(src + k) != 0.0f) v |= 1u << k;
+        bits[i] = (uint8_t)v;
+    }
+}
+
+int launch_pack_labels(const float *y, size_t n_cw, int NZ, uint8_t *bits, cudaStream_t st) {
+    const int hb = (NZ + 7) / 8;
+    const size_t want = (n_cw * (size_t)hb + 255) / 256;
+    const int grid = (int)(want < (size_t)148 * 16 ? want : (size_t)148 * 16);
+    pack_labels_kernel<<<grid, 256, 0, st>>>(y, n_cw, NZ, hb, bits);
+    return (int)cudaGetLastError();
+}
+
 }  // namespace nldpc

@@ -115,8 +115,24 @@ int spec_launch_boosted(int id, const DecodeArgs &a, int sm_count, cudaStream_t 
 
 int spec_backward_scratch_rows(int id) {
     switch (id) {
-        case 0: return 2 * gen::Bg2Z16::E + gen::Bg2Z16::N;
-        case 1: return 2 * gen::WimaxZ24::E + gen::WimaxZ24::N;
+        case 0: return gen::Bg2Z16::kXRegs > 0 ? gen::Bg2Z16::kXRegs : 1;
+        case 1: return gen::WimaxZ24::kXRegs > 0 ? gen::WimaxZ24::kXRegs : 1;
+        default: return 0;
+    }
+}
+
+bool spec_backward_covers(int id, int mode, int T, bool has_cn_w, bool has_vn_w, bool ucn, int qbit) {
+    switch (id) {
+        case 0: return spec_bwd_covers<gen::Bg2Z16>(mode, T, has_cn_w, has_vn_w, ucn, qbit);
+        case 1: return spec_bwd_covers<gen::WimaxZ24>(mode, T, has_cn_w, has_vn_w, ucn, qbit);
+        default: return false;
+    }
+}
+
+size_t spec_dump_bytes_per_cw_iter(int id, int mode) {
+    switch (id) {
+        case 0: return mode == 2 ? BwdStage<gen::Bg2Z16, 2>::kCwBytes : BwdStage<gen::Bg2Z16, 0>::kCwBytes;
+        case 1: return mode == 2 ? BwdStage<gen::WimaxZ24, 2>::kCwBytes : BwdStage<gen::WimaxZ24, 0>::kCwBytes;
         default: return 0;
     }
 }

@@ -70,18 +70,16 @@ struct Folder {
 
 template <class G, int MODE>
 struct BwdLane {
-    static constexpr bool kMask = MODE != 0;     // Boosted: the output clamp mask gates the upstream gradient
     static constexpr int Z = G::Z;
     float *lane;              // &slab[z]
     float *rot[Z];            // &slab[(z + s) mod Z]
-    const float *hv;          // &hist_v2c[t][b][0][0]
+    const char *hv;           // this codeword's check-packed records of iteration t (DecodeArgs::hist_fmt 1)
     const float *gt;          // &gout[t][b][0]
-    const uint8_t *mk;        // &hist_mask[t][b][0] or nullptr
-    const float *xin;         // CN inputs of the degree-1 blocks: &xa[b][0] (Neural) or &hist_xin[t+1][b][0]
+    const uint8_t *mk;        // &hist_mask[t][b][0], or nullptr when the clamp mask is already folded into gout
     int wb_base;              // constant-arena offset of {w,b}[t][0]
     Folder fold;              // weight-gradient terms of this iteration -> per-CTA totals
     float *chn;               // &scratch[cta][0][tid]: VN-weight chain state of the looped degree-1 blocks (kVn), by register index
-    const float *xprev;       // &hist_xin[t][b][0] (kVn)
+    const float *xprev;       // channel-input state entering iteration t: &hist_xin[t][b][0], or &xa[b][0] for t = 0 (kVn)
     const float *vw;          // w_VN[t] (kVn)
     bool last_iter;           // t == T - 1: the chain starts from zero
     float lo, hi;
@@ -94,7 +92,7 @@ struct BwdLane {
     __device__ __forceinline__ float g_at(int q) const {
         const float gv = __ldg(gt + q);
         bool keep = valid;
-        if constexpr (kMask) keep = keep && (__ldg(mk + q) != 0);
+        if (mk) keep = keep && (__ldg(mk + q) != 0);
         return keep ? gv : 0.0f;
     }
 };
@@ -151,32 +149,98 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-template <class G>
+__device__ __forceinline__ void cp_async8(const void *dst_smem, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(const void *dst_smem, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+
+// Staging slot of one check, per thread.  The forward wrote the check's CN inputs as ONE contiguous record per check lane
+// (check-packed dump, DecodeArgs::hist_fmt 1; degree-1 edges included), so a check costs one to three copies instead of one
+// per edge, and no rotated addresses:
+//   fp16 records (QMS q=5): two 16-byte entries [entry][thread]: the record (4 / 8 / 16 halfs), or — checks with a
+//     degree-1 edge, whose records have at most 8 halfs — record + {upstream gradient, mask word, xprev, -};
+//   fp32 records: kMaxRowDeg + 3 4-byte entries [entry][thread]: D values, then gradient, mask word, xprev.
+// The fp16 slots are small enough for three of them: the loops fetch two checks ahead.
+template <class G, int MODE>
 struct BwdStage {
-    static constexpr int kEnt = G::kMaxRowDeg + 2;     // per check: D operand values, then (gradient, mask word) of its degree-1 edge
+    static constexpr bool kHalf = MODE == 2;
+    static constexpr int kEntF = kHalf ? 8 : G::kMaxRowDeg + 3;      // floats per thread and slot
+    static constexpr int kSlots = kHalf ? 3 : 2;
+    static constexpr size_t kCwBytes = kHalf ? (size_t)G::kDumpH * G::Z * 2 : (size_t)G::kDumpF * G::Z * 4;   // per codeword and iteration
+    // address of extra `comp` (0 gradient, 1 mask word, 2 xprev) of this thread in slot `stg` (= &slot[tid] in float units)
+    template <int kThreads>
+    __device__ static __forceinline__ const float *extra(const float *stg, int comp) {
+        if constexpr (kHalf) return stg + 3 * (int)threadIdx.x + 4 * kThreads + comp;     // float4 entry 1 of this thread
+        else return stg + (G::kMaxRowDeg + comp) * kThreads;
+    }
 };
 
-// operands of one check: the forward's CN inputs (dumped v2c, or the channel-input state for degree-1 blocks) and, for
-// degree-1 blocks, the upstream gradient of the block (their dc2v) with its clamp-mask byte
+// issue the copies of one record: D values of the check starting at element offset OFF (per lane) of this codeword-iteration
+template <class G, int MODE, int kThreads, int D>
+__device__ __forceinline__ void record_issue(const BwdLane<G, MODE> &c, const float *stg, int off) {
+    using St = BwdStage<G, MODE>;
+    if constexpr (St::kHalf) {
+        constexpr int P = G::dump_slots_h(D);
+        const char *src = c.hv + ((size_t)off * G::Z + (size_t)c.z * P) * 2;
+        const float *dst = stg + 3 * (int)threadIdx.x;           // float4 entry 0 of this thread
+        if constexpr (P == 4) cp_async8(dst, src);
+        else cp_async16(dst, src);
+        if constexpr (P == 16) cp_async16(dst + 4 * kThreads, src + 16);
+    } else {
+        const float *src = reinterpret_cast<const float *>(c.hv) + (size_t)off * G::Z + (size_t)c.z * D;
+#pragma unroll
+        for (int k = 0; k < D; k++) cp_async4(stg + k * kThreads, src + k);
+    }
+}
+template <class G, int MODE, int kThreads, int D>
+__device__ __forceinline__ void record_fetch(const float *stg, float *pv) {
+    using St = BwdStage<G, MODE>;
+    if constexpr (St::kHalf) {
+        constexpr int P = G::dump_slots_h(D);
+        uint32_t w[P / 2];
+        const float *src = stg + 3 * (int)threadIdx.x;
+        if constexpr (P == 4) {
+            const uint2 v = *reinterpret_cast<const uint2 *>(src);
+            w[0] = v.x; w[1] = v.y;
+        } else {
+#pragma unroll
+            for (int i = 0; i < P / 8; i++) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(src + i * 4 * kThreads);
+                w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            const __half2 h = *reinterpret_cast<const __half2 *>(&w[k >> 1]);
+            pv[k] = (k & 1) ? __high2float(h) : __low2float(h);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < D; k++) pv[k] = stg[k * kThreads];
+    }
+}
+
+// unrolled checks: record + (for a degree-1 edge) the upstream gradient of its block with the clamp-mask word
 template <class G, int MODE, int kThreads, class... Es>
 __device__ __forceinline__ void cn_check_bwd_issue(const BwdLane<G, MODE> &c, const float *stg) {
+    using St = BwdStage<G, MODE>;
     constexpr int D = sizeof...(Es);
-    constexpr int rows[D] = {Es::row...};
     constexpr int shf[D] = {Es::shift...};
+    constexpr int eix[D] = {Es::e...};
     constexpr int col1[D] = {Es::col1...};
-    constexpr int Z = G::Z;
     constexpr int n_deg1 = ((Es::col1 >= 0 ? 1 : 0) + ...);
     static_assert(n_deg1 <= 1 && D <= G::kMaxRowDeg, "staging holds one degree-1 edge per check");
+    static_assert(!(St::kHalf && n_deg1 > 0 && G::dump_slots_h(D) > 8), "fp16 slot: the extras share the second entry");
+    record_issue<G, MODE, kThreads, D>(c, stg, St::kHalf ? G::dump_off_h(eix[0]) : G::dump_off_f(eix[0]));
 #pragma unroll
     for (int k = 0; k < D; k++) {
-        const int zz = (int)(c.rot[shf[k]] - (c.lane - c.z));
-        if (col1[k] < 0) {                                       // stored edge: message row
-            cp_async4(stg + k * kThreads, c.hv + (rows[k] - G::kXRows) * Z + zz);
-        } else {                                                 // degree-1 block: channel input, upstream gradient (+ mask)
-            const int q = col1[k] * Z + zz;
-            cp_async4(stg + k * kThreads, c.xin + q);
-            cp_async4(stg + G::kMaxRowDeg * kThreads, c.gt + q);
-            if constexpr (MODE != 0) cp_async4(stg + (G::kMaxRowDeg + 1) * kThreads, c.mk + (q & ~3));
+        if (col1[k] >= 0) {
+            const int zz = (int)(c.rot[shf[k]] - (c.lane - c.z));
+            const int q = col1[k] * G::Z + zz;
+            cp_async4(St::template extra<kThreads>(stg, 0), c.gt + q);
+            if (c.mk) cp_async4(St::template extra<kThreads>(stg, 1), c.mk + (q & ~3));
         }
     }
     cp_async_commit();
@@ -184,18 +248,19 @@ __device__ __forceinline__ void cn_check_bwd_issue(const BwdLane<G, MODE> &c, co
 
 template <class G, int MODE, int kThreads, class... Es>
 __device__ __forceinline__ void cn_check_bwd_fetch(const BwdLane<G, MODE> &c, const float *stg, float *pv, float *pg) {
+    using St = BwdStage<G, MODE>;
     constexpr int D = sizeof...(Es);
     constexpr int shf[D] = {Es::shift...};
     constexpr int col1[D] = {Es::col1...};
+    record_fetch<G, MODE, kThreads, D>(stg, pv);   // (padding lanes carry codeword 0's values: harmless, every gradient they meet is zero)
 #pragma unroll
     for (int k = 0; k < D; k++) {
-        pv[k] = stg[k * kThreads];     // (padding lanes carry codeword 0's values: harmless, every gradient they meet is zero)
         if (col1[k] >= 0) {
-            const float gv = stg[G::kMaxRowDeg * kThreads];
+            const float gv = *St::template extra<kThreads>(stg, 0);
             bool keep = c.valid;
-            if constexpr (MODE != 0) {
+            if (c.mk) {
                 const int zz = (int)(c.rot[shf[k]] - (c.lane - c.z));
-                const uint32_t w = __float_as_uint(stg[(G::kMaxRowDeg + 1) * kThreads]);
+                const uint32_t w = __float_as_uint(*St::template extra<kThreads>(stg, 1));
                 keep = keep && (((w >> (8 * ((col1[k] * G::Z + zz) & 3))) & 0xffu) != 0);
             }
             pg[k] = keep ? gv : 0.0f;
@@ -346,52 +411,44 @@ __device__ __forceinline__ int rot_lane(int z, int s) {
 }
 
 template <class G, int MODE, bool kVn, int kThreads, int D>
-__device__ __forceinline__ void cn_loop_issue(const BwdLane<G, MODE> &c, const float *stg, int w0) {
+__device__ __forceinline__ void cn_loop_issue(const BwdLane<G, MODE> &c, const float *stg, int w0, int rec_off) {
+    using St = BwdStage<G, MODE>;
     constexpr int Z = G::Z;
-    static_assert(D + 4 <= BwdStage<G>::kEnt, "staging entries");
-#pragma unroll
-    for (int k = 0; k < D; k++) {
-        const uint32_t w = c_desc[w0 + k];
-        const int row = w & 0xff, zz = rot_lane<G>(c.z, (w >> 8) & 0xff);
-        cp_async4(stg + k * kThreads, c.hv + (row - G::kXRows) * Z + zz);
-    }
+    static_assert(D + 1 <= G::kMaxRowDeg && (!St::kHalf || G::dump_slots_h(D + 1) <= 8), "staging entries");
+    record_issue<G, MODE, kThreads, D + 1>(c, stg, rec_off);       // D stored edges + the degree-1 edge
     const int q = (int)(c_desc[w0 + D] & 0xff) * Z + c.z;          // degree-1 block J, identity circulant
-    cp_async4(stg + D * kThreads, c.xin + q);
-    cp_async4(stg + (D + 1) * kThreads, c.gt + q);
-    if constexpr (MODE != 0) cp_async4(stg + (D + 2) * kThreads, c.mk + (q & ~3));
-    if constexpr (kVn) cp_async4(stg + (D + 3) * kThreads, c.xprev + q);
+    cp_async4(St::template extra<kThreads>(stg, 0), c.gt + q);
+    if (c.mk) cp_async4(St::template extra<kThreads>(stg, 1), c.mk + (q & ~3));
+    if constexpr (kVn) cp_async4(St::template extra<kThreads>(stg, 2), c.xprev + q);
     cp_async_commit();
 }
 
 template <class G, int MODE, bool kVn, int kThreads, int D>
 __device__ __forceinline__ void cn_loop_compute(BwdLane<G, MODE> &c, const float *stg, int w0, float chain_prev) {
+    using St = BwdStage<G, MODE>;
     constexpr int Z = G::Z, NE = D + 1;
     float *slab0 = c.lane - c.z;
     float pv[NE], dc[NE], gw[NE], gb[NE], du[NE];
     float2 wb[NE];
     float *msg[D];
-    int eix[NE];
+    record_fetch<G, MODE, kThreads, NE>(stg, pv);
 #pragma unroll
     for (int k = 0; k < D; k++) {
         const uint32_t w = c_desc[w0 + k];
         msg[k] = slab0 + (w & 0xff) * Z + rot_lane<G>(c.z, (w >> 8) & 0xff);
-        eix[k] = w >> 16;
-        pv[k] = stg[k * kThreads];
         dc[k] = *msg[k];
-        wb[k] = c_wb[c.wb_base + eix[k]];
+        wb[k] = c_wb[c.wb_base + (w >> 16)];
     }
     const uint32_t w1 = c_desc[w0 + D];
     const int J = w1 & 0xff, ridx = (w1 >> 8) & 0xff;
-    eix[D] = w1 >> 16;
     const int q = J * Z + c.z;
-    pv[D] = stg[D * kThreads];
     {
-        const float gv = stg[(D + 1) * kThreads];
+        const float gv = *St::template extra<kThreads>(stg, 0);
         bool keep = c.valid;
-        if constexpr (MODE != 0) keep = keep && (((__float_as_uint(stg[(D + 2) * kThreads]) >> (8 * (q & 3))) & 0xffu) != 0);
+        if (c.mk) keep = keep && (((__float_as_uint(*St::template extra<kThreads>(stg, 1)) >> (8 * (q & 3))) & 0xffu) != 0);
         dc[D] = keep ? gv : 0.0f;
     }
-    wb[D] = c_wb[c.wb_base + eix[D]];
+    wb[D] = c_wb[c.wb_base + (w1 >> 16)];
     cn_bwd_math<MODE, NE>(pv, dc, wb, c.lo, c.hi, gw, gb, du);
     // fold order (RowOrder::cls mirrors it): weight rows, (Neural) bias rows, (kVn) the VN row of block J
     c.fold.reserve(NE);
@@ -406,7 +463,7 @@ __device__ __forceinline__ void cn_loop_compute(BwdLane<G, MODE> &c, const float
     for (int k = 0; k < D; k++) *msg[k] = du[k];
     if constexpr (kVn) {     // VN-weight chain step of block J (VnChainStep), inline: the block belongs to this check alone
         float dx = chain_prev + du[D];
-        const float xp = stg[(D + 3) * kThreads];
+        const float xp = *St::template extra<kThreads>(stg, 2);
         const float w = __ldg(c.vw + J);
         if constexpr (MODE == 2) {
             if (!(fabsf(mulf(xp, w)) <= 7.5f)) dx = 0.0f;
@@ -419,50 +476,61 @@ __device__ __forceinline__ void cn_loop_compute(BwdLane<G, MODE> &c, const float
 
 template <class G, int MODE, bool kVn, int kThreads>
 struct CnBwdLoops {
+    using St = BwdStage<G, MODE>;
     BwdLane<G, MODE> &c;
     const float *stg;         // &stage[0][0][tid]
     int base;                 // first descriptor word of this graph in c_desc
     // VN-weight chain state of the check's degree-1 block (own slot, written by this thread one iteration ago; L2, not the
-    // non-coherent L1).  Loaded one check ahead into a loop-carried register: ptxas cannot sink it across the back edge.
+    // non-coherent L1).  Loaded ahead into loop-carried registers: ptxas cannot sink it across the back edge.
     template <int D>
     __device__ __forceinline__ float chain_state(int w0) const {
         if constexpr (!kVn) return 0.0f;
         if (c.last_iter) return 0.0f;
         return __ldcg(c.chn + ((c_desc[w0 + D] >> 8) & 0xff) * kThreads);
     }
-    template <int D, int FIRST, int COUNT>
+    // one class: COUNT checks with D stored edges each, records REC apart starting at OFFH / OFFF; operands are fetched
+    // kSlots - 1 checks ahead
+    template <int D, int FIRST, int COUNT, int OFFH, int OFFF>
     __device__ __forceinline__ void cls() {
-        constexpr int kStage = BwdStage<G>::kEnt * kThreads;
-        cn_loop_issue<G, MODE, kVn, kThreads, D>(c, stg, base + FIRST);
-        // chain state two checks ahead (the scratch rows compete with the streamed dump in L2 and often come from HBM)
+        constexpr int kStage = St::kEntF * kThreads, kAhead = St::kSlots - 1;
+        constexpr int REC = St::kHalf ? G::dump_slots_h(D + 1) : D + 1, OFF = St::kHalf ? OFFH : OFFF;
+#pragma unroll
+        for (int j = 0; j < kAhead; j++)
+            if (j < COUNT) cn_loop_issue<G, MODE, kVn, kThreads, D>(c, stg + j * kStage, base + FIRST + j * (D + 1), OFF + j * REC);
         float chain_cur = chain_state<D>(base + FIRST);
         float chain_next = COUNT > 1 ? chain_state<D>(base + FIRST + (D + 1)) : 0.0f;
+        int slot_c = 0, slot_i = kAhead % St::kSlots;        // slot being computed / being filled
 #pragma unroll 1
         for (int i = 0; i < COUNT; i++) {
             const int w0 = base + FIRST + i * (D + 1);
             float chain_next2 = 0.0f;
             if (i + 2 < COUNT) chain_next2 = chain_state<D>(w0 + 2 * (D + 1));
-            if (i + 1 < COUNT) {
-                cn_loop_issue<G, MODE, kVn, kThreads, D>(c, stg + ((i + 1) & 1) * kStage, w0 + (D + 1));
+            if (i + kAhead < COUNT) {
+                cn_loop_issue<G, MODE, kVn, kThreads, D>(c, stg + slot_i * kStage, w0 + kAhead * (D + 1), OFF + (i + kAhead) * REC);
+                cp_async_wait<kAhead>();
+            } else if (kAhead > 1 && i + 1 < COUNT) {
                 cp_async_wait<1>();
             } else {
                 cp_async_wait<0>();
             }
-            cn_loop_compute<G, MODE, kVn, kThreads, D>(c, stg + (i & 1) * kStage, w0, chain_cur);
+            cn_loop_compute<G, MODE, kVn, kThreads, D>(c, stg + slot_c * kStage, w0, chain_cur);
             chain_cur = chain_next;
             chain_next = chain_next2;
+            slot_c = slot_c + 1 == St::kSlots ? 0 : slot_c + 1;
+            slot_i = slot_i + 1 == St::kSlots ? 0 : slot_i + 1;
         }
     }
 };
 
 template <class G, int MODE, bool kVn, int kThreads>
 struct CnBwd {
+    using St = BwdStage<G, MODE>;
     BwdLane<G, MODE> &c;
     const float *stg;         // &stage[0][0][tid]
     int n_ld = 0, n_chk = 0;  // (compile-time after inlining: the sequence is straight-line)
     template <int SLOT, class... Es>
     __device__ __forceinline__ void ld() {
-        cn_check_bwd_issue<G, MODE, kThreads, Es...>(c, stg + SLOT * BwdStage<G>::kEnt * kThreads);
+        cn_check_bwd_issue<G, MODE, kThreads, Es...>(c, stg + SLOT * St::kEntF * kThreads);
         n_ld++;
     }
     template <int SLOT, class... Es>
@@ -471,7 +539,7 @@ struct CnBwd {
         else cp_async_wait<0>();
         n_chk++;
         float pv[G::kMaxRowDeg], pg[G::kMaxRowDeg];
-        cn_check_bwd_fetch<G, MODE, kThreads, Es...>(c, stg + SLOT * BwdStage<G>::kEnt * kThreads, pv, pg);
+        cn_check_bwd_fetch<G, MODE, kThreads, Es...>(c, stg + SLOT * St::kEntF * kThreads, pv, pg);
         cn_check_bwd_core<G, MODE, kVn, kThreads, Es...>(c, pv, pg);
     }
 };
@@ -537,7 +605,7 @@ struct RowOrder {
         ((order[n++] = (uint16_t)Es::e), ...);
         if constexpr (MODE == 0) ((order[n++] = (uint16_t)(G::E + Es::e)), ...);
     }
-    template <int D, int FIRST, int COUNT>
+    template <int D, int FIRST, int COUNT, int OFFH, int OFFF>
     __device__ __forceinline__ void cls() {
         for (int i = 0; i < COUNT; i++) {
             const int w0 = base + FIRST + i * (D + 1);
@@ -571,12 +639,14 @@ struct SpecBwdCfg {
     static constexpr int kSlabF = slab_floats(G::S * G::Z, 0, G::Z);
     static constexpr size_t slab_bytes() { return (size_t)kCwPerCta * kSlabF * 4; }
     __host__ __device__ static constexpr int rows(int mode, bool vn) { return mode == 0 ? 2 * G::E : G::E + (vn ? G::N : 0); }
-    static constexpr size_t stage_bytes() { return (size_t)2 * BwdStage<G>::kEnt * kThreads * 4; }
+    __host__ __device__ static constexpr size_t stage_floats(int mode) {
+        return mode == 2 ? (size_t)BwdStage<G, 2>::kSlots * BwdStage<G, 2>::kEntF * kThreads : (size_t)BwdStage<G, 0>::kSlots * BwdStage<G, 0>::kEntF * kThreads;
+    }
     static constexpr size_t fold_bytes() { return (size_t)kWarps * kFoldRows * kFoldStride * 4; }
     static constexpr size_t order_bytes(int mode, bool vn) { return ((size_t)rows(mode, vn) * 2 + 15) & ~(size_t)15; }
     // message slabs + operand staging (2 stages) + fold buffers + per-CTA totals [T][rows] + position -> row table
     static constexpr size_t smem_bytes(int T, int mode, bool vn) {
-        return slab_bytes() + stage_bytes() + fold_bytes() + (size_t)T * rows(mode, vn) * 4 + order_bytes(mode, vn) + 64;
+        return slab_bytes() + stage_floats(mode) * 4 + fold_bytes() + (size_t)T * rows(mode, vn) * 4 + order_bytes(mode, vn) + 64;
     }
 };
 
@@ -588,8 +658,8 @@ __global__ void __launch_bounds__(SpecBwdCfg<G>::kThreads, 1) nldpc_spec_backwar
     constexpr int kThreads = Cfg::kThreads, kRows = Cfg::rows(MODE, kVn);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *slabs = reinterpret_cast<float *>(smem_raw);
-    float *stage = slabs + (size_t)Cfg::kCwPerCta * Cfg::kSlabF;   // [2][kEnt][kThreads]
-    float *foldb = stage + 2 * BwdStage<G>::kEnt * kThreads;       // [kWarps][kFoldRows][kFoldStride]
+    float *stage = slabs + (size_t)Cfg::kCwPerCta * Cfg::kSlabF;   // [kSlots][kEntF][kThreads] (BwdStage)
+    float *foldb = stage + Cfg::stage_floats(MODE);                // [kWarps][kFoldRows][kFoldStride]
     float *tot = foldb + Cfg::kWarps * kFoldRows * kFoldStride;     // [T][kRows], by fold position
     uint16_t *order = reinterpret_cast<uint16_t *>(tot + (size_t)a.T * kRows);      // [kRows] position -> row
 
@@ -640,15 +710,14 @@ __global__ void __launch_bounds__(SpecBwdCfg<G>::kThreads, 1) nldpc_spec_backwar
         }
         phase_sync();
         for (int t = a.T - 1; t >= 0; t--) {
-            c.hv = a.hist_v2c + (((size_t)t * a.B + bb) * G::S) * Z;
+            c.hv = reinterpret_cast<const char *>(a.hist_v2c) + ((size_t)t * a.B + bb) * BwdStage<G, MODE>::kCwBytes;
             c.gt = a.gout + ((size_t)t * a.B + bb) * NZ;
-            c.mk = (MODE != 0) ? a.hist_mask + ((size_t)t * a.B + bb) * NZ : nullptr;
-            c.xin = (MODE == 0) ? a.xa + bb * NZ : a.hist_xin + ((size_t)(t + 1) * a.B + bb) * NZ;
+            c.mk = (MODE != 0 && a.hist_mask) ? a.hist_mask + ((size_t)t * a.B + bb) * NZ : nullptr;
             c.wb_base = wb_off + t * E;
             c.last_iter = (t == a.T - 1);
             c.fold.begin(tot + (size_t)t * kRows);
             if constexpr (kVn) {
-                c.xprev = a.hist_xin + ((size_t)t * a.B + bb) * NZ;
+                c.xprev = (t == 0) ? a.xa + bb * NZ : a.hist_xin + ((size_t)t * a.B + bb) * NZ;      // (row 0 is the raw input)
                 c.vw = a.vn_w + (size_t)t * N;
             }
             {
@@ -672,7 +741,7 @@ __global__ void __launch_bounds__(SpecBwdCfg<G>::kThreads, 1) nldpc_spec_backwar
             if constexpr (kVn) {
                 VnChainSum<G, MODE> s{c, dxb};
                 G::vcols(s);
-                vn_chain_batches<G, MODE, kThreads, 0>(c, chain, dxb, a.hist_xin + ((size_t)t * a.B + bb) * NZ, a.vn_w + (size_t)t * N);
+                vn_chain_batches<G, MODE, kThreads, 0>(c, chain, dxb, c.xprev, c.vw);
             }
             c.fold.flush();
         }
@@ -733,20 +802,24 @@ int spec_bwd_launch_one(const BwdArgs &a, int wb_off, int graph_slot, int sm_cou
     return (int)cudaGetLastError();
 }
 
+// the configurations the specialised sweep takes (nldpc_spec.cuh: spec_backward_covers)
+template <class G>
+bool spec_bwd_covers(int mode, int T, bool has_cn_w, bool has_vn_w, bool ucn, int qbit) {
+    if (G::kDeg1Smem != 0) return false;                      // the lane-private chain assumes identity circulants on degree-1 blocks
+    if (mode != 0 && (ucn || !has_cn_w)) return false;        // no CN weights: nothing but VN rows to learn; keep it simple
+    if (mode == 2 && qbit != 5) return false;
+    return SpecBwdCfg<G>::smem_bytes(T, mode, mode != 0 && has_vn_w) <= (size_t)kSmemBudget;
+}
+
 // 0 launched, >0 cudaError_t, -1 not covered (caller uses the table-driven kernel).
 // kBoosted selects which kernels this translation unit instantiates: every kernel must live in exactly ONE unit, because
 // it reads that unit's constant arena (a second instantiation elsewhere would be folded with this one by the linker and
 // read the other unit's, never written, arena).
 template <class G, bool kBoosted>
 int spec_bwd_launch(const BwdArgs &a, int graph_slot, int sm_count, cudaStream_t st) {
-    if (G::kDeg1Smem != 0) return -1;                         // the lane-private chain assumes identity circulants on degree-1 blocks
-    if (!a.scratch || kBoosted != (a.mode != 0)) return -1;
+    if (!a.scratch || kBoosted != (a.mode != 0) || a.hist_fmt != 1) return -1;      // (the sweep reads the check-packed dump)
+    if (!spec_bwd_covers<G>(a.mode, a.T, a.w != nullptr, a.gvn != nullptr, a.ucn_mix || a.hist_ucn, a.qbit)) return -1;
     const bool capturing = stream_is_capturing(st);           // CUDA graph capture: see ConstArena::acquire_captured
-    if (a.mode != 0 && (a.ucn_mix || a.hist_ucn)) return -1;
-    if (a.mode == 2 && a.qbit != 5) return -1;
-    if (a.mode != 0 && !a.w) return -1;                       // no CN weights: nothing but VN rows to learn; keep it simple
-    using Cfg = SpecBwdCfg<G>;
-    if (Cfg::smem_bytes(a.T, a.mode, a.gvn != nullptr) > (size_t)kSmemBudget) return -1;
     ConstArena &arena = arena_for_current_device();
     const int len = a.T * G::E;
     cudaError_t err = cudaSuccess;

@@ -16,6 +16,8 @@
 //
 // Exactness contract: see nldpc_generic.cu / oracle/nldpc_oracle.c.
 #pragma once
+#include <cuda_fp16.h>
+
 #include <type_traits>
 
 #include "nldpc_common.cuh"
@@ -90,11 +92,34 @@ __device__ __forceinline__ float condition(float x, float lo, float hi) {       
 }
 
 // Boosted output: clamp(xa_origin + total, range) (:520-521); the training dump records whether the clamp passes gradient
+// Fused training forward (DecodeArgs::ybits): the value that leaves is dL/dout = c_t * upstream / n * (sigmoid(out) - y), zeroed
+// where the clamp blocks the gradient, and the loss terms max(x,0) - x*y + log(1 + exp(-|x|)) (LDPCDecoderLoss.py:73-108, BCE
+// branch; y is 0 or 1) are summed per lane: accA the max() part, accL log2(1 + exp(-|x|)); the kernel folds both with c_t
+// after each phase.  MUFU approximations (ex2 / rcp / lg2, relative error ~2^-22): this is the floating-point part of the
+// path, compared with the reference's autograd at 3e-5.
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+template <class L>
+__device__ __forceinline__ float bce_fused(L &c, int q, float out, bool pass) {
+    const bool y1 = (c.yb[q >> 5] >> (q & 31)) & 1u;
+    const float e = ex2_approx(-1.4426950408889634f * fabsf(out));
+    const float d = 1.0f + e;
+    const float r = rcp_approx(d);
+    float s = (out >= 0.0f) ? r : e * r;             // sigmoid(out)
+    s = y1 ? s - 1.0f : s;
+    c.accA += fmaxf(y1 ? -out : out, 0.0f);
+    c.accL += lg2_approx(d);
+    return pass ? s * c.cg : 0.0f;
+}
 template <class L>
 __device__ __forceinline__ float boosted_out(L &c, int q, float xo, float tot) {
     const float sum = addf(xo, tot);
-    if (c.mask) c.mask[q] = (sum >= c.lo && sum <= c.hi) ? 1 : 0;
-    return clamp_rng(sum, c.lo, c.hi);
+    const bool pass = sum >= c.lo && sum <= c.hi;
+    if (c.mask) c.mask[q] = pass ? 1 : 0;
+    const float out = clamp_rng(sum, c.lo, c.hi);
+    if (c.yb) return bce_fused(c, q, out, pass);
+    return out;
 }
 
 // Where xa_origin lives when VN weights make the on-chip channel value (xa_input) drift away from it — the `kXo` parameter:
@@ -190,6 +215,10 @@ struct NeuralLane {
     float lo, hi;            // allowed_llr_range
     float *llr_last;         // &llr_last[b][0][0] ([Z][E]) while the last iteration's CN phase runs, else nullptr
     uint8_t *mask;           // training dump: &hist_mask[t_emit][b][0] of the iteration being emitted, or nullptr
+    char *dump;              // training dump, check-packed format: this codeword's records of the running iteration, or nullptr
+    const uint32_t *yb;      // fused loss: this codeword's packed label bits (shared memory), or nullptr
+    float cg;                // fused loss: c_t * upstream / n of the iteration being emitted
+    float accA, accL;        // fused loss: partial sums of the running phase (see bce_fused)
 
     // ---- emission of one marginal value -------------------------------------------------------------------
     // un-rotated: this lane holds bit (J, z)
@@ -439,6 +468,38 @@ struct ReloadXreg {
 // pointers and a store through one may alias a load through another as far as it can tell.
 // The same stage also fetches the edges' {w, b} pairs: the constant load (LDC) has its own latency, and issued right before
 // the multiply that needs it the multiply stalled on it (ncu: short_scoreboard on FMUL, 13 % of all stall samples).
+// training dump, check-packed (hist_fmt 1): the check's CN inputs as this check lane read them, one contiguous record per lane
+// ([record][Z][P]).  QMS q=5: every CN input is a sum of multiples of 0.5 (quantised channel value + quantised messages,
+// |sum| <= 7.5 * (kMaxColDeg + 1)), i.e. exact in fp16 -> records of 4 / 8 / 16 halfs; otherwise D floats.
+template <class G, int MODE, class... Es>
+__device__ __forceinline__ void dump_check(const NeuralLane<G> &c, const float *raw) {
+    constexpr int D = sizeof...(Es);
+    constexpr int eix[D] = {Es::e...};
+    if constexpr (MODE == 2) {
+        constexpr int P = G::dump_slots_h(D), off = G::dump_off_h(eix[0]);
+        static_assert(off >= 0, "check not in the dump table");
+        uint32_t w[P / 2];
+#pragma unroll
+        for (int i = 0; i < P / 2; i++) {
+            const __half2 h = __floats2half2_rn(2 * i < D ? raw[2 * i] : 0.0f, 2 * i + 1 < D ? raw[2 * i + 1] : 0.0f);
+            w[i] = *reinterpret_cast<const uint32_t *>(&h);
+        }
+        char *p = c.dump + ((size_t)off * G::Z + (size_t)c.z * P) * 2;
+        if constexpr (P == 4) {
+            __stcs(reinterpret_cast<uint2 *>(p), make_uint2(w[0], w[1]));
+        } else {
+#pragma unroll
+            for (int i = 0; i < P / 8; i++) __stcs(reinterpret_cast<uint4 *>(p) + i, make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]));
+        }
+    } else {
+        constexpr int off = G::dump_off_f(eix[0]);
+        static_assert(off >= 0, "check not in the dump table");
+        float *p = reinterpret_cast<float *>(c.dump) + (size_t)off * G::Z + (size_t)c.z * D;
+#pragma unroll
+        for (int k = 0; k < D; k++) __stcs(p + k, raw[k]);
+    }
+}
+
 template <class G, bool kEmit, bool kConstW, class... Es>
 __device__ __forceinline__ void cn_load(const NeuralLane<G> &c, float *raw, float2 *wb) {
     constexpr int D = sizeof...(Es);
@@ -464,6 +525,9 @@ __device__ __forceinline__ void cn_check_core(NeuralLane<G> &c, const float *raw
     constexpr int shf[D] = {Es::shift...};
     constexpr int eix[D] = {Es::e...};
     constexpr int col1[D] = {Es::col1...};
+    if constexpr (kEmit) {
+        if (c.dump) dump_check<G, 0, Es...>(c, raw);
+    }
     float u[D];
 #pragma unroll
     for (int k = 0; k < D; k++) u[k] = (kZeroSafe && raw[k] == 0.0f) ? -10000.0f : raw[k];
@@ -519,6 +583,9 @@ __device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c, const fl
     constexpr int shf[D] = {Es::shift...};
     constexpr int eix[D] = {Es::e...};
     constexpr int col1[D] = {Es::col1...};
+    if constexpr (kEmit) {
+        if (c.dump) dump_check<G, MODE, Es...>(c, raw);
+    }
     float u[D];
 #pragma unroll
     for (int k = 0; k < D; k++) {
@@ -763,9 +830,17 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
     c.hi = a.llr_hi;
     c.llr_last = nullptr;
     c.mask = nullptr;
+    c.dump = nullptr;
+    c.yb = nullptr;
+    c.cg = 0.0f;
+    c.accA = c.accL = 0.0f;
 #pragma unroll
     for (int s = 0; s < Z; s++) c.rot[s] = slab + ((z + s) % Z);
     uint8_t *hb_mine = hstage + (size_t)cw_in_cta * Cfg::kHardStride;
+    // check-packed training dump: bytes per codeword and iteration
+    constexpr size_t kDumpCw = (MODE == 2) ? (size_t)G::kDumpH * Z * 2 : (size_t)G::kDumpF * Z * 4;
+    const bool fused = MODE != 0 && kEvery && a.ybits != nullptr;      // fused BCE: `soft` receives dL/dout (see bce_fused)
+    static_assert(Cfg::kHardBytes % 4 == 0 || MODE == 0, "packed labels are staged as 32-bit words");
 
     const int n_units = (a.B + Shape::kCw - 1) / Shape::kCw;
     const int unit_stride = gridDim.x * Cfg::kGroups;
@@ -775,7 +850,7 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
 
     // phase barrier: group-local (a CTA-wide lockstep variant, so that all warps stream the same code, bought nothing:
     // 42.4 vs 43.2 M cw/s in round 1)
-    auto phase_sync = [&]() { group_sync<Shape::kLanes>(grp); };
+    auto phase_sync = [&]() __attribute__((always_inline)) { group_sync<Shape::kLanes>(grp); };
     // The decode of one work unit.  kSafe = false is the fast path, which assumes that no CN input of the group is exactly
     // zero: the channel LLRs are screened once, the VN phase tracks min |v2c| (half an instruction per edge), and when a zero
     // shows up the unit is abandoned (return false) and decoded again from its channel LLRs with kSafe = true, whose CN phase
@@ -819,13 +894,13 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
         }
         c.zmin = 10000.0f;
         // per-iteration pieces shared by both output modes
-        auto xin_update = [&](int t) {
+        auto xin_update = [&](int t) __attribute__((always_inline)) {
             if constexpr (kXo) {
                 ScaleXin<G, MODE> sc{c, a.vn_w + (size_t)t * G::N};
                 G::blocks(sc);
             }
         };
-        auto cn_run = [&](auto emit_tag) {
+        auto cn_run = [&](auto emit_tag) __attribute__((always_inline)) {
             constexpr bool kEmitNow = decltype(emit_tag)::value;
             if constexpr (MODE == 0) {
                 CnNeural<G, kEmitNow, kConstW, kSafe> f{c};
@@ -836,9 +911,23 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
             }
         };
         float *soft_cw = (soft_any && c.valid) ? a.soft + (size_t)b * NZ : nullptr;     // + t*B*NZ in ALL mode
+        float lacc = 0.0f;                      // fused loss: sum_t c_t * (terms of this lane), this unit
+        // fold the loss terms the phase that just ended has produced (they belong to the output of iteration t_out)
+        auto loss_fold = [&](int t_out) __attribute__((always_inline)) {
+            if (fused) {
+                lacc += __ldg(a.coef + t_out) * (c.accA + 0.6931471805599453f * c.accL);
+                c.accA = c.accL = 0.0f;
+            }
+        };
+        if (fused) {
+            // this codeword's packed labels -> the (unused: training asks for no hard decisions) hard-decision staging bytes
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(a.ybits + (size_t)min(b, a.B - 1) * Cfg::kHardBytes);
+            for (int q = z; q < Cfg::kHardBytes / 4; q += Z) reinterpret_cast<uint32_t *>(hb_mine)[q] = __ldg(src + q);
+            c.yb = reinterpret_cast<const uint32_t *>(hb_mine);        // (first read: after the phase barrier of iteration 0)
+        }
         const size_t soft_iter = (size_t)a.B * NZ;
         uint8_t *hb_cw = hard_any ? hb_mine : nullptr;
-        auto flush_hard = [&](int t_out) {
+        auto flush_hard = [&](int t_out) __attribute__((always_inline)) {
             // group-cooperative copy of the staged packed decisions to global memory (16 B per lane-step)
             group_sync<Shape::kLanes>(grp);
             uint8_t *dst = a.hard + ((hard_all ? (size_t)t_out * a.B : 0) + b0) * Cfg::kHardBytes;
@@ -865,7 +954,7 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
 
         // list mode with output staging: the finished [N*Z] row of every codeword of the group -> soft[t_out][b], one bulk
         // TMA store each (the rows sit behind the codewords' slabs, see Staged<>)
-        auto flush_soft = [&](int t_out) {
+        auto flush_soft = [&](int t_out) __attribute__((always_inline)) {
             if constexpr (kStage) {
                 if (soft_any && (soft_all || t_out == a.T - 1)) {
                     fence_proxy_async();                     // this lane's staging writes -> visible to the async proxy
@@ -887,12 +976,15 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
                 c.bt = a.b + (size_t)t * G::E;
                 c.wb_base = a.wb_off + t * G::E;
                 const bool dump = a.hist_v2c != nullptr && c.valid;     // training dump for the backward kernel
-                if (MODE != 0 && dump && t == 0) {
+                const bool packed = a.hist_fmt == 1;                     // check-packed records (written by the CN phase)
+                if (MODE != 0 && dump && !packed && t == 0) {
                     DumpXin<G> d{c, a.hist_xin + (size_t)b * NZ + z};
                     G::blocks(d);
                 }
                 xin_update(t);
-                if (MODE != 0 && dump) {
+                // channel-input state after this iteration's update: every row in the slot-major format; in the packed format
+                // only what the VN-weight chain of the backward sweep reads (rows 1..T-1, and only when there are VN weights)
+                if (MODE != 0 && dump && (!packed || (kXo && t + 1 < a.T))) {
                     DumpXin<G> d{c, a.hist_xin + ((size_t)(t + 1) * a.B + b) * NZ + z};
                     G::blocks(d);
                 }
@@ -902,14 +994,16 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
                 } else {
                     c.soft = (soft_all && soft_cw) ? soft_cw + (size_t)(t - 1) * soft_iter : nullptr;
                     c.hb = hard_all ? hb_cw : nullptr;
-                    c.mask = (MODE != 0 && dump) ? a.hist_mask + ((size_t)(t - 1) * a.B + b) * NZ : nullptr;
+                    c.mask = (MODE != 0 && dump && a.hist_mask) ? a.hist_mask + ((size_t)(t - 1) * a.B + b) * NZ : nullptr;
+                    if (fused) c.cg = __ldg(a.coef + (t - 1)) * a.ginv;
                     stage_wait(c);       // (graphs without degree-1 blocks emit only here; a no-op wait otherwise)
                     VnStep<G, true, MODE, kXoMode> f{c};
                     run_vcols<G>(f);
+                    loss_fold(t - 1);
                     flush_soft(t - 1);
                     if (hard_all) flush_hard(t - 1);
                 }
-                if (dump) {   // the v2c every CN phase reads, slot-major (same slot order as the table-driven kernels)
+                if (dump && !packed) {   // the v2c every CN phase reads, slot-major (same slot order as the table-driven kernels)
                     float *hv = a.hist_v2c + (((size_t)t * a.B + b) * G::S) * Z + z;
                     for (int q = 0; q < G::S; q++) hv[(size_t)q * Z] = c.lane[(G::kXRows + q) * Z];
                 }
@@ -917,11 +1011,14 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
                 const bool last = t == a.T - 1;
                 c.soft = (soft_cw && (soft_all || last)) ? soft_cw + (soft_all ? (size_t)t * soft_iter : 0) : nullptr;
                 c.hb = (hard_all || last) ? hb_cw : nullptr;
-                c.mask = (MODE != 0 && dump) ? a.hist_mask + ((size_t)t * a.B + b) * NZ : nullptr;
+                c.mask = (MODE != 0 && dump && a.hist_mask) ? a.hist_mask + ((size_t)t * a.B + b) * NZ : nullptr;
+                c.dump = (dump && packed) ? reinterpret_cast<char *>(a.hist_v2c) + ((size_t)t * a.B + b) * kDumpCw : nullptr;
+                if (fused) c.cg = __ldg(a.coef + t) * a.ginv;
                 c.llr_last = !c.valid ? nullptr
                              : (a.llr_all ? a.llr_all + ((size_t)t * a.B + b) * Z * G::E
                                           : ((last && a.llr_last) ? a.llr_last + (size_t)b * Z * G::E : nullptr));
                 cn_run(std::true_type{});
+                loss_fold(t);
                 phase_sync();
             }
         } else {
@@ -959,11 +1056,22 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
             c.soft = soft_cw ? soft_cw + (soft_all ? (size_t)(a.T - 1) * soft_iter : 0) : nullptr;
             c.hb = hb_cw;
             c.mask = (MODE != 0 && kEvery && a.hist_mask && c.valid) ? a.hist_mask + ((size_t)(a.T - 1) * a.B + b) * NZ : nullptr;
+            c.dump = nullptr;
             if constexpr (kEvery) stage_wait(c);
             Marginal<G, MODE, kXoMode> f{c};
             G::vcols(f);
             if constexpr (kEvery) flush_soft(a.T - 1);
             if (hard_any) flush_hard(a.T - 1);
+        }
+        if constexpr (MODE != 0 && kEvery) {
+            if (fused) {      // (cg of the last iteration is still set from its CN phase)
+                loss_fold(a.T - 1);
+                float v = c.valid ? lacc : 0.0f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if ((threadIdx.x & 31) == 0) atomicAdd(a.loss_acc, (double)v);
+                c.yb = nullptr;
+            }
         }
         return true;
     };      // run_unit

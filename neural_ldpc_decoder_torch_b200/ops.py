@@ -294,8 +294,10 @@ def _(xa, vn_w, cn_w, ucn_w, graph_id, T, decoder_type, qbit, llr_lo, llr_hi, co
 @torch.library.custom_op("nldpc::boosted_backward", mutates_args=())
 def boosted_backward(xa: torch.Tensor, vn_w: Optional[torch.Tensor], cn_w: Optional[torch.Tensor], ucn_w: Optional[torch.Tensor],
                      gout: torch.Tensor, graph_id: int, T: int, decoder_type: int, qbit: int, llr_lo: float, llr_hi: float,
-                     compute_ucn: bool, ucn_mix: bool, dump: Optional[torch.Tensor] = None) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """gradients w.r.t. the folded weight rows (vn [T,N], cn [T,E], ucn [T,E]; empty where absent)"""
+                     compute_ucn: bool, ucn_mix: bool, dump: Optional[torch.Tensor] = None,
+                     dump_fmt: int = 0) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """gradients w.r.t. the folded weight rows (vn [T,N], cn [T,E], ucn [T,E]; empty where absent).  `dump`: the training dump
+    the forward op wrote (want_dump), `dump_fmt` its format (nldpc_boosted_dump_format of that forward call)."""
     g = _lib.graph_by_id(graph_id)
     _check_cuda_f32("xa", xa)
     _check_cuda_f32("gout", gout)
@@ -316,13 +318,14 @@ def boosted_backward(xa: torch.Tensor, vn_w: Optional[torch.Tensor], cn_w: Optio
     with torch.cuda.device(dev):
         rc = _lib.lib().nldpc_boosted_backward(g.ptr, ctypes.byref(cfg), _ptr(xa), _ptr(vn_w), _ptr(cn_w), _ptr(ucn_w), _ptr(gout), B, T,
                                                _ptr(gvn) if gvn.numel() else _vp(0), _ptr(gcn) if gcn.numel() else _vp(0),
-                                               _ptr(gucn) if gucn.numel() else _vp(0), _ptr(ws), nbytes, int(have_dump), _stream(xa))
+                                               _ptr(gucn) if gucn.numel() else _vp(0), _ptr(ws), nbytes,
+                                               (1 + int(dump_fmt)) if have_dump else 0, _stream(xa))
     _lib.check(rc, "nldpc_boosted_backward")
     return gvn, gcn, gucn
 
 
 @boosted_backward.register_fake
-def _(xa, vn_w, cn_w, ucn_w, gout, graph_id, T, decoder_type, qbit, llr_lo, llr_hi, compute_ucn, ucn_mix, dump=None):
+def _(xa, vn_w, cn_w, ucn_w, gout, graph_id, T, decoder_type, qbit, llr_lo, llr_hi, compute_ucn, ucn_mix, dump=None, dump_fmt=0):
     g = _lib.graph_by_id(graph_id)
     return (xa.new_empty((T, g.N) if vn_w is not None else (0,)), xa.new_empty((T, g.E) if cn_w is not None else (0,)),
             xa.new_empty((T, g.E) if (ucn_w is not None and ucn_mix) else (0,)))
@@ -335,6 +338,14 @@ def _boosted_setup_ctx(ctx, inputs, output):
     ctx.cfg = (graph_id, T, dec, qbit, lo, hi, compute_ucn, ucn_mix)
     ctx.stateful = llr_init is not None or xin_init is not None or app_init is not None
     ctx.have_dump = bool(want_dump)
+    ctx.dump_fmt = 0
+    if want_dump:       # the format the forward call wrote (its state pointers matter: stateful runs use the table-driven kernels)
+        g = _lib.graph_by_id(graph_id)
+        one = ctypes.c_void_p(1)
+        cfg = _lib.BoostedCfg(dec, qbit, lo, hi, int(compute_ucn), int(ucn_mix), one if llr_init is not None else None,
+                              one if xin_init is not None else None, one if want_xin else None,
+                              one if app_init is not None else None, None, 0, None)
+        ctx.dump_fmt = int(_lib.lib().nldpc_boosted_dump_format(g.ptr, ctypes.byref(cfg), T, int(cn_w is not None), int(vn_w is not None)))
     ctx.soft_all = soft_mode == _lib.NLDPC_OUT_ALL
     # autograd would otherwise hand the backward a ZERO tensor for every output without a gradient — including one the size
     # of the training dump (20 GB at B = 65536, T = 20: 5 ms of fill per step)
@@ -354,12 +365,120 @@ def _boosted_bwd(ctx, gsoft, gllr, gxin, ghard, gdump):
         raise _lib.NldpcError("backward through a run that continues from stored state needs the training dump of that run "
                               "(call the forward op with want_dump=True)")
     gvn, gcn, gucn = torch.ops.nldpc.boosted_backward(xa, vn_w, cn_w, ucn_w, gsoft.contiguous(), graph_id, T, dec, qbit, lo, hi,
-                                                      compute_ucn, ucn_mix, dump)
+                                                      compute_ucn, ucn_mix, dump, ctx.dump_fmt)
     return (None, gvn if vn_w is not None else None, gcn if cn_w is not None else None,
             gucn if (ucn_w is not None and ucn_mix) else None) + (None,) * 16
 
 
 boosted_forward.register_autograd(_boosted_bwd, setup_context=_boosted_setup_ctx)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fused training step: forward + multi-iteration BCE + dL/dout in one launch, the sweep reads the workspace
+def pack_labels(y: torch.Tensor) -> torch.Tensor:
+    """y [B, N*Z] fp32 labels (0 / 1) -> uint8 [B, ceil(N*Z/8)], bit i of a codeword = (y[i] != 0), LSB first — the packing of
+    the decode ops' hard decisions."""
+    _check_cuda_f32("y", y)
+    if y.dim() != 2:
+        raise ValueError("y must be [B, N*Z]")
+    y = y.contiguous()
+    bits = torch.empty((y.shape[0], (y.shape[1] + 7) // 8), dtype=torch.uint8, device=y.device)
+    with torch.cuda.device(y.device):
+        rc = _lib.lib().nldpc_pack_labels(_ptr(y), y.shape[0], y.shape[1], _ptr(bits), _stream(y))
+    _lib.check(rc, "nldpc_pack_labels")
+    return bits
+
+
+def _train_cfg(decoder_type, qbit, llr_lo, llr_hi):
+    return _lib.BoostedCfg(decoder_type, qbit, llr_lo, llr_hi, 0, 0, None, None, None, None, None, 0, None)
+
+
+def boosted_train_covered(graph_id, decoder_type, qbit, llr_lo, llr_hi, T, has_cn_w, has_vn_w) -> bool:
+    """does the fused training path (boosted_train_loss) take this configuration?"""
+    g = _lib.graph_by_id(graph_id)
+    cfg = _train_cfg(decoder_type, qbit, llr_lo, llr_hi)
+    return int(_lib.lib().nldpc_boosted_train_workspace_bytes(g.ptr, ctypes.byref(cfg), 1, T, int(has_cn_w), int(has_vn_w))) > 0
+
+
+class _BoostedTrainLoss(torch.autograd.Function):
+    """L = sum_t coef[t] * mean bce_with_logits(out_t, y) of the Boosted decoder run from the zero state, differentiable w.r.t.
+    the folded weight rows.  forward: nldpc_boosted_train_forward (one launch: T iterations + loss + dL/dout + dump);
+    backward: nldpc_boosted_train_backward (the sweep)."""
+
+    @staticmethod
+    def forward(ctx, xa, vn_w, cn_w, ybits, coef, graph_id, T, decoder_type, qbit, llr_lo, llr_hi):
+        g = _lib.graph_by_id(graph_id)
+        _check_cuda_f32("xa", xa)
+        if xa.dim() != 3 or xa.shape[1] != g.N or xa.shape[2] != g.Z:
+            raise ValueError(f"xa must be [B, {g.N}, {g.Z}], got {tuple(xa.shape)}")
+        B, dev = xa.shape[0], xa.device
+        if dev.index != g.device_index:
+            raise ValueError("graph handle and tensors live on different devices")
+        xa = _aligned16(xa)
+        vn_w = _opt_f32("vn_w", vn_w, (T, g.N), dev)
+        cn_w = _opt_f32("cn_w", cn_w, (T, g.E), dev)
+        _check_cuda_f32("coef", coef)
+        if ybits.dtype != torch.uint8 or tuple(ybits.shape) != (B, g.hard_bytes) or ybits.device != dev or coef.numel() != T:
+            raise ValueError("ybits must be uint8 [B, ceil(N*Z/8)] (ops.pack_labels) and coef [T]")
+        ybits, coef = ybits.contiguous(), coef.contiguous()
+        cfg = _train_cfg(decoder_type, qbit, llr_lo, llr_hi)
+        nbytes = int(_lib.lib().nldpc_boosted_train_workspace_bytes(g.ptr, ctypes.byref(cfg), B, T, int(cn_w is not None), int(vn_w is not None)))
+        if nbytes == 0:
+            raise _lib.NldpcError("boosted_train_loss: configuration not covered by the fused training kernels (boosted_train_covered)")
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        loss_sum = torch.empty((1,), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().nldpc_boosted_train_forward(g.ptr, ctypes.byref(cfg), _ptr(xa), _ptr(vn_w), _ptr(cn_w), B, T, _ptr(ybits),
+                                                        _ptr(coef), 1.0, _ptr(loss_sum), _ptr(ws), nbytes, _stream(xa))
+        _lib.check(rc, "nldpc_boosted_train_forward")
+        ctx.save_for_backward(xa, vn_w, cn_w, ws)
+        ctx.cfg = (graph_id, T, decoder_type, qbit, llr_lo, llr_hi)
+        ctx.set_materialize_grads(False)
+        return (loss_sum[0] / float(B * g.NZ)).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, gloss):
+        if gloss is None:
+            return (None,) * 11
+        xa, vn_w, cn_w, ws = ctx.saved_tensors
+        graph_id, T, decoder_type, qbit, llr_lo, llr_hi = ctx.cfg
+        g = _lib.graph_by_id(graph_id)
+        B, dev = xa.shape[0], xa.device
+        cfg = _train_cfg(decoder_type, qbit, llr_lo, llr_hi)
+        gvn = torch.empty((T, g.N), dtype=torch.float32, device=dev) if vn_w is not None else None
+        gcn = torch.empty((T, g.E), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().nldpc_boosted_train_backward(g.ptr, ctypes.byref(cfg), _ptr(xa), _ptr(vn_w), _ptr(cn_w), B, T, _ptr(gvn),
+                                                         _ptr(gcn), _ptr(ws), ws.numel(), _stream(xa))
+        _lib.check(rc, "nldpc_boosted_train_backward")
+        gl = gloss.to(torch.float32)            # the sweep ran with upstream 1; the weight gradients are linear in it
+        return (None, gvn * gl if gvn is not None else None, gcn * gl) + (None,) * 8
+
+
+def boosted_train_loss(xa, vn_w, cn_w, ybits, coef, graph_id, T, decoder_type, qbit, llr_lo, llr_hi):
+    """see _BoostedTrainLoss; vn_w [T,N] | None, cn_w [T,E] folded rows, ybits from pack_labels, coef [T] normalised weights"""
+    return _BoostedTrainLoss.apply(xa, vn_w, cn_w, ybits, coef, graph_id, T, decoder_type, qbit, llr_lo, llr_hi)
+
+
+def iteration_coefs(n, etha, coeff_param, device):
+    """normalised iteration weights etha^{c_t} / sum_t etha^{c_t} of LDPCDecoderLoss (LDPCDecoderLoss.py:88-106) as a cached
+    device tensor (one H2D copy per distinct vector, none per step: CUDA-graph capturable)"""
+    if coeff_param is None:
+        coeffs = [1] * n
+    else:
+        coeffs = list(coeff_param) if isinstance(coeff_param, (list, tuple)) else [coeff_param] * n
+    w = [float(pow(etha, c)) for c in coeffs]
+    tot = sum(w)
+    key = (device, tuple(v / tot if tot > 0 else v for v in w))
+    coef = _coef_cache.get(key)
+    if coef is None:
+        if len(_coef_cache) > 64:
+            _coef_cache.clear()
+        coef = _coef_cache[key] = torch.tensor(key[1], dtype=torch.float32, device=device)
+    return coef
+
+
+_coef_cache = {}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -429,9 +548,6 @@ def _bce_bwd(ctx, gloss, ggout):
 multi_iter_bce.register_autograd(_bce_bwd, setup_context=_bce_setup_ctx)
 
 
-_coef_cache = {}
-
-
 def fused_multi_iter_bce(outputs, y, etha=1.0, coeff_param=None):
     """Drop-in for LDPCDecoderLoss(BCE)(outputs, y, coeff_param) when `outputs` is the list a decoder's forward returned
     (views of ONE [T, B, N*Z] tensor): a single fused kernel for the loss and its gradient.  Returns None when the list
@@ -445,19 +561,7 @@ def fused_multi_iter_bce(outputs, y, etha=1.0, coeff_param=None):
     for t, o in enumerate(outputs):
         if o._base is not base or o.storage_offset() != base.storage_offset() + t * step or tuple(o.shape) != tuple(base.shape[1:]):
             return None
-    T = len(outputs)
-    if coeff_param is None:
-        coeffs = [1] * T
-    else:
-        coeffs = list(coeff_param) if isinstance(coeff_param, (list, tuple)) else [coeff_param] * T
-    w = [float(pow(etha, c)) for c in coeffs]
-    tot = sum(w)
-    key = (base.device, tuple(v / tot if tot > 0 else v for v in w))
-    coef = _coef_cache.get(key)
-    if coef is None:                # one H2D copy per distinct coefficient vector, none per step (CUDA-graph capturable)
-        if len(_coef_cache) > 64:
-            _coef_cache.clear()
-        coef = _coef_cache[key] = torch.tensor(key[1], dtype=torch.float32, device=base.device)
+    coef = iteration_coefs(len(outputs), etha, coeff_param, base.device)
     loss, _ = torch.ops.nldpc.multi_iter_bce(base, y.to(torch.float32), coef, False)    # the gradient is produced in backward
     return 1.0 * loss
 

@@ -126,6 +126,7 @@ class FusedTrainer:
                 p.grad = self.flat_grad[off:off + k].view(p.shape)
                 off += k
         self.device = dev
+        self.fused_loss = True       # use model.fused_bce_loss (one launch for forward + BCE + dL/dout) where it is covered
         self._graph = None
         self._want_graph = bool(graph)
         self._static = None
@@ -161,8 +162,14 @@ class FusedTrainer:
     def _step_body(self, x, y):
         from . import ops
         self.flat_grad.zero_()                                            # grads accumulate in place into the flat vector
-        outputs = self.model(x, target_iter=list(range(self.n_iters))) if self._takes_target_iter() else self.model(x)
-        loss = self.criterion(outputs, y, coeff_param=list(range(len(outputs))))
+        loss = None
+        if self.fused_loss and hasattr(self.model, "fused_bce_loss") and self._criterion_is_fused_bce() \
+                and self.n_iters == int(self.model.iter_node_counts):
+            # forward + multi-iteration BCE + dL/dout in ONE launch (no [T, B, N*Z] tensor crosses HBM twice); None = not covered
+            loss = self.model.fused_bce_loss(x, y, etha=self.criterion.etha, coeff_param=list(range(self.n_iters)))
+        if loss is None:
+            outputs = self.model(x, target_iter=list(range(self.n_iters))) if self._takes_target_iter() else self.model(x)
+            loss = self.criterion(outputs, y, coeff_param=list(range(len(outputs))))
         loss.backward()
         world = self._world()
         if world > 1:
@@ -171,6 +178,10 @@ class FusedTrainer:
         ops.clip_adam_clamp_(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.state, 1.0 / world, self.max_grad_norm,
                              self.lr, self.betas, self.eps, self.clamp, lr_dev=self.lr_dev)
         return loss.detach()
+
+    def _criterion_is_fused_bce(self):
+        from .boosted_neural_ldpc_decoder.struct.LossType import LossType
+        return getattr(self.criterion, "loss_type", None) == LossType.BCE and bool(getattr(self.criterion, "fused", False))
 
     def _takes_target_iter(self):
         return hasattr(self.model, "fetch_param")                        # the Boosted decoder; the Neural forward takes xa only

@@ -194,3 +194,99 @@ def test_two_streams_do_not_share_constant_arena_ranges():
             assert torch.equal(conc[i][0], serial[i][0])
             scale = float(serial[i][1].abs().max())
             assert float((conc[i][1] - serial[i][1]).abs().max()) <= 3e-5 * scale
+
+
+# ---- fused training forward (forward + multi-iteration BCE + dL/dout in one launch) ---------------------------------------
+@pytest.mark.parametrize("tag", ["d4", "cn1vn2_ms", "cn2vn3_qms"])
+def test_fused_bce_loss_matches_reference_autograd(tag):
+    """model.fused_bce_loss(x, y) == LDPCDecoderLoss(BCE)(model(x), y): loss and gradients against the REFERENCE's autograd
+    goldens (same fixtures and tolerances as the two-call form above; fp32, tolerance 3e-5 of the largest gradient)"""
+    d = load_golden(f"train_boosted_{tag}")
+    T = int(d["T"])
+    m = build_module(d, device="cuda")
+    x, y = torch.from_numpy(d["xa"]).cuda(), torch.from_numpy(d["y"]).cuda()
+    loss = m.fused_bce_loss(x, y, etha=float(d["etha"]), coeff_param=list(range(T)))
+    assert loss is not None, "the built-in codes with CN weights are covered by the fused path"
+    assert abs(loss.item() - float(d["loss64"])) < 5e-6 * max(1.0, abs(float(d["loss64"])))
+    loss.backward()
+    for n, p in m.named_parameters():
+        ref = d["grad_" + n]
+        got = p.grad.cpu().numpy()
+        scale = max(np.abs(ref).max(), 1e-6)
+        assert np.abs(got - ref).max() < 3e-5 * scale + 1e-9, (n, got.reshape(-1)[:3], ref.reshape(-1)[:3])
+    # an upstream factor reaches the weight gradients
+    g1 = {n: p.grad.clone() for n, p in m.named_parameters()}
+    for p in m.parameters():
+        p.grad = None
+    (0.25 * m.fused_bce_loss(x, y, etha=float(d["etha"]), coeff_param=list(range(T)))).backward()
+    for n, p in m.named_parameters():
+        assert float((p.grad - 0.25 * g1[n]).abs().max()) <= 2e-6 * float(g1[n].abs().max()) + 1e-12
+
+
+@pytest.mark.parametrize("code,B", [("nr_bg2_set0", 148 * 16 + 3), ("wimax_n576_r34", 37), ("nr_bg2_set0", 1)])
+@pytest.mark.parametrize("kind", ["ms_cn", "qms_cn_vn", "qms_cn2_vn2"])
+def test_fused_bce_loss_equals_two_call_form(code, B, kind):
+    """ragged batches, random (non-zero) codeword labels, etha != 1: the fused launch against forward() + LDPCDecoderLoss +
+    backward() of the same module (which the tests above pin to the reference)"""
+    from neural_ldpc_decoder_torch_b200 import TannerGraph, load_basegraph
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder import ConnectingMatrix, ConnectingMatrixTorch
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.BoostedNeuralLDPCDecoder import BoostedNeuralLDPCDecoder
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.LDPCDecoderLoss import LDPCDecoderLoss
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.DecoderType import DecoderType
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.LossType import LossType
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.NodeWeightSharingConfig import NodeWeightSharingConfig
+    from neural_ldpc_decoder_torch_b200.training import DeviceBatchGenerator
+    bg, Z = load_basegraph(code)
+    graph = TannerGraph(bg, Z)
+    dev = torch.device("cuda")
+    T = 5
+    qbit = 5 if kind.startswith("qms") else None
+    x, y = DeviceBatchGenerator(graph, [1.0, 2.0, 3.0], dev, seed=11, qms_qbit=qbit)(B)
+    sharing = {"ms_cn": (1, 0, 0), "qms_cn_vn": (3, 0, 3), "qms_cn2_vn2": (2, 0, 2)}[kind]
+    dec = DecoderType.MS if kind == "ms_cn" else DecoderType.QMS
+    cm = ConnectingMatrixTorch(ConnectingMatrix(Z=Z, basegraph=bg), device=dev)
+    m = BoostedNeuralLDPCDecoder(T, B, cm, node_weight_sharing_config=NodeWeightSharingConfig(*sharing), decoding_type=dec).to(dev)
+    m.store_llr = "none"
+    gen = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.copy_((0.6 + 0.8 * torch.rand(p.shape, generator=gen)).to(dev))
+    crit = LDPCDecoderLoss(LossType.BCE, etha=1.2)
+    ref_loss = crit(m(x, target_iter=list(range(T))), y, coeff_param=list(range(T)))
+    ref_loss.backward()
+    ref = {n: p.grad.clone() for n, p in m.named_parameters()}
+    for p in m.parameters():
+        p.grad = None
+    loss = m.fused_bce_loss(x, y, etha=1.2, coeff_param=list(range(T)))
+    assert loss is not None
+    loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < 5e-6 * max(1.0, abs(ref_loss.item()))
+    for n, p in m.named_parameters():
+        scale = max(float(ref[n].abs().max()), 1e-9)
+        assert float((p.grad - ref[n]).abs().max()) < 3e-5 * scale, (n, float((p.grad - ref[n]).abs().max()), scale)
+
+
+def test_fused_bce_loss_declines_what_it_does_not_cover():
+    from neural_ldpc_decoder_torch_b200 import load_basegraph
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder import ConnectingMatrix, ConnectingMatrixTorch
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.BoostedNeuralLDPCDecoder import BoostedNeuralLDPCDecoder
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.DecoderType import DecoderType
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.NodeWeightSharingConfig import NodeWeightSharingConfig
+    bg, Z = load_basegraph("wimax_n576_r34")
+    dev = torch.device("cuda")
+    cm = ConnectingMatrixTorch(ConnectingMatrix(Z=Z, basegraph=bg), device=dev)
+    x = torch.randn(4, bg.shape[1], Z, device=dev)
+    y = torch.zeros(4, bg.shape[1] * Z, device=dev)
+    for sharing, dec in (((3, 3, 0), DecoderType.QMS), ((0, 0, 3), DecoderType.QMS), ((3, 0, 0), DecoderType.SP)):
+        m = BoostedNeuralLDPCDecoder(3, 4, cm, node_weight_sharing_config=NodeWeightSharingConfig(*sharing), decoding_type=dec).to(dev)
+        assert m.fused_bce_loss(x, y) is None
+
+
+def test_pack_labels_matches_numpy_packbits():
+    from neural_ldpc_decoder_torch_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(2)
+    for B, NZ in ((5, 832), (3, 576), (2, 13)):
+        y = (torch.rand((B, NZ), generator=g, device="cuda") > 0.5).float()
+        got = ops.pack_labels(y).cpu().numpy()
+        ref = np.packbits(y.cpu().numpy().astype(np.uint8), axis=1, bitorder="little")
+        assert np.array_equal(got, ref)
