@@ -59,6 +59,7 @@ struct DecodeArgs {
     // as check-packed per-lane records [T][B][record][Z][P] (fp16 for QMS q=5, fp32 otherwise; degree-1 edges included),
     // hist_xin only rows 1..T-1 and only with VN weights, hist_mask may be nullptr
     int hist_fmt;
+    int desc_base;           // specialised training-mode forward: this graph's first word in the constant descriptor table (set by the launcher)
     // fused multi-iteration BCE (training forward, Boosted): with `ybits` set the kernel writes dL/dout instead of out to `soft`
     // (clamp mask folded in) and accumulates sum_t c_t * sum_i bce(out_t[i], y[i]) into *loss_acc
     const uint8_t *ybits;    // [B][ceil(N*Z/8)] label bits, bit i of a codeword = y[i] != 0 (same packing as `hard`)

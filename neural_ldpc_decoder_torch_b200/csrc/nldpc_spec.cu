@@ -43,6 +43,7 @@ int launch_neural(const DecodeArgs &a, int sm_count, cudaStream_t st) {
     using Every = typename KernelCfg<G, true, false>::type;       // list mode may carry output staging rows
     using Last = typename KernelCfg<G, false, false>::type;
     const int n_units = (a.B + Last::Shape::kCw - 1) / Last::Shape::kCw;
+    if (a.hist_v2c && a.hist_fmt != 1) return -1;      // slot-major training dump: the table-driven kernel writes that format
     const bool every = a.soft_mode == 1 || a.hard_mode == 1 || a.hist_v2c != nullptr;
     const int grid = std::min(n_units, sm_count * (every ? Every::kCtasPerSm : Last::kCtasPerSm));
     DecodeArgs args = a;
@@ -88,8 +89,8 @@ int spec_find(const int32_t *bg, int M, int N, int Z) {
 
 int spec_prepare(int id) {
     switch (id) {
-        case 0: { int rc = prepare<gen::Bg2Z16>(); return rc ? rc : spec_boosted_prepare_bg2(); }
-        case 1: { int rc = prepare<gen::WimaxZ24>(); return rc ? rc : spec_boosted_prepare_wimax(); }
+        case 0: { int rc = prepare<gen::Bg2Z16>(); if (!rc) rc = spec_boosted_prepare_bg2(); return rc ? rc : spec_train_prepare_bg2(); }
+        case 1: { int rc = prepare<gen::WimaxZ24>(); if (!rc) rc = spec_boosted_prepare_wimax(); return rc ? rc : spec_train_prepare_wimax(); }
         default: return -1;
     }
 }
@@ -106,6 +107,13 @@ int spec_launch_neural(int id, const DecodeArgs &a, int sm_count, cudaStream_t s
 }
 
 int spec_launch_boosted(int id, const DecodeArgs &a, int sm_count, cudaStream_t st) {
+    if (a.hist_v2c) {       // training dump: the training variant (check-packed records) or the table-driven kernel (slot-major)
+        switch (id) {
+            case 0: return spec_train_launch_bg2(a, sm_count, st);
+            case 1: return spec_train_launch_wimax(a, sm_count, st);
+            default: return -1;
+        }
+    }
     switch (id) {
         case 0: return spec_boosted_launch_bg2(a, sm_count, st);
         case 1: return spec_boosted_launch_wimax(a, sm_count, st);

@@ -24,6 +24,10 @@ int spec_boosted_prepare_bg2();
 int spec_boosted_launch_bg2(const DecodeArgs &a, int sm_count, cudaStream_t st);
 int spec_boosted_prepare_wimax();
 int spec_boosted_launch_wimax(const DecodeArgs &a, int sm_count, cudaStream_t st);
+int spec_train_prepare_bg2();
+int spec_train_launch_bg2(const DecodeArgs &a, int sm_count, cudaStream_t st);
+int spec_train_prepare_wimax();
+int spec_train_launch_wimax(const DecodeArgs &a, int sm_count, cudaStream_t st);
 int spec_boosted_backward_bg2(const BwdArgs &a, int sm_count, cudaStream_t st);
 int spec_boosted_backward_wimax(const BwdArgs &a, int sm_count, cudaStream_t st);
 }  // namespace nldpc

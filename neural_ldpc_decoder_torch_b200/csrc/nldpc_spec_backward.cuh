@@ -22,10 +22,6 @@
 
 namespace nldpc {
 
-// runtime descriptors of the looped checks (G::loop_desc()), per translation unit like c_wb; graph id * kDescStride is the base
-constexpr int kDescStride = 512;
-__constant__ uint32_t c_desc[2 * kDescStride];
-
 __device__ __forceinline__ float bwd_warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -403,13 +399,6 @@ __device__ __forceinline__ void cn_check_bwd_core(BwdLane<G, MODE> &c, const flo
 // truncation experiments put the cliff between 80 KB and 160 KB.  The 38 "extension" checks of BG2 differ only in their
 // table entries, so they run as four short loops (one per stored-edge count) over one-word descriptors in constant memory:
 // ~4 more address instructions per edge, but a body of ~5 K instructions.
-template <class G>
-__device__ __forceinline__ int rot_lane(int z, int s) {
-    int zz = z + s;
-    if constexpr ((G::Z & (G::Z - 1)) == 0) return zz & (G::Z - 1);
-    else return zz >= G::Z ? zz - G::Z : zz;
-}
-
 template <class G, int MODE, bool kVn, int kThreads, int D>
 __device__ __forceinline__ void cn_loop_issue(const BwdLane<G, MODE> &c, const float *stg, int w0, int rec_off) {
     using St = BwdStage<G, MODE>;
@@ -760,25 +749,6 @@ __global__ void __launch_bounds__(SpecBwdCfg<G>::kThreads, 1) nldpc_spec_backwar
 }
 
 namespace {
-
-// descriptors of the looped checks -> this translation unit's c_desc, once per device.  Synchronous on purpose: when the call
-// returns the table is in place for launches on ANY stream (the flag is shared by all of them).
-template <class G>
-cudaError_t ensure_loop_desc(int graph_slot, bool capturing) {
-    static_assert(G::kLoopDescWords <= kDescStride, "descriptor slot too small");
-    static std::mutex mu;
-    static bool done[64] = {};
-    if (G::kLoopChecks == 0) return cudaSuccess;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    std::lock_guard<std::mutex> lock(mu);
-    if (done[dev & 63]) return cudaSuccess;
-    if (capturing) return cudaErrorStreamCaptureUnsupported;      // first use inside a capture: the caller falls back
-    cudaError_t e = cudaMemcpyToSymbol(c_desc, G::loop_desc(), sizeof(uint32_t) * G::kLoopDescWords,
-                                       sizeof(uint32_t) * (size_t)graph_slot * kDescStride, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) done[dev & 63] = true;
-    return e;
-}
 
 template <class G, int MODE, bool kVn>
 int spec_bwd_launch_one(const BwdArgs &a, int wb_off, int graph_slot, int sm_count, cudaStream_t st, bool capturing) {

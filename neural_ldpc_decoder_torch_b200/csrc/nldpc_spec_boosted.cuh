@@ -47,7 +47,7 @@ template <class G>
 int boosted_launch(const DecodeArgs &a, int sm_count, cudaStream_t st) {
     const bool qms5 = a.decoder_type == 2 && a.qbit == 5, ms = a.decoder_type == 1;
     if (!(qms5 || ms) || a.compute_ucn || a.llr_init || a.xin_init || a.xin_out || a.app_init) return -1;
-    if (a.hist_v2c && a.soft_mode != 1) return -1;      // the training dump rides on the every-iteration variant
+    if (a.hist_v2c) return -1;      // training dumps: the training variant (nldpc_spec_train.cuh), tried first by the dispatcher
     const bool capturing = stream_is_capturing(st);      // CUDA graph capture: fixed arena range, no launch-time bookkeeping
     ConstArena &arena = arena_for_current_device();
     const int len = a.T * G::E;

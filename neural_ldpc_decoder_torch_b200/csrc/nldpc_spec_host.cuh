@@ -141,6 +141,25 @@ inline cudaError_t upload_wb(ConstArena &arena, const float *w, const float *b, 
                                    cudaMemcpyDeviceToDevice, st);
 }
 
+// descriptors of the looped checks -> this translation unit's c_desc, once per device.  Synchronous on purpose: when the call
+// returns the table is in place for launches on ANY stream (the flag is shared by all of them).
+template <class G>
+cudaError_t ensure_loop_desc(int graph_slot, bool capturing) {
+    static_assert(G::kLoopDescWords <= kDescStride, "descriptor slot too small");
+    static std::mutex mu;
+    static bool done[64] = {};
+    if (G::kLoopChecks == 0) return cudaSuccess;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (done[dev & 63]) return cudaSuccess;
+    if (capturing) return cudaErrorStreamCaptureUnsupported;      // first use inside a capture: the caller falls back
+    cudaError_t e = cudaMemcpyToSymbol(c_desc, G::loop_desc(), sizeof(uint32_t) * G::kLoopDescWords,
+                                       sizeof(uint32_t) * (size_t)graph_slot * kDescStride, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) done[dev & 63] = true;
+    return e;
+}
+
 template <class K>
 cudaError_t set_smem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);

@@ -30,6 +30,32 @@ namespace nldpc {
 constexpr int kConstFloat2 = 7680;                 // 60 KB of the 64 KB constant bank
 __constant__ float2 c_wb[kConstFloat2];   // this header is included by exactly one translation unit (nldpc_spec.cu)
 
+// Runtime descriptors of the checks that run as LOOPS (G::loop_desc(), one 32-bit word per edge; backward sweep and the
+// training-mode forward), per translation unit like c_wb; graph slot * kDescStride is the base of a code's table
+constexpr int kDescStride = 512;
+__constant__ uint32_t c_desc[2 * kDescStride];
+
+template <class G>
+__device__ __forceinline__ int rot_lane(int z, int s) {      // (z + s) mod Z
+    int zz = z + s;
+    if constexpr ((G::Z & (G::Z - 1)) == 0) return zz & (G::Z - 1);
+    else return zz >= G::Z ? zz - G::Z : zz;
+}
+
+// Training-mode forward: a graph type wrapped in Train<> (below, after slab_floats) keeps the channel LLRs of ALL blocks in
+// shared rows — the register-resident ones of the decode kernels cannot be indexed by a loop — so that the structurally
+// identical "extension" checks run as loops over runtime descriptors like in the backward sweep.  The fully unrolled
+// every-iteration body with dump, loss and export code in it was 12.6 K instructions = 197 KB and instruction-delivery bound
+// (ncu: no_instruction 3.3 of 8 stall cycles per issue, issue slots 25 % busy; profiles/r02_ncu_train_forward_unrolled_summary.txt).
+template <class G, class = void>
+struct train_traits {
+    static constexpr bool on = false;
+};
+template <class G>
+struct train_traits<G, std::void_t<decltype(G::kTrainVariant)>> {
+    static constexpr bool on = G::kTrainVariant;
+};
+
 #ifdef NLDPC_DEBUG_COUNT
 __device__ unsigned g_dbg_restarts;
 extern "C" unsigned nldpc_debug_restarts() { unsigned v = 0; cudaMemcpyFromSymbol(&v, g_dbg_restarts, 4); return v; }
@@ -115,10 +141,12 @@ __device__ __forceinline__ float bce_fused(L &c, int q, float out, bool pass) {
 template <class L>
 __device__ __forceinline__ float boosted_out(L &c, int q, float xo, float tot) {
     const float sum = addf(xo, tot);
-    const bool pass = sum >= c.lo && sum <= c.hi;
-    if (c.mask) c.mask[q] = pass ? 1 : 0;
     const float out = clamp_rng(sum, c.lo, c.hi);
-    if (c.yb) return bce_fused(c, q, out, pass);
+    if constexpr (train_traits<typename L::GraphT>::on) {
+        const bool pass = sum >= c.lo && sum <= c.hi;
+        if (c.mask) c.mask[q] = pass ? 1 : 0;             // two-call training: dL/dout arrives from autograd, the mask gates it
+        if (c.yb) return bce_fused(c, q, out, pass);      // fused training: dL/dout leaves instead of out
+    }
     return out;
 }
 
@@ -196,6 +224,7 @@ __device__ __forceinline__ bool group_any(int group_in_cta, bool pred) {
 // Per-thread state of the Neural decode (NeuralLDPCDecoder.py:44-100).
 template <class G>
 struct NeuralLane {
+    using GraphT = G;
     static constexpr int Z = G::Z, N = G::N, NZ = G::N * G::Z;
     float *lane;             // &slab[z]               un-rotated accesses (VN phase)
     float *rot[Z];           // &slab[(z + s) mod Z]   rotated accesses   (CN phase), indexed by the immediate shift
@@ -229,6 +258,7 @@ struct NeuralLane {
         } else {
             if (soft) st_global_stream(soft + J * Z + z, v);
         }
+        if constexpr (train_traits<G>::on) return;      // (training asks for no hard decisions)
         if (hb) {
             if constexpr (Z == 16 || Z == 32) {
                 const unsigned bal = __ballot_sync(0xffffffffu, v < 0.0f);
@@ -251,6 +281,7 @@ struct NeuralLane {
         } else {
             if (soft) st_global_stream(soft + J * Z + zz, v);
         }
+        if constexpr (train_traits<G>::on) return;
         if (hb) {
             if constexpr (Z == 16 || Z == 32) {
                 const unsigned bal = __ballot_sync(0xffffffffu, v < 0.0f);
@@ -391,6 +422,7 @@ struct Marginal {
 template <class G, int DEST>
 __device__ __forceinline__ float &xa_ref(NeuralLane<G> &c) {
     if constexpr (DEST >= 0) return c.lane[DEST * G::Z];
+    else if constexpr (train_traits<G>::on) return c.lane[(G::kXRows + G::S + (-DEST - 1)) * G::Z];   // Train<>: behind the message rows
     else return c.xreg[-DEST - 1];
 }
 
@@ -471,13 +503,10 @@ struct ReloadXreg {
 // training dump, check-packed (hist_fmt 1): the check's CN inputs as this check lane read them, one contiguous record per lane
 // ([record][Z][P]).  QMS q=5: every CN input is a sum of multiples of 0.5 (quantised channel value + quantised messages,
 // |sum| <= 7.5 * (kMaxColDeg + 1)), i.e. exact in fp16 -> records of 4 / 8 / 16 halfs; otherwise D floats.
-template <class G, int MODE, class... Es>
-__device__ __forceinline__ void dump_check(const NeuralLane<G> &c, const float *raw) {
-    constexpr int D = sizeof...(Es);
-    constexpr int eix[D] = {Es::e...};
+template <class G, int MODE, int D>
+__device__ __forceinline__ void dump_record(const NeuralLane<G> &c, const float *raw, int off) {      // off: elements per lane
     if constexpr (MODE == 2) {
-        constexpr int P = G::dump_slots_h(D), off = G::dump_off_h(eix[0]);
-        static_assert(off >= 0, "check not in the dump table");
+        constexpr int P = G::dump_slots_h(D);
         uint32_t w[P / 2];
 #pragma unroll
         for (int i = 0; i < P / 2; i++) {
@@ -492,12 +521,18 @@ __device__ __forceinline__ void dump_check(const NeuralLane<G> &c, const float *
             for (int i = 0; i < P / 8; i++) __stcs(reinterpret_cast<uint4 *>(p) + i, make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]));
         }
     } else {
-        constexpr int off = G::dump_off_f(eix[0]);
-        static_assert(off >= 0, "check not in the dump table");
         float *p = reinterpret_cast<float *>(c.dump) + (size_t)off * G::Z + (size_t)c.z * D;
 #pragma unroll
         for (int k = 0; k < D; k++) __stcs(p + k, raw[k]);
     }
+}
+template <class G, int MODE, class... Es>
+__device__ __forceinline__ void dump_check(const NeuralLane<G> &c, const float *raw) {
+    constexpr int D = sizeof...(Es);
+    constexpr int eix[D] = {Es::e...};
+    constexpr int off = MODE == 2 ? G::dump_off_h(eix[0]) : G::dump_off_f(eix[0]);
+    static_assert(off >= 0, "check not in the dump table");
+    dump_record<G, MODE, D>(c, raw, off);
 }
 
 template <class G, bool kEmit, bool kConstW, class... Es>
@@ -509,7 +544,8 @@ __device__ __forceinline__ void cn_load(const NeuralLane<G> &c, float *raw, floa
     constexpr int col1[D] = {Es::col1...};
 #pragma unroll
     for (int k = 0; k < D; k++)
-        raw[k] = rows[k] >= 0 ? c.rot[shf[k]][rows[k] * G::Z] : c.xreg[rows[k] < 0 ? -rows[k] - 1 : 0];
+        raw[k] = rows[k] >= 0 ? c.rot[shf[k]][rows[k] * G::Z]
+                 : (train_traits<G>::on ? c.lane[(G::kXRows + G::S + (rows[k] < 0 ? -rows[k] - 1 : 0)) * G::Z] : c.xreg[rows[k] < 0 ? -rows[k] - 1 : 0]);
 #pragma unroll
     for (int k = 0; k < D; k++) {
         if (col1[k] >= 0 && !kEmit) continue;                            // unstored edge, marginal not wanted now
@@ -525,7 +561,7 @@ __device__ __forceinline__ void cn_check_core(NeuralLane<G> &c, const float *raw
     constexpr int shf[D] = {Es::shift...};
     constexpr int eix[D] = {Es::e...};
     constexpr int col1[D] = {Es::col1...};
-    if constexpr (kEmit) {
+    if constexpr (kEmit) {       // (training dump of the Neural decoder: a run-time switch of its every-iteration kernel)
         if (c.dump) dump_check<G, 0, Es...>(c, raw);
     }
     float u[D];
@@ -583,7 +619,7 @@ __device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c, const fl
     constexpr int shf[D] = {Es::shift...};
     constexpr int eix[D] = {Es::e...};
     constexpr int col1[D] = {Es::col1...};
-    if constexpr (kEmit) {
+    if constexpr (kEmit && train_traits<G>::on) {
         if (c.dump) dump_check<G, MODE, Es...>(c, raw);
     }
     float u[D];
@@ -660,6 +696,112 @@ __device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c, const fl
 #ifndef NLDPC_PIPE_CN
 #define NLDPC_PIPE_CN 1     // 1: the next check's inputs are loaded before the current check computes
 #endif
+// ---- Train<> variant: the "extension" checks (D stored edges + ONE trailing degree-1 block with an identity circulant; 38 of
+// BG2's 42) as loops over the runtime descriptors of G::loop_classes — same arithmetic as cn_check_boosted_core, table entries
+// from constant memory instead of immediates.  word k < D: slab row | shift << 8 | edge << 16; word D: block J | x-row index << 8
+// | edge << 16.  The block's marginal leaves from here (every iteration: this is list mode), its xa_origin is fetched from
+// global memory one check ahead into a loop-carried register when VN weights make it differ from the on-chip xa_input.
+template <class G, int MODE, int kXo>
+struct CnBoostedLoops {
+    NeuralLane<G> &c;
+    int base;                 // first descriptor word of this graph in c_desc
+    __device__ __forceinline__ float xo_ahead(int w0, int D) const {
+        if constexpr (kXo == 2) return __ldg(c.xa_cw + (int)(c_desc[w0 + D] & 0xff) * G::Z + c.z);
+        else return 0.0f;
+    }
+    template <int D, int FIRST, int COUNT, int OFFH, int OFFF>
+    __device__ __forceinline__ void cls() {
+        constexpr int Z = G::Z, NE = D + 1;
+        constexpr int REC = MODE == 2 ? G::dump_slots_h(NE) : NE, OFF = MODE == 2 ? OFFH : OFFF;
+        float *slab0 = c.lane - c.z;
+        float xo_next = xo_ahead(base + FIRST, D);
+#pragma unroll 1
+        for (int i = 0; i < COUNT; i++) {
+            const int w0 = base + FIRST + i * NE;
+            const float xo_raw = xo_next;
+            if (i + 1 < COUNT) xo_next = xo_ahead(w0 + NE, D);
+            float raw[NE], wk[NE], u[NE];
+            float *msg[D];
+            int lidx[NE];             // self.llr index of the edge's message: [rotated lane][edge]
+#pragma unroll
+            for (int k = 0; k < D; k++) {
+                const uint32_t w = c_desc[w0 + k];
+                const int zz = rot_lane<G>(c.z, (w >> 8) & 0xff);
+                msg[k] = slab0 + (w & 0xff) * Z + zz;
+                lidx[k] = zz * G::E + (int)(w >> 16);
+                raw[k] = *msg[k];
+                wk[k] = c_wb[c.wb_base + (w >> 16)].x;
+            }
+            const uint32_t w1 = c_desc[w0 + D];
+            const int J = w1 & 0xff;
+            raw[D] = c.lane[(G::kXRows + G::S + ((w1 >> 8) & 0xff)) * Z];        // xa_input of block J, own lane
+            wk[D] = c_wb[c.wb_base + (w1 >> 16)].x;
+            lidx[D] = c.z * G::E + (int)(w1 >> 16);
+            if (c.dump) dump_record<G, MODE, NE>(c, raw, OFF + i * REC);
+#pragma unroll
+            for (int k = 0; k < NE; k++) {
+                if constexpr (MODE == 2) {
+                    u[k] = quant5_grid(raw[k]);
+                } else {
+                    const float v = condition<MODE>(raw[k], c.lo, c.hi);
+                    u[k] = (v == 0.0f) ? 0.0001f : v;
+                }
+            }
+            constexpr int H = (NE + 1) / 2;
+            float se[H + 1];
+            se[H] = 10000.0f;
+#pragma unroll
+            for (int q = H - 1; q >= 0; q--) {
+                if (2 * q + 1 < NE) se[q] = fmin3(fabsf(u[2 * q]), fabsf(u[2 * q + 1]), se[q + 1]);
+                else se[q] = fminf(fabsf(u[2 * q]), se[q + 1]);
+            }
+            unsigned x = (NE & 1) ? 0x80000000u : 0u;
+#pragma unroll
+            for (int k = 0; k < NE; k++) x ^= __float_as_uint(u[k]);
+            float pe = 10000.0f;
+            float c2v_last = 0.0f;
+#pragma unroll
+            for (int k = 0; k < NE; k++) {
+                const int q = k >> 1;
+                float mag;
+                if ((k & 1) == 0) {
+                    if (k + 1 < NE) mag = fmin3(pe, fabsf(u[k + 1]), se[q + 1]);
+                    else mag = fminf(pe, se[q + 1]);
+                } else {
+                    mag = fmin3(pe, fabsf(u[k - 1]), se[q + 1]);
+                    pe = fmin3(pe, fabsf(u[k - 1]), fabsf(u[k]));
+                }
+                float c2v;
+                if constexpr (MODE == 2) {
+                    float m = fmaxf(mulf(mag, wk[k]), 0.0f);
+                    constexpr float kMagic = 6291456.0f;
+                    m = addf(addf(fminf(m, 7.5f), kMagic), -kMagic);
+                    const unsigned sb = (x ^ __float_as_uint(u[k])) & 0x80000000u;
+                    c2v = __uint_as_float(__float_as_uint(m) | sb);
+                    c2v = (mag == 0.0f) ? 0.0f : c2v;
+                } else {
+                    const float madj = (mag > 0.0001f) ? mag : addf(mag, -0.0001f);
+                    float m = fmaxf(mulf(fabsf(madj), wk[k]), 0.0f);
+                    m = condition<MODE>(m, c.lo, c.hi);
+                    const unsigned sb = (x ^ __float_as_uint(u[k]) ^ __float_as_uint(madj)) & 0x80000000u;
+                    c2v = __uint_as_float(__float_as_uint(m) | sb);
+                    c2v = (madj == 0.0f) ? 0.0f : c2v;
+                }
+                if (c.llr_last) c.llr_last[lidx[k]] = c2v;                         // self.llr[t + 1][b][z][e] (:512)
+                if (k < D) *msg[k] = c2v;
+                else c2v_last = c2v;
+            }
+            // marginal of block J (degree 1: out = xa_origin + (0 + c2v), :513-526), un-rotated: this lane holds bit (J, z)
+            const int qbit = J * Z + c.z;
+            float xo;
+            if constexpr (kXo == 2) xo = (MODE == 2) ? quant5_grid(xo_raw) : xo_raw;      // (a zero's sign is absorbed by the sum)
+            else xo = raw[D];
+            const float v = boosted_out(c, qbit, xo, addf(0.0f, c2v_last));
+            if (c.soft) st_global_stream(c.soft + qbit, v);
+        }
+    }
+};
+
 template <class G, bool kEmit, int MODE, int kXo>
 struct CnBoosted {
     NeuralLane<G> &c;
@@ -718,6 +860,13 @@ constexpr int slab_floats(int base, int extra, int z) {      // slab stride == Z
     return s;
 }
 
+// see train_traits: all channel LLRs in shared rows (kXRegs extra rows behind the message rows), extension checks as loops
+template <class G0>
+struct Train : G0 {
+    static constexpr bool kTrainVariant = true;
+    static constexpr int kSlab = slab_floats(G0::kSlab, G0::kXRegs * G0::Z, G0::Z);
+};
+
 #ifndef NLDPC_STAGE_OUT
 #define NLDPC_STAGE_OUT 1   // 1: list-mode soft outputs leave through shared staging rows + bulk TMA stores (see Staged<>)
 #endif
@@ -775,24 +924,32 @@ struct SpecCfg {
 
 // The configuration a kernel variant runs with (kernel and launchers must agree): xa_origin rows only in list mode with VN
 // weights (see xo_global); output staging in list mode whenever it does not cost resident codewords.
-template <class G, bool kEvery, bool kXo>
+// The training variant (kTrain: every-iteration outputs + training dump [+ fused loss], Boosted only) runs on Train<G>: no xo
+// rows (xa_origin is re-read from global memory where VN weights make it differ) and no output staging, so that its larger
+// slab still leaves the CTA all its codewords.
+template <class G0, bool kEvery, bool kXo, bool kTrain = false>
 struct KernelCfg {
-    static constexpr bool kXoRows = kXo && kEvery;
+    using G = std::conditional_t<kTrain, Train<G0>, G0>;
+    static constexpr bool kXoRows = kXo && kEvery && !kTrain;
     using Plain = SpecCfg<G, kXoRows, false>;
     using Stage = SpecCfg<G, kXoRows, true>;
-    static constexpr bool kStage = NLDPC_STAGE_OUT && kEvery &&
+    static constexpr bool kStage = NLDPC_STAGE_OUT && kEvery && !kTrain &&
                                    (Stage::kCtasPerSm * Stage::kCwPerCta >= Plain::kCtasPerSm * Plain::kCwPerCta);
     using type = std::conditional_t<kStage, Stage, Plain>;
 };
 // kEvery: outputs are produced after every iteration (drop-in list mode / per-iteration hard decisions);
 // otherwise only after the last one (throughput mode) and the loop body carries no output code at all.
-template <class G0, bool kEvery, bool kConstW, int MODE = 0, bool kXo = false>
-__global__ void __launch_bounds__(KernelCfg<G0, kEvery, kXo>::type::kThreads, KernelCfg<G0, kEvery, kXo>::type::kCtasPerSm)
+template <class G0, bool kEvery, bool kConstW, int MODE = 0, bool kXo = false, bool kTrain = false>
+__global__ void __launch_bounds__(KernelCfg<G0, kEvery, kXo, kTrain>::type::kThreads, KernelCfg<G0, kEvery, kXo, kTrain>::type::kCtasPerSm)
 nldpc_spec_neural_kernel(const DecodeArgs a) {
-    using Cfg = typename KernelCfg<G0, kEvery, kXo>::type;
-    constexpr bool kStage = KernelCfg<G0, kEvery, kXo>::kStage;
-    using G = std::conditional_t<kStage, Staged<G0, Cfg::kStageOff>, G0>;      // (same graph program; emit() writes staging rows)
-    constexpr int kXoMode = !kXo ? 0 : (kEvery ? 1 : 2);
+    using Cfg = typename KernelCfg<G0, kEvery, kXo, kTrain>::type;
+    constexpr bool kStage = KernelCfg<G0, kEvery, kXo, kTrain>::kStage;
+    using G1 = typename KernelCfg<G0, kEvery, kXo, kTrain>::G;
+    using G = std::conditional_t<kStage, Staged<G1, Cfg::kStageOff>, G1>;      // (same graph program; emit() writes staging rows)
+    constexpr int kXoMode = !kXo ? 0 : ((kEvery && !kTrain) ? 1 : 2);
+    static_assert(!kTrain || (kEvery && MODE != 0), "the training variant is an every-iteration Boosted kernel");
+    // training dump / fused loss support: the Boosted training variant, and the Neural every-iteration kernel (run-time switch)
+    constexpr bool kDumps = kTrain || (MODE == 0 && kEvery);
     static_assert(MODE == 0 || kConstW, "the Boosted variants read their weights from the constant arena");
     static_assert(MODE != 0 || !kXo, "xo rows only exist for the Boosted decoder with VN weights");
     using Shape = typename Cfg::Shape;
@@ -839,7 +996,7 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
     uint8_t *hb_mine = hstage + (size_t)cw_in_cta * Cfg::kHardStride;
     // check-packed training dump: bytes per codeword and iteration
     constexpr size_t kDumpCw = (MODE == 2) ? (size_t)G::kDumpH * Z * 2 : (size_t)G::kDumpF * Z * 4;
-    const bool fused = MODE != 0 && kEvery && a.ybits != nullptr;      // fused BCE: `soft` receives dL/dout (see bce_fused)
+    const bool fused = kTrain && a.ybits != nullptr;      // fused BCE: `soft` receives dL/dout (see bce_fused)
     static_assert(Cfg::kHardBytes % 4 == 0 || MODE == 0, "packed labels are staged as 32-bit words");
 
     const int n_units = (a.B + Shape::kCw - 1) / Shape::kCw;
@@ -905,6 +1062,14 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
             if constexpr (MODE == 0) {
                 CnNeural<G, kEmitNow, kConstW, kSafe> f{c};
                 run_checks<G>(f);
+            } else if constexpr (kTrain) {
+                // the checks that differ structurally stay unrolled, the extension checks run as descriptor loops
+                CnBoosted<G, true, MODE, kXoMode> f{c};
+                G::checks_pipelined_rest(f);
+                if constexpr (G::kLoopChecks > 0) {
+                    CnBoostedLoops<G, MODE, kXoMode> l{c, a.desc_base};
+                    G::loop_classes(l);
+                }
             } else {
                 CnBoosted<G, kEmitNow, MODE, kXoMode> f{c};
                 run_checks<G>(f);
@@ -975,18 +1140,16 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
                 c.wt = a.w + (size_t)t * G::E;
                 c.bt = a.b + (size_t)t * G::E;
                 c.wb_base = a.wb_off + t * G::E;
-                const bool dump = a.hist_v2c != nullptr && c.valid;     // training dump for the backward kernel
-                const bool packed = a.hist_fmt == 1;                     // check-packed records (written by the CN phase)
-                if (MODE != 0 && dump && !packed && t == 0) {
-                    DumpXin<G> d{c, a.hist_xin + (size_t)b * NZ + z};
-                    G::blocks(d);
-                }
+                // training dump for the backward sweep: check-packed records written by the CN phase (hist_fmt 1; launches that
+                // want the slot-major format of the table-driven sweep run on the table-driven forward, see the launchers)
+                const bool dump = kDumps && a.hist_v2c != nullptr && c.valid;
                 xin_update(t);
-                // channel-input state after this iteration's update: every row in the slot-major format; in the packed format
-                // only what the VN-weight chain of the backward sweep reads (rows 1..T-1, and only when there are VN weights)
-                if (MODE != 0 && dump && (!packed || (kXo && t + 1 < a.T))) {
-                    DumpXin<G> d{c, a.hist_xin + ((size_t)(t + 1) * a.B + b) * NZ + z};
-                    G::blocks(d);
+                // channel-input state after this iteration's update: what the VN-weight chain of the sweep reads (rows 1..T-1)
+                if constexpr (kTrain && kXo) {
+                    if (dump && t + 1 < a.T) {
+                        DumpXin<G> d{c, a.hist_xin + ((size_t)(t + 1) * a.B + b) * NZ + z};
+                        G::blocks(d);
+                    }
                 }
                 if (t == 0) {
                     VnFirst<G> f{c};
@@ -994,8 +1157,10 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
                 } else {
                     c.soft = (soft_all && soft_cw) ? soft_cw + (size_t)(t - 1) * soft_iter : nullptr;
                     c.hb = hard_all ? hb_cw : nullptr;
-                    c.mask = (MODE != 0 && dump && a.hist_mask) ? a.hist_mask + ((size_t)(t - 1) * a.B + b) * NZ : nullptr;
-                    if (fused) c.cg = __ldg(a.coef + (t - 1)) * a.ginv;
+                    if constexpr (kTrain) {
+                        c.mask = (dump && a.hist_mask) ? a.hist_mask + ((size_t)(t - 1) * a.B + b) * NZ : nullptr;
+                        if (fused) c.cg = __ldg(a.coef + (t - 1)) * a.ginv;
+                    }
                     stage_wait(c);       // (graphs without degree-1 blocks emit only here; a no-op wait otherwise)
                     VnStep<G, true, MODE, kXoMode> f{c};
                     run_vcols<G>(f);
@@ -1003,17 +1168,15 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
                     flush_soft(t - 1);
                     if (hard_all) flush_hard(t - 1);
                 }
-                if (dump && !packed) {   // the v2c every CN phase reads, slot-major (same slot order as the table-driven kernels)
-                    float *hv = a.hist_v2c + (((size_t)t * a.B + b) * G::S) * Z + z;
-                    for (int q = 0; q < G::S; q++) hv[(size_t)q * Z] = c.lane[(G::kXRows + q) * Z];
-                }
                 phase_sync();
                 const bool last = t == a.T - 1;
                 c.soft = (soft_cw && (soft_all || last)) ? soft_cw + (soft_all ? (size_t)t * soft_iter : 0) : nullptr;
                 c.hb = (hard_all || last) ? hb_cw : nullptr;
-                c.mask = (MODE != 0 && dump && a.hist_mask) ? a.hist_mask + ((size_t)t * a.B + b) * NZ : nullptr;
-                c.dump = (dump && packed) ? reinterpret_cast<char *>(a.hist_v2c) + ((size_t)t * a.B + b) * kDumpCw : nullptr;
-                if (fused) c.cg = __ldg(a.coef + t) * a.ginv;
+                if constexpr (kDumps) c.dump = dump ? reinterpret_cast<char *>(a.hist_v2c) + ((size_t)t * a.B + b) * kDumpCw : nullptr;
+                if constexpr (kTrain) {
+                    c.mask = (dump && a.hist_mask) ? a.hist_mask + ((size_t)t * a.B + b) * NZ : nullptr;
+                    if (fused) c.cg = __ldg(a.coef + t) * a.ginv;
+                }
                 c.llr_last = !c.valid ? nullptr
                              : (a.llr_all ? a.llr_all + ((size_t)t * a.B + b) * Z * G::E
                                           : ((last && a.llr_last) ? a.llr_last + (size_t)b * Z * G::E : nullptr));
@@ -1055,7 +1218,7 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
         {
             c.soft = soft_cw ? soft_cw + (soft_all ? (size_t)(a.T - 1) * soft_iter : 0) : nullptr;
             c.hb = hb_cw;
-            c.mask = (MODE != 0 && kEvery && a.hist_mask && c.valid) ? a.hist_mask + ((size_t)(a.T - 1) * a.B + b) * NZ : nullptr;
+            if constexpr (kTrain) c.mask = (a.hist_v2c && a.hist_mask && c.valid) ? a.hist_mask + ((size_t)(a.T - 1) * a.B + b) * NZ : nullptr;
             c.dump = nullptr;
             if constexpr (kEvery) stage_wait(c);
             Marginal<G, MODE, kXoMode> f{c};
@@ -1063,7 +1226,7 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
             if constexpr (kEvery) flush_soft(a.T - 1);
             if (hard_any) flush_hard(a.T - 1);
         }
-        if constexpr (MODE != 0 && kEvery) {
+        if constexpr (kTrain) {
             if (fused) {      // (cg of the last iteration is still set from its CN phase)
                 loss_fold(a.T - 1);
                 float v = c.valid ? lacc : 0.0f;
