@@ -155,8 +155,10 @@ __device__ __forceinline__ void cp_async16(const void *dst_smem, const void *src
 // Staging slot of one check, per thread.  The forward wrote the check's CN inputs as ONE contiguous record per check lane
 // (check-packed dump, DecodeArgs::hist_fmt 1; degree-1 edges included), so a check costs one to three copies instead of one
 // per edge, and no rotated addresses:
-//   fp16 records (QMS q=5): two 16-byte entries [entry][thread]: the record (4 / 8 / 16 halfs), or — checks with a
-//     degree-1 edge, whose records have at most 8 halfs — record + {upstream gradient, mask word, xprev, -};
+//   fp16 records (QMS q=5): per WARP two arrays of 16-byte entries [entry][lane]: the record (4 / 8 / 16 halfs), or — checks
+//     with a degree-1 edge, whose records have at most 8 halfs — the record in entry 0 and, in the space of the warp's entry-1
+//     array, 4-byte arrays [comp][lane] {upstream gradient, mask word, xprev} (component-major: consecutive lanes, consecutive
+//     banks).  Warp-private on purpose: warps drift apart, and a lane's extras alias OTHER lanes' entry-1 records;
 //   fp32 records: kMaxRowDeg + 3 4-byte entries [entry][thread]: D values, then gradient, mask word, xprev.
 // The fp16 slots are small enough for three of them: the loops fetch two checks ahead.
 template <class G, int MODE>
@@ -165,11 +167,17 @@ struct BwdStage {
     static constexpr int kEntF = kHalf ? 8 : G::kMaxRowDeg + 3;      // floats per thread and slot
     static constexpr int kSlots = kHalf ? 3 : 2;
     static constexpr size_t kCwBytes = kHalf ? (size_t)G::kDumpH * G::Z * 2 : (size_t)G::kDumpF * G::Z * 4;   // per codeword and iteration
-    // address of extra `comp` (0 gradient, 1 mask word, 2 xprev) of this thread in slot `stg` (= &slot[tid] in float units)
+    // `stg` = this thread's place in a slot: fp32 &slot[0][tid]; fp16 &slot[warp][entry 0][lane] (256 floats per warp).
+    // address of extra `comp` (0 gradient, 1 mask word, 2 xprev) of this thread
     template <int kThreads>
     __device__ static __forceinline__ const float *extra(const float *stg, int comp) {
-        if constexpr (kHalf) return stg + 3 * (int)threadIdx.x + 4 * kThreads + comp;     // float4 entry 1 of this thread
+        if constexpr (kHalf) return stg + 128 + comp * 32 - 3 * (int)(threadIdx.x & 31);
         else return stg + (G::kMaxRowDeg + comp) * kThreads;
+    }
+    template <int kThreads>
+    __device__ static __forceinline__ const float *thread_base(const float *stage) {
+        if constexpr (kHalf) return stage + (int)(threadIdx.x >> 5) * 256 + 4 * (int)(threadIdx.x & 31);
+        else return stage + threadIdx.x;
     }
 };
 
@@ -180,10 +188,9 @@ __device__ __forceinline__ void record_issue(const BwdLane<G, MODE> &c, const fl
     if constexpr (St::kHalf) {
         constexpr int P = G::dump_slots_h(D);
         const char *src = c.hv + ((size_t)off * G::Z + (size_t)c.z * P) * 2;
-        const float *dst = stg + 3 * (int)threadIdx.x;           // float4 entry 0 of this thread
-        if constexpr (P == 4) cp_async8(dst, src);
-        else cp_async16(dst, src);
-        if constexpr (P == 16) cp_async16(dst + 4 * kThreads, src + 16);
+        if constexpr (P == 4) cp_async8(stg, src);
+        else cp_async16(stg, src);
+        if constexpr (P == 16) cp_async16(stg + 128, src + 16);
     } else {
         const float *src = reinterpret_cast<const float *>(c.hv) + (size_t)off * G::Z + (size_t)c.z * D;
 #pragma unroll
@@ -196,14 +203,13 @@ __device__ __forceinline__ void record_fetch(const float *stg, float *pv) {
     if constexpr (St::kHalf) {
         constexpr int P = G::dump_slots_h(D);
         uint32_t w[P / 2];
-        const float *src = stg + 3 * (int)threadIdx.x;
         if constexpr (P == 4) {
-            const uint2 v = *reinterpret_cast<const uint2 *>(src);
+            const uint2 v = *reinterpret_cast<const uint2 *>(stg);
             w[0] = v.x; w[1] = v.y;
         } else {
 #pragma unroll
             for (int i = 0; i < P / 8; i++) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(src + i * 4 * kThreads);
+                const uint4 v = *reinterpret_cast<const uint4 *>(stg + i * 128);
                 w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
             }
         }
@@ -718,11 +724,12 @@ __global__ void __launch_bounds__(SpecBwdCfg<G>::kThreads, 1) nldpc_spec_backwar
             }
             phase_sync();
             {
-                CnBwd<G, MODE, kVn, kThreads> f{c, stage + tid};
+                const float *stg = BwdStage<G, MODE>::template thread_base<kThreads>(stage);
+                CnBwd<G, MODE, kVn, kThreads> f{c, stg};
                 G::checks_pipelined_rest(f);
                 if constexpr (G::kLoopChecks > 0) {
                     c.fold.flush();      // the loops carry the fold counters in registers: enter them from a known state
-                    CnBwdLoops<G, MODE, kVn, kThreads> l{c, stage + tid, desc_base};
+                    CnBwdLoops<G, MODE, kVn, kThreads> l{c, stg, desc_base};
                     G::loop_classes(l);
                 }
             }

@@ -144,8 +144,8 @@ __device__ __forceinline__ float boosted_out(L &c, int q, float xo, float tot) {
     const float out = clamp_rng(sum, c.lo, c.hi);
     if constexpr (train_traits<typename L::GraphT>::on) {
         const bool pass = sum >= c.lo && sum <= c.hi;
+        if (c.yb) return bce_fused(c, q, out, pass);      // fused training: dL/dout leaves instead of out (all lanes of a launch)
         if (c.mask) c.mask[q] = pass ? 1 : 0;             // two-call training: dL/dout arrives from autograd, the mask gates it
-        if (c.yb) return bce_fused(c, q, out, pass);      // fused training: dL/dout leaves instead of out
     }
     return out;
 }
@@ -159,7 +159,7 @@ __device__ __forceinline__ float boosted_out(L &c, int q, float xo, float tot) {
 template <int MODE, class L>
 __device__ __forceinline__ float xo_global(const L &c, int q) {
     const float v = __ldg(c.xa_cw + q);
-    if constexpr (MODE == 2) return quant5(v);
+    if constexpr (MODE == 2) return quant5_grid(v);      // (+0.0 where quant5 gives -0.0: absorbed by the sum it enters, xo + (0 + ...))
     else return v;
 }
 
@@ -460,7 +460,9 @@ struct ScaleXin {
     template <int J, int DEST>
     __device__ __forceinline__ void put() {
         float x = mulf(xa_ref<G, DEST>(c), __ldg(vw + J));
-        if constexpr (MODE == 2) x = quant5(x);
+        // quant5_grid: +0.0 where quant5 gives -0.0.  The value is only ever added to +0-started sums, quantised again by the CN
+        // phase, or multiplied — a zero's sign reaches no output.
+        if constexpr (MODE == 2) x = quant5_grid(x);
         xa_ref<G, DEST>(c) = x;
     }
 };
@@ -705,6 +707,7 @@ template <class G, int MODE, int kXo>
 struct CnBoostedLoops {
     NeuralLane<G> &c;
     int base;                 // first descriptor word of this graph in c_desc
+    bool want_llr;            // the launch exports self.llr (warp-uniform)
     __device__ __forceinline__ float xo_ahead(int w0, int D) const {
         if constexpr (kXo == 2) return __ldg(c.xa_cw + (int)(c_desc[w0 + D] & 0xff) * G::Z + c.z);
         else return 0.0f;
@@ -722,13 +725,13 @@ struct CnBoostedLoops {
             if (i + 1 < COUNT) xo_next = xo_ahead(w0 + NE, D);
             float raw[NE], wk[NE], u[NE];
             float *msg[D];
-            int lidx[NE];             // self.llr index of the edge's message: [rotated lane][edge]
+            int zl[NE];               // variable lane of the edge's message (self.llr is [lane][edge])
 #pragma unroll
             for (int k = 0; k < D; k++) {
                 const uint32_t w = c_desc[w0 + k];
                 const int zz = rot_lane<G>(c.z, (w >> 8) & 0xff);
                 msg[k] = slab0 + (w & 0xff) * Z + zz;
-                lidx[k] = zz * G::E + (int)(w >> 16);
+                zl[k] = zz;
                 raw[k] = *msg[k];
                 wk[k] = c_wb[c.wb_base + (w >> 16)].x;
             }
@@ -736,7 +739,7 @@ struct CnBoostedLoops {
             const int J = w1 & 0xff;
             raw[D] = c.lane[(G::kXRows + G::S + ((w1 >> 8) & 0xff)) * Z];        // xa_input of block J, own lane
             wk[D] = c_wb[c.wb_base + (w1 >> 16)].x;
-            lidx[D] = c.z * G::E + (int)(w1 >> 16);
+            zl[D] = c.z;
             if (c.dump) dump_record<G, MODE, NE>(c, raw, OFF + i * REC);
 #pragma unroll
             for (int k = 0; k < NE; k++) {
@@ -787,7 +790,9 @@ struct CnBoostedLoops {
                     c2v = __uint_as_float(__float_as_uint(m) | sb);
                     c2v = (madj == 0.0f) ? 0.0f : c2v;
                 }
-                if (c.llr_last) c.llr_last[lidx[k]] = c2v;                         // self.llr[t + 1][b][z][e] (:512)
+                if (want_llr) {                                                    // (warp-uniform: training rarely exports self.llr)
+                    if (c.llr_last) c.llr_last[zl[k] * G::E + (int)(c_desc[w0 + k] >> 16)] = c2v;      // self.llr[t + 1][b][z][e] (:512)
+                }
                 if (k < D) *msg[k] = c2v;
                 else c2v_last = c2v;
             }
@@ -1067,7 +1072,7 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
                 CnBoosted<G, true, MODE, kXoMode> f{c};
                 G::checks_pipelined_rest(f);
                 if constexpr (G::kLoopChecks > 0) {
-                    CnBoostedLoops<G, MODE, kXoMode> l{c, a.desc_base};
+                    CnBoostedLoops<G, MODE, kXoMode> l{c, a.desc_base, a.llr_all != nullptr || a.llr_last != nullptr};
                     G::loop_classes(l);
                 }
             } else {
