@@ -381,7 +381,7 @@ __device__ __forceinline__ void cn_check_bwd_core(BwdLane<G, MODE> &c, const flo
     for (int k = 0; k < D; k++) {
         if (col1[k] < 0) dc[k] = c.rot[shf[k]][rows[k] * Z];
         else dc[k] = pg[k];
-        wb[k] = c_wb[c.wb_base + eix[k]];
+        wb[k] = wb_at<MODE != 0>(c.wb_base + eix[k]);
     }
     cn_bwd_math<MODE, D>(pv, dc, wb, c.lo, c.hi, gw, gb, du);
     // fold order (RowOrder::chk mirrors it): the check's weight rows, then (Neural) its bias rows
@@ -432,7 +432,7 @@ __device__ __forceinline__ void cn_loop_compute(BwdLane<G, MODE> &c, const float
         const uint32_t w = c_desc[w0 + k];
         msg[k] = slab0 + (w & 0xff) * Z + rot_lane<G>(c.z, (w >> 8) & 0xff);
         dc[k] = *msg[k];
-        wb[k] = c_wb[c.wb_base + (w >> 16)];
+        wb[k] = wb_at<MODE != 0>(c.wb_base + (int)(w >> 16));
     }
     const uint32_t w1 = c_desc[w0 + D];
     const int J = w1 & 0xff, ridx = (w1 >> 8) & 0xff;
@@ -443,7 +443,7 @@ __device__ __forceinline__ void cn_loop_compute(BwdLane<G, MODE> &c, const float
         if (c.mk) keep = keep && (((__float_as_uint(*St::template extra<kThreads>(stg, 1)) >> (8 * (q & 3))) & 0xffu) != 0);
         dc[D] = keep ? gv : 0.0f;
     }
-    wb[D] = c_wb[c.wb_base + (w1 >> 16)];
+    wb[D] = wb_at<MODE != 0>(c.wb_base + (int)(w1 >> 16));
     cn_bwd_math<MODE, NE>(pv, dc, wb, c.lo, c.hi, gw, gb, du);
     // fold order (RowOrder::cls mirrors it): weight rows, (Neural) bias rows, (kVn) the VN row of block J
     c.fold.reserve(NE);
@@ -660,7 +660,8 @@ __global__ void __launch_bounds__(SpecBwdCfg<G>::kThreads, 1) nldpc_spec_backwar
 
     const int tid = threadIdx.x, warp = tid >> 5, ln = tid & 31;
     const int grp = tid / Shape::kLanes, gl = tid - grp * Shape::kLanes;
-    const int cwl = gl / Z, z = gl - cwl * Z;
+    int cwl, z;
+    Shape::map(gl, cwl, z);      // (Z = 24: the bank-conflict-free lane mapping of the forward, GroupShape::map)
     const int cw_in_cta = grp * Shape::kCw + cwl;
     // row indices of the graph program count the forward's channel rows too: point kXRows rows before this codeword's messages
     float *slab = slabs + (size_t)cw_in_cta * Cfg::kSlabF - G::kXRows * Z;
@@ -798,18 +799,20 @@ int spec_bwd_launch(const BwdArgs &a, int graph_slot, int sm_count, cudaStream_t
     if (!spec_bwd_covers<G>(a.mode, a.T, a.w != nullptr, a.gvn != nullptr, a.ucn_mix || a.hist_ucn, a.qbit)) return -1;
     const bool capturing = stream_is_capturing(st);           // CUDA graph capture: see ConstArena::acquire_captured
     ConstArena &arena = arena_for_current_device();
-    const int len = a.T * G::E;
+    const int n_w = a.T * G::E;
+    const int len = kBoosted ? (n_w + 1) / 2 : n_w;      // float2 units: Boosted launches store plain floats (wb_at)
     cudaError_t err = cudaSuccess;
     const int off = capturing ? arena.acquire_captured(len, st, &err) : arena.acquire(len, st, &err);
     if (err != cudaSuccess) return (int)err;
     if (off < 0) return -1;
-    if ((err = upload_wb(arena, a.w, a.mode == 0 ? a.b : nullptr, off, len, st)) != cudaSuccess) return (int)err;
+    if ((err = kBoosted ? upload_w(arena, a.w, off, n_w, st) : upload_wb(arena, a.w, a.b, off, len, st)) != cudaSuccess) return (int)err;
     int rc;
     if constexpr (!kBoosted) {
         rc = spec_bwd_launch_one<G, 0, false>(a, off, graph_slot, sm_count, st, capturing);
     } else {
-        if (a.mode == 1) rc = a.gvn ? spec_bwd_launch_one<G, 1, true>(a, off, graph_slot, sm_count, st, capturing) : spec_bwd_launch_one<G, 1, false>(a, off, graph_slot, sm_count, st, capturing);
-        else rc = a.gvn ? spec_bwd_launch_one<G, 2, true>(a, off, graph_slot, sm_count, st, capturing) : spec_bwd_launch_one<G, 2, false>(a, off, graph_slot, sm_count, st, capturing);
+        const int offf = 2 * off;                        // float units
+        if (a.mode == 1) rc = a.gvn ? spec_bwd_launch_one<G, 1, true>(a, offf, graph_slot, sm_count, st, capturing) : spec_bwd_launch_one<G, 1, false>(a, offf, graph_slot, sm_count, st, capturing);
+        else rc = a.gvn ? spec_bwd_launch_one<G, 2, true>(a, offf, graph_slot, sm_count, st, capturing) : spec_bwd_launch_one<G, 2, false>(a, offf, graph_slot, sm_count, st, capturing);
     }
     if (capturing) return rc;
     const cudaError_t rel = arena.release_after(off, len, st);

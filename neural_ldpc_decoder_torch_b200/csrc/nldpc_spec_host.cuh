@@ -160,6 +160,19 @@ cudaError_t ensure_loop_desc(int graph_slot, bool capturing) {
     return e;
 }
 
+// weights only (Boosted decoders): n plain floats at arena offset `off` (float2 units), absent weights = 1.0
+__global__ void pack_w_kernel(const float *__restrict__ w, float *__restrict__ dst, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = w ? w[i] : 1.0f;
+}
+inline cudaError_t upload_w(ConstArena &arena, const float *w, int off, int n, cudaStream_t st) {
+    pack_w_kernel<<<(n + 255) / 256, 256, 0, st>>>(w, reinterpret_cast<float *>(arena.stage + off), n);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbolAsync(c_wb, arena.stage + off, sizeof(float2) * (size_t)((n + 1) / 2), sizeof(float2) * (size_t)off,
+                                   cudaMemcpyDeviceToDevice, st);
+}
+
 template <class K>
 cudaError_t set_smem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);

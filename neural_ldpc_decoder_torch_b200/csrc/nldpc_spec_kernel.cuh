@@ -28,7 +28,15 @@ namespace nldpc {
 // uniform datapath (LDCU) so they cost no LSU bandwidth.  The arena is a ring shared by in-flight launches
 // (see ConstArena in nldpc_spec.cu); launches whose weights do not fit use the LDG variant (kConstW = false).
 constexpr int kConstFloat2 = 7680;                 // 60 KB of the 64 KB constant bank
-__constant__ float2 c_wb[kConstFloat2];   // this header is included by exactly one translation unit (nldpc_spec.cu)
+__constant__ float2 c_wb[kConstFloat2];   // one copy per translation unit that instantiates specialised kernels
+// The Boosted decoders have weights only (no biases): their launches store plain floats in the arena (half the space: T * E
+// floats, so an eager launch and a CUDA-graph-captured one of the training configuration fit side by side) and index it in
+// float units; the Neural decoder stores {w, b} pairs and indexes in float2 units.
+template <bool kScalarW>
+__device__ __forceinline__ float2 wb_at(int idx) {
+    if constexpr (kScalarW) return make_float2(reinterpret_cast<const float *>(c_wb)[idx], 0.0f);
+    else return c_wb[idx];
+}
 
 // Runtime descriptors of the checks that run as LOOPS (G::loop_desc(), one 32-bit word per edge; backward sweep and the
 // training-mode forward), per translation unit like c_wb; graph slot * kDescStride is the base of a code's table
@@ -54,6 +62,20 @@ struct train_traits {
 template <class G>
 struct train_traits<G, std::void_t<decltype(G::kTrainVariant)>> {
     static constexpr bool on = G::kTrainVariant;
+};
+// Neural decoder: the every-iteration kernel that also writes the training dump is its own instantiation (Dumping<G>), so that
+// the list-mode decode carries no per-check branch (basic-block boundaries between checks cost the cross-check scheduling)
+template <class G0>
+struct Dumping : G0 {
+    static constexpr bool kDumpVariant = true;
+};
+template <class G, class = void>
+struct dump_traits {
+    static constexpr bool on = false;
+};
+template <class G>
+struct dump_traits<G, std::void_t<decltype(G::kDumpVariant)>> {
+    static constexpr bool on = G::kDumpVariant;
 };
 
 #ifdef NLDPC_DEBUG_COUNT
@@ -189,6 +211,21 @@ struct GroupShape {
     static constexpr int kCw = kLanes / Z;      // codewords per group
     static constexpr int kWarps = kLanes / 32;
     static_assert(kLanes != 0, "specialised kernels exist for Z in {16, 24, 32}");
+    // Which (codeword, lane z) a thread of the group works on.  Z | 32: consecutive threads = consecutive lanes of a codeword.
+    // Z = 24 (4 codewords on 3 warps): warp w of the group takes lanes 8w .. 8w+7 of ALL four codewords.  With the slab stride
+    // == 24 (mod 32) the four codewords' rows start 24 banks apart, so the 4 x 8 lanes of a warp fall on four disjoint 8-bank
+    // windows — for the un-rotated accesses and, because a rotation moves all four 8-lane runs by the same amount (a run that
+    // wraps at z = 24 continues 8 banks further, exactly where the next codeword's window ended), for every circulant shift.
+    // The codeword-major mapping left warps straddling codewords: 35 % of all shared wavefronts were bank-conflict replays (ncu).
+    __device__ static __forceinline__ void map(int gl, int &cwl, int &z) {
+        if constexpr (Z == 24) {
+            cwl = (gl & 31) >> 3;
+            z = ((gl >> 5) << 3) | (gl & 7);
+        } else {
+            cwl = gl / Z;
+            z = gl - cwl * Z;
+        }
+    }
 };
 
 template <int kLanes>
@@ -268,7 +305,11 @@ struct NeuralLane {
                     if (z == 0) reinterpret_cast<uint32_t *>(hb)[J] = bal;
                 }
             } else {
-                if (v < 0.0f) atomicOr(reinterpret_cast<unsigned *>(hb) + ((J * Z + z) >> 5), 1u << ((J * Z + z) & 31));
+                // Z = 24: the warp holds lanes 8w .. 8w+7 of four codewords (GroupShape::map): 8 ballot bits = one whole byte
+                // of the codeword's packed row
+                static_assert(Z % 8 == 0, "byte-aligned lane runs");
+                const unsigned bal = __ballot_sync(0xffffffffu, v < 0.0f);
+                if ((threadIdx.x & 7) == 0) hb[(J * Z + z) >> 3] = (uint8_t)(bal >> (threadIdx.x & 24));
             }
         }
     }
@@ -537,7 +578,7 @@ __device__ __forceinline__ void dump_check(const NeuralLane<G> &c, const float *
     dump_record<G, MODE, D>(c, raw, off);
 }
 
-template <class G, bool kEmit, bool kConstW, class... Es>
+template <class G, bool kEmit, bool kConstW, bool kScalarW, class... Es>
 __device__ __forceinline__ void cn_load(const NeuralLane<G> &c, float *raw, float2 *wb) {
     constexpr int D = sizeof...(Es);
     constexpr int rows[D] = {Es::row...};
@@ -551,7 +592,7 @@ __device__ __forceinline__ void cn_load(const NeuralLane<G> &c, float *raw, floa
 #pragma unroll
     for (int k = 0; k < D; k++) {
         if (col1[k] >= 0 && !kEmit) continue;                            // unstored edge, marginal not wanted now
-        if constexpr (kConstW) wb[k] = c_wb[c.wb_base + eix[k]];
+        if constexpr (kConstW) wb[k] = wb_at<kScalarW>(c.wb_base + eix[k]);
         else wb[k] = make_float2(__ldg(c.wt + eix[k]), __ldg(c.bt + eix[k]));
     }
 }
@@ -563,7 +604,7 @@ __device__ __forceinline__ void cn_check_core(NeuralLane<G> &c, const float *raw
     constexpr int shf[D] = {Es::shift...};
     constexpr int eix[D] = {Es::e...};
     constexpr int col1[D] = {Es::col1...};
-    if constexpr (kEmit) {       // (training dump of the Neural decoder: a run-time switch of its every-iteration kernel)
+    if constexpr (kEmit && dump_traits<G>::on) {       // (training dump of the Neural decoder: Dumping<G> instantiation)
         if (c.dump) dump_check<G, 0, Es...>(c, raw);
     }
     float u[D];
@@ -733,12 +774,12 @@ struct CnBoostedLoops {
                 msg[k] = slab0 + (w & 0xff) * Z + zz;
                 zl[k] = zz;
                 raw[k] = *msg[k];
-                wk[k] = c_wb[c.wb_base + (w >> 16)].x;
+                wk[k] = wb_at<true>(c.wb_base + (int)(w >> 16)).x;
             }
             const uint32_t w1 = c_desc[w0 + D];
             const int J = w1 & 0xff;
             raw[D] = c.lane[(G::kXRows + G::S + ((w1 >> 8) & 0xff)) * Z];        // xa_input of block J, own lane
-            wk[D] = c_wb[c.wb_base + (w1 >> 16)].x;
+            wk[D] = wb_at<true>(c.wb_base + (int)(w1 >> 16)).x;
             zl[D] = c.z;
             if (c.dump) dump_record<G, MODE, NE>(c, raw, OFF + i * REC);
 #pragma unroll
@@ -815,12 +856,12 @@ struct CnBoosted {
     float2 wb[2][G::kMaxRowDeg];
     template <class... Es>
     __device__ __forceinline__ void chk() {
-        cn_load<G, kEmit, true, Es...>(c, raw[0], wb[0]);
+        cn_load<G, kEmit, true, true, Es...>(c, raw[0], wb[0]);
         cn_check_boosted_core<G, kEmit, MODE, kXo, Es...>(c, raw[0], wb[0]);
     }
     template <int SLOT, class... Es>
     __device__ __forceinline__ void ld() {
-        cn_load<G, kEmit, true, Es...>(c, raw[SLOT], wb[SLOT]);
+        cn_load<G, kEmit, true, true, Es...>(c, raw[SLOT], wb[SLOT]);
     }
     template <int SLOT, class... Es>
     __device__ __forceinline__ void chk() {
@@ -836,12 +877,12 @@ struct CnNeural {
     float2 wb[2][G::kMaxRowDeg];
     template <class... Es>
     __device__ __forceinline__ void chk() {
-        cn_load<G, kEmit, kConstW, Es...>(c, raw[0], wb[0]);
+        cn_load<G, kEmit, kConstW, false, Es...>(c, raw[0], wb[0]);
         cn_check_core<G, kEmit, kConstW, kZeroSafe, Es...>(c, raw[0], wb[0]);
     }
     template <int SLOT, class... Es>
     __device__ __forceinline__ void ld() {
-        cn_load<G, kEmit, kConstW, Es...>(c, raw[SLOT], wb[SLOT]);
+        cn_load<G, kEmit, kConstW, false, Es...>(c, raw[SLOT], wb[SLOT]);
     }
     template <int SLOT, class... Es>
     __device__ __forceinline__ void chk() {
@@ -945,16 +986,18 @@ struct KernelCfg {
 // kEvery: outputs are produced after every iteration (drop-in list mode / per-iteration hard decisions);
 // otherwise only after the last one (throughput mode) and the loop body carries no output code at all.
 template <class G0, bool kEvery, bool kConstW, int MODE = 0, bool kXo = false, bool kTrain = false>
-__global__ void __launch_bounds__(KernelCfg<G0, kEvery, kXo, kTrain>::type::kThreads, KernelCfg<G0, kEvery, kXo, kTrain>::type::kCtasPerSm)
+__global__ void __launch_bounds__(KernelCfg<G0, kEvery, kXo, kTrain && MODE != 0>::type::kThreads, KernelCfg<G0, kEvery, kXo, kTrain && MODE != 0>::type::kCtasPerSm)
 nldpc_spec_neural_kernel(const DecodeArgs a) {
-    using Cfg = typename KernelCfg<G0, kEvery, kXo, kTrain>::type;
-    constexpr bool kStage = KernelCfg<G0, kEvery, kXo, kTrain>::kStage;
-    using G1 = typename KernelCfg<G0, kEvery, kXo, kTrain>::G;
+    // kTrain: Boosted -> the Train<> variant (all channel LLRs in shared rows, extension checks as loops, dump + fused loss);
+    //         Neural  -> the list-mode kernel plus the training dump (Dumping<>)
+    constexpr bool kTrainWrap = kTrain && MODE != 0;
+    using Cfg = typename KernelCfg<G0, kEvery, kXo, kTrainWrap>::type;
+    constexpr bool kStage = KernelCfg<G0, kEvery, kXo, kTrainWrap>::kStage;
+    using G1 = std::conditional_t<kTrainWrap, Train<G0>, std::conditional_t<kTrain, Dumping<G0>, G0>>;
     using G = std::conditional_t<kStage, Staged<G1, Cfg::kStageOff>, G1>;      // (same graph program; emit() writes staging rows)
     constexpr int kXoMode = !kXo ? 0 : ((kEvery && !kTrain) ? 1 : 2);
-    static_assert(!kTrain || (kEvery && MODE != 0), "the training variant is an every-iteration Boosted kernel");
-    // training dump / fused loss support: the Boosted training variant, and the Neural every-iteration kernel (run-time switch)
-    constexpr bool kDumps = kTrain || (MODE == 0 && kEvery);
+    static_assert(!kTrain || kEvery, "the training variants are every-iteration kernels");
+    constexpr bool kDumps = kTrain;
     static_assert(MODE == 0 || kConstW, "the Boosted variants read their weights from the constant arena");
     static_assert(MODE != 0 || !kXo, "xo rows only exist for the Boosted decoder with VN weights");
     using Shape = typename Cfg::Shape;
@@ -970,8 +1013,8 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
     // of indexed LDC loads into vector registers whose latency the multiply waited for (ncu: short_scoreboard on FMUL).
     const int grp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0) / Shape::kWarps;
     const int gl = threadIdx.x - grp * Shape::kLanes;       // lane within the group
-    const int cwl = gl / Z;                                 // codeword within the group
-    const int z = gl - cwl * Z;
+    int cwl, z;                                             // codeword within the group, lane within the codeword
+    Shape::map(gl, cwl, z);
     const int cw_in_cta = grp * Shape::kCw + cwl;
     float *slab = slabs + (size_t)cw_in_cta * Cfg::kSlabF;
     uint64_t *bar = bars + grp;
@@ -1001,7 +1044,7 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
     uint8_t *hb_mine = hstage + (size_t)cw_in_cta * Cfg::kHardStride;
     // check-packed training dump: bytes per codeword and iteration
     constexpr size_t kDumpCw = (MODE == 2) ? (size_t)G::kDumpH * Z * 2 : (size_t)G::kDumpF * Z * 4;
-    const bool fused = kTrain && a.ybits != nullptr;      // fused BCE: `soft` receives dL/dout (see bce_fused)
+    const bool fused = kTrainWrap && a.ybits != nullptr;      // fused BCE: `soft` receives dL/dout (see bce_fused)
     static_assert(Cfg::kHardBytes % 4 == 0 || MODE == 0, "packed labels are staged as 32-bit words");
 
     const int n_units = (a.B + Shape::kCw - 1) / Shape::kCw;
@@ -1036,7 +1079,7 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
                 tma_load_1d(slabs + (size_t)(grp * Shape::kCw + q) * Cfg::kSlabF + G::kXRows * Z, a.xa + (size_t)(b0 + q) * NZ,
                             (uint32_t)(NZ * sizeof(float)), bar);
         }
-        if constexpr (Z != 16 && Z != 32) {   // atomicOr staging must start from zero
+        if constexpr (Z != 16 && Z != 32 && (G::kXRegs + G::kDeg1Smem > 0)) {   // atomicOr staging (rotated emission) must start from zero
             if (hard_any) for (int q = z; q < Cfg::kHardStride / 4; q += Z) reinterpret_cast<unsigned *>(hb_mine)[q] = 0u;
         }
         if (ncw > 0) {
@@ -1067,7 +1110,7 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
             if constexpr (MODE == 0) {
                 CnNeural<G, kEmitNow, kConstW, kSafe> f{c};
                 run_checks<G>(f);
-            } else if constexpr (kTrain) {
+            } else if constexpr (kTrainWrap) {
                 // the checks that differ structurally stay unrolled, the extension checks run as descriptor loops
                 CnBoosted<G, true, MODE, kXoMode> f{c};
                 G::checks_pipelined_rest(f);
@@ -1115,7 +1158,7 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
                     dst[(size_t)q * Cfg::kHardBytes + r] = src[(size_t)q * Cfg::kHardStride + r];
                 }
             }
-            if constexpr (Z != 16 && Z != 32) {
+            if constexpr (Z != 16 && Z != 32 && (G::kXRegs + G::kDeg1Smem > 0)) {
                 group_sync<Shape::kLanes>(grp);
                 for (int q = z; q < Cfg::kHardStride / 4; q += Z) reinterpret_cast<unsigned *>(hb_mine)[q] = 0u;
             }
@@ -1150,7 +1193,7 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
                 const bool dump = kDumps && a.hist_v2c != nullptr && c.valid;
                 xin_update(t);
                 // channel-input state after this iteration's update: what the VN-weight chain of the sweep reads (rows 1..T-1)
-                if constexpr (kTrain && kXo) {
+                if constexpr (kTrainWrap && kXo) {
                     if (dump && t + 1 < a.T) {
                         DumpXin<G> d{c, a.hist_xin + ((size_t)(t + 1) * a.B + b) * NZ + z};
                         G::blocks(d);
@@ -1162,7 +1205,7 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
                 } else {
                     c.soft = (soft_all && soft_cw) ? soft_cw + (size_t)(t - 1) * soft_iter : nullptr;
                     c.hb = hard_all ? hb_cw : nullptr;
-                    if constexpr (kTrain) {
+                    if constexpr (kTrainWrap) {
                         c.mask = (dump && a.hist_mask) ? a.hist_mask + ((size_t)(t - 1) * a.B + b) * NZ : nullptr;
                         if (fused) c.cg = __ldg(a.coef + (t - 1)) * a.ginv;
                     }
@@ -1178,7 +1221,7 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
                 c.soft = (soft_cw && (soft_all || last)) ? soft_cw + (soft_all ? (size_t)t * soft_iter : 0) : nullptr;
                 c.hb = (hard_all || last) ? hb_cw : nullptr;
                 if constexpr (kDumps) c.dump = dump ? reinterpret_cast<char *>(a.hist_v2c) + ((size_t)t * a.B + b) * kDumpCw : nullptr;
-                if constexpr (kTrain) {
+                if constexpr (kTrainWrap) {
                     c.mask = (dump && a.hist_mask) ? a.hist_mask + ((size_t)t * a.B + b) * NZ : nullptr;
                     if (fused) c.cg = __ldg(a.coef + t) * a.ginv;
                 }
@@ -1223,7 +1266,7 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
         {
             c.soft = soft_cw ? soft_cw + (soft_all ? (size_t)(a.T - 1) * soft_iter : 0) : nullptr;
             c.hb = hb_cw;
-            if constexpr (kTrain) c.mask = (a.hist_v2c && a.hist_mask && c.valid) ? a.hist_mask + ((size_t)(a.T - 1) * a.B + b) * NZ : nullptr;
+            if constexpr (kTrainWrap) c.mask = (a.hist_v2c && a.hist_mask && c.valid) ? a.hist_mask + ((size_t)(a.T - 1) * a.B + b) * NZ : nullptr;
             c.dump = nullptr;
             if constexpr (kEvery) stage_wait(c);
             Marginal<G, MODE, kXoMode> f{c};
@@ -1231,7 +1274,7 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
             if constexpr (kEvery) flush_soft(a.T - 1);
             if (hard_any) flush_hard(a.T - 1);
         }
-        if constexpr (kTrain) {
+        if constexpr (kTrainWrap) {
             if (fused) {      // (cg of the last iteration is still set from its CN phase)
                 loss_fold(a.T - 1);
                 float v = c.valid ? lacc : 0.0f;
