@@ -318,6 +318,25 @@ def other_configs(dev, B, steps=20):
         cm2 = bn.ConnectingMatrixTorch(bn.ConnectingMatrix(Z=Z2, basegraph=bg2), device=dev)
         m2 = BoostedNeuralLDPCDecoder(20, B, cm2, node_weight_sharing_config=NodeWeightSharingConfig(3, 0, 3), decoding_type=DecoderType.QMS).to(dev)
         measure("BoostedNeuralLDPCDecoder BG2 z=16, QMS q=5, cn=3 / vn=3, 20 iterations, batch %d (train config, decode only)" % B, lambda: m2.decode_hard(x2))
+        # the headline decoder end to end with NARROW host LLRs (nldpc_neural_decode_host_narrow): the fp32 path is bound by the
+        # host->device link (3328 B per codeword); fp16 values / int8 codes are expanded on the device, results bit-identical to
+        # the decode of the widened values (tests/test_neural_gpu.py::test_host_api_narrow_llr_transports_equal_the_widened_decode)
+        mn = nn_.NeuralLDPCDecoder(T_ITERS, B, nn_.ConnectingMatrixTorch(nn_.ConnectingMatrix(Z=Z2, basegraph=bg2), device=dev)).to(dev)
+        xh = torch.from_numpy(synth_llr_numpy(B, g2.N, Z2, 4242))
+        for name, xin, kw, nbytes in (("fp16 values", xh.to(torch.float16).pin_memory(), {}, 2),
+                                      ("int8 codes (x = 0.25 q)", torch.clamp(torch.round(xh / 0.25), -127, 127).to(torch.int8).pin_memory(), {"scale": 0.25}, 1)):
+            for _ in range(3):
+                mn.decode_host(xin, **kw)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(10):
+                mn.decode_host(xin, **kw)
+            dt = (time.perf_counter() - t0) / 10
+            out.append({"workload": "NeuralLDPCDecoder BG2 z=16, 10 iterations, batch %d (the headline workload) end to end through the host API with "
+                                    "%s: pinned host in, packed decisions on the host out; %d B H2D + %d B D2H per codeword"
+                                    % (B, name, g2.N * Z2 * nbytes, (g2.N * Z2 + 7) // 8),
+                        "value": B / dt, "unit": UNIT, "ms_per_step": dt * 1e3})
+        del mn, xh
         # Functions.evaluate_ber_fer on the device (nldpc_count_errors): the one HBM-bound kernel of the path
         soft = torch.randn((10, B, g2.N * Z2), device=dev) * 4.0 + 3.0
         yz = torch.zeros((B, g2.N * Z2), device=dev)

@@ -86,6 +86,16 @@ int nldpc_neural_forward(const nldpc_graph_t *g, const float *xa_dev, const floa
 int nldpc_neural_decode_host(const nldpc_graph_t *g, const float *xa_host, const float *w_host, const float *b_host,
                              int B, int T, int soft_mode, float *soft_host, int hard_mode, uint8_t *hard_host);
 
+/* The same with the channel LLRs in a narrower host format: the path is host->device-link bound (3 328 B per BG2 codeword in
+ * fp32), and receivers usually hold quantised LLRs anyway.  NLDPC_LLR_F16: IEEE half values; NLDPC_LLR_Q8: int8 codes,
+ * x = scale * q.  Each chunk is expanded to fp32 on the device and decoded by the same kernels: the results are bit-identical
+ * to nldpc_neural_decode_host on the widened values (exact whenever the caller's LLRs are representable in the format). */
+#define NLDPC_LLR_F16 1
+#define NLDPC_LLR_Q8 2
+int nldpc_neural_decode_host_narrow(const nldpc_graph_t *g, const void *x_host, int x_format, float scale, const float *w_host,
+                                    const float *b_host, int B, int T, int soft_mode, float *soft_host, int hard_mode,
+                                    uint8_t *hard_host);
+
 /* Backward of nldpc_neural_forward w.r.t. w and b (closed form of autograd through
  * NeuralLDPCDecoder.py:54-98).  The forward is re-run in a training-dump mode that
  * spills the per-iteration v2c to `workspace_dev` (HBM is idle in this kernel), then the iterations are

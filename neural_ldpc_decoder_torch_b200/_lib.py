@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NLDPC_LIB_PATH") or os.path.join(_HERE, "libnldpc_b200.so")   # env override: kernel experiments only
 
 NLDPC_OUT_NONE, NLDPC_OUT_ALL, NLDPC_OUT_LAST = 0, 1, 2
+NLDPC_LLR_F16, NLDPC_LLR_Q8 = 1, 2      # nldpc_neural_decode_host_narrow input formats
 NLDPC_DEC_SP, NLDPC_DEC_MS, NLDPC_DEC_QMS = 0, 1, 2
 
 _lib = None
@@ -63,6 +64,8 @@ def lib():
             L.nldpc_neural_forward.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, ci, vp, vp]
             L.nldpc_neural_decode_host.restype = ci
             L.nldpc_neural_decode_host.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, ci, vp]
+            L.nldpc_neural_decode_host_narrow.restype = ci
+            L.nldpc_neural_decode_host_narrow.argtypes = [vp, vp, ci, ctypes.c_float, vp, vp, ci, ci, ci, vp, ci, vp]
             L.nldpc_backward_workspace_bytes.restype = ctypes.c_size_t
             L.nldpc_backward_workspace_bytes.argtypes = [vp, ci, ci, ci]
             L.nldpc_neural_backward.restype = ci

@@ -312,9 +312,17 @@ static int ws_reserve(void **p, size_t *have, size_t need) {
     return 0;
 }
 
-extern "C" int nldpc_neural_decode_host(const nldpc_graph_t *gc, const float *xa_host, const float *w_host, const float *b_host,
-                                        int B, int T, int soft_mode, float *soft_host, int hard_mode, uint8_t *hard_host) {
+namespace nldpc {
+int launch_q8_to_f32(const int8_t *in, float *out, size_t n, float scale, int sm_count, cudaStream_t st);
+int launch_f16_to_f32(const void *in, float *out, size_t n, int sm_count, cudaStream_t st);
+}
+// x_format: 0 fp32 (copied straight into the decode kernel's input buffer), NLDPC_LLR_F16 / NLDPC_LLR_Q8: the chunk arrives in the
+// narrow format and is expanded on the device (1-2 % of a decode) — the host -> device link is the bound of this path
+static int neural_decode_host_impl(const nldpc_graph_t *gc, const void *xa_host_v, int x_format, float scale, const float *w_host,
+                                   const float *b_host, int B, int T, int soft_mode, float *soft_host, int hard_mode, uint8_t *hard_host) {
     nldpc_graph *g = const_cast<nldpc_graph *>(gc);
+    const float *xa_host = reinterpret_cast<const float *>(xa_host_v);
+    const size_t in_bytes = x_format == NLDPC_LLR_F16 ? 2 : (x_format == NLDPC_LLR_Q8 ? 1 : 4);
     if (!g || B < 0 || T <= 0) return fail(NLDPC_E_INVALID, "nldpc_neural_decode_host: bad argument");
     if (B == 0) return NLDPC_OK;
     if (!xa_host || !w_host || !b_host) return fail(NLDPC_E_INVALID, "nldpc_neural_decode_host: NULL input pointer");
@@ -350,6 +358,7 @@ extern "C" int nldpc_neural_decode_host(const nldpc_graph_t *gc, const float *xa
         if (int rc = ws_reserve(&g->ws[i][0], &g->ws_bytes[i][0], (size_t)chunk * NZ * 4)) return rc;
         if (soft_per_cw) if (int rc = ws_reserve(&g->ws[i][1], &g->ws_bytes[i][1], (size_t)chunk * soft_per_cw * 4)) return rc;
         if (hard_per_cw) if (int rc = ws_reserve(&g->ws[i][2], &g->ws_bytes[i][2], (size_t)chunk * hard_per_cw)) return rc;
+        if (x_format != 0) if (int rc = ws_reserve(&g->ws[i][3], &g->ws_bytes[i][3], (size_t)chunk * NZ * in_bytes)) return rc;
     }
     float *d_w = (float *)g->ws_wb, *d_b = d_w + (size_t)T * E;
 #define HTRY(expr)                                                                                 \
@@ -370,7 +379,15 @@ extern "C" int nldpc_neural_decode_host(const nldpc_graph_t *gc, const float *xa
         float *d_xa = (float *)g->ws[s][0], *d_soft = (float *)g->ws[s][1];
         uint8_t *d_hard = (uint8_t *)g->ws[s][2];
         const int nbw = sched[c];
-        HTRY(cudaMemcpyAsync(d_xa, xa_host + (size_t)b0 * NZ, (size_t)nbw * NZ * 4, cudaMemcpyHostToDevice, st));
+        if (x_format == 0) {
+            HTRY(cudaMemcpyAsync(d_xa, xa_host + (size_t)b0 * NZ, (size_t)nbw * NZ * 4, cudaMemcpyHostToDevice, st));
+        } else {
+            HTRY(cudaMemcpyAsync(g->ws[s][3], (const char *)xa_host_v + (size_t)b0 * NZ * in_bytes, (size_t)nbw * NZ * in_bytes,
+                                 cudaMemcpyHostToDevice, st));
+            const int erc = x_format == NLDPC_LLR_F16 ? launch_f16_to_f32(g->ws[s][3], d_xa, (size_t)nbw * NZ, g->sm_count, st)
+                                                      : launch_q8_to_f32((const int8_t *)g->ws[s][3], d_xa, (size_t)nbw * NZ, scale, g->sm_count, st);
+            if (erc) { cudaDeviceSynchronize(); return fail(erc, std::string("nldpc_neural_decode_host_narrow: ") + cudaGetErrorString((cudaError_t)erc)); }
+        }
         int rc = nldpc_neural_forward(g, d_xa, d_w, d_b, nbw, T, soft_mode, d_soft, hard_mode, d_hard, st);
         if (rc) { cudaDeviceSynchronize(); return rc; }
         // the chunk's device layout is [T][nbw][..]; the host layout is [T][B][..]
@@ -390,6 +407,18 @@ extern "C" int nldpc_neural_decode_host(const nldpc_graph_t *gc, const float *xa
     for (int i = 0; i < nbuf; i++) HTRY(cudaStreamSynchronize(g->streams[i]));
 #undef HTRY
     return NLDPC_OK;
+}
+
+extern "C" int nldpc_neural_decode_host(const nldpc_graph_t *g, const float *xa_host, const float *w_host, const float *b_host,
+                                        int B, int T, int soft_mode, float *soft_host, int hard_mode, uint8_t *hard_host) {
+    return neural_decode_host_impl(g, xa_host, 0, 1.0f, w_host, b_host, B, T, soft_mode, soft_host, hard_mode, hard_host);
+}
+
+extern "C" int nldpc_neural_decode_host_narrow(const nldpc_graph_t *g, const void *x_host, int x_format, float scale, const float *w_host,
+                                               const float *b_host, int B, int T, int soft_mode, float *soft_host, int hard_mode,
+                                               uint8_t *hard_host) {
+    if (x_format != NLDPC_LLR_F16 && x_format != NLDPC_LLR_Q8) return fail(NLDPC_E_INVALID, "nldpc_neural_decode_host_narrow: x_format must be NLDPC_LLR_F16 or NLDPC_LLR_Q8");
+    return neural_decode_host_impl(g, x_host, x_format, scale, w_host, b_host, B, T, soft_mode, soft_host, hard_mode, hard_host);
 }
 
 // ---- backward ------------------------------------------------------------------------------------------------

@@ -128,15 +128,17 @@ class NeuralLDPCDecoder(nn.Module):
         return ops.neural_hard_direct(xa, w, b, gid, all_iters)
 
     @torch.no_grad()
-    def decode_host(self, xa_cpu, device=None, soft=False, hard=True):
-        """End-to-end host API: CPU float32 tensor in, CPU results out (chunked H2D / decode / D2H overlap)."""
+    def decode_host(self, xa_cpu, device=None, soft=False, hard=True, scale=1.0):
+        """End-to-end host API: CPU tensor in, CPU results out (chunked H2D / decode / D2H overlap).  xa_cpu float32, or
+        float16 values / int8 codes (x = scale * q) for callers whose LLRs are quantised anyway: the link carries 2 / 1 byte per
+        LLR instead of 4 and the result equals the decode of the widened values bit for bit."""
         from .. import _lib
         device = torch.device(device if device is not None else "cuda")
         gid = self.conn_mat.graph_id(device)
         w, b = self._stacked_nograd(self._param_device())
         return ops.neural_decode_host(gid, xa_cpu.contiguous(), w.cpu().contiguous(), b.cpu().contiguous(),
                                       _lib.NLDPC_OUT_ALL if soft else _lib.NLDPC_OUT_NONE,
-                                      _lib.NLDPC_OUT_LAST if hard else _lib.NLDPC_OUT_NONE)
+                                      _lib.NLDPC_OUT_LAST if hard else _lib.NLDPC_OUT_NONE, scale=scale)
 
 
 def _add_dense_buffers(module, state_dict, prefix, local_metadata):

@@ -182,11 +182,17 @@ def _neural_bwd(ctx, gout):
 neural_forward.register_autograd(_neural_bwd, setup_context=_neural_setup_ctx)
 
 
-def neural_decode_host(graph_id, xa_host, w_host, b_host, soft_mode=_lib.NLDPC_OUT_NONE, hard_mode=_lib.NLDPC_OUT_LAST):
+def neural_decode_host(graph_id, xa_host, w_host, b_host, soft_mode=_lib.NLDPC_OUT_NONE, hard_mode=_lib.NLDPC_OUT_LAST, scale=1.0):
     """End-to-end host-buffer decode (nldpc_neural_decode_host): CPU tensors in, CPU tensors out; the
-    H2D copy, the kernel and the D2H copy of consecutive chunks overlap inside the library."""
+    H2D copy, the kernel and the D2H copy of consecutive chunks overlap inside the library.
+    xa_host float32, or — the path is host->device-link bound — float16 values / int8 codes (x = scale * q), expanded on the
+    device (nldpc_neural_decode_host_narrow): bit-identical to decoding the widened values."""
     g = _lib.graph_by_id(graph_id)
-    for n, t in (("xa", xa_host), ("w", w_host), ("b", b_host)):
+    if xa_host.is_cuda or xa_host.dtype not in (torch.float32, torch.float16, torch.int8) or not xa_host.is_contiguous():
+        raise ValueError("xa must be a contiguous float32 / float16 / int8 CPU tensor")
+    if tuple(xa_host.shape[1:]) != (g.N, g.Z):
+        raise ValueError(f"xa must be [B, {g.N}, {g.Z}], got {tuple(xa_host.shape)}")
+    for n, t in (("w", w_host), ("b", b_host)):
         if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
             raise ValueError(f"{n} must be a contiguous float32 CPU tensor")
     B, T = xa_host.shape[0], w_host.shape[0]
@@ -197,8 +203,13 @@ def neural_decode_host(graph_id, xa_host, w_host, b_host, soft_mode=_lib.NLDPC_O
     if hard_mode != _lib.NLDPC_OUT_NONE:
         hard = torch.empty((T, B, g.hard_bytes) if hard_mode == _lib.NLDPC_OUT_ALL else (B, g.hard_bytes),
                            dtype=torch.uint8, pin_memory=True)
-    rc = _lib.lib().nldpc_neural_decode_host(g.ptr, _ptr(xa_host), _ptr(w_host), _ptr(b_host), B, T, soft_mode, _ptr(soft),
-                                             hard_mode, _ptr(hard))
+    if xa_host.dtype == torch.float32:
+        rc = _lib.lib().nldpc_neural_decode_host(g.ptr, _ptr(xa_host), _ptr(w_host), _ptr(b_host), B, T, soft_mode, _ptr(soft),
+                                                 hard_mode, _ptr(hard))
+    else:
+        fmt = _lib.NLDPC_LLR_F16 if xa_host.dtype == torch.float16 else _lib.NLDPC_LLR_Q8
+        rc = _lib.lib().nldpc_neural_decode_host_narrow(g.ptr, _ptr(xa_host), fmt, float(scale), _ptr(w_host), _ptr(b_host), B, T,
+                                                        soft_mode, _ptr(soft), hard_mode, _ptr(hard))
     _lib.check(rc, "nldpc_neural_decode_host")
     return soft, hard
 
