@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define NLDPC_ABI_VERSION 2
+#define NLDPC_ABI_VERSION 3
 
 /* error codes (negative); positive return values are cudaError_t */
 #define NLDPC_OK 0
@@ -132,7 +132,10 @@ typedef struct nldpc_boosted_cfg {
     const float *app_init_dev; /* [B][N*Z] previous output used by the UCN indicator of the first executed iteration;
                                   NULL = use the channel input (the curr_iter == 0 rule, :340-341) */
     /* Training: when non-NULL (forward only, soft_mode = ALL) the kernel also spills what nldpc_boosted_backward needs;
-     * at least nldpc_backward_workspace_bytes(g, B, T, 1) bytes.  Pass the same buffer with have_dump = 1 to the backward. */
+     * at least nldpc_backward_workspace_bytes(g, B, T, 1) bytes.  Pass the same buffer to the backward with
+     * have_dump = 1 + nldpc_boosted_dump_format(g, cfg, T, cn_w != NULL, vn_w != NULL) of THIS call (1 = slot-major rows of the
+     * table-driven kernels, 2 = check-packed records of the specialised kernels).  With a dump buffer the call must ask for
+     * soft_mode = NLDPC_OUT_ALL and hard_mode = NLDPC_OUT_NONE. */
     void *train_dump_dev;
     size_t train_dump_bytes;
     /* Optional [T][B][Z][E] fp32: receives self.llr[t + 1] of EVERY executed iteration (the reference stores each one,
