@@ -482,7 +482,7 @@ struct PlaceXa {
             zm = fminf(zm, fabsf(v));
             xa_ref<G, DEST>(c) = v;
         } else {
-            const float xq = (MODE == 2) ? quant5(v) : v;
+            const float xq = (MODE == 2) ? quant5_grid(v) : v;      // (+0.0 zeros: the CN phase reads raw sign words)
             if constexpr (kXo != 0) {
                 if constexpr (kXo == 1) c.lane[c.xo_off + J * G::Z] = xq;
                 xa_ref<G, DEST>(c) = v;
@@ -669,10 +669,14 @@ __device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c, const fl
 #pragma unroll
     for (int k = 0; k < D; k++) {
         if constexpr (MODE == 2) {
-            // QMS q=5: every non-zero input is a multiple of 0.5, so the reference's zero handling — 0 -> +1e-4 (:391-393),
-            // then mag - 1e-4 where mag <= 1e-4 (:416), i.e. 1e-4 - 1e-4 = 0 — is "a zero counts as positive and as
-            // magnitude 0": quant5_grid yields +0.0 for every zero, so neither step needs an instruction.
-            u[k] = quant5_grid(raw[k]);
+            // QMS q=5.  (1) Every CN input is ALREADY on the 0.5 grid: it is a sum of the quantised channel value and quantised
+            // messages (|sum| <= 7.5 * 24, exact in fp32), so the reference's re-quantisation (:386-389) is just the clamp to
+            // +-7.5 — and the clamp is free: the min network below starts from 7.5 instead of 10000 (min over the others of
+            // min(|x|, 7.5)), the sign comes from the raw word.  (2) Every non-zero input is >= 0.5 in magnitude, so the
+            // reference's zero handling — 0 -> +1e-4 (:391-393), then mag - 1e-4 where mag <= 1e-4 (:416), i.e. 1e-4 - 1e-4 = 0 —
+            // is "a zero counts as positive and as magnitude 0"; zeros are +0.0 here (the +0-started VN sums and quant5_grid
+            // never produce -0.0), so neither step needs an instruction.  Conditioning cost per edge: none.
+            u[k] = raw[k];
         } else {
             const float v = condition<MODE>(raw[k], c.lo, c.hi);
             u[k] = (v == 0.0f) ? 0.0001f : v;                            // x + 1e-4 * [x == 0] (:391-393)
@@ -680,7 +684,8 @@ __device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c, const fl
     }
     constexpr int H = (D + 1) / 2;
     float se[H + 1];
-    se[H] = 10000.0f;
+    constexpr float kCap = MODE == 2 ? 7.5f : 10000.0f;      // (:74-75 cap; QMS: the clamp of the re-quantisation, see above)
+    se[H] = kCap;
 #pragma unroll
     for (int q = H - 1; q >= 0; q--) {
         if (2 * q + 1 < D) se[q] = fmin3(fabsf(u[2 * q]), fabsf(u[2 * q + 1]), se[q + 1]);
@@ -689,7 +694,7 @@ __device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c, const fl
     unsigned x = (D & 1) ? 0x80000000u : 0u;
 #pragma unroll
     for (int k = 0; k < D; k++) x ^= __float_as_uint(u[k]);
-    float pe = 10000.0f;
+    float pe = kCap;
 #pragma unroll
     for (int k = 0; k < D; k++) {
         const int q = k >> 1;
@@ -785,7 +790,7 @@ struct CnBoostedLoops {
 #pragma unroll
             for (int k = 0; k < NE; k++) {
                 if constexpr (MODE == 2) {
-                    u[k] = quant5_grid(raw[k]);
+                    u[k] = raw[k];             // already on the grid; the clamp to +-7.5 is the min network's cap (cn_check_boosted_core)
                 } else {
                     const float v = condition<MODE>(raw[k], c.lo, c.hi);
                     u[k] = (v == 0.0f) ? 0.0001f : v;
@@ -793,7 +798,8 @@ struct CnBoostedLoops {
             }
             constexpr int H = (NE + 1) / 2;
             float se[H + 1];
-            se[H] = 10000.0f;
+            constexpr float kCap = MODE == 2 ? 7.5f : 10000.0f;
+            se[H] = kCap;
 #pragma unroll
             for (int q = H - 1; q >= 0; q--) {
                 if (2 * q + 1 < NE) se[q] = fmin3(fabsf(u[2 * q]), fabsf(u[2 * q + 1]), se[q + 1]);
@@ -802,7 +808,7 @@ struct CnBoostedLoops {
             unsigned x = (NE & 1) ? 0x80000000u : 0u;
 #pragma unroll
             for (int k = 0; k < NE; k++) x ^= __float_as_uint(u[k]);
-            float pe = 10000.0f;
+            float pe = kCap;
             float c2v_last = 0.0f;
 #pragma unroll
             for (int k = 0; k < NE; k++) {
