@@ -919,12 +919,20 @@ struct Train : G0 {
     static constexpr int kSlab = slab_floats(G0::kSlab, G0::kXRegs * G0::Z, G0::Z);
 };
 
+#ifndef NLDPC_PREFETCH
+// 1: throughput-mode kernels bulk-load the NEXT unit's channel LLRs into a landing buffer during the current unit's decode.
+// Measured (round 2) and left off: 47.19 vs 47.43 M cw/s on BG2, 66.3 vs 69.8 on WiMAX — the other warp of the scheduler
+// already covers the ~1 us a group waits for its bulk load, and the extra group barrier + 53 KB of shared memory cost more.
+#define NLDPC_PREFETCH 0
+#endif
 #ifndef NLDPC_STAGE_OUT
 #define NLDPC_STAGE_OUT 1   // 1: list-mode soft outputs leave through shared staging rows + bulk TMA stores (see Staged<>)
 #endif
 
-// kXoRows: N extra rows per codeword for xa_origin; kStage: N extra rows staging the soft output row (list mode)
-template <class G, bool kXoRows = false, bool kStage = false>
+// kXoRows: N extra rows per codeword for xa_origin; kStage: N extra rows staging the soft output row (list mode);
+// kPf: a landing buffer of N*Z floats per codeword OUTSIDE the slab, into which the NEXT work unit's channel LLRs are
+// bulk-loaded while the current unit decodes (throughput mode, where the shared memory left over allows it)
+template <class G, bool kXoRows = false, bool kStage = false, bool kPf = false>
 struct SpecCfg {
     using Shape = GroupShape<G::Z>;
     static constexpr int kNZ = G::N * G::Z;
@@ -934,7 +942,8 @@ struct SpecCfg {
     static_assert(!kStage || ((kStageOff * 4) % 16 == 0 && (kSlabF * 4) % 16 == 0 && (kNZ * 4) % 16 == 0), "bulk-store source alignment");
     static constexpr int kHardBytes = (G::N * G::Z + 7) / 8;
     static constexpr int kHardStride = (kHardBytes + 15) & ~15;           // per-codeword staging, 16 B multiple
-    static constexpr int kPerCw = kSlabF * 4 + kHardStride;              // shared bytes per codeword
+    static constexpr bool kPrefetch = kPf;
+    static constexpr int kPerCw = kSlabF * 4 + kHardStride + (kPf ? kNZ * 4 : 0);      // shared bytes per codeword
     // CTA shape.  Warp k of a CTA runs on SM sub-partition k mod 4 and the kernel is issue-bound per sub-partition, so what
     // counts is how evenly the resident warps spread over the four of them, not how many there are (measured on BG2:
     // 2 CTAs x 5 warps put 4/2/2/2 warps on the sub-partitions and ran 20 % SLOWER than 2 x 4 warps although 25 % more
@@ -985,9 +994,14 @@ struct KernelCfg {
     static constexpr bool kXoRows = kXo && kEvery && !kTrain;
     using Plain = SpecCfg<G, kXoRows, false>;
     using Stage = SpecCfg<G, kXoRows, true>;
+    using Pf = SpecCfg<G, kXoRows, false, true>;
     static constexpr bool kStage = NLDPC_STAGE_OUT && kEvery && !kTrain &&
                                    (Stage::kCtasPerSm * Stage::kCwPerCta >= Plain::kCtasPerSm * Plain::kCwPerCta);
-    using type = std::conditional_t<kStage, Stage, Plain>;
+    // throughput mode: prefetch the next unit's channel LLRs when the landing buffer costs no resident codewords and leaves
+    // the CTA shape alone (BG2: 179.0 + 53.2 KB of the 227 KB)
+    static constexpr bool kPrefetch = NLDPC_PREFETCH && !kEvery && !kTrain && Pf::kCtasPerSm == Plain::kCtasPerSm &&
+                                      Pf::kGroups == Plain::kGroups;
+    using type = std::conditional_t<kStage, Stage, std::conditional_t<kPrefetch, Pf, Plain>>;
 };
 // kEvery: outputs are produced after every iteration (drop-in list mode / per-iteration hard decisions);
 // otherwise only after the last one (throughput mode) and the loop body carries no output code at all.
@@ -1012,6 +1026,10 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
     float *slabs = reinterpret_cast<float *>(smem_raw);
     uint8_t *hstage = smem_raw + (size_t)Cfg::kCwPerCta * Cfg::kSlabF * 4;
     uint64_t *bars = reinterpret_cast<uint64_t *>(hstage + (size_t)Cfg::kCwPerCta * Cfg::kHardStride);
+    constexpr bool kPrefetch = Cfg::kPrefetch;
+    // landing buffer of the prefetch, [codeword in CTA][N*Z] (behind the barriers, 16-byte aligned: 8 * kGroups + 16 is)
+    float *pfbuf = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(bars) + ((size_t)Cfg::kGroups * 8 + 15) / 16 * 16);
+    int pf_unit = -1;           // the unit whose channel LLRs are in (or on their way into) the landing buffer
 
     // group within the CTA, through a shuffle from lane 0: the value is the same, but the compiler now KNOWS it is warp-uniform,
     // so everything derived from it (work-unit loop, iteration counter, weight offsets in the constant arena) lives on the
@@ -1055,6 +1073,7 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
 
     const int n_units = (a.B + Shape::kCw - 1) / Shape::kCw;
     const int unit_stride = gridDim.x * Cfg::kGroups;
+    const int unit_end_all = a.unit_end > 0 ? min(a.unit_end, n_units) : n_units;      // this launch's units are [unit_begin, unit_end_all)
     uint32_t phase = 0;
     const bool soft_all = a.soft_mode == 1, hard_all = a.hard_mode == 1;
     const bool soft_any = a.soft_mode != 0, hard_any = a.hard_mode != 0;
@@ -1078,13 +1097,21 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
         const int ncw = max(0, min(Shape::kCw, a.B - b0));
         constexpr bool kSafe = decltype(safe_tag)::value;
         // ---- bulk-TMA the group's channel LLRs (one 1-D copy per codeword) ----
-        if (gl == 0 && ncw > 0) {
-            fence_proxy_async();
-            mbar_arrive_expect_tx(bar, (uint32_t)(ncw * NZ * sizeof(float)));
-            for (int q = 0; q < ncw; q++)
-                tma_load_1d(slabs + (size_t)(grp * Shape::kCw + q) * Cfg::kSlabF + G::kXRows * Z, a.xa + (size_t)(b0 + q) * NZ,
-                            (uint32_t)(NZ * sizeof(float)), bar);
-        }
+        // destination: the message rows of the slabs (staging, not yet live) or, with prefetching, the landing buffer
+        auto issue_load = [&](int u) __attribute__((always_inline)) {
+            const int ub0 = u * Shape::kCw;
+            const int n = max(0, min(Shape::kCw, a.B - ub0));
+            if (gl == 0 && n > 0) {
+                fence_proxy_async();
+                mbar_arrive_expect_tx(bar, (uint32_t)(n * NZ * sizeof(float)));
+                for (int q = 0; q < n; q++) {
+                    float *dst = kPrefetch ? pfbuf + (size_t)(grp * Shape::kCw + q) * NZ
+                                           : slabs + (size_t)(grp * Shape::kCw + q) * Cfg::kSlabF + G::kXRows * Z;
+                    tma_load_1d(dst, a.xa + (size_t)(ub0 + q) * NZ, (uint32_t)(NZ * sizeof(float)), bar);
+                }
+            }
+        };
+        if (!kPrefetch || pf_unit != unit) issue_load(unit);
         if constexpr (Z != 16 && Z != 32 && (G::kXRegs + G::kDeg1Smem > 0)) {   // atomicOr staging (rotated emission) must start from zero
             if (hard_any) for (int q = z; q < Cfg::kHardStride / 4; q += Z) reinterpret_cast<unsigned *>(hb_mine)[q] = 0u;
         }
@@ -1097,8 +1124,20 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
         // (shared rows / registers).  Lane z only ever touches element z of a row in the VN phase, so no barrier is needed
         // before iteration 0 overwrites the staging area.
         {
-            PlaceXa<G, MODE, kXoMode> pl{c, c.lane + G::kXRows * Z, 1.0f};
+            PlaceXa<G, MODE, kXoMode> pl{c, kPrefetch ? pfbuf + (size_t)cw_in_cta * NZ + z : c.lane + G::kXRows * Z, 1.0f};
             G::blocks(pl);
+            if constexpr (kPrefetch) {
+                // the landing buffer has been read by every lane of the group: start the NEXT unit's load now, it has this
+                // unit's whole decode (~50 us) to arrive (pass 2 visits scattered units: no prefetch there)
+                group_sync<Shape::kLanes>(grp);
+                const int next = unit + unit_stride;
+                if (!kSafe && next < unit_end_all) {
+                    issue_load(next);
+                    pf_unit = next;
+                } else {
+                    pf_unit = -1;
+                }
+            }
             if constexpr (MODE == 0 && !kSafe) {
                 if (group_any<Shape::kLanes>(grp, pl.zm == 0.0f)) return false;
             }
@@ -1299,7 +1338,7 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
     // Pass 1 runs every unit on the fast path and notes the abandoned ones in a 64-bit mask (the host never gives a group more
     // than 64 units per launch, see spec_units_per_launch); pass 2 — cold code BEHIND the hot loop, not inside it — decodes those.
     const int unit_first = a.unit_begin + (int)blockIdx.x + grp * (int)gridDim.x;
-    const int unit_end = a.unit_end > 0 ? min(a.unit_end, n_units) : n_units;
+    const int unit_end = unit_end_all;
     unsigned long long failed = 0ull;
     {
         int k = 0;
