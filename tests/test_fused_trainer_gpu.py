@@ -118,9 +118,10 @@ def test_fused_trainer_neural_decoder():
         assert float((a.detach() - b.detach()).abs().max()) < 1e-5
 
 
-@pytest.mark.parametrize("graph", [False])
+@pytest.mark.parametrize("graph", [False, True])
 def test_fused_trainer_data_parallel_nccl(graph):
-    """2 ranks over NCCL on shards of one batch follow a single process on the whole batch (tools/check_fused_trainer_ddp.py)"""
+    """2 ranks over NCCL on shards of one batch follow a single process on the whole batch (tools/check_fused_trainer_ddp.py);
+    graph=True: the whole step INCLUDING the NCCL all-reduce of the flat gradient replayed from a CUDA graph"""
     import json
     import os
     import subprocess
@@ -130,7 +131,7 @@ def test_fused_trainer_data_parallel_nccl(graph):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29533" if graph else "29532", os.path.join(root, "tools", "check_fused_trainer_ddp.py")] + (["--graph"] if graph else [])
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-1500:]
     line = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
     assert line["ok"] and line["ranks_identical"] and line["weights_moved_by"] > 1e-3

@@ -60,8 +60,6 @@ def main():
         if g1_full is None:
             g1_full = tr_full.flat_grad.clone()          # clipped gradient of step 1 (both runs start from the same weights)
     # (2) N ranks, contiguous shards, one all-reduce of the flat gradient per step
-    if args.graph and world > 1:
-        raise SystemExit("FusedTrainer(graph=True) is single-process only (see its docstring)")
     if args.backend == "nccl":
         dist.init_process_group("nccl", device_id=dev)
     else:
@@ -100,6 +98,9 @@ def main():
         print(json.dumps({"check": "fused_trainer_ddp", "world": world, "graph": args.graph, "steps": args.steps, "batch": B,
                           "max_weight_diff_vs_single_process": float(errs), "weights_moved_by": moved,
                           "ranks_identical": bool(same.item()), "step1_grad_max_diff": gdiff, "step1_grad_absmax": gmax, "loss_full": loss_full, "loss_sharded_mean": loss_part, "ok": ok}))
+    tr.close()                   # (graph mode: a live graph that holds NCCL kernels makes destroy_process_group() hang)
+    tr_full.close()
+    torch.cuda.synchronize()
     dist.destroy_process_group()
     if rank == 0 and not ok:
         sys.exit(1)
