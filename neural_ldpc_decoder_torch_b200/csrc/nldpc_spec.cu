@@ -35,6 +35,8 @@ int prepare() {
     if ((e = set_smem(nldpc_spec_neural_kernel<G, true, false>, Every::kSmemBytes)) != cudaSuccess) return (int)e;
     if ((e = set_smem(nldpc_spec_neural_kernel<G, false, true>, Last::kSmemBytes)) != cudaSuccess) return (int)e;
     if ((e = set_smem(nldpc_spec_neural_kernel<G, false, false>, Last::kSmemBytes)) != cudaSuccess) return (int)e;
+    if ((e = set_smem(nldpc_spec_neural_kernel<G, true, true, 0, false, false, true>, Every::kSmemBytes)) != cudaSuccess) return (int)e;   // soft only
+    if ((e = set_smem(nldpc_spec_neural_kernel<G, true, false, 0, false, false, true>, Every::kSmemBytes)) != cudaSuccess) return (int)e;
     if ((e = set_smem(nldpc_spec_neural_kernel<G, true, true, 0, false, true>, Every::kSmemBytes)) != cudaSuccess) return (int)e;      // + training dump
     if ((e = set_smem(nldpc_spec_neural_kernel<G, true, false, 0, false, true>, Every::kSmemBytes)) != cudaSuccess) return (int)e;
     return 0;
@@ -72,16 +74,20 @@ int launch_neural(const DecodeArgs &a, int sm_count, cudaStream_t st) {
         }
         return cudaGetLastError();
     };
-    const bool dump = a.hist_v2c != nullptr;      // training dump: the Dumping<> instantiation of the every-iteration kernel
+    // every-iteration instantiations: + training dump (Dumping<>), soft outputs only (SoftOnly<>: what forward() asks for), or both outputs
+    const bool dump = a.hist_v2c != nullptr, soft_only = a.hard_mode == 0;
+    if (dump && !soft_only) return -1;      // (a training dump with hard decisions: not a combination the module ever asks for)
     if (off >= 0) {
         if ((err = upload_wb(arena, a.w, a.b, off, len, st)) != cudaSuccess) return (int)err;
-        err = dump ? launch_all(nldpc_spec_neural_kernel<G, true, true, 0, false, true>, nldpc_spec_neural_kernel<G, false, true>)
-                   : launch_all(nldpc_spec_neural_kernel<G, true, true>, nldpc_spec_neural_kernel<G, false, true>);
+        err = dump        ? launch_all(nldpc_spec_neural_kernel<G, true, true, 0, false, true>, nldpc_spec_neural_kernel<G, false, true>)
+              : soft_only ? launch_all(nldpc_spec_neural_kernel<G, true, true, 0, false, false, true>, nldpc_spec_neural_kernel<G, false, true>)
+                          : launch_all(nldpc_spec_neural_kernel<G, true, true>, nldpc_spec_neural_kernel<G, false, true>);
         if (err != cudaSuccess || capturing) return (int)err;
         return (int)arena.release_after(off, len, st);
     }
-    return (int)(dump ? launch_all(nldpc_spec_neural_kernel<G, true, false, 0, false, true>, nldpc_spec_neural_kernel<G, false, false>)
-                      : launch_all(nldpc_spec_neural_kernel<G, true, false>, nldpc_spec_neural_kernel<G, false, false>));
+    return (int)(dump        ? launch_all(nldpc_spec_neural_kernel<G, true, false, 0, false, true>, nldpc_spec_neural_kernel<G, false, false>)
+                 : soft_only ? launch_all(nldpc_spec_neural_kernel<G, true, false, 0, false, false, true>, nldpc_spec_neural_kernel<G, false, false>)
+                             : launch_all(nldpc_spec_neural_kernel<G, true, false>, nldpc_spec_neural_kernel<G, false, false>));
 }
 
 }  // namespace

@@ -78,6 +78,21 @@ struct dump_traits<G, std::void_t<decltype(G::kDumpVariant)>> {
     static constexpr bool on = G::kDumpVariant;
 };
 
+// List mode as forward() uses it asks for soft outputs only: SoftOnly<G> compiles the hard-decision code out of the 52
+// emission sites per iteration (predicated off they still issue: 312 of 3 613 instructions per warp-iteration)
+template <class G0>
+struct SoftOnly : G0 {
+    static constexpr bool kNoHardVariant = true;
+};
+template <class G, class = void>
+struct nohard_traits {
+    static constexpr bool on = false;
+};
+template <class G>
+struct nohard_traits<G, std::void_t<decltype(G::kNoHardVariant)>> {
+    static constexpr bool on = G::kNoHardVariant;
+};
+
 #ifdef NLDPC_DEBUG_COUNT
 __device__ unsigned g_dbg_restarts;
 extern "C" unsigned nldpc_debug_restarts() { unsigned v = 0; cudaMemcpyFromSymbol(&v, g_dbg_restarts, 4); return v; }
@@ -295,7 +310,7 @@ struct NeuralLane {
         } else {
             if (soft) st_global_stream(soft + J * Z + z, v);
         }
-        if constexpr (train_traits<G>::on) return;      // (training asks for no hard decisions)
+        if constexpr (train_traits<G>::on || nohard_traits<G>::on) return;      // (training / soft-only list mode: no hard decisions)
         if (hb) {
             if constexpr (Z == 16 || Z == 32) {
                 const unsigned bal = __ballot_sync(0xffffffffu, v < 0.0f);
@@ -322,7 +337,7 @@ struct NeuralLane {
         } else {
             if (soft) st_global_stream(soft + J * Z + zz, v);
         }
-        if constexpr (train_traits<G>::on) return;
+        if constexpr (train_traits<G>::on || nohard_traits<G>::on) return;
         if (hb) {
             if constexpr (Z == 16 || Z == 32) {
                 const unsigned bal = __ballot_sync(0xffffffffu, v < 0.0f);
@@ -1005,7 +1020,7 @@ struct KernelCfg {
 };
 // kEvery: outputs are produced after every iteration (drop-in list mode / per-iteration hard decisions);
 // otherwise only after the last one (throughput mode) and the loop body carries no output code at all.
-template <class G0, bool kEvery, bool kConstW, int MODE = 0, bool kXo = false, bool kTrain = false>
+template <class G0, bool kEvery, bool kConstW, int MODE = 0, bool kXo = false, bool kTrain = false, bool kNoHard = false>
 __global__ void __launch_bounds__(KernelCfg<G0, kEvery, kXo, kTrain && MODE != 0>::type::kThreads, KernelCfg<G0, kEvery, kXo, kTrain && MODE != 0>::type::kCtasPerSm)
 nldpc_spec_neural_kernel(const DecodeArgs a) {
     // kTrain: Boosted -> the Train<> variant (all channel LLRs in shared rows, extension checks as loops, dump + fused loss);
@@ -1013,7 +1028,9 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
     constexpr bool kTrainWrap = kTrain && MODE != 0;
     using Cfg = typename KernelCfg<G0, kEvery, kXo, kTrainWrap>::type;
     constexpr bool kStage = KernelCfg<G0, kEvery, kXo, kTrainWrap>::kStage;
-    using G1 = std::conditional_t<kTrainWrap, Train<G0>, std::conditional_t<kTrain, Dumping<G0>, G0>>;
+    static_assert(!kNoHard || (kEvery && MODE == 0), "the soft-only variant is a Neural every-iteration kernel");
+    using G1 = std::conditional_t<kTrainWrap, Train<G0>,
+                                  std::conditional_t<kTrain, Dumping<SoftOnly<G0>>, std::conditional_t<kNoHard, SoftOnly<G0>, G0>>>;
     using G = std::conditional_t<kStage, Staged<G1, Cfg::kStageOff>, G1>;      // (same graph program; emit() writes staging rows)
     constexpr int kXoMode = !kXo ? 0 : ((kEvery && !kTrain) ? 1 : 2);
     static_assert(!kTrain || kEvery, "the training variants are every-iteration kernels");
