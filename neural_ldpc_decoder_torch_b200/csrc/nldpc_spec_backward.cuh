@@ -145,6 +145,13 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+#ifndef NLDPC_BWD_L2_PREFETCH
+// 1: pull the next iteration's records / gradients / channel inputs of a codeword into L2 a whole iteration ahead.  Measured in
+// both rounds and left off: 21.3 vs 19.3 ms per sweep in round 2 (the scratch rows it had competed with in round 1 are gone;
+// it still loses — the streamed lines are evicted again before the cp.async two checks ahead of the compute asks for them).
+#define NLDPC_BWD_L2_PREFETCH 0
+#endif
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async8(const void *dst_smem, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
@@ -712,6 +719,21 @@ __global__ void __launch_bounds__(SpecBwdCfg<G>::kThreads, 1) nldpc_spec_backwar
             c.wb_base = wb_off + t * E;
             c.last_iter = (t == a.T - 1);
             c.fold.begin(tot + (size_t)t * kRows);
+#if NLDPC_BWD_L2_PREFETCH
+            // The records, upstream gradients and channel inputs of the NEXT iteration of the sweep (t - 1) stream from HBM
+            // exactly once; pull this codeword's lines into L2 a whole iteration (~15 K instructions) ahead, so that the
+            // cp.async two checks ahead of the compute finds them there.  (Experiment knob, off: see NLDPC_BWD_L2_PREFETCH.)
+            if (t > 0 && c.valid) {
+                const char *p0 = reinterpret_cast<const char *>(a.hist_v2c) + ((size_t)(t - 1) * a.B + bb) * BwdStage<G, MODE>::kCwBytes;
+                for (int off = z * 128; off < (int)BwdStage<G, MODE>::kCwBytes; off += Z * 128) prefetch_l2(p0 + off);
+                const char *p1 = reinterpret_cast<const char *>(a.gout + ((size_t)(t - 1) * a.B + bb) * NZ);
+                for (int off = z * 128; off < NZ * 4; off += Z * 128) prefetch_l2(p1 + off);
+                if constexpr (kVn) {
+                    const char *p2 = reinterpret_cast<const char *>(t - 1 == 0 ? a.xa + bb * NZ : a.hist_xin + ((size_t)(t - 1) * a.B + bb) * NZ);
+                    for (int off = z * 128; off < NZ * 4; off += Z * 128) prefetch_l2(p2 + off);
+                }
+            }
+#endif
             if constexpr (kVn) {
                 c.xprev = (t == 0) ? a.xa + bb * NZ : a.hist_xin + ((size_t)t * a.B + bb) * NZ;      // (row 0 is the raw input)
                 c.vw = a.vn_w + (size_t)t * N;
