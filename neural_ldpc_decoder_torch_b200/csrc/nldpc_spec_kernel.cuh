@@ -764,11 +764,10 @@ __device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c, const fl
 // from constant memory instead of immediates.  word k < D: slab row | shift << 8 | edge << 16; word D: block J | x-row index << 8
 // | edge << 16.  The block's marginal leaves from here (every iteration: this is list mode), its xa_origin is fetched from
 // global memory one check ahead into a loop-carried register when VN weights make it differ from the on-chip xa_input.
-template <class G, int MODE, int kXo>
-struct CnBoostedLoops {
+template <class G, int MODE, int kXo, bool kLlr>      // kLlr: the launch exports self.llr (compile-time: predicated off, the
+struct CnBoostedLoops {                              // export still issued 4 % of the kernel's instructions)
     NeuralLane<G> &c;
     int base;                 // first descriptor word of this graph in c_desc
-    bool want_llr;            // the launch exports self.llr (warp-uniform)
     __device__ __forceinline__ float xo_ahead(int w0, int D) const {
         if constexpr (kXo == 2) return __ldg(c.xa_cw + (int)(c_desc[w0 + D] & 0xff) * G::Z + c.z);
         else return 0.0f;
@@ -852,7 +851,7 @@ struct CnBoostedLoops {
                     c2v = __uint_as_float(__float_as_uint(m) | sb);
                     c2v = (madj == 0.0f) ? 0.0f : c2v;
                 }
-                if (want_llr) {                                                    // (warp-uniform: training rarely exports self.llr)
+                if constexpr (kLlr) {
                     if (c.llr_last) c.llr_last[zl[k] * G::E + (int)(c_desc[w0 + k] >> 16)] = c2v;      // self.llr[t + 1][b][z][e] (:512)
                 }
                 if (k < D) *msg[k] = c2v;
@@ -1177,8 +1176,13 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
                 CnBoosted<G, true, MODE, kXoMode> f{c};
                 G::checks_pipelined_rest(f);
                 if constexpr (G::kLoopChecks > 0) {
-                    CnBoostedLoops<G, MODE, kXoMode> l{c, a.desc_base, a.llr_all != nullptr || a.llr_last != nullptr};
-                    G::loop_classes(l);
+                    if (a.llr_all != nullptr || a.llr_last != nullptr) {
+                        CnBoostedLoops<G, MODE, kXoMode, true> l{c, a.desc_base};
+                        G::loop_classes(l);
+                    } else {
+                        CnBoostedLoops<G, MODE, kXoMode, false> l{c, a.desc_base};
+                        G::loop_classes(l);
+                    }
                 }
             } else {
                 CnBoosted<G, kEmitNow, MODE, kXoMode> f{c};
