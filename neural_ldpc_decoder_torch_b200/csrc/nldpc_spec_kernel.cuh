@@ -768,102 +768,139 @@ template <class G, int MODE, int kXo, bool kLlr>      // kLlr: the launch export
 struct CnBoostedLoops {                              // export still issued 4 % of the kernel's instructions)
     NeuralLane<G> &c;
     int base;                 // first descriptor word of this graph in c_desc
-    __device__ __forceinline__ float xo_ahead(int w0, int D) const {
-        if constexpr (kXo == 2) return __ldg(c.xa_cw + (int)(c_desc[w0 + D] & 0xff) * G::Z + c.z);
-        else return 0.0f;
+    // operands of one looped check (D stored edges + the degree-1 edge)
+    template <int D>
+    struct Ops {
+        float raw[D + 1], wk[D + 1];
+        int moff[D];              // message slot of edge k, floats from the codeword's slab base
+        int zl[D];                // its variable lane (self.llr is [lane][edge])
+        uint32_t w1;              // descriptor of the degree-1 edge: block J | x-row index << 8 | edge << 16
+        float xo_raw;             // xa_origin of block J (kXo == 2: re-read from global memory / L2)
+    };
+    template <int D>
+    __device__ __forceinline__ void load(Ops<D> &o, int w0) const {
+        constexpr int Z = G::Z;
+        const float *slab0 = c.lane - c.z;
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            const uint32_t w = c_desc[w0 + k];
+            const int zz = rot_lane<G>(c.z, (w >> 8) & 0xff);
+            o.moff[k] = (int)(w & 0xff) * Z + zz;
+            o.zl[k] = zz;
+            o.raw[k] = slab0[o.moff[k]];
+            o.wk[k] = wb_at<true>(c.wb_base + (int)(w >> 16)).x;
+        }
+        o.w1 = c_desc[w0 + D];
+        o.raw[D] = c.lane[(G::kXRows + G::S + ((o.w1 >> 8) & 0xff)) * Z];        // xa_input of block J, own lane
+        o.wk[D] = wb_at<true>(c.wb_base + (int)(o.w1 >> 16)).x;
+        if constexpr (kXo == 2) o.xo_raw = __ldg(c.xa_cw + (int)(o.w1 & 0xff) * Z + c.z);
+        else o.xo_raw = 0.0f;
     }
+    // the arithmetic of one check: c2v of its D + 1 edges (cn_check_boosted_core with run-time table entries)
+    template <int D>
+    __device__ __forceinline__ void math(const Ops<D> &o, float *c2v) const {
+        constexpr int NE = D + 1;
+        const float *raw = o.raw, *wk = o.wk;
+        float u[NE];
+#pragma unroll
+        for (int k = 0; k < NE; k++) {
+            if constexpr (MODE == 2) {
+                u[k] = raw[k];             // already on the grid; the clamp to +-7.5 is the min network's cap (cn_check_boosted_core)
+            } else {
+                const float v = condition<MODE>(raw[k], c.lo, c.hi);
+                u[k] = (v == 0.0f) ? 0.0001f : v;
+            }
+        }
+        constexpr int H = (NE + 1) / 2;
+        float se[H + 1];
+        constexpr float kCap = MODE == 2 ? 7.5f : 10000.0f;
+        se[H] = kCap;
+#pragma unroll
+        for (int q = H - 1; q >= 0; q--) {
+            if (2 * q + 1 < NE) se[q] = fmin3(fabsf(u[2 * q]), fabsf(u[2 * q + 1]), se[q + 1]);
+            else se[q] = fminf(fabsf(u[2 * q]), se[q + 1]);
+        }
+        unsigned x = (NE & 1) ? 0x80000000u : 0u;
+#pragma unroll
+        for (int k = 0; k < NE; k++) x ^= __float_as_uint(u[k]);
+        float pe = kCap;
+#pragma unroll
+        for (int k = 0; k < NE; k++) {
+            const int q = k >> 1;
+            float mag;
+            if ((k & 1) == 0) {
+                if (k + 1 < NE) mag = fmin3(pe, fabsf(u[k + 1]), se[q + 1]);
+                else mag = fminf(pe, se[q + 1]);
+            } else {
+                mag = fmin3(pe, fabsf(u[k - 1]), se[q + 1]);
+                pe = fmin3(pe, fabsf(u[k - 1]), fabsf(u[k]));
+            }
+            if constexpr (MODE == 2) {
+                float m = fmaxf(mulf(mag, wk[k]), 0.0f);
+                constexpr float kMagic = 6291456.0f;
+                m = addf(addf(fminf(m, 7.5f), kMagic), -kMagic);
+                const unsigned sb = (x ^ __float_as_uint(u[k])) & 0x80000000u;
+                const float v = __uint_as_float(__float_as_uint(m) | sb);
+                c2v[k] = (mag == 0.0f) ? 0.0f : v;
+            } else {
+                const float madj = (mag > 0.0001f) ? mag : addf(mag, -0.0001f);
+                float m = fmaxf(mulf(fabsf(madj), wk[k]), 0.0f);
+                m = condition<MODE>(m, c.lo, c.hi);
+                const unsigned sb = (x ^ __float_as_uint(u[k]) ^ __float_as_uint(madj)) & 0x80000000u;
+                const float v = __uint_as_float(__float_as_uint(m) | sb);
+                c2v[k] = (madj == 0.0f) ? 0.0f : v;
+            }
+        }
+    }
+    // scatter the messages back, export, and emit the marginal of block J (degree 1: out = xa_origin + (0 + c2v), :513-526;
+    // un-rotated: this lane holds bit (J, z))
+    template <int D>
+    __device__ __forceinline__ void finish(const Ops<D> &o, const float *c2v, int w0, int rec_off) {
+        constexpr int Z = G::Z, NE = D + 1;
+        float *slab0 = c.lane - c.z;
+        if (c.dump) dump_record<G, MODE, NE>(c, o.raw, rec_off);
+#pragma unroll
+        for (int k = 0; k < NE; k++) {
+            if constexpr (kLlr) {
+                const int zlane = k < D ? o.zl[k < D ? k : 0] : c.z;
+                if (c.llr_last) c.llr_last[zlane * G::E + (int)(c_desc[w0 + k] >> 16)] = c2v[k];      // self.llr[t + 1][b][z][e] (:512)
+            }
+            if (k < D) slab0[o.moff[k < D ? k : 0]] = c2v[k];
+        }
+        const int qbit = (int)(o.w1 & 0xff) * Z + c.z;
+        float xo;
+        if constexpr (kXo == 2) xo = (MODE == 2) ? quant5_grid(o.xo_raw) : o.xo_raw;      // (a zero's sign is absorbed by the sum)
+        else xo = o.raw[D];
+        const float v = boosted_out(c, qbit, xo, addf(0.0f, c2v[D]));
+        if (c.soft) st_global_stream(c.soft + qbit, v);
+    }
+    // Checks of a class are processed in PAIRS: both checks' operands are loaded first (they touch different edges), then the
+    // two independent arithmetic chains sit next to each other in one basic block — the per-check chain (descriptor ->
+    // address -> load -> min network -> multiply -> quantise -> sign -> store) alone leaves a warp waiting on fixed
+    // latencies (ncu: `wait` 1.13 cycles per issue at 2 warps per scheduler)
     template <int D, int FIRST, int COUNT, int OFFH, int OFFF>
     __device__ __forceinline__ void cls() {
-        constexpr int Z = G::Z, NE = D + 1;
+        constexpr int NE = D + 1;
         constexpr int REC = MODE == 2 ? G::dump_slots_h(NE) : NE, OFF = MODE == 2 ? OFFH : OFFF;
-        float *slab0 = c.lane - c.z;
-        float xo_next = xo_ahead(base + FIRST, D);
+        const int w00 = base + FIRST;
+        int i = 0;
 #pragma unroll 1
-        for (int i = 0; i < COUNT; i++) {
-            const int w0 = base + FIRST + i * NE;
-            const float xo_raw = xo_next;
-            if (i + 1 < COUNT) xo_next = xo_ahead(w0 + NE, D);
-            float raw[NE], wk[NE], u[NE];
-            float *msg[D];
-            int zl[NE];               // variable lane of the edge's message (self.llr is [lane][edge])
-#pragma unroll
-            for (int k = 0; k < D; k++) {
-                const uint32_t w = c_desc[w0 + k];
-                const int zz = rot_lane<G>(c.z, (w >> 8) & 0xff);
-                msg[k] = slab0 + (w & 0xff) * Z + zz;
-                zl[k] = zz;
-                raw[k] = *msg[k];
-                wk[k] = wb_at<true>(c.wb_base + (int)(w >> 16)).x;
-            }
-            const uint32_t w1 = c_desc[w0 + D];
-            const int J = w1 & 0xff;
-            raw[D] = c.lane[(G::kXRows + G::S + ((w1 >> 8) & 0xff)) * Z];        // xa_input of block J, own lane
-            wk[D] = wb_at<true>(c.wb_base + (int)(w1 >> 16)).x;
-            zl[D] = c.z;
-            if (c.dump) dump_record<G, MODE, NE>(c, raw, OFF + i * REC);
-#pragma unroll
-            for (int k = 0; k < NE; k++) {
-                if constexpr (MODE == 2) {
-                    u[k] = raw[k];             // already on the grid; the clamp to +-7.5 is the min network's cap (cn_check_boosted_core)
-                } else {
-                    const float v = condition<MODE>(raw[k], c.lo, c.hi);
-                    u[k] = (v == 0.0f) ? 0.0001f : v;
-                }
-            }
-            constexpr int H = (NE + 1) / 2;
-            float se[H + 1];
-            constexpr float kCap = MODE == 2 ? 7.5f : 10000.0f;
-            se[H] = kCap;
-#pragma unroll
-            for (int q = H - 1; q >= 0; q--) {
-                if (2 * q + 1 < NE) se[q] = fmin3(fabsf(u[2 * q]), fabsf(u[2 * q + 1]), se[q + 1]);
-                else se[q] = fminf(fabsf(u[2 * q]), se[q + 1]);
-            }
-            unsigned x = (NE & 1) ? 0x80000000u : 0u;
-#pragma unroll
-            for (int k = 0; k < NE; k++) x ^= __float_as_uint(u[k]);
-            float pe = kCap;
-            float c2v_last = 0.0f;
-#pragma unroll
-            for (int k = 0; k < NE; k++) {
-                const int q = k >> 1;
-                float mag;
-                if ((k & 1) == 0) {
-                    if (k + 1 < NE) mag = fmin3(pe, fabsf(u[k + 1]), se[q + 1]);
-                    else mag = fminf(pe, se[q + 1]);
-                } else {
-                    mag = fmin3(pe, fabsf(u[k - 1]), se[q + 1]);
-                    pe = fmin3(pe, fabsf(u[k - 1]), fabsf(u[k]));
-                }
-                float c2v;
-                if constexpr (MODE == 2) {
-                    float m = fmaxf(mulf(mag, wk[k]), 0.0f);
-                    constexpr float kMagic = 6291456.0f;
-                    m = addf(addf(fminf(m, 7.5f), kMagic), -kMagic);
-                    const unsigned sb = (x ^ __float_as_uint(u[k])) & 0x80000000u;
-                    c2v = __uint_as_float(__float_as_uint(m) | sb);
-                    c2v = (mag == 0.0f) ? 0.0f : c2v;
-                } else {
-                    const float madj = (mag > 0.0001f) ? mag : addf(mag, -0.0001f);
-                    float m = fmaxf(mulf(fabsf(madj), wk[k]), 0.0f);
-                    m = condition<MODE>(m, c.lo, c.hi);
-                    const unsigned sb = (x ^ __float_as_uint(u[k]) ^ __float_as_uint(madj)) & 0x80000000u;
-                    c2v = __uint_as_float(__float_as_uint(m) | sb);
-                    c2v = (madj == 0.0f) ? 0.0f : c2v;
-                }
-                if constexpr (kLlr) {
-                    if (c.llr_last) c.llr_last[zl[k] * G::E + (int)(c_desc[w0 + k] >> 16)] = c2v;      // self.llr[t + 1][b][z][e] (:512)
-                }
-                if (k < D) *msg[k] = c2v;
-                else c2v_last = c2v;
-            }
-            // marginal of block J (degree 1: out = xa_origin + (0 + c2v), :513-526), un-rotated: this lane holds bit (J, z)
-            const int qbit = J * Z + c.z;
-            float xo;
-            if constexpr (kXo == 2) xo = (MODE == 2) ? quant5_grid(xo_raw) : xo_raw;      // (a zero's sign is absorbed by the sum)
-            else xo = raw[D];
-            const float v = boosted_out(c, qbit, xo, addf(0.0f, c2v_last));
-            if (c.soft) st_global_stream(c.soft + qbit, v);
+        for (; i + 1 < COUNT; i += 2) {
+            Ops<D> A, B;
+            float ca[NE], cb[NE];
+            load<D>(A, w00 + i * NE);
+            load<D>(B, w00 + (i + 1) * NE);
+            math<D>(A, ca);
+            math<D>(B, cb);
+            finish<D>(A, ca, w00 + i * NE, OFF + i * REC);
+            finish<D>(B, cb, w00 + (i + 1) * NE, OFF + (i + 1) * REC);
+        }
+        if (i < COUNT) {
+            Ops<D> A;
+            float ca[NE];
+            load<D>(A, w00 + i * NE);
+            math<D>(A, ca);
+            finish<D>(A, ca, w00 + i * NE, OFF + i * REC);
         }
     }
 };
