@@ -98,6 +98,9 @@ __device__ unsigned g_dbg_restarts;
 extern "C" unsigned nldpc_debug_restarts() { unsigned v = 0; cudaMemcpyFromSymbol(&v, g_dbg_restarts, 4); return v; }
 #endif
 // scheduling knobs (experiments: tools/build_variant.sh)
+#ifndef NLDPC_TRAIN_GANG
+#define NLDPC_TRAIN_GANG 2  // looped checks of the training forward processed together (independent arithmetic chains side by side)
+#endif
 #ifndef NLDPC_VN_QOUTER
 #define NLDPC_VN_QOUTER 1   // 1: VN chain pairs written operand-major
 #endif
@@ -878,30 +881,34 @@ struct CnBoostedLoops {                              // export still issued 4 % 
     // two independent arithmetic chains sit next to each other in one basic block — the per-check chain (descriptor ->
     // address -> load -> min network -> multiply -> quantise -> sign -> store) alone leaves a warp waiting on fixed
     // latencies (ncu: `wait` 1.13 cycles per issue at 2 warps per scheduler)
+    template <int D, int GANG>
+    __device__ __forceinline__ void gang(int w0, int rec_off, int rec) {
+        constexpr int NE = D + 1;
+        Ops<D> o[GANG];
+        float cv[GANG][NE];
+#pragma unroll
+        for (int g = 0; g < GANG; g++) load<D>(o[g], w0 + g * NE);
+#pragma unroll
+        for (int g = 0; g < GANG; g++) math<D>(o[g], cv[g]);
+#pragma unroll
+        for (int g = 0; g < GANG; g++) finish<D>(o[g], cv[g], w0 + g * NE, rec_off + g * rec);
+    }
     template <int D, int FIRST, int COUNT, int OFFH, int OFFF>
     __device__ __forceinline__ void cls() {
         constexpr int NE = D + 1;
         constexpr int REC = MODE == 2 ? G::dump_slots_h(NE) : NE, OFF = MODE == 2 ? OFFH : OFFF;
+        constexpr int kGang = NLDPC_TRAIN_GANG;
         const int w00 = base + FIRST;
         int i = 0;
 #pragma unroll 1
-        for (; i + 1 < COUNT; i += 2) {
-            Ops<D> A, B;
-            float ca[NE], cb[NE];
-            load<D>(A, w00 + i * NE);
-            load<D>(B, w00 + (i + 1) * NE);
-            math<D>(A, ca);
-            math<D>(B, cb);
-            finish<D>(A, ca, w00 + i * NE, OFF + i * REC);
-            finish<D>(B, cb, w00 + (i + 1) * NE, OFF + (i + 1) * REC);
+        for (; i + kGang <= COUNT; i += kGang) gang<D, kGang>(w00 + i * NE, OFF + i * REC, REC);
+        if constexpr (kGang > 2) {
+            if (i + 2 <= COUNT) {
+                gang<D, 2>(w00 + i * NE, OFF + i * REC, REC);
+                i += 2;
+            }
         }
-        if (i < COUNT) {
-            Ops<D> A;
-            float ca[NE];
-            load<D>(A, w00 + i * NE);
-            math<D>(A, ca);
-            finish<D>(A, ca, w00 + i * NE, OFF + i * REC);
-        }
+        if (i < COUNT) gang<D, 1>(w00 + i * NE, OFF + i * REC, REC);
     }
 };
 
