@@ -297,11 +297,10 @@ __device__ __forceinline__ void cn_bwd_math(const float *pv, const float *dc, co
     for (int k = 0; k < D; k++) {
         float v = pv[k];
         if constexpr (MODE == 2) {
-            // QMS q=5 as in the forward fast path (cn_check_boosted_core): grid rounding on the FADD pipe gives +0.0 for a
-            // zero, which stands for the reference's "+1e-4, then mag - 1e-4 = 0"; no gradient flows through it either
-            // way (relu'(0) = 0).
+            // QMS q=5 as in the forward fast path (cn_check_boosted_core): the recorded CN input is already on the 0.5 grid
+            // (zeros are +0.0, standing for the reference's "+1e-4, then mag - 1e-4 = 0"; no gradient flows through them:
+            // relu'(0) = 0), so the re-quantisation is the clamp — taken on the magnitude below, the sign is the raw word's.
             pass[k] = fabsf(v) <= 7.5f;
-            v = quant5_grid(v);
         } else if constexpr (MODE == 1) {
             pass[k] = (v >= lo && v <= hi);
             v = clamp_rng(v, lo, hi);
@@ -311,6 +310,7 @@ __device__ __forceinline__ void cn_bwd_math(const float *pv, const float *dc, co
         }
         u[k] = v;
         float a = fabsf(v);
+        if constexpr (MODE == 2) a = fminf(a, 7.5f);
         if constexpr (MODE == 0) {
             sb[k] = (v == 0.0f) ? kSign : __float_as_uint(v);
             a = (a > 0.0f) ? a : 10000.0f;
