@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""kernel-level breakdown of one FusedTrainer step (torch profiler): python tools/prof_train_fused.py [B] [fused=1|0]"""
+"""kernel-level breakdown of one FusedTrainer step (torch profiler): python tools/prof_train_fused.py [B] [fused=1|0] [T]"""
 import os
 import sys
 
@@ -19,7 +19,7 @@ from neural_ldpc_decoder_torch_b200.training import DeviceBatchGenerator, FusedT
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 fused = (sys.argv[2] != "0") if len(sys.argv) > 2 else True
-T = 20
+T = int(sys.argv[3]) if len(sys.argv) > 3 else 20
 dev = torch.device("cuda")
 bg, Z = load_basegraph("nr_bg2_set0")
 graph = TannerGraph(bg, Z)
