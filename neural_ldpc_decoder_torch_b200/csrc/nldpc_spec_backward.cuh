@@ -145,6 +145,9 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+#ifndef NLDPC_BWD_SLOTS
+#define NLDPC_BWD_SLOTS 3   // staging slots of the fp16-record loops: operands are fetched NLDPC_BWD_SLOTS - 1 checks ahead
+#endif
 #ifndef NLDPC_BWD_L2_PREFETCH
 // 1: pull the next iteration's records / gradients / channel inputs of a codeword into L2 a whole iteration ahead.  Measured in
 // both rounds and left off: 21.3 vs 19.3 ms per sweep in round 2 (the scratch rows it had competed with in round 1 are gone;
@@ -172,7 +175,7 @@ template <class G, int MODE>
 struct BwdStage {
     static constexpr bool kHalf = MODE == 2;
     static constexpr int kEntF = kHalf ? 8 : G::kMaxRowDeg + 3;      // floats per thread and slot
-    static constexpr int kSlots = kHalf ? 3 : 2;
+    static constexpr int kSlots = kHalf ? NLDPC_BWD_SLOTS : 2;
     static constexpr size_t kCwBytes = kHalf ? (size_t)G::kDumpH * G::Z * 2 : (size_t)G::kDumpF * G::Z * 4;   // per codeword and iteration
     // `stg` = this thread's place in a slot: fp32 &slot[0][tid]; fp16 &slot[warp][entry 0][lane] (256 floats per warp).
     // address of extra `comp` (0 gradient, 1 mask word, 2 xprev) of this thread
