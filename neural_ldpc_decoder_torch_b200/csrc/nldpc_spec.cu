@@ -78,7 +78,11 @@ int launch_neural(const DecodeArgs &a, int sm_count, cudaStream_t st) {
     const bool dump = a.hist_v2c != nullptr, soft_only = a.hard_mode == 0;
     if (dump && !soft_only) return -1;      // (a training dump with hard decisions: not a combination the module ever asks for)
     if (off >= 0) {
+#if NLDPC_CN_PAIR
+        if ((err = upload_wb_paired<G>(arena, a.w, a.b, off, len, st)) != cudaSuccess) return (int)err;
+#else
         if ((err = upload_wb(arena, a.w, a.b, off, len, st)) != cudaSuccess) return (int)err;
+#endif
         err = dump        ? launch_all(nldpc_spec_neural_kernel<G, true, true, 0, false, true>, nldpc_spec_neural_kernel<G, false, true>)
               : soft_only ? launch_all(nldpc_spec_neural_kernel<G, true, true, 0, false, false, true>, nldpc_spec_neural_kernel<G, false, true>)
                           : launch_all(nldpc_spec_neural_kernel<G, true, true>, nldpc_spec_neural_kernel<G, false, true>);

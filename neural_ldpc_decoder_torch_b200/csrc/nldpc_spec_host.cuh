@@ -141,6 +141,46 @@ inline cudaError_t upload_wb(ConstArena &arena, const float *w, const float *b, 
                                    cudaMemcpyDeviceToDevice, st);
 }
 
+// Neural forward kernels (NLDPC_CN_PAIR): the same T * E {w, b} values in the pair layout of WbPlan — float offsets within an
+// iteration's 2 * E floats from the generated table G::wb_pair_off(), copied to the device once (never during a capture:
+// captured Neural launches read their weights with LDG and do not come here).
+__global__ void pack_wb_paired_kernel(const float *__restrict__ w, const float *__restrict__ b, const int *__restrict__ tab,
+                                      float *__restrict__ dst, int E, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int t = i / E, e = i - t * E;
+    float *it = dst + (size_t)t * 2 * E;
+    it[tab[e]] = w ? w[i] : 1.0f;
+    it[tab[E + e]] = b ? b[i] : 0.0f;
+}
+template <class G>
+cudaError_t upload_wb_paired(ConstArena &arena, const float *w, const float *b, int off, int len, cudaStream_t st) {
+    static std::mutex mu;
+    static int *tabs[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int *tab = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!tabs[dev & 63]) {
+            cudaError_t e = cudaMalloc((void **)&tabs[dev & 63], sizeof(int) * 2 * G::E);
+            if (e != cudaSuccess) return e;
+            e = cudaMemcpy(tabs[dev & 63], G::wb_pair_off(), sizeof(int) * 2 * G::E, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) {
+                cudaFree(tabs[dev & 63]);
+                tabs[dev & 63] = nullptr;
+                return e;
+            }
+        }
+        tab = tabs[dev & 63];
+    }
+    pack_wb_paired_kernel<<<(len + 255) / 256, 256, 0, st>>>(w, b, tab, reinterpret_cast<float *>(arena.stage + off), G::E, len);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbolAsync(c_wb, arena.stage + off, sizeof(float2) * (size_t)len, sizeof(float2) * (size_t)off,
+                                   cudaMemcpyDeviceToDevice, st);
+}
+
 // descriptors of the looped checks -> this translation unit's c_desc, once per device.  Synchronous on purpose: when the call
 // returns the table is in place for launches on ANY stream (the flag is shared by all of them).
 template <class G>

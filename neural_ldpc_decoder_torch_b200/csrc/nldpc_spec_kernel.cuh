@@ -133,6 +133,13 @@ __device__ __forceinline__ f2 add2(f2 a, f2 b) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+// packed multiply (SASS FMUL2).  Only ever used where NO addition consumes the product (see the note above): the sign of a
+// c2v message, relu(m) * (+-1.0).
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+    f2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 __device__ __forceinline__ float fmin3(float a, float b, float c) {
     float d;
     asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));   // one FMNMX3
@@ -596,6 +603,62 @@ __device__ __forceinline__ void dump_check(const NeuralLane<G> &c, const float *
     dump_record<G, MODE, D>(c, raw, off);
 }
 
+// ---- pair layout of the Neural decoder's {w, b} (NLDPC_CN_PAIR) ----------------------------------------------------
+// The STORED edges of a check are taken two at a time.  A pair (a, b) owns two consecutive float2 entries of the arena,
+// (w_a, w_b) and (b_a, b_b): the two products go to a register pair with scalar FMULs, ONE packed add (FADD2) adds the b
+// pair straight from a uniform register pair, and after the ReLU one packed multiply (FMUL2) by (+-1.0, +-1.0) applies
+// the two signs: 10 instructions per pair instead of 12 (two LOP3 fewer on the half-rate ALU pipe).  The leftover stored
+// edge and the unstored degree-1 edges keep a (w, b) entry.  Offsets = tools/gen_kernels.py: G::wb_pair_off() (host side).
+#ifndef NLDPC_CN_PAIR
+#define NLDPC_CN_PAIR 1
+#endif
+#ifndef NLDPC_CN_SIGNMUL      // 1: sign applied by the packed multiply (FMA pipe); 0: OR-ed in (LOP3, ALU pipe)
+#define NLDPC_CN_SIGNMUL 0
+#endif
+template <int D>
+struct WbPlanT {
+    int entry[D];      // float2 entry (relative to the iteration's base): pair -> entry of (w_a, w_b), +1 = (b_a, b_b); single -> (w, b)
+    int role[D];       // 0 single, 1 first of a pair, 2 second of a pair
+    int mate[D];       // the other edge of the pair
+};
+template <class... Es>
+struct WbPlan {
+    static constexpr int D = sizeof...(Es);
+    __host__ __device__ static constexpr WbPlanT<D> make() {
+        constexpr int col1[D] = {Es::col1...};
+        constexpr int eix[D] = {Es::e...};
+        WbPlanT<D> p{};
+        int entry = eix[0], prev = -1;
+        for (int k = 0; k < D; k++) {
+            p.role[k] = 0;
+            p.mate[k] = -1;
+            if (col1[k] >= 0) continue;
+            if (prev < 0) {
+                prev = k;
+            } else {
+                p.entry[prev] = p.entry[k] = entry;
+                p.role[prev] = 1;
+                p.role[k] = 2;
+                p.mate[prev] = k;
+                p.mate[k] = prev;
+                entry += 2;
+                prev = -1;
+            }
+        }
+        if (prev >= 0) p.entry[prev] = entry++;
+        for (int k = 0; k < D; k++)
+            if (col1[k] >= 0) p.entry[k] = entry++;
+        return p;
+    }
+    __host__ __device__ static constexpr bool consecutive() {
+        constexpr int eix[D] = {Es::e...};
+        for (int k = 0; k < D; k++)
+            if (eix[k] != eix[0] + k) return false;
+        return true;
+    }
+    static_assert(consecutive(), "the edges of a check are consecutive in the weight vectors");
+};
+
 template <class G, bool kEmit, bool kConstW, bool kScalarW, class... Es>
 __device__ __forceinline__ void cn_load(const NeuralLane<G> &c, float *raw, float2 *wb) {
     constexpr int D = sizeof...(Es);
@@ -607,6 +670,22 @@ __device__ __forceinline__ void cn_load(const NeuralLane<G> &c, float *raw, floa
     for (int k = 0; k < D; k++)
         raw[k] = rows[k] >= 0 ? c.rot[shf[k]][rows[k] * G::Z]
                  : (train_traits<G>::on ? c.lane[(G::kXRows + G::S + (rows[k] < 0 ? -rows[k] - 1 : 0)) * G::Z] : c.xreg[rows[k] < 0 ? -rows[k] - 1 : 0]);
+    if constexpr (NLDPC_CN_PAIR && !kScalarW) {
+        // pair layout: wb[first of a pair] = (w_a, w_b), wb[second] = (b_a, b_b), wb[single] = (w, b)
+        constexpr WbPlanT<D> pl = WbPlan<Es...>::make();
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            if (col1[k] >= 0 && !kEmit) continue;
+            if constexpr (kConstW) {
+                wb[k] = c_wb[c.wb_base + pl.entry[k] + (pl.role[k] == 2 ? 1 : 0)];
+            } else {
+                if (pl.role[k] == 1) wb[k] = make_float2(__ldg(c.wt + eix[k]), __ldg(c.wt + eix[pl.mate[k] >= 0 ? pl.mate[k] : 0]));
+                else if (pl.role[k] == 2) wb[k] = make_float2(__ldg(c.bt + eix[pl.mate[k] >= 0 ? pl.mate[k] : 0]), __ldg(c.bt + eix[k]));
+                else wb[k] = make_float2(__ldg(c.wt + eix[k]), __ldg(c.bt + eix[k]));
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < D; k++) {
         if (col1[k] >= 0 && !kEmit) continue;                            // unstored edge, marginal not wanted now
@@ -644,6 +723,60 @@ __device__ __forceinline__ void cn_check_core(NeuralLane<G> &c, const float *raw
 #pragma unroll
     for (int k = 0; k < D; k++) x ^= __float_as_uint(u[k]);
     float pe = 10000.0f;
+#if NLDPC_CN_PAIR
+    {
+        constexpr WbPlanT<D> pl = WbPlan<Es...>::make();
+        float mg[D], r[D], sg[D], cv[D];
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            const int q = k >> 1;
+            if ((k & 1) == 0) {
+                if (k + 1 < D) mg[k] = fmin3(pe, fabsf(u[k + 1]), se[q + 1]);
+                else mg[k] = fminf(pe, se[q + 1]);
+            } else {
+                mg[k] = fmin3(pe, fabsf(u[k - 1]), se[q + 1]);
+                pe = fmin3(pe, fabsf(u[k - 1]), fabsf(u[k]));
+            }
+        }
+        // sign as a factor: x1 = +-1.0 with the sign of the product of all inputs (negated for odd D, see x), and
+        // sg[k] = x1 with the sign of input k taken out again = -(product of the signs of the OTHER inputs) (:77-80, :89-91)
+        const unsigned x1 = (x & 0x80000000u) | 0x3f800000u;
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            if (col1[k] >= 0 && !kEmit) continue;                        // unstored edge, marginal not wanted now
+            if constexpr (NLDPC_CN_SIGNMUL) sg[k] = __uint_as_float(x1 ^ (__float_as_uint(u[k]) & 0x80000000u));
+            // |o| * w + b, ReLU
+            if (pl.role[k] == 0) r[k] = fmaxf(addf(mulf(mg[k], wb[k].x), wb[k].y), 0.0f);
+        }
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            if (pl.role[k] != 1) continue;
+            const int m2 = pl.mate[k] >= 0 ? pl.mate[k] : 0;
+            const f2 s = add2(pack2(mulf(mg[k], wb[k].x), mulf(mg[m2], wb[k].y)), pack2(wb[m2].x, wb[m2].y));
+            r[k] = fmaxf(lo(s), 0.0f);
+            r[m2] = fmaxf(hi(s), 0.0f);
+            if constexpr (NLDPC_CN_SIGNMUL) {
+                const f2 v = mul2(pack2(r[k], r[m2]), pack2(sg[k], sg[m2]));
+                cv[k] = lo(v);
+                cv[m2] = hi(v);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            if (col1[k] >= 0 && !kEmit) continue;
+            float c2v;
+            if constexpr (NLDPC_CN_SIGNMUL) c2v = pl.role[k] == 0 ? mulf(r[k], sg[k]) : cv[k];
+            else c2v = __uint_as_float(__float_as_uint(r[k]) | ((x ^ __float_as_uint(u[k])) & 0x80000000u));
+            if (col1[k] < 0) {
+                c.rot[shf[k]][rows[k] * G::Z] = c2v;                     // scatter back (:82-86), in place
+            } else {
+                // degree-1 block col1: out = xa + (0 + c2v) at lane (h + s) mod Z (:94-98)
+                if constexpr (kEmit) c.emit_rot(col1[k], shf[k], addf(raw[k], addf(0.0f, c2v)));
+            }
+        }
+        return;
+    }
+#endif
 #pragma unroll
     for (int k = 0; k < D; k++) {
         const int q = k >> 1;
