@@ -50,14 +50,14 @@ int boosted_launch(const DecodeArgs &a, int sm_count, cudaStream_t st) {
     if (a.hist_v2c) return -1;      // training dumps: the training variant (nldpc_spec_train.cuh), tried first by the dispatcher
     const bool capturing = stream_is_capturing(st);      // CUDA graph capture: fixed arena range, no launch-time bookkeeping
     ConstArena &arena = arena_for_current_device();
-    const int n_w = a.T * G::E, len = (n_w + 1) / 2;      // plain floats in the arena (wb_at<true>), len in float2 units
+    const int n_w = a.T * kWPitch<G>, len = (n_w + 1) / 2;      // plain floats in the arena (wb_at<true>), even pitch per iteration; len in float2 units
     cudaError_t err = cudaSuccess;
     const int off = capturing ? arena.acquire_captured(len, st, &err) : arena.acquire(len, st, &err);
     if (err != cudaSuccess) return (int)err;
     if (off < 0) return -1;
     DecodeArgs args = a;
     args.wb_off = 2 * off;                               // float units
-    if ((err = upload_w(arena, a.w, off, n_w, st)) != cudaSuccess) return (int)err;   // cn_w (or 1.0)
+    if ((err = upload_w_pitched(arena, a.w, off, a.T, G::E, kWPitch<G>, st)) != cudaSuccess) return (int)err;   // cn_w (or 1.0)
     int rc;
     if (ms) rc = a.vn_w ? boosted_launch_one<G, 1, true>(args, sm_count, st) : boosted_launch_one<G, 1, false>(args, sm_count, st);
     else rc = a.vn_w ? boosted_launch_one<G, 2, true>(args, sm_count, st) : boosted_launch_one<G, 2, false>(args, sm_count, st);

@@ -213,6 +213,22 @@ inline cudaError_t upload_w(ConstArena &arena, const float *w, int off, int n, c
                                    cudaMemcpyDeviceToDevice, st);
 }
 
+// the same for the specialised Boosted FORWARD kernels: iteration t's E weights at float offset t * pitch (pitch even, kWPitch)
+__global__ void pack_w_pitched_kernel(const float *__restrict__ w, float *__restrict__ dst, int E, int pitch, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int t = i / pitch, e = i - t * pitch;
+    dst[i] = (w && e < E) ? w[t * E + e] : 1.0f;
+}
+inline cudaError_t upload_w_pitched(ConstArena &arena, const float *w, int off, int T, int E, int pitch, cudaStream_t st) {
+    const int n = T * pitch;
+    pack_w_pitched_kernel<<<(n + 255) / 256, 256, 0, st>>>(w, reinterpret_cast<float *>(arena.stage + off), E, pitch, n);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbolAsync(c_wb, arena.stage + off, sizeof(float2) * (size_t)((n + 1) / 2), sizeof(float2) * (size_t)off,
+                                   cudaMemcpyDeviceToDevice, st);
+}
+
 template <class K>
 cudaError_t set_smem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);

@@ -140,6 +140,14 @@ __device__ __forceinline__ f2 mul2(f2 a, f2 b) {
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {      // FADD2 with a negated operand
+    f2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+#ifndef NLDPC_VN_QMS_TOTAL      // QMS q=5 VN phase: (x + total) - m[k] instead of the ordered chains (exact either way)
+#define NLDPC_VN_QMS_TOTAL 1
+#endif
 __device__ __forceinline__ float fmin3(float a, float b, float c) {
     float d;
     asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));   // one FMNMX3
@@ -410,8 +418,34 @@ struct VnStep {
         constexpr int D = sizeof...(R);
         constexpr int rows[D] = {R...};
         const float *m = mm[SLOT];
-        float pre[D];
         const float x = xx[SLOT];
+#if NLDPC_VN_QMS_TOTAL
+        if constexpr (MODE == 2) {
+            // QMS q=5: the channel value and every message are multiples of 0.5 with |.| <= 7.5, so every partial sum of the
+            // reference's ordered chain (:49, :56-58) is exact — and so is ANY order.  v2c[k] = (x + total) - m[k]: D/2 packed
+            // adds for the total and D/2 packed subtractions instead of D^2/4 chain steps (BG2: blocks of degree up to 23).
+            // Zeros: messages may be -0.0, the total starts from +0.0 like the reference's sums, x is +0.0 for zeros
+            // (quant5_grid), so x + total is never -0.0 and (x + total) - m[k] is +0.0 whenever it is zero — as x + (+0-started
+            // sum of the others) is.
+            f2 acc = pack2(0.0f, 0.0f);
+#pragma unroll
+            for (int k = 0; k + 1 < D; k += 2) acc = add2(acc, pack2(m[k], m[k + 1]));
+            float p = addf(lo(acc), hi(acc));
+            if constexpr (D & 1) p = addf(p, m[D - 1]);
+            const float xt = addf(x, p);
+#pragma unroll
+            for (int k = 0; k + 1 < D; k += 2) {
+                const f2 s = sub2(pack2(xt, xt), pack2(m[k], m[k + 1]));
+                c.lane[rows[k] * G::Z] = lo(s);
+                c.lane[rows[k + 1] * G::Z] = hi(s);
+            }
+            if constexpr (D & 1) c.lane[rows[D - 1] * G::Z] = addf(xt, -m[D - 1]);
+            if constexpr (kEmit)
+                c.template emit<J>(boosted_out(c, J * G::Z + c.z, kXo == 2 ? xo_global<MODE>(c, J * G::Z + c.z) : (kXo == 1 ? c.lane[c.xo_off + J * G::Z] : x), p));   // Boosted :520-521
+            return;
+        }
+#endif
+        float pre[D];
         float p = 0.0f;                       // running prefix ((0 + m0) + m1) + ...
 #pragma unroll
         for (int k = 0; k < D; k++) {
@@ -615,6 +649,19 @@ __device__ __forceinline__ void dump_check(const NeuralLane<G> &c, const float *
 #ifndef NLDPC_CN_SIGNMUL      // 1: sign applied by the packed multiply (FMA pipe); 0: OR-ed in (LOP3, ALU pipe)
 #define NLDPC_CN_SIGNMUL 0
 #endif
+// Boosted decoders (plain float weights in the arena, MODE != 0): an iteration's E weights start at an EVEN float offset
+// (pitch kWPitch), so the weights of edges (e, e + 1), e even, are one aligned 64-bit constant: QMS q=5 multiplies two stored
+// edges of a check with ONE FMUL2 (uniform register pair operand) and quantises both with two FADD2 (NLDPC_QMS_PAIR).
+#ifndef NLDPC_QMS_PAIR
+#define NLDPC_QMS_PAIR 1
+#endif
+template <class G>
+constexpr int kWPitch = (G::E + 1) & ~1;
+// edge k is the first of a QMS pair: even edge index, the next edge belongs to the same check, both are computed now
+template <bool kEmit, int D>
+__host__ __device__ constexpr bool qms_pair_first(const int *eix, const int *col1, int k) {
+    return (eix[k] & 1) == 0 && k + 1 < D && (kEmit || (col1[k] < 0 && col1[k + 1] < 0));
+}
 template <int D>
 struct WbPlanT {
     int entry[D];      // float2 entry (relative to the iteration's base): pair -> entry of (w_a, w_b), +1 = (b_a, b_b); single -> (w, b)
@@ -659,7 +706,7 @@ struct WbPlan {
     static_assert(consecutive(), "the edges of a check are consecutive in the weight vectors");
 };
 
-template <class G, bool kEmit, bool kConstW, bool kScalarW, class... Es>
+template <class G, bool kEmit, bool kConstW, bool kScalarW, bool kPairW, class... Es>
 __device__ __forceinline__ void cn_load(const NeuralLane<G> &c, float *raw, float2 *wb) {
     constexpr int D = sizeof...(Es);
     constexpr int rows[D] = {Es::row...};
@@ -683,6 +730,18 @@ __device__ __forceinline__ void cn_load(const NeuralLane<G> &c, float *raw, floa
                 else if (pl.role[k] == 2) wb[k] = make_float2(__ldg(c.bt + eix[pl.mate[k] >= 0 ? pl.mate[k] : 0]), __ldg(c.bt + eix[k]));
                 else wb[k] = make_float2(__ldg(c.wt + eix[k]), __ldg(c.bt + eix[k]));
             }
+        }
+        return;
+    }
+    if constexpr (NLDPC_QMS_PAIR && kScalarW && kConstW && kPairW) {
+        // wb[first of a pair] = (w_k, w_k+1): one LDCU.64; everything else (w, 0)
+        const int hb = c.wb_base >> 1;      // (wb_base is even: even arena offset + t * kWPitch)
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            if (col1[k] >= 0 && !kEmit) continue;
+            if (k > 0 && qms_pair_first<kEmit, D>(eix, col1, k - 1)) continue;      // second of a pair
+            if (qms_pair_first<kEmit, D>(eix, col1, k)) wb[k] = c_wb[hb + eix[k] / 2];
+            else wb[k] = wb_at<true>(c.wb_base + eix[k]);
         }
         return;
     }
@@ -740,21 +799,27 @@ __device__ __forceinline__ void cn_check_core(NeuralLane<G> &c, const float *raw
         }
         // sign as a factor: x1 = +-1.0 with the sign of the product of all inputs (negated for odd D, see x), and
         // sg[k] = x1 with the sign of input k taken out again = -(product of the signs of the OTHER inputs) (:77-80, :89-91)
-        const unsigned x1 = (x & 0x80000000u) | 0x3f800000u;
+        // NLDPC_CN_SIGNMUL == 2: the ReLU leaves the ALU pipe too: m + |m| = 2 relu(m) exactly (+0 for m <= 0, -0 included),
+        // and the sign factor is +-0.5 (exact scaling)
+        constexpr bool kReluAdd = NLDPC_CN_SIGNMUL == 2;
+        const unsigned x1 = (x & 0x80000000u) | (kReluAdd ? 0x3f000000u : 0x3f800000u);
 #pragma unroll
         for (int k = 0; k < D; k++) {
             if (col1[k] >= 0 && !kEmit) continue;                        // unstored edge, marginal not wanted now
             if constexpr (NLDPC_CN_SIGNMUL) sg[k] = __uint_as_float(x1 ^ (__float_as_uint(u[k]) & 0x80000000u));
             // |o| * w + b, ReLU
-            if (pl.role[k] == 0) r[k] = fmaxf(addf(mulf(mg[k], wb[k].x), wb[k].y), 0.0f);
+            if (pl.role[k] == 0) {
+                const float m = addf(mulf(mg[k], wb[k].x), wb[k].y);
+                r[k] = kReluAdd ? addf(m, fabsf(m)) : fmaxf(m, 0.0f);
+            }
         }
 #pragma unroll
         for (int k = 0; k < D; k++) {
             if (pl.role[k] != 1) continue;
             const int m2 = pl.mate[k] >= 0 ? pl.mate[k] : 0;
             const f2 s = add2(pack2(mulf(mg[k], wb[k].x), mulf(mg[m2], wb[k].y)), pack2(wb[m2].x, wb[m2].y));
-            r[k] = fmaxf(lo(s), 0.0f);
-            r[m2] = fmaxf(hi(s), 0.0f);
+            r[k] = kReluAdd ? addf(lo(s), fabsf(lo(s))) : fmaxf(lo(s), 0.0f);
+            r[m2] = kReluAdd ? addf(hi(s), fabsf(hi(s))) : fmaxf(hi(s), 0.0f);
             if constexpr (NLDPC_CN_SIGNMUL) {
                 const f2 v = mul2(pack2(r[k], r[m2]), pack2(sg[k], sg[m2]));
                 cv[k] = lo(v);
@@ -846,6 +911,7 @@ __device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c, const fl
 #pragma unroll
     for (int k = 0; k < D; k++) x ^= __float_as_uint(u[k]);
     float pe = kCap;
+    float pm[D];      // (NLDPC_QMS_PAIR: quantised magnitudes, written pairwise)
 #pragma unroll
     for (int k = 0; k < D; k++) {
         const int q = k >> 1;
@@ -858,9 +924,33 @@ __device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c, const fl
             pe = fmin3(pe, fabsf(u[k - 1]), fabsf(u[k]));
         }
         if (col1[k] >= 0 && !kEmit) continue;
-        const float wk = wb[k].x;
         float c2v;
-        if constexpr (MODE == 2) {
+        if constexpr (MODE == 2 && NLDPC_QMS_PAIR) {
+            // (arithmetic as in the scalar branch below; two stored edges share the multiply and the two quantiser adds)
+            constexpr float kMagic = 6291456.0f;
+            if (qms_pair_first<kEmit, D>(eix, col1, k)) {
+                // mag of edge k + 1 (the min network above, one step ahead)
+                float mag1;
+                if (((k + 1) & 1) == 0) {
+                    if (k + 2 < D) mag1 = fmin3(pe, fabsf(u[k + 2]), se[((k + 1) >> 1) + 1]);
+                    else mag1 = fminf(pe, se[((k + 1) >> 1) + 1]);
+                } else {
+                    mag1 = fmin3(pe, fabsf(u[k]), se[((k + 1) >> 1) + 1]);
+                }
+                const f2 pr = mul2(pack2(mag, mag1), pack2(wb[k].x, wb[k].y));
+                const float a0 = fminf(fmaxf(lo(pr), 0.0f), 7.5f), a1 = fminf(fmaxf(hi(pr), 0.0f), 7.5f);
+                const f2 qv = add2(add2(pack2(a0, a1), pack2(kMagic, kMagic)), pack2(-kMagic, -kMagic));
+                pm[k] = lo(qv);
+                pm[k + 1] = hi(qv);
+            } else if (!(k > 0 && qms_pair_first<kEmit, D>(eix, col1, k - 1))) {
+                const float m = fminf(fmaxf(mulf(mag, wb[k].x), 0.0f), 7.5f);
+                pm[k] = addf(addf(m, kMagic), -kMagic);
+            }
+            const unsigned sb = (x ^ __float_as_uint(u[k])) & 0x80000000u;
+            c2v = __uint_as_float(__float_as_uint(pm[k]) | sb);
+            if constexpr (kEmit) c2v = (mag == 0.0f) ? 0.0f : c2v;
+        } else if constexpr (MODE == 2) {
+            const float wk = wb[k].x;
             // madj == mag >= 0 (see above); m >= 0 so only the upper clamp of the quantiser can bind
             float m = fmaxf(mulf(mag, wk), 0.0f);                             // |o| * W, ReLU (:431-505)
             constexpr float kMagic = 6291456.0f;
@@ -871,6 +961,7 @@ __device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c, const fl
             // +0-started sums that consume it, so only iterations whose messages are exported (self.llr) pay for it.
             if constexpr (kEmit) c2v = (mag == 0.0f) ? 0.0f : c2v;
         } else {
+            const float wk = wb[k].x;
             const float madj = (mag > 0.0001f) ? mag : addf(mag, -0.0001f);   // (:416)
             float m = fmaxf(mulf(fabsf(madj), wk), 0.0f);                     // |o| * W, ReLU (:431-505)
             m = condition<MODE>(m, c.lo, c.hi);                               // (:507-510)
@@ -1053,12 +1144,12 @@ struct CnBoosted {
     float2 wb[2][G::kMaxRowDeg];
     template <class... Es>
     __device__ __forceinline__ void chk() {
-        cn_load<G, kEmit, true, true, Es...>(c, raw[0], wb[0]);
+        cn_load<G, kEmit, true, true, MODE == 2, Es...>(c, raw[0], wb[0]);
         cn_check_boosted_core<G, kEmit, MODE, kXo, Es...>(c, raw[0], wb[0]);
     }
     template <int SLOT, class... Es>
     __device__ __forceinline__ void ld() {
-        cn_load<G, kEmit, true, true, Es...>(c, raw[SLOT], wb[SLOT]);
+        cn_load<G, kEmit, true, true, MODE == 2, Es...>(c, raw[SLOT], wb[SLOT]);
     }
     template <int SLOT, class... Es>
     __device__ __forceinline__ void chk() {
@@ -1074,12 +1165,12 @@ struct CnNeural {
     float2 wb[2][G::kMaxRowDeg];
     template <class... Es>
     __device__ __forceinline__ void chk() {
-        cn_load<G, kEmit, kConstW, false, Es...>(c, raw[0], wb[0]);
+        cn_load<G, kEmit, kConstW, false, false, Es...>(c, raw[0], wb[0]);
         cn_check_core<G, kEmit, kConstW, kZeroSafe, Es...>(c, raw[0], wb[0]);
     }
     template <int SLOT, class... Es>
     __device__ __forceinline__ void ld() {
-        cn_load<G, kEmit, kConstW, false, Es...>(c, raw[SLOT], wb[SLOT]);
+        cn_load<G, kEmit, kConstW, false, false, Es...>(c, raw[SLOT], wb[SLOT]);
     }
     template <int SLOT, class... Es>
     __device__ __forceinline__ void chk() {
@@ -1430,7 +1521,7 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
             for (int t = 0; t < a.T; t++) {
                 c.wt = a.w + (size_t)t * G::E;
                 c.bt = a.b + (size_t)t * G::E;
-                c.wb_base = a.wb_off + t * G::E;
+                c.wb_base = a.wb_off + t * (MODE != 0 ? kWPitch<G> : G::E);
                 // training dump for the backward sweep: check-packed records written by the CN phase (hist_fmt 1; launches that
                 // want the slot-major format of the table-driven sweep run on the table-driven forward, see the launchers)
                 const bool dump = kDumps && a.hist_v2c != nullptr && c.valid;
@@ -1479,7 +1570,7 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
             for (int t = 0; t < a.T; t++) {
                 c.wt = a.w + (size_t)t * G::E;
                 c.bt = a.b + (size_t)t * G::E;
-                c.wb_base = a.wb_off + t * G::E;
+                c.wb_base = a.wb_off + t * (MODE != 0 ? kWPitch<G> : G::E);
                 xin_update(t);
                 if (t == 0) {
                     VnFirst<G> f{c};

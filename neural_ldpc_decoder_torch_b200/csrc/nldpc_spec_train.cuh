@@ -47,14 +47,14 @@ int train_launch(const DecodeArgs &a, int graph_slot, int sm_count, cudaStream_t
     if (err == cudaErrorStreamCaptureUnsupported && capturing) return -1;      // first use inside a capture
     if (err != cudaSuccess) return (int)err;
     ConstArena &arena = arena_for_current_device();
-    const int n_w = a.T * G::E, len = (n_w + 1) / 2;      // plain floats in the arena (wb_at<true>), len in float2 units
+    const int n_w = a.T * kWPitch<G>, len = (n_w + 1) / 2;      // plain floats in the arena (wb_at<true>), even pitch per iteration; len in float2 units
     const int off = capturing ? arena.acquire_captured(len, st, &err) : arena.acquire(len, st, &err);
     if (err != cudaSuccess) return (int)err;
     if (off < 0) return -1;
     DecodeArgs args = a;
     args.wb_off = 2 * off;                               // float units
     args.desc_base = graph_slot * kDescStride;
-    if ((err = upload_w(arena, a.w, off, n_w, st)) != cudaSuccess) return (int)err;   // cn_w (or 1.0)
+    if ((err = upload_w_pitched(arena, a.w, off, a.T, G::E, kWPitch<G>, st)) != cudaSuccess) return (int)err;   // cn_w (or 1.0)
     int rc;
     if (ms) rc = a.vn_w ? train_launch_one<G, 1, true>(args, sm_count, st) : train_launch_one<G, 1, false>(args, sm_count, st);
     else rc = a.vn_w ? train_launch_one<G, 2, true>(args, sm_count, st) : train_launch_one<G, 2, false>(args, sm_count, st);
