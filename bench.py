@@ -565,7 +565,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback",
                          "note": "iteration loop is on-chip bound by design: 11 KB of fp32 messages per codeword cap the SM at 8 warps; ncu "
-                                 "(profiles/r02_ncu_neural_bg2_packed_summary.txt): issue slots 63 % busy at 2 warps per scheduler, stalls = dependency "
+                                 "(profiles/r02b_ncu_neural_bg2_packed_summary.txt): issue slots 63 % busy at 2 warps per scheduler, stalls = dependency "
                                  "wait / pipe contention / shared-memory latency, shared-memory bank conflicts 0.04 %, DRAM 1.6 %; see DESIGN.md"},
             "list_mode": {"value": list_value, "unit": UNIT, "ms_per_step": ms_list / n_list,
                           "note": "drop-in forward(): T fp32 outputs [B, N*Z] per step (36608 B/codeword)",
