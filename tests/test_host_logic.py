@@ -229,3 +229,36 @@ def test_reference_written_checkpoints_load_strictly(tmp_path):
     wider = NeuralLDPCDecoder(3, 2, ConnectingMatrixTorch(ConnectingMatrix(Z=Z + 1, basegraph=bg)))
     with pytest.raises(RuntimeError):
         ck.load("ref_ckpt_neural_toy.pth", wider)
+
+
+@pytest.mark.parametrize("code,header", [("nr_bg2_set0", "nldpc_graph_bg2z16.cuh"), ("wimax_n576_r34", "nldpc_graph_wimaxz24.cuh")])
+def test_generated_weight_pair_layout(code, header):
+    """csrc/generated/*.cuh: wb_pair_off() (the host table of the Neural {w, b} pair layout, tools/gen_kernels.py) is a
+    permutation of an iteration's 2*E floats that stays inside each check's own 2*D floats, pairs are (w_a, w_b)(b_a, b_b) in
+    two consecutive 8-byte entries, singles are (w, b) in one — what csrc/nldpc_spec_kernel.cuh WbPlan derives at compile time."""
+    import os
+    import re
+
+    from neural_ldpc_decoder_torch_b200 import TannerGraph, load_basegraph
+    here = os.path.dirname(os.path.abspath(__file__))
+    src = open(os.path.join(here, "..", "neural_ldpc_decoder_torch_b200", "csrc", "generated", header)).read()
+    m = re.search(r"wb_pair_off\(\) \{\s*static const int t\[2 \* E\] = \{([^}]*)\}", src)
+    assert m, "generated header has no wb_pair_off table (run tools/gen_kernels.py)"
+    tab = [int(v) for v in m.group(1).split(",")]
+    bg, Z = load_basegraph(code)
+    g = TannerGraph(bg, Z)
+    E = g.E
+    assert len(tab) == 2 * E and sorted(tab) == list(range(2 * E))
+    woff, boff = tab[:E], tab[E:]
+    col_deg = np.bincount(np.asarray(g.ecol), minlength=g.N)
+    for i in range(g.M):
+        es = list(range(int(g.row_ptr[i]), int(g.row_ptr[i + 1])))
+        inside = range(2 * es[0], 2 * (es[-1] + 1))
+        assert all(woff[e] in inside and boff[e] in inside for e in es)
+        stored = [e for e in es if col_deg[int(g.ecol[e])] >= 2]
+        for a, b in zip(stored[0::2], stored[1::2]):
+            assert woff[a] % 4 in (0, 2) and woff[a] % 2 == 0 and woff[b] == woff[a] + 1
+            assert boff[a] == woff[a] + 2 and boff[b] == woff[a] + 3
+        singles = ([stored[-1]] if len(stored) % 2 else []) + [e for e in es if col_deg[int(g.ecol[e])] < 2]
+        for e in singles:
+            assert woff[e] % 2 == 0 and boff[e] == woff[e] + 1
