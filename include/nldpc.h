@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define NLDPC_ABI_VERSION 3
+#define NLDPC_ABI_VERSION 4
 
 /* error codes (negative); positive return values are cudaError_t */
 #define NLDPC_OK 0
@@ -141,6 +141,11 @@ typedef struct nldpc_boosted_cfg {
     /* Optional [T][B][Z][E] fp32: receives self.llr[t + 1] of EVERY executed iteration (the reference stores each one,
      * :512) from the same single launch; NULL = only llr_last_dev (if given) is written. */
     float *llr_all_dev;
+    /* Row pitch (in floats) of llr_all_dev AND llr_last_dev: element [..][b][z][e] lives at ((.. * B + b) * Z + z) * llr_pitch + e.
+     * 0 = E (the reference's dense [B][Z][E]).  A pitch that is a multiple of 4 (16-byte rows: WiMAX E = 88 as is, BG2 E = 197
+     * padded to 200) lets the specialised kernels export the state with 16-byte stores from the variable-lane view of the
+     * messages instead of one 4-byte store per lane and edge (BoostedNeuralLDPCDecoder.py:512 is the tensor being filled). */
+    int32_t llr_pitch;
 } nldpc_boosted_cfg_t;
 
 /* Replaces the loop of BoostedNeuralLDPCDecoder.forward (:320-531) for iterations 0..T-1 from a

@@ -28,7 +28,7 @@ class BoostedCfg(ctypes.Structure):
                 ("llr_hi", ctypes.c_float), ("compute_ucn", ctypes.c_int32), ("ucn_mix", ctypes.c_int32),
                 ("llr_init", ctypes.c_void_p), ("xin_init", ctypes.c_void_p), ("xin_out", ctypes.c_void_p),
                 ("app_init", ctypes.c_void_p), ("train_dump", ctypes.c_void_p), ("train_dump_bytes", ctypes.c_size_t),
-                ("llr_all", ctypes.c_void_p)]
+                ("llr_all", ctypes.c_void_p), ("llr_pitch", ctypes.c_int32)]
 
 
 def build(verbose=False):

@@ -549,6 +549,8 @@ extern "C" int nldpc_boosted_forward(const nldpc_graph_t *g, const nldpc_boosted
     a.xa = xa_dev; a.w = cn_w_dev; a.b = ucn_w_dev; a.vn_w = vn_w_dev; a.B = B; a.T = T;
     a.soft_mode = soft_mode; a.soft = soft_dev; a.hard_mode = hard_mode; a.hard = hard_dev; a.llr_last = llr_last_dev;
     a.llr_all = cfg->llr_all_dev;
+    if (cfg->llr_pitch != 0 && cfg->llr_pitch < g->E) return fail(NLDPC_E_INVALID, "nldpc_boosted_forward: llr_pitch smaller than E");
+    a.llr_pitch = cfg->llr_pitch > 0 ? cfg->llr_pitch : g->E;
     a.wb_off = -1;
     a.decoder_type = cfg->decoder_type; a.qbit = cfg->qbit; a.compute_ucn = cfg->compute_ucn; a.ucn_mix = cfg->ucn_mix;
     a.llr_lo = cfg->llr_lo; a.llr_hi = cfg->llr_hi;

@@ -40,6 +40,7 @@ struct DecodeArgs {
     int hard_mode; uint8_t *hard;
     float *llr_last;   // Boosted: [B][Z][E] or nullptr
     float *llr_all;    // Boosted: [T][B][Z][E] (self.llr[t+1] of every executed iteration) or nullptr
+    int llr_pitch;     // row pitch (floats) of llr_last / llr_all: [..][b][z][e] at ((.. * B + b) * Z + z) * llr_pitch + e  (>= E)
     int unit_begin, unit_end;   // specialised kernels: work units [unit_begin, unit_end) of this launch (unit_end 0 = all)
     int wb_off;        // specialised kernels: offset (float2 units) of this launch's weights in the constant arena, -1 = use w/b pointers
     // boosted config

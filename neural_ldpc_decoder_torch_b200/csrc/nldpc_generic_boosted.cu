@@ -37,7 +37,8 @@ struct BoostedCtx {
     int app_row0;                // first slab row holding the APP used by the UCN indicator (xin rows at "t == 0")
     int xo_row0, app_store_row0; // xo rows; rows receiving this iteration's output (or -1)
     bool want_c2v1;              // compute the c2v of degree-1 edges even when nothing is emitted (llr_last)
-    float *llr_last;             // &llr_last[b][z][0] (stride E per lane) or nullptr
+    float *llr_last;             // &llr_last[b][z][0] (stride llr_pitch per lane) or nullptr
+    int llr_pitch;
     int E;
     uint8_t *mask_out;           // training dump: &hist_mask[t][b][0] of the iteration being emitted, or nullptr
     uint8_t *ucn_out;            // training dump: &hist_ucn[t][b][0] ([M][Z]) or nullptr
@@ -130,7 +131,7 @@ __device__ __forceinline__ void cn_check_boosted(float *__restrict__ slab, int h
         m = is_qms ? quantf(m, bc.qbit) : clampf(m, bc.lo, bc.hi);                               // (:507-510)
         const float sg = (o[k] > 0.0f) ? 1.0f : ((o[k] < 0.0f) ? -1.0f : 0.0f);
         const float c2v = mulf(m, sg);                                                           // (:512)
-        if (bc.llr_last) bc.llr_last[(size_t)zz[k] * bc.E + e] = c2v;
+        if (bc.llr_last) bc.llr_last[(size_t)zz[k] * bc.llr_pitch + e] = c2v;
         if (j1 < 0) slab[addr[k]] = c2v;
         else if (emit_now) emit_boosted(ec, bc, slab, g.Z, j1 * g.Z + zz[k], addf(0.0f, c2v));
     }
@@ -257,8 +258,9 @@ nldpc_generic_boosted_kernel(const GraphDev g, const DecodeArgs a, const Boosted
                 bc.xo_row0 = lay.xo_row0;
                 bc.app_store_row0 = track_app ? lay.app_row0 : -1;
                 bc.want_c2v1 = (last && a.llr_last != nullptr) || a.llr_all != nullptr;
-                bc.llr_last = a.llr_all ? a.llr_all + ((size_t)t * a.B + b) * Z * g.E
-                                        : ((last && a.llr_last) ? a.llr_last + (size_t)b * Z * g.E : nullptr);
+                bc.llr_pitch = a.llr_pitch;
+                bc.llr_last = a.llr_all ? a.llr_all + ((size_t)t * a.B + b) * Z * a.llr_pitch
+                                        : ((last && a.llr_last) ? a.llr_last + (size_t)b * Z * a.llr_pitch : nullptr);
                 bc.E = g.E;
                 bc.mask_out = a.hist_mask ? a.hist_mask + ((size_t)t * a.B + b) * NZ : nullptr;
                 bc.ucn_out = (a.hist_ucn && track_app) ? a.hist_ucn + ((size_t)t * a.B + b) * g.M * Z : nullptr;

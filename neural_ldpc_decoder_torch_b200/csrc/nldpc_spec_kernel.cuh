@@ -104,6 +104,14 @@ extern "C" unsigned nldpc_debug_restarts() { unsigned v = 0; cudaMemcpyFromSymbo
 #ifndef NLDPC_VN_QOUTER
 #define NLDPC_VN_QOUTER 1   // 1: VN chain pairs written operand-major
 #endif
+#ifndef NLDPC_LLR_VEC
+#define NLDPC_LLR_VEC 1     // Boosted state export with 16-byte stores after the CN phase (LlrExport) when the rows allow it
+#endif
+#ifndef NLDPC_LLR_VEC_LAST
+#define NLDPC_LLR_VEC_LAST 0     // ... also for the single export of the last-iteration (throughput) kernels: OFF.  With it the
+#endif                           // WiMAX throughput kernel wrote its packed decisions to a wrong address although the export
+                                 // itself never ran (decode_hard passes no llr pointer) — not understood, and one export per
+                                 // decode is not worth finding out: the every-iteration kernels are where the 16.5 GB go.
 #ifndef NLDPC_PIPE_CN
 #define NLDPC_PIPE_CN 1     // 1: the next check's inputs are loaded before the current check computes
 #endif
@@ -312,7 +320,8 @@ struct NeuralLane {
     int xo_off;              // float offset from the xin rows to the xo rows (0: xa_origin and xa_input are the same rows)
     const float *xa_cw;      // &xa[b][0] in global memory (kXo == 2)
     float lo, hi;            // allowed_llr_range
-    float *llr_last;         // &llr_last[b][0][0] ([Z][E]) while the last iteration's CN phase runs, else nullptr
+    float *llr_last;         // &llr_last[b][0][0] ([Z][llr_pitch]) while the last iteration's CN phase runs, else nullptr
+    int llr_pitch;           // row pitch of the state tensors (floats, >= E; DecodeArgs::llr_pitch)
     uint8_t *mask;           // training dump: &hist_mask[t_emit][b][0] of the iteration being emitted, or nullptr
     char *dump;              // training dump, check-packed format: this codeword's records of the running iteration, or nullptr
     const uint32_t *yb;      // fused loss: this codeword's packed label bits (shared memory), or nullptr
@@ -971,7 +980,7 @@ __device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c, const fl
             c2v = (madj == 0.0f) ? 0.0f : c2v;                                // m * sign(0) (:512)
         }
         if constexpr (kEmit) {
-            if (c.llr_last) c.llr_last[(size_t)(c.rot[shf[k]] - (c.lane - c.z)) * G::E + eix[k]] = c2v;   // self.llr[T][b][z][e]
+            if (c.llr_last) c.llr_last[(size_t)(c.rot[shf[k]] - (c.lane - c.z)) * c.llr_pitch + eix[k]] = c2v;   // self.llr[T][b][z][e]
         }
         if (col1[k] < 0) {
             c.rot[shf[k]][rows[k] * G::Z] = c2v;
@@ -986,6 +995,46 @@ __device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c, const fl
 #ifndef NLDPC_PIPE_CN
 #define NLDPC_PIPE_CN 1     // 1: the next check's inputs are loaded before the current check computes
 #endif
+// ---- Boosted state export, vector form (self.llr[t + 1], BoostedNeuralLDPCDecoder.py:512) ---------------------------------
+// The CN phase scatters each c2v to its VARIABLE lane, so a 4-byte store per lane and edge hits 16 different rows of the
+// [B][Z][pitch] tensor: one 32-byte sector per 4 bytes, L2-request bound (0.7 TB/s).  After the phase (and its group sync) lane
+// z owns row z of the tensor in the variable-lane view of the slab: it walks the edges in weight order (G::checks) and writes 4
+// consecutive ones with ONE 16-byte store.  Needs 16-byte rows (llr_pitch % 4 == 0: WiMAX E = 88 as is, others padded by the
+// caller) and a graph whose messages are ALL stored in the slab (no degree-1 blocks: WiMAX).  BG2's 38 degree-1 edges have no
+// slab row: parking them in 38 registers per lane across the CN phase made every BG2 kernel spill (measured: 255 registers +
+// 120-330 bytes of spill traffic), so BG2 keeps the scalar export.  Must run before the next VN phase (in place).
+template <class G>
+struct LlrExport {
+    NeuralLane<G> &c;
+    float *dst;              // &llr[..][b][z][0], 16-byte aligned
+    float q[3];
+    __device__ __forceinline__ void first_deg1() {}
+    template <class... Es>
+    __device__ __forceinline__ void chk() {
+        constexpr int D = sizeof...(Es);
+        constexpr int rows[D] = {Es::row...};
+        constexpr int eix[D] = {Es::e...};
+        constexpr int col1[D] = {Es::col1...};
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            static_assert(G::kXRegs == 0 && G::kDeg1Smem == 0, "every message of the graph is stored in the slab");
+            const float v = c.lane[rows[k] * G::Z];
+            if ((eix[k] & 3) == 3) __stcs(reinterpret_cast<float4 *>(dst + eix[k] - 3), make_float4(q[0], q[1], q[2], v));
+            else q[eix[k] & 3] = v;
+        }
+    }
+    __device__ __forceinline__ void finish() {
+#pragma unroll
+        for (int i = 0; i < (G::E & 3); i++) __stcs(dst + (G::E & ~3) + i, q[i]);
+    }
+};
+template <class G>
+__device__ __forceinline__ void llr_export(NeuralLane<G> &c, float *cw_base) {      // cw_base = &llr[..][b][0][0]
+    LlrExport<G> ex{c, cw_base + (size_t)c.z * c.llr_pitch, {0.0f, 0.0f, 0.0f}};
+    G::checks(ex);
+    ex.finish();
+}
+
 // ---- Train<> variant: the "extension" checks (D stored edges + ONE trailing degree-1 block with an identity circulant; 38 of
 // BG2's 42) as loops over the runtime descriptors of G::loop_classes — same arithmetic as cn_check_boosted_core, table entries
 // from constant memory instead of immediates.  word k < D: slab row | shift << 8 | edge << 16; word D: block J | x-row index << 8
@@ -1090,7 +1139,7 @@ struct CnBoostedLoops {                              // export still issued 4 % 
         for (int k = 0; k < NE; k++) {
             if constexpr (kLlr) {
                 const int zlane = k < D ? o.zl[k < D ? k : 0] : c.z;
-                if (c.llr_last) c.llr_last[zlane * G::E + (int)(c_desc[w0 + k] >> 16)] = c2v[k];      // self.llr[t + 1][b][z][e] (:512)
+                if (c.llr_last) c.llr_last[zlane * c.llr_pitch + (int)(c_desc[w0 + k] >> 16)] = c2v[k];      // self.llr[t + 1][b][z][e] (:512)
             }
             if (k < D) slab0[o.moff[k < D ? k : 0]] = c2v[k];
         }
@@ -1342,6 +1391,7 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
     c.lo = a.llr_lo;
     c.hi = a.llr_hi;
     c.llr_last = nullptr;
+    c.llr_pitch = a.llr_pitch;
     c.mask = nullptr;
     c.dump = nullptr;
     c.yb = nullptr;
@@ -1361,6 +1411,10 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
     uint32_t phase = 0;
     const bool soft_all = a.soft_mode == 1, hard_all = a.hard_mode == 1;
     const bool soft_any = a.soft_mode != 0, hard_any = a.hard_mode != 0;
+    // Boosted decode variants (not the training variant, which exports from its loops): self.llr leaves through LlrExport when the
+    // caller's rows are 16-byte aligned
+    constexpr bool kLlrVec = NLDPC_LLR_VEC && MODE != 0 && !kTrainWrap && G::kDeg1Smem == 0 && G::kXRegs == 0;
+    const bool llr_vec_ok = kLlrVec && (a.llr_pitch & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.llr_all) | reinterpret_cast<uintptr_t>(a.llr_last)) & 15) == 0;
 
     // phase barrier: group-local (a CTA-wide lockstep variant, so that all warps stream the same code, bought nothing:
     // 42.4 vs 43.2 M cw/s in round 1)
@@ -1560,11 +1614,21 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
                     if (fused) c.cg = __ldg(a.coef + t) * a.ginv;
                 }
                 c.llr_last = !c.valid ? nullptr
-                             : (a.llr_all ? a.llr_all + ((size_t)t * a.B + b) * Z * G::E
-                                          : ((last && a.llr_last) ? a.llr_last + (size_t)b * Z * G::E : nullptr));
+                             : (a.llr_all ? a.llr_all + ((size_t)t * a.B + b) * Z * a.llr_pitch
+                                          : ((last && a.llr_last) ? a.llr_last + (size_t)b * Z * a.llr_pitch : nullptr));
+                float *llr_vec = nullptr;      // vector export after the phase instead of the scalar stores inside it (LlrExport)
+                if constexpr (kLlrVec) {
+                    if (llr_vec_ok) {
+                        llr_vec = c.llr_last;
+                        c.llr_last = nullptr;
+                    }
+                }
                 cn_run(std::true_type{});
                 loss_fold(t);
                 phase_sync();
+                if constexpr (kLlrVec) {
+                    if (llr_vec) llr_export<G>(c, llr_vec);
+                }
             }
         } else {
             for (int t = 0; t < a.T; t++) {
@@ -1585,8 +1649,21 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
                 } else {
                     c.soft = soft_cw;
                     c.hb = hb_cw;
-                    c.llr_last = (a.llr_last && c.valid) ? a.llr_last + (size_t)b * Z * G::E : nullptr;
+                    c.llr_last = (a.llr_last && c.valid) ? a.llr_last + (size_t)b * Z * a.llr_pitch : nullptr;
+                    float *llr_vec = nullptr;
+                    if constexpr (kLlrVec && NLDPC_LLR_VEC_LAST) {
+                        if (llr_vec_ok) {
+                            llr_vec = c.llr_last;
+                            c.llr_last = nullptr;
+                        }
+                    }
                     cn_run(std::true_type{});
+                    if constexpr (kLlrVec && NLDPC_LLR_VEC_LAST) {
+                        if (llr_vec_ok && a.llr_last) {      // (launch-uniform: the barrier is taken by every lane of the group)
+                            phase_sync();
+                            if (llr_vec) llr_export<G>(c, llr_vec);
+                        }
+                    }
                 }
                 phase_sync();
             }

@@ -238,8 +238,11 @@ def _opt_f32(name, t, shape, device):
 
 
 def boosted_forward_direct(xa, vn_w, cn_w, ucn_w, graph_id, T, decoder_type, qbit, llr_lo, llr_hi, compute_ucn, ucn_mix, llr_init,
-                           xin_init, app_init, llr_mode, want_xin, soft_mode, hard_mode, want_dump=False):
+                           xin_init, app_init, llr_mode, want_xin, soft_mode, hard_mode, want_dump=False, pad_llr=False):
     """Body of nldpc::boosted_forward, callable without the dispatcher (decode-only callers that hold no autograd state).
+    pad_llr: allocate the llr state with 16-byte rows (row pitch E rounded up to a multiple of 4 floats, nldpc_boosted_cfg_t
+    llr_pitch) and return the [.., :E] view of it (same shape and values; not contiguous when E % 4 != 0).  16-byte rows are what
+    the vector state export of the specialised kernels needs (graphs without degree-1 blocks; WiMAX's E = 88 has them as is).
     T consecutive iterations of the Boosted loop body.  Returns (soft [T,B,N*Z] | [B,N*Z] | empty per soft_mode,
     llr [B,Z,E] (llr_mode 1: self.llr[t_last+1]) | [T,B,Z,E] (llr_mode 2: every executed iteration, :512) | empty (0),
     xin_out [B,N,Z] | empty, packed hard decisions per hard_mode | empty, training dump | 1 byte).
@@ -261,7 +264,9 @@ def boosted_forward_direct(xa, vn_w, cn_w, ucn_w, graph_id, T, decoder_type, qbi
     soft = torch.empty(_out_shape(soft_mode, T, B, g.NZ), dtype=torch.float32, device=dev)
     hard = torch.empty(_out_shape(hard_mode, T, B, g.hard_bytes), dtype=torch.uint8, device=dev)
     llr_mode = int(llr_mode)
-    llr_last = torch.empty(_llr_shape(llr_mode, T, B, g), dtype=torch.float32, device=dev)
+    llr_pitch = ((g.E + 3) // 4) * 4 if (pad_llr and llr_mode) else g.E
+    llr_shape = _llr_shape(llr_mode, T, B, g)
+    llr_last = torch.empty(llr_shape[:-1] + (llr_pitch,) if llr_mode else llr_shape, dtype=torch.float32, device=dev)
     xin_out = torch.empty((B, g.N, g.Z) if want_xin else (0,), dtype=torch.float32, device=dev)
     nbytes = int(_lib.lib().nldpc_backward_workspace_bytes(g.ptr, B, T, 1)) if want_dump else 0
     dump = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=dev)
@@ -271,13 +276,15 @@ def boosted_forward_direct(xa, vn_w, cn_w, ucn_w, graph_id, T, decoder_type, qbi
                           xin_out.data_ptr() if want_xin else None,
                           app_init.data_ptr() if app_init is not None else None,
                           dump.data_ptr() if want_dump else None, nbytes,
-                          llr_last.data_ptr() if llr_mode == 2 else None)
+                          llr_last.data_ptr() if llr_mode == 2 else None, llr_pitch)
     with torch.cuda.device(dev):
         rc = _lib.lib().nldpc_boosted_forward(g.ptr, ctypes.byref(cfg), _ptr(xa), _ptr(vn_w), _ptr(cn_w), _ptr(ucn_w), B, T,
                                               soft_mode, _ptr(soft) if soft_mode else _vp(0), hard_mode,
                                               _ptr(hard) if hard_mode else _vp(0),
                                               _ptr(llr_last) if llr_mode == 1 else _vp(0), _stream(xa))
     _lib.check(rc, "nldpc_boosted_forward")
+    if llr_mode and llr_pitch != g.E:
+        llr_last = llr_last[..., :g.E]
     return soft, llr_last, xin_out, hard, dump
 
 

@@ -102,7 +102,7 @@ def test_c_abi_exports_every_declared_symbol():
     assert len(names) >= 8
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/nldpc.h but not exported"
-    assert lib.nldpc_abi_version() == 3
+    assert lib.nldpc_abi_version() == 4
 
 
 def test_product_package_never_imports_oracle():
