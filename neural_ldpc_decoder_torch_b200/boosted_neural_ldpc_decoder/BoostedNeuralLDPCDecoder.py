@@ -361,7 +361,10 @@ class BoostedNeuralLDPCDecoder(nn.Module):
             soft, llr_out, xin_out, _, _ = run_op(
                 x_run, vn_w, cn_w, ucn_w, gid, len(run), dec, int(self.decoder_qms_qbit),
                 float(self.allowed_llr_range.start), float(self.allowed_llr_range.end), bool(compute_ucn), bool(ucn_mix),
-                llr_init, xin_state, app_init, llr_mode, want_xin, 1, 0, want_dump)
+                llr_init, xin_state, app_init, llr_mode, want_xin, 1, 0, want_dump,
+                # 16-byte state rows (BG2: E = 197 at pitch 200) let the kernels export self.llr with vector stores; the
+                # tensors stored below are the [..., :E] views (same shape and values as the reference's, :512)
+                **({"pad_llr": True} if inference else {}))
             for k, t in enumerate(run):
                 self.outputs[t] = soft[k]
                 if llr_mode == 2:

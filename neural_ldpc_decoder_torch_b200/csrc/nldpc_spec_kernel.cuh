@@ -321,7 +321,12 @@ struct NeuralLane {
     const float *xa_cw;      // &xa[b][0] in global memory (kXo == 2)
     float lo, hi;            // allowed_llr_range
     float *llr_last;         // &llr_last[b][0][0] ([Z][llr_pitch]) while the last iteration's CN phase runs, else nullptr
+    float *llr_d1;           // same tensor, used by the degree-1 edges of the unrolled CN phase (== llr_last, except while the
+                             // stored edges leave through LlrExport: then llr_last is nullptr and only these keep their store)
     int llr_pitch;           // row pitch of the state tensors (floats, >= E; DecodeArgs::llr_pitch)
+    float *llr_row;          // inline vector export (llr_inline<G>): &llr[..][b][z][0] of this lane's own row, or nullptr
+    float llr_q[3];          // ... the open group of 4 consecutive edges
+    bool llr_inl;            // ... launch-uniform: this launch exports that way (every lane takes the extra warp sync)
     uint8_t *mask;           // training dump: &hist_mask[t_emit][b][0] of the iteration being emitted, or nullptr
     char *dump;              // training dump, check-packed format: this codeword's records of the running iteration, or nullptr
     const uint32_t *yb;      // fused loss: this codeword's packed label bits (shared memory), or nullptr
@@ -880,9 +885,20 @@ __device__ __forceinline__ void cn_check_core(NeuralLane<G> &c, const float *raw
 // Boosted MS / QMS check update, BoostedNeuralLDPCDecoder.py:380-526 (no UCN mixing): condition the inputs (quantise or
 // clamp), nudge exact zeros to +1e-4, min over the others, mag - 1e-4 [mag <= 1e-4], o = mag * sgn, |o| * W_cn, ReLU,
 // condition again, * sign(o) (sign(0) = 0).  kXo: xa_origin lives in its own rows (VN weights make xa_input drift).
+// Inline vector export of self.llr[t + 1] (see LlrExport below for the problem).  When a lane group is one warp (Z | 32) and the
+// degree-1 blocks are lane-private, every check can export its own messages right after it has scattered them: one warp sync,
+// then lane z reads the D stored messages of ITS row back from the slab, has the degree-1 message of its row still in a register
+// (nothing is parked across the phase — 38 registers per lane for BG2, which spilled), and closes groups of 4 consecutive edges
+// with one 16-byte store each (the open group, <= 3 values, rides in NeuralLane::llr_q across checks).
+template <class G>
+__device__ __forceinline__ constexpr bool llr_inline() {
+    return NLDPC_LLR_VEC && GroupShape<G::Z>::kLanes == 32 && G::kDeg1Smem == 0 && G::kXRegs > 0 && !train_traits<G>::on;
+}
+
 template <class G, bool kEmit, int MODE, int kXo, class... Es>
 __device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c, const float *raw, const float2 *wb) {
     constexpr int D = sizeof...(Es);
+    float own[D];            // (inline export: the messages of this lane's own degree-1 edges)
     constexpr int rows[D] = {Es::row...};
     constexpr int shf[D] = {Es::shift...};
     constexpr int eix[D] = {Es::e...};
@@ -980,7 +996,11 @@ __device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c, const fl
             c2v = (madj == 0.0f) ? 0.0f : c2v;                                // m * sign(0) (:512)
         }
         if constexpr (kEmit) {
-            if (c.llr_last) c.llr_last[(size_t)(c.rot[shf[k]] - (c.lane - c.z)) * c.llr_pitch + eix[k]] = c2v;   // self.llr[T][b][z][e]
+            float *const st = col1[k] >= 0 ? c.llr_d1 : c.llr_last;
+            if (st) st[(size_t)(c.rot[shf[k]] - (c.lane - c.z)) * c.llr_pitch + eix[k]] = c2v;   // self.llr[T][b][z][e]
+            if constexpr (llr_inline<G>()) {
+                if (col1[k] >= 0) own[k] = c2v;
+            }
         }
         if (col1[k] < 0) {
             c.rot[shf[k]][rows[k] * G::Z] = c2v;
@@ -988,6 +1008,21 @@ __device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c, const fl
             const int q = col1[k] * G::Z + (int)(c.rot[shf[k]] - (c.lane - c.z));
             const float xo = kXo == 2 ? xo_global<MODE>(c, q) : (kXo == 1 ? c.rot[shf[k]][c.xo_off + col1[k] * G::Z] : raw[k]);
             c.emit_rot(col1[k], shf[k], boosted_out(c, q, xo, addf(0.0f, c2v)));   // (:513-526)
+        }
+    }
+    if constexpr (kEmit && llr_inline<G>()) {
+        if (c.llr_inl) {
+            __syncwarp();
+            if (c.llr_row) {
+#pragma unroll
+                for (int k = 0; k < D; k++) {
+                    const float v = col1[k] >= 0 ? own[k] : c.lane[rows[k] * G::Z];
+                    if ((eix[k] & 3) == 3)
+                        __stcs(reinterpret_cast<float4 *>(c.llr_row + eix[k] - 3), make_float4(c.llr_q[0], c.llr_q[1], c.llr_q[2], v));
+                    else
+                        c.llr_q[eix[k] & 3] = v;
+                }
+            }
         }
     }
 }
@@ -999,38 +1034,54 @@ __device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c, const fl
 // The CN phase scatters each c2v to its VARIABLE lane, so a 4-byte store per lane and edge hits 16 different rows of the
 // [B][Z][pitch] tensor: one 32-byte sector per 4 bytes, L2-request bound (0.7 TB/s).  After the phase (and its group sync) lane
 // z owns row z of the tensor in the variable-lane view of the slab: it walks the edges in weight order (G::checks) and writes 4
-// consecutive ones with ONE 16-byte store.  Needs 16-byte rows (llr_pitch % 4 == 0: WiMAX E = 88 as is, others padded by the
-// caller) and a graph whose messages are ALL stored in the slab (no degree-1 blocks: WiMAX).  BG2's 38 degree-1 edges have no
-// slab row: parking them in 38 registers per lane across the CN phase made every BG2 kernel spill (measured: 255 registers +
-// 120-330 bytes of spill traffic), so BG2 keeps the scalar export.  Must run before the next VN phase (in place).
+// consecutive ones with ONE 16-byte store.  Needs 16-byte rows (llr_pitch % 4 == 0: WiMAX E = 88 as is, BG2's E = 197 padded to
+// 200 by the caller).  Degree-1 edges with an identity circulant (BG2: 38 of 197) have no slab row — their message is computed
+// by the lane that owns the tensor row, which keeps its 4-byte store inside the CN phase (NeuralLane::llr_d1); parking the 38
+// values in registers until here made every BG2 kernel spill (measured).  They are HOLES of this pass: an aligned group of 4
+// with holes leaves as 8- / 4-byte pieces (`holes` is a compile-time constant after inlining: edges and groups are immediates).
+// Must run before the next VN phase (in place).
 template <class G>
 struct LlrExport {
     NeuralLane<G> &c;
     float *dst;              // &llr[..][b][z][0], 16-byte aligned
-    float q[3];
+    float q[4];
+    unsigned holes;
     __device__ __forceinline__ void first_deg1() {}
+    __device__ __forceinline__ void flush(int e0, int n) {      // elements e0 .. e0 + n - 1 of the aligned group starting at e0
+        if (n == 4 && holes == 0) {
+            __stcs(reinterpret_cast<float4 *>(dst + e0), make_float4(q[0], q[1], q[2], q[3]));
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const bool a = 2 * h < n && !((holes >> (2 * h)) & 1), b = 2 * h + 1 < n && !((holes >> (2 * h + 1)) & 1);
+                if (a && b) __stcs(reinterpret_cast<float2 *>(dst + e0 + 2 * h), make_float2(q[2 * h], q[2 * h + 1]));
+                else if (a) __stcs(dst + e0 + 2 * h, q[2 * h]);
+                else if (b) __stcs(dst + e0 + 2 * h + 1, q[2 * h + 1]);
+            }
+        }
+        holes = 0;
+    }
     template <class... Es>
     __device__ __forceinline__ void chk() {
         constexpr int D = sizeof...(Es);
         constexpr int rows[D] = {Es::row...};
         constexpr int eix[D] = {Es::e...};
         constexpr int col1[D] = {Es::col1...};
+        static_assert(G::kDeg1Smem == 0, "degree-1 blocks are lane-private (identity circulants)");
 #pragma unroll
         for (int k = 0; k < D; k++) {
-            static_assert(G::kXRegs == 0 && G::kDeg1Smem == 0, "every message of the graph is stored in the slab");
-            const float v = c.lane[rows[k] * G::Z];
-            if ((eix[k] & 3) == 3) __stcs(reinterpret_cast<float4 *>(dst + eix[k] - 3), make_float4(q[0], q[1], q[2], v));
-            else q[eix[k] & 3] = v;
+            if (col1[k] >= 0) holes |= 1u << (eix[k] & 3);
+            else q[eix[k] & 3] = c.lane[rows[k] * G::Z];
+            if ((eix[k] & 3) == 3) flush(eix[k] - 3, 4);
         }
     }
     __device__ __forceinline__ void finish() {
-#pragma unroll
-        for (int i = 0; i < (G::E & 3); i++) __stcs(dst + (G::E & ~3) + i, q[i]);
+        if ((G::E & 3) != 0) flush(G::E & ~3, G::E & 3);
     }
 };
 template <class G>
 __device__ __forceinline__ void llr_export(NeuralLane<G> &c, float *cw_base) {      // cw_base = &llr[..][b][0][0]
-    LlrExport<G> ex{c, cw_base + (size_t)c.z * c.llr_pitch, {0.0f, 0.0f, 0.0f}};
+    LlrExport<G> ex{c, cw_base + (size_t)c.z * c.llr_pitch, {0.0f, 0.0f, 0.0f, 0.0f}, 0u};
     G::checks(ex);
     ex.finish();
 }
@@ -1391,6 +1442,9 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
     c.lo = a.llr_lo;
     c.hi = a.llr_hi;
     c.llr_last = nullptr;
+    c.llr_d1 = nullptr;
+    c.llr_row = nullptr;
+    c.llr_inl = false;
     c.llr_pitch = a.llr_pitch;
     c.mask = nullptr;
     c.dump = nullptr;
@@ -1413,8 +1467,10 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
     const bool soft_any = a.soft_mode != 0, hard_any = a.hard_mode != 0;
     // Boosted decode variants (not the training variant, which exports from its loops): self.llr leaves through LlrExport when the
     // caller's rows are 16-byte aligned
-    constexpr bool kLlrVec = NLDPC_LLR_VEC && MODE != 0 && !kTrainWrap && G::kDeg1Smem == 0 && G::kXRegs == 0;
-    const bool llr_vec_ok = kLlrVec && (a.llr_pitch & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.llr_all) | reinterpret_cast<uintptr_t>(a.llr_last)) & 15) == 0;
+    // (graphs with lane-private degree-1 blocks and one-warp groups export inline instead, llr_inline<G>: BG2)
+    constexpr bool kLlrInl = MODE != 0 && !kTrainWrap && llr_inline<G>();
+    constexpr bool kLlrVec = NLDPC_LLR_VEC && MODE != 0 && !kTrainWrap && G::kDeg1Smem == 0 && !kLlrInl;
+    const bool llr_vec_ok = (kLlrVec || kLlrInl) && (a.llr_pitch & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.llr_all) | reinterpret_cast<uintptr_t>(a.llr_last)) & 15) == 0;
 
     // phase barrier: group-local (a CTA-wide lockstep variant, so that all warps stream the same code, bought nothing:
     // 42.4 vs 43.2 M cw/s in round 1)
@@ -1616,6 +1672,7 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
                 c.llr_last = !c.valid ? nullptr
                              : (a.llr_all ? a.llr_all + ((size_t)t * a.B + b) * Z * a.llr_pitch
                                           : ((last && a.llr_last) ? a.llr_last + (size_t)b * Z * a.llr_pitch : nullptr));
+                c.llr_d1 = c.llr_last;
                 float *llr_vec = nullptr;      // vector export after the phase instead of the scalar stores inside it (LlrExport)
                 if constexpr (kLlrVec) {
                     if (llr_vec_ok) {
@@ -1623,7 +1680,23 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
                         c.llr_last = nullptr;
                     }
                 }
+                if constexpr (kLlrInl) {      // ... or check by check inside the phase (llr_inline<G>)
+                    c.llr_inl = llr_vec_ok && (a.llr_all != nullptr || (last && a.llr_last != nullptr));
+                    if (c.llr_inl) {
+                        c.llr_row = c.llr_last ? c.llr_last + (size_t)c.z * a.llr_pitch : nullptr;
+                        c.llr_last = nullptr;
+                        c.llr_d1 = nullptr;
+                    }
+                }
                 cn_run(std::true_type{});
+                if constexpr (kLlrInl) {
+                    if (c.llr_row) {
+#pragma unroll
+                        for (int i = 0; i < (G::E & 3); i++) __stcs(c.llr_row + (G::E & ~3) + i, c.llr_q[i]);
+                    }
+                    c.llr_row = nullptr;
+                    c.llr_inl = false;
+                }
                 loss_fold(t);
                 phase_sync();
                 if constexpr (kLlrVec) {
@@ -1650,6 +1723,7 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
                     c.soft = soft_cw;
                     c.hb = hb_cw;
                     c.llr_last = (a.llr_last && c.valid) ? a.llr_last + (size_t)b * Z * a.llr_pitch : nullptr;
+                    c.llr_d1 = c.llr_last;
                     float *llr_vec = nullptr;
                     if constexpr (kLlrVec && NLDPC_LLR_VEC_LAST) {
                         if (llr_vec_ok) {

@@ -267,6 +267,40 @@ def test_boosted_host_api_int8_llrs(code, sharing, B, T, graphs):
     assert np.array_equal(hard_h.numpy()[:k], np.packbits(ref[-1] < 0, axis=1, bitorder="little"))
 
 
+@pytest.mark.parametrize("code,sharing,dec,q,B,T", [
+    ("bg2", (3, 0, 3), "QMS", 5, 37, 6), ("bg2", (3, 0, 0), "MS", 5, 37, 5), ("bg2", (1, 1, 2), "MS", 5, 2, 3),
+    ("wimax", (3, 0, 0), "QMS", 5, 21, 5), ("wimax", (3, 0, 3), "MS", 5, 9, 4), ("bg2", (2, 0, 0), "QMS", 4, 5, 3)])
+def test_boosted_state_of_every_iteration_under_no_grad(code, sharing, dec, q, B, T, graphs):
+    """forward() under torch.no_grad() leaves self.llr[t + 1] of EVERY iteration (BoostedNeuralLDPCDecoder.py:512) — the path whose
+    state leaves the kernel with 16-byte stores (rows at pitch 200 for BG2's E = 197: inline export check by check; WiMAX: export
+    pass after each CN phase).  Odd batches: the last warp holds one valid and one padding codeword."""
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder import ConnectingMatrix, ConnectingMatrixTorch, Functions
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.BoostedNeuralLDPCDecoder import BoostedNeuralLDPCDecoder
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.DecoderType import DecoderType
+    from neural_ldpc_decoder_torch_b200.boosted_neural_ldpc_decoder.struct.NodeWeightSharingConfig import NodeWeightSharingConfig
+    bg, Z = graphs[code]
+    rs = np.random.RandomState(7 * B + T)
+    xa = awgn_llr(code, B, seed=B + 1, sigma=0.9)
+    xa[0, :2] = 0.0
+    if dec == "QMS":
+        xa = Functions.Cal_MSA_Q(xa, q).astype(np.float32)
+    cm = ConnectingMatrixTorch(ConnectingMatrix(Z=Z, basegraph=bg), device=torch.device("cuda"))
+    m = BoostedNeuralLDPCDecoder(T, B, cm, node_weight_sharing_config=NodeWeightSharingConfig(*sharing),
+                                 decoding_type=DecoderType[dec], decoder_qms_qbit=q).cuda()
+    with torch.no_grad():
+        for p in m.parameters():
+            p.copy_(torch.from_numpy(rs.uniform(0.4, 1.3, size=tuple(p.shape)).astype(np.float32)))
+        out = to_np(m(torch.from_numpy(xa).cuda()))
+    state = [l.cpu().numpy() for l in m.llr]
+    ref, llr = oracle_forward(m.cpu(), xa, return_llr=True)
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+    assert len(state) == T + 1
+    for t in range(T + 1):
+        assert state[t].shape == (B, Z, llr.shape[2])
+        want = np.ascontiguousarray(llr[t].transpose(0, 2, 1))
+        assert np.array_equal(state[t].view(np.uint32), want.view(np.uint32)), f"self.llr[{t}] differs"
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_boosted_golden_under_no_grad(name):
     """validation-loop use (forward under torch.no_grad(): live-gathered weights, dispatcher-free op) == the autograd path,
