@@ -327,6 +327,8 @@ struct NeuralLane {
     float *llr_row;          // inline vector export (llr_inline<G>): &llr[..][b][z][0] of this lane's own row, or nullptr
     float llr_q[3];          // ... the open group of 4 consecutive edges
     bool llr_inl;            // ... launch-uniform: this launch exports that way (every lane takes the extra warp sync)
+    bool llr_sc;             // warp-uniform: some lane may hold llr_last / llr_d1 (the scalar export runs behind ONE uniform branch per
+                             // check; as a per-edge predicate it cost 9 % of the executed instructions of launches that never store)
     uint8_t *mask;           // training dump: &hist_mask[t_emit][b][0] of the iteration being emitted, or nullptr
     char *dump;              // training dump, check-packed format: this codeword's records of the running iteration, or nullptr
     const uint32_t *yb;      // fused loss: this codeword's packed label bits (shared memory), or nullptr
@@ -898,7 +900,7 @@ __device__ __forceinline__ constexpr bool llr_inline() {
 template <class G, bool kEmit, int MODE, int kXo, class... Es>
 __device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c, const float *raw, const float2 *wb) {
     constexpr int D = sizeof...(Es);
-    float own[D];            // (inline export: the messages of this lane's own degree-1 edges)
+    float cv[kEmit ? D : 1]; // (kEmit: the messages, for the state export behind the loop)
     constexpr int rows[D] = {Es::row...};
     constexpr int shf[D] = {Es::shift...};
     constexpr int eix[D] = {Es::e...};
@@ -996,11 +998,7 @@ __device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c, const fl
             c2v = (madj == 0.0f) ? 0.0f : c2v;                                // m * sign(0) (:512)
         }
         if constexpr (kEmit) {
-            float *const st = col1[k] >= 0 ? c.llr_d1 : c.llr_last;
-            if (st) st[(size_t)(c.rot[shf[k]] - (c.lane - c.z)) * c.llr_pitch + eix[k]] = c2v;   // self.llr[T][b][z][e]
-            if constexpr (llr_inline<G>()) {
-                if (col1[k] >= 0) own[k] = c2v;
-            }
+            cv[k] = c2v;
         }
         if (col1[k] < 0) {
             c.rot[shf[k]][rows[k] * G::Z] = c2v;
@@ -1010,13 +1008,22 @@ __device__ __forceinline__ void cn_check_boosted_core(NeuralLane<G> &c, const fl
             c.emit_rot(col1[k], shf[k], boosted_out(c, q, xo, addf(0.0f, c2v)));   // (:513-526)
         }
     }
+    if constexpr (kEmit) {
+        if (c.llr_sc) {
+#pragma unroll
+            for (int k = 0; k < D; k++) {
+                float *const st = col1[k] >= 0 ? c.llr_d1 : c.llr_last;
+                if (st) st[(size_t)(c.rot[shf[k]] - (c.lane - c.z)) * c.llr_pitch + eix[k]] = cv[k];   // self.llr[T][b][z][e]
+            }
+        }
+    }
     if constexpr (kEmit && llr_inline<G>()) {
         if (c.llr_inl) {
             __syncwarp();
             if (c.llr_row) {
 #pragma unroll
                 for (int k = 0; k < D; k++) {
-                    const float v = col1[k] >= 0 ? own[k] : c.lane[rows[k] * G::Z];
+                    const float v = col1[k] >= 0 ? cv[k] : c.lane[rows[k] * G::Z];
                     if ((eix[k] & 3) == 3)
                         __stcs(reinterpret_cast<float4 *>(c.llr_row + eix[k] - 3), make_float4(c.llr_q[0], c.llr_q[1], c.llr_q[2], v));
                     else
@@ -1445,6 +1452,7 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
     c.llr_d1 = nullptr;
     c.llr_row = nullptr;
     c.llr_inl = false;
+    c.llr_sc = false;
     c.llr_pitch = a.llr_pitch;
     c.mask = nullptr;
     c.dump = nullptr;
@@ -1673,19 +1681,22 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
                              : (a.llr_all ? a.llr_all + ((size_t)t * a.B + b) * Z * a.llr_pitch
                                           : ((last && a.llr_last) ? a.llr_last + (size_t)b * Z * a.llr_pitch : nullptr));
                 c.llr_d1 = c.llr_last;
+                c.llr_sc = a.llr_all != nullptr || (last && a.llr_last != nullptr);
                 float *llr_vec = nullptr;      // vector export after the phase instead of the scalar stores inside it (LlrExport)
                 if constexpr (kLlrVec) {
                     if (llr_vec_ok) {
                         llr_vec = c.llr_last;
                         c.llr_last = nullptr;
+                        c.llr_sc = c.llr_sc && G::kXRegs > 0;      // (degree-1 edges, if any, keep their scalar store)
                     }
                 }
                 if constexpr (kLlrInl) {      // ... or check by check inside the phase (llr_inline<G>)
-                    c.llr_inl = llr_vec_ok && (a.llr_all != nullptr || (last && a.llr_last != nullptr));
+                    c.llr_inl = llr_vec_ok && c.llr_sc;
                     if (c.llr_inl) {
                         c.llr_row = c.llr_last ? c.llr_last + (size_t)c.z * a.llr_pitch : nullptr;
                         c.llr_last = nullptr;
                         c.llr_d1 = nullptr;
+                        c.llr_sc = false;
                     }
                 }
                 cn_run(std::true_type{});
@@ -1724,11 +1735,13 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
                     c.hb = hb_cw;
                     c.llr_last = (a.llr_last && c.valid) ? a.llr_last + (size_t)b * Z * a.llr_pitch : nullptr;
                     c.llr_d1 = c.llr_last;
+                    c.llr_sc = a.llr_last != nullptr;
                     float *llr_vec = nullptr;
                     if constexpr (kLlrVec && NLDPC_LLR_VEC_LAST) {
                         if (llr_vec_ok) {
                             llr_vec = c.llr_last;
                             c.llr_last = nullptr;
+                            c.llr_sc = c.llr_sc && G::kXRegs > 0;
                         }
                     }
                     cn_run(std::true_type{});
