@@ -1552,6 +1552,28 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
                 G::blocks(sc);
             }
         };
+        // inline state export around an emitting CN phase (llr_inline<G>): c.llr_last / c.llr_sc have just been set for the phase
+        auto llr_inline_begin = [&]() __attribute__((always_inline)) {
+            if constexpr (kLlrInl) {
+                c.llr_inl = llr_vec_ok && c.llr_sc;
+                if (c.llr_inl) {
+                    c.llr_row = c.llr_last ? c.llr_last + (size_t)c.z * a.llr_pitch : nullptr;
+                    c.llr_last = nullptr;
+                    c.llr_d1 = nullptr;
+                    c.llr_sc = false;
+                }
+            }
+        };
+        auto llr_inline_end = [&]() __attribute__((always_inline)) {
+            if constexpr (kLlrInl) {
+                if (c.llr_row) {      // the open group: E % 4 trailing edges
+#pragma unroll
+                    for (int i = 0; i < (G::E & 3); i++) __stcs(c.llr_row + (G::E & ~3) + i, c.llr_q[i]);
+                }
+                c.llr_row = nullptr;
+                c.llr_inl = false;
+            }
+        };
         auto cn_run = [&](auto emit_tag) __attribute__((always_inline)) {
             constexpr bool kEmitNow = decltype(emit_tag)::value;
             if constexpr (MODE == 0) {
@@ -1690,24 +1712,9 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
                         c.llr_sc = c.llr_sc && G::kXRegs > 0;      // (degree-1 edges, if any, keep their scalar store)
                     }
                 }
-                if constexpr (kLlrInl) {      // ... or check by check inside the phase (llr_inline<G>)
-                    c.llr_inl = llr_vec_ok && c.llr_sc;
-                    if (c.llr_inl) {
-                        c.llr_row = c.llr_last ? c.llr_last + (size_t)c.z * a.llr_pitch : nullptr;
-                        c.llr_last = nullptr;
-                        c.llr_d1 = nullptr;
-                        c.llr_sc = false;
-                    }
-                }
+                llr_inline_begin();      // ... or check by check inside the phase (llr_inline<G>)
                 cn_run(std::true_type{});
-                if constexpr (kLlrInl) {
-                    if (c.llr_row) {
-#pragma unroll
-                        for (int i = 0; i < (G::E & 3); i++) __stcs(c.llr_row + (G::E & ~3) + i, c.llr_q[i]);
-                    }
-                    c.llr_row = nullptr;
-                    c.llr_inl = false;
-                }
+                llr_inline_end();
                 loss_fold(t);
                 phase_sync();
                 if constexpr (kLlrVec) {
@@ -1744,7 +1751,9 @@ nldpc_spec_neural_kernel(const DecodeArgs a) {
                             c.llr_sc = c.llr_sc && G::kXRegs > 0;
                         }
                     }
+                    llr_inline_begin();
                     cn_run(std::true_type{});
+                    llr_inline_end();
                     if constexpr (kLlrVec && NLDPC_LLR_VEC_LAST) {
                         if (llr_vec_ok && a.llr_last) {      // (launch-uniform: the barrier is taken by every lane of the group)
                             phase_sync();

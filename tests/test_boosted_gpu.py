@@ -299,6 +299,14 @@ def test_boosted_state_of_every_iteration_under_no_grad(code, sharing, dec, q, B
         assert state[t].shape == (B, Z, llr.shape[2])
         want = np.ascontiguousarray(llr[t].transpose(0, 2, 1))
         assert np.array_equal(state[t].view(np.uint32), want.view(np.uint32)), f"self.llr[{t}] differs"
+    # store_llr = "last": only self.llr[T], exported by the last iteration of the throughput-style kernels
+    m = m.cuda()
+    m.store_llr = "last"
+    with torch.no_grad():
+        out = to_np(m(torch.from_numpy(xa).cuda()))
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+    want = np.ascontiguousarray(llr[T].transpose(0, 2, 1))
+    assert np.array_equal(m.llr[T].cpu().numpy().view(np.uint32), want.view(np.uint32))
 
 
 @pytest.mark.parametrize("name", CASES)
