@@ -16,6 +16,9 @@ launch (`store_llr = "all"`, default), so partial `target_iter` calls read exact
 (zeros where nothing was ever stored).  `store_llr = "last"` keeps only the state after the last iteration of a run and
 `"none"` skips the export (12.6 KB per BG2 codeword-iteration): throughput settings; with them a call that would continue
 from an iteration whose state was not stored raises instead of reading stale data.
+Under `torch.no_grad()` the state tensors are `[B, Z, :E]` views of rows padded to a multiple of 4 floats (BG2: 197 of 200;
+WiMAX's 88 needs none) — same shape and values as the reference's, not contiguous when padded (`.reshape` / `.contiguous()`
+where a flat view is wanted): 16-byte rows are what lets the kernels write them with vector stores.
 """
 from typing import Optional
 
