@@ -240,8 +240,8 @@ def _opt_f32(name, t, shape, device):
 def boosted_forward_direct(xa, vn_w, cn_w, ucn_w, graph_id, T, decoder_type, qbit, llr_lo, llr_hi, compute_ucn, ucn_mix, llr_init,
                            xin_init, app_init, llr_mode, want_xin, soft_mode, hard_mode, want_dump=False, pad_llr=False):
     """Body of nldpc::boosted_forward, callable without the dispatcher (decode-only callers that hold no autograd state).
-    pad_llr: allocate the llr state with 16-byte rows (row pitch E rounded up to a multiple of 4 floats, nldpc_boosted_cfg_t
-    llr_pitch) and return the [.., :E] view of it (same shape and values; not contiguous when E % 4 != 0).  16-byte rows are what
+    pad_llr: True = allocate the llr state with 16-byte rows (row pitch E rounded up to a multiple of 4 floats, nldpc_boosted_cfg_t
+    llr_pitch), an int = that row pitch; returns the [.., :E] view of it (same shape and values; not contiguous when pitch != E).  16-byte rows are what
     the vector state export of the specialised kernels needs (graphs without degree-1 blocks; WiMAX's E = 88 has them as is).
     T consecutive iterations of the Boosted loop body.  Returns (soft [T,B,N*Z] | [B,N*Z] | empty per soft_mode,
     llr [B,Z,E] (llr_mode 1: self.llr[t_last+1]) | [T,B,Z,E] (llr_mode 2: every executed iteration, :512) | empty (0),
@@ -264,9 +264,12 @@ def boosted_forward_direct(xa, vn_w, cn_w, ucn_w, graph_id, T, decoder_type, qbi
     soft = torch.empty(_out_shape(soft_mode, T, B, g.NZ), dtype=torch.float32, device=dev)
     hard = torch.empty(_out_shape(hard_mode, T, B, g.hard_bytes), dtype=torch.uint8, device=dev)
     llr_mode = int(llr_mode)
-    llr_pitch = ((g.E + 3) // 4) * 4 if (pad_llr and llr_mode) else g.E
+    if pad_llr is True:
+        llr_pitch = ((g.E + 3) // 4) * 4 if llr_mode else g.E
+    else:
+        llr_pitch = int(pad_llr) if (pad_llr and llr_mode) else g.E      # an explicit row pitch in floats (the library rejects < E)
     llr_shape = _llr_shape(llr_mode, T, B, g)
-    llr_last = torch.empty(llr_shape[:-1] + (llr_pitch,) if llr_mode else llr_shape, dtype=torch.float32, device=dev)
+    llr_last = torch.empty(llr_shape[:-1] + (max(llr_pitch, 1),) if llr_mode else llr_shape, dtype=torch.float32, device=dev)
     xin_out = torch.empty((B, g.N, g.Z) if want_xin else (0,), dtype=torch.float32, device=dev)
     nbytes = int(_lib.lib().nldpc_backward_workspace_bytes(g.ptr, B, T, 1)) if want_dump else 0
     dump = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=dev)

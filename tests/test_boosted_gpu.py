@@ -309,6 +309,37 @@ def test_boosted_state_of_every_iteration_under_no_grad(code, sharing, dec, q, B
     assert np.array_equal(m.llr[T].cpu().numpy().view(np.uint32), want.view(np.uint32))
 
 
+@pytest.mark.parametrize("name", [CASES[1], CASES[3]])
+def test_boosted_state_row_pitch_through_the_c_abi(name):
+    """nldpc_boosted_cfg_t.llr_pitch (include/nldpc.h): any pitch >= E gives the same [.., :E] values — multiples of 4 take the
+    vector exports, the others the scalar one with the caller's pitch; a pitch below E is refused (NLDPC_E_INVALID)."""
+    from neural_ldpc_decoder_torch_b200 import ops, _lib
+    d = load_golden(name)
+    T = int(d["T"])
+    xa = torch.from_numpy(d["xa"]).cuda()
+    m = build_module(d, device="cuda")
+    with torch.no_grad():
+        vn_w, cn_w, ucn_w, compute_ucn, ucn_mix = m.fold_weights(list(range(T)), xa.device)
+    E = int(m.conn_mat.sum_edge)
+    dec = {"SP": 0, "MS": 1, "QMS": 2}[m.decoding_type.name]
+
+    def run(mode, pitch):
+        with torch.no_grad():
+            return ops.boosted_forward_direct(xa, vn_w, cn_w, ucn_w, m.conn_mat.graph_id(xa.device), T, dec, int(m.decoder_qms_qbit),
+                                              float(m.allowed_llr_range.start), float(m.allowed_llr_range.end), bool(compute_ucn),
+                                              bool(ucn_mix), None, None, None, mode, False, 1, 0, False, pad_llr=pitch)
+    for mode in (1, 2):
+        soft0, llr0 = run(mode, False)[:2]
+        assert llr0.is_contiguous() and llr0.shape[-1] == E
+        for pitch in (True, E + 7, ((E + 3) // 4) * 4 + 4):
+            soft, llr = run(mode, pitch)[:2]
+            assert llr.shape == llr0.shape
+            assert torch.equal(soft.view(torch.int32), soft0.view(torch.int32))
+            assert torch.equal(llr.contiguous().view(torch.int32), llr0.view(torch.int32)), (mode, pitch)
+    with pytest.raises(_lib.NldpcError):
+        run(2, E - 1)
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_boosted_golden_under_no_grad(name):
     """validation-loop use (forward under torch.no_grad(): live-gathered weights, dispatcher-free op) == the autograd path,
